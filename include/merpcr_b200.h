@@ -1,0 +1,143 @@
+/*
+ * merpcr_b200.h -- C ABI of the B200-native STS-search path (libmerpcr_b200.so).
+ *
+ * The reference (FOI-Bioinformatics/merpcr, pure Python) has no native seam; the preserved surface is its
+ * Python API and CLI (merpcr_b200/engine.py, merpcr_b200/cli.py mirror them).  This header is the boundary
+ * between that thin host code and the hand-written sm_100a kernels.  Each entry point names the reference
+ * function(s) it replaces (paths relative to /root/reference/src/merpcr/).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MPCR_E* code; mpcr_last_error() gives the text
+ *     (thread-local);
+ *   - "d_" pointers are device memory owned by the caller (torch tensors in the Python host), "h_" pointers
+ *     are host memory; the library never frees caller memory;
+ *   - every launch goes onto the caller's stream (cudaStream_t passed as void*); functions are asynchronous
+ *     unless documented otherwise;
+ *   - one context per device; a context is not thread-safe, distinct contexts may be used concurrently;
+ *   - there is NO CPU fallback: every compute entry point fails with MPCR_ECUDA when no device is usable.
+ *
+ * Genome layout in HBM ("planes").  Contigs are concatenated in a padded global base
+ * coordinate: contig c starts at gstart[c], a multiple of 128, and gstart[c+1] >= gstart[c] + length[c] + 1;
+ * the gaps are zero (invalid).  For a base with global coordinate g and plane origin o (multiple of 128):
+ *   plane2  2 bit/base  : word (g-o)/32 of uint64, bits [2*((g-o)%32), +2)   A0 C1 G2 T3(U3), other -> 0
+ *   plane4  4 bit/base  : word (g-o)/16 of uint64, bits [4*((g-o)%16), +4)   IUPAC mask A1 C2 G4 T8 ... N15, X/other 0
+ *   valid   1 bit/base  : word (g-o)/64 of uint64, bit (g-o)%64              1 iff the base is A/C/G/T/U
+ * Algorithmic traffic is 0.75 B/bp (plane2 + plane4); `valid` is a derived private acceleration plane.
+ */
+#ifndef MERPCR_B200_H
+#define MERPCR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCR_ABI_VERSION 1
+
+enum {
+    MPCR_OK = 0,
+    MPCR_EINVAL = -1,   /* bad argument (the Python host raises ValueError)              */
+    MPCR_ECUDA = -2,    /* CUDA runtime error / no device                                */
+    MPCR_ENOMEM = -3,   /* allocation failure                                            */
+    MPCR_ESTATE = -4,   /* call order violated (e.g. scan before table build)            */
+    MPCR_EOVERFLOW = -5 /* hit buffer too small; *count holds the required capacity      */
+};
+
+typedef struct mpcr_ctx mpcr_ctx;
+
+/* Search parameters: the constructor arguments of MerPCR (core/engine.py:47-57), validated as :80-97. */
+typedef struct mpcr_params {
+    int32_t wordsize;           /* -W  3..16   */
+    int32_t margin;             /* -M  0..10000 */
+    int32_t mismatches;         /* -N  0..10   */
+    int32_t three_prime_match;  /* -X  >= 0    */
+    int32_t iupac_mode;         /* -I  0/1     */
+} mpcr_params;
+
+/* One contig of the padded global coordinate (see layout above). */
+typedef struct mpcr_contig {
+    uint64_t gstart;  /* multiple of 128 */
+    uint32_t length;  /* true contig length in bases, < 2^31 */
+    uint32_t reserved;
+} mpcr_contig;
+
+/* One hit = one output line of MerPCR.search (core/engine.py:437-444, models.py:52-58 STSHit).
+ * Positions are 0-based inclusive, contig-local; rec = 2*sts_line_index + (0 for "+", 1 for "-").
+ * rank / hash_off complete the reference's output-order key. */
+typedef struct mpcr_hit {
+    uint32_t contig;
+    uint32_t pos1;
+    uint32_t pos2;
+    uint32_t rec;
+    uint32_t rank;      /* 0 for delta=0, 2i-1 for delta=-i, 2i for delta=+i (engine.py:543-593) */
+    uint32_t hash_off;  /* hash_offset of the record (engine.py:486)                          */
+} mpcr_hit;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+int mpcr_abi_version(void);
+const char *mpcr_last_error(void);
+
+/* Replaces MerPCR.__init__/_validate_parameters (core/engine.py:47-97). MPCR_EINVAL <-> ValueError. */
+int mpcr_ctx_create(int device, const mpcr_params *params, mpcr_ctx **out);
+void mpcr_ctx_destroy(mpcr_ctx *ctx);
+/* Multiprocessor count of the context's device (grid sizing is a multiple of this). */
+int mpcr_ctx_sm_count(const mpcr_ctx *ctx);
+
+/* ---- (1) FASTA ingest --------------------------------------------------------------------------- */
+/* Replaces the sequence half of FASTALoader.load_file (io/fasta.py:58-61) + the per-base scode lookup of
+ * MerPCR._process_thread (core/engine.py:455,472,497): packs n filtered ASCII bases (device memory) into the
+ * three planes at global base dst_base (multiple of 64).  h_lut[256] maps a byte to
+ * (nibble | code2 << 4 | clean << 6); it is copied to the device by the call.  Words fully inside
+ * [dst_base, dst_base + n) are overwritten, the last partial word is written with zero padding. */
+int mpcr_pack_sequence(mpcr_ctx *ctx, const uint8_t *d_ascii, uint64_t n, uint64_t dst_base,
+                       uint64_t plane_origin, void *d_plane2, void *d_plane4, void *d_valid,
+                       const uint8_t *h_lut, void *stream);
+
+/* Device-side FASTA text ingest (io/fasta.py:43-66 on raw file bytes): see mpcr_fasta_* in a later ABI rev. */
+
+/* ---- (2) primer word-hash table ----------------------------------------------------------------- */
+/* Replaces the hashing half of MerPCR.load_sts_file + _hash_value + _reverse_complement + _insert_sts
+ * (core/engine.py:253-281, 324-359).  Input = the accepted STS lines after the host-side text rules
+ * (engine.py:216-251): for line i, upper-cased primer1 = blob[off[2i] .. off[2i+1]) and primer2 =
+ * blob[off[2i+1] .. off[2i+2]); pcr_size[i] already adjusted (engine.py:245-247) and clamped to 2^31-1.
+ * h_primer_lut[256]: byte -> (nibble | never_match << 4 | zero_code_char << 5) for the primer side of
+ * _compare_seqs.  All pointers are HOST memory; the call copies them, builds both strand records per line
+ * (record 2i = "+", 2i+1 = "-"), hashes, and builds the bucket table on the device.  Synchronous. */
+int mpcr_table_build(mpcr_ctx *ctx, const uint8_t *h_blob, const uint64_t *h_off, const uint32_t *h_pcr_size,
+                     uint32_t n_lines, const uint8_t *h_primer_lut, void *stream);
+/* Read back per-record results of the build (2*n_lines entries each): hash_offset (-1 = record not
+ * inserted: no clean W-mer, engine.py:266-270,275-281) and the reference's big-endian hash value. */
+int mpcr_table_records(mpcr_ctx *ctx, int32_t *h_hash_offset, uint32_t *h_hash);
+/* Debug/test readback of the encoded primers of one record (nibble words then aux words). */
+int mpcr_table_primer_words(mpcr_ctx *ctx, uint32_t rec, int which /*1|2*/, uint64_t *h_words, uint32_t max_words,
+                            uint32_t *n_words);
+
+/* ---- (3)+(4)+(5) scanner, verifier, hit emitter ------------------------------------------------- */
+/* Replaces MerPCR._process_thread + _match_sts + _compare_seqs (core/engine.py:453-642) over the hash
+ * positions whose global base coordinate lies in [shard_begin, shard_end) (multiples of 128; pass 0 and
+ * UINT64_MAX for everything).  The planes must cover every base the shard can touch:
+ * [shard_begin - mpcr_halo_left(), shard_end + mpcr_halo_right()) clipped to the genome.
+ * Hits are appended (unordered) to d_hits; *d_count receives the TRUE number of hits even when it
+ * exceeds capacity (the caller re-runs with a larger buffer; nothing is silently truncated). */
+int mpcr_scan(mpcr_ctx *ctx, const mpcr_contig *h_contigs, uint32_t n_contigs, const void *d_plane2,
+              const void *d_plane4, const void *d_valid, uint64_t plane_origin, uint64_t plane_bases,
+              uint64_t shard_begin, uint64_t shard_end, mpcr_hit *d_hits, uint64_t capacity,
+              uint64_t *d_count, void *stream);
+uint64_t mpcr_halo_left(const mpcr_ctx *ctx);
+uint64_t mpcr_halo_right(const mpcr_ctx *ctx);
+
+/* Replaces the sort of MerPCR.search (core/engine.py:434) including its tie order: orders n hits by
+ * (contig, pos1, hash_off, rec, rank) == "stable sort of discovery order by pos1" (SURVEY.md A.7). */
+int mpcr_sort_hits(mpcr_ctx *ctx, mpcr_hit *d_hits, uint64_t n, void *stream);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t mpcr_launch_count(const mpcr_ctx *ctx);
+/* Name / elapsed-ms of the most recent scan kernel as timed by CUDA events on its stream (0 if none). */
+float mpcr_last_scan_ms(mpcr_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MERPCR_B200_H */

@@ -1,0 +1,121 @@
+"""Command-line interface: same flags, me-PCR `K=V` translation, logging and exit codes as the reference's
+`merpcr/cli.py:19-266` (argparse exits 2 on bad values; any failure in the run exits 1)."""
+from __future__ import annotations
+
+import argparse
+import logging
+import sys
+from typing import List
+
+from .engine import (DEFAULT_IUPAC_MODE, DEFAULT_MARGIN, DEFAULT_MISMATCHES, DEFAULT_PCR_SIZE, DEFAULT_THREADS,
+                     DEFAULT_THREE_PRIME_MATCH, DEFAULT_WORDSIZE, MerPCR)
+
+DEFAULT_MAX_STS_LINE_LENGTH = 1022
+_MEPCR_FLAGS = {"M": "-M", "N": "-N", "W": "-W", "X": "-X", "T": "-T", "Q": "-Q", "Z": "-Z", "I": "-I", "S": "-S",
+                "O": "-O"}
+
+
+def convert_mepcr_arguments(args: List[str]) -> List[str]:
+    """`M=50` -> `-M 50`; `P=...` (Mac priority) dropped; `-help` -> `--help` (cli.py:19-62)."""
+    out: List[str] = []
+    for arg in args:
+        if len(arg) >= 3 and arg[1] == "=" and arg[0] in "MNWXTQZISOP":
+            if arg[0] != "P":
+                out.extend([_MEPCR_FLAGS[arg[0]], arg[2:]])
+        elif arg == "-help":
+            out.append("--help")
+        else:
+            out.append(arg)
+    return out
+
+
+def setup_logging(quiet: int, debug: bool) -> None:
+    """cli.py:65-76."""
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s - %(levelname)s - %(message)s")
+    logger = logging.getLogger("merpcr")
+    if debug:
+        logger.setLevel(logging.DEBUG)
+    elif quiet == 0:
+        logger.setLevel(logging.INFO)
+    else:
+        logger.setLevel(logging.WARNING)
+
+
+def _bounded(name: str, lo, hi, fmt: str):
+    def parse(value):
+        ivalue = int(value)
+        if (lo is not None and ivalue < lo) or (hi is not None and ivalue > hi):
+            raise argparse.ArgumentTypeError(fmt.format(ivalue))
+        return ivalue
+    parse.__name__ = name
+    return parse
+
+
+margin_type = _bounded("margin_type", 0, 10000, "Margin must be between 0-10000, got {}")
+mismatch_type = _bounded("mismatch_type", 0, 10, "Mismatches must be between 0-10, got {}")
+wordsize_type = _bounded("wordsize_type", 3, 16, "Word size must be between 3-16, got {}")
+threads_type = _bounded("threads_type", 1, None, "Threads must be > 0, got {}")
+pcr_size_type = _bounded("pcr_size_type", 1, 10000, "PCR size must be between 1-10000, got {}")
+sts_line_length_type = _bounded("sts_line_length_type", 1, None, "STS line length must be > 0, got {}")
+
+
+def create_parser() -> argparse.ArgumentParser:
+    """cli.py:127-214."""
+    parser = argparse.ArgumentParser(description="merPCR - Modern Electronic Rapid PCR",
+                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("sts_file", type=str, help="STS file (tab-delimited)")
+    parser.add_argument("fasta_file", type=str, help="FASTA sequence file")
+    parser.add_argument("-M", "--margin", type=margin_type, default=DEFAULT_MARGIN,
+                        help=f"Margin (default: {DEFAULT_MARGIN})")
+    parser.add_argument("-N", "--mismatches", type=mismatch_type, default=DEFAULT_MISMATCHES,
+                        help=f"Number of mismatches allowed (default: {DEFAULT_MISMATCHES})")
+    parser.add_argument("-W", "--wordsize", type=wordsize_type, default=DEFAULT_WORDSIZE,
+                        help=f"Word size (default: {DEFAULT_WORDSIZE})")
+    parser.add_argument("-T", "--threads", type=threads_type, default=DEFAULT_THREADS,
+                        help=f"Number of threads (default: {DEFAULT_THREADS})")
+    parser.add_argument("-X", "--three-prime-match", type=int, default=DEFAULT_THREE_PRIME_MATCH,
+                        help="Number of 3'-ward bases in which to disallow mismatches "
+                             f"(default: {DEFAULT_THREE_PRIME_MATCH})")
+    parser.add_argument("-O", "--output", type=str, default=None, help="Output file name (default: stdout)")
+    parser.add_argument("-Q", "--quiet", type=int, choices=[0, 1], default=1, help="Quiet flag (0=verbose, 1=quiet)")
+    parser.add_argument("-Z", "--default-pcr-size", type=pcr_size_type, default=DEFAULT_PCR_SIZE,
+                        help=f"Default PCR size (default: {DEFAULT_PCR_SIZE})")
+    parser.add_argument("-I", "--iupac", type=int, choices=[0, 1], default=DEFAULT_IUPAC_MODE,
+                        help="IUPAC flag (0=don't honor IUPAC ambiguity symbols, 1=honor IUPAC symbols)")
+    parser.add_argument("-S", "--max-sts-line-length", type=sts_line_length_type, default=DEFAULT_MAX_STS_LINE_LENGTH,
+                        help=f"Max. line length for the STS file (default: {DEFAULT_MAX_STS_LINE_LENGTH})")
+    parser.add_argument("-v", "--version", action="version", version="merPCR version 1.0.0")
+    parser.add_argument("--debug", action="store_true", help="Enable debug logging")
+    return parser
+
+
+def main() -> int:
+    """cli.py:217-266."""
+    args = create_parser().parse_args(convert_mepcr_arguments(sys.argv[1:]))
+    setup_logging(args.quiet, args.debug)
+    logger = logging.getLogger("merpcr")
+    try:
+        mer_pcr = MerPCR(wordsize=args.wordsize, margin=args.margin, mismatches=args.mismatches,
+                         three_prime_match=args.three_prime_match, iupac_mode=args.iupac,
+                         default_pcr_size=args.default_pcr_size, threads=args.threads,
+                         max_sts_line_length=args.max_sts_line_length)
+        if not mer_pcr.load_sts_file(args.sts_file):
+            logger.error(f"Failed to load STS file: {args.sts_file}")
+            return 1
+        fasta_records = mer_pcr.load_fasta_file(args.fasta_file)
+        if not fasta_records:
+            logger.error(f"Failed to load FASTA file: {args.fasta_file}")
+            return 1
+        hit_count = mer_pcr.search(fasta_records, args.output)
+        logger.info(f"Search complete: {hit_count} hits found")
+        return 0
+    except Exception as e:  # noqa: BLE001  (cli.py:260-266 maps every failure to exit 1)
+        logger.error(f"Error: {str(e)}")
+        if args.debug:
+            import traceback
+            traceback.print_exc()
+        return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

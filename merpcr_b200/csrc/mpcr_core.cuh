@@ -1,0 +1,289 @@
+// mpcr_core.cuh -- data layout + the per-position semantics of the STS search, shared by every kernel.
+//
+// Everything here is __host__ __device__ so that tests/host_emul.cpp can run the very same verification
+// logic serially on a CPU against the oracle (test infrastructure only -- the product never runs it on the
+// host).  Reference citations are relative to /root/reference/src/merpcr/.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define MPCR_HD __host__ __device__ __forceinline__
+#else
+#define MPCR_HD inline
+#endif
+
+namespace mpcr {
+
+// ---------------------------------------------------------------------------------------------------------
+// Layout
+// ---------------------------------------------------------------------------------------------------------
+
+static constexpr uint64_t kLane1 = 0x1111111111111111ull;  // LSB of every nibble
+static constexpr int kTileBases = 32768;                   // hash positions per tile (multiple of 128)
+static constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
+
+// One record = one strand of one STS line (core/models.py:17-29 + engine.py:253-281).
+struct RecMeta {
+    uint32_t pcr_size;  // engine.py:245-247 adjusted, clamped to 2^31-1
+    uint32_t key;       // seed W-mer, little-endian digits (base i of the word in bits [2i,2i+1])
+    uint32_t hash_be;   // the reference's hash value (engine.py:350), for read-back only
+    uint32_t p1_word;   // offset (uint64 units) of primer1's words in the primer blob
+    uint32_t p2_word;
+    uint16_t len1, len2;
+    uint16_t hash_off;  // engine.py:339-353
+    uint16_t flags;     // bit0: inserted in the table
+    uint32_t pad;
+};
+static_assert(sizeof(RecMeta) == 32, "RecMeta layout");
+
+// A tile = up to kTileBases consecutive hash positions of ONE contig.
+struct TileDesc {
+    int64_t gbase;     // plane-relative base index of the tile's first base (multiple of 128)
+    uint32_t contig;   // contig index
+    uint32_t lstart;   // contig-local coordinate of the tile's first base
+    uint32_t length;   // true contig length L
+    uint32_t nbases;   // bases of the contig inside this tile
+};
+static_assert(sizeof(TileDesc) == 24, "TileDesc layout");
+
+struct SearchParams {
+    int W, M, N, X, iupac;
+};
+
+MPCR_HD uint32_t wmask_of(int W) { return W >= 16 ? 0xFFFFFFFFu : ((1u << (2 * W)) - 1u); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Alphabet (engine.py:99-172).  The genome-side LUT is built by the host (merpcr_b200/alphabet.py) because it
+// depends on the mode; the primer-side tables below are fixed.
+// ---------------------------------------------------------------------------------------------------------
+
+// engine.py:102-109 scode: 0..3 or 4 (= AMBIG)
+MPCR_HD int scode_of(uint8_t c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': case 'U': case 'u': return 3;
+        default: return 4;
+    }
+}
+
+// engine.py:112-135,359: complement, unknown -> 'N'
+MPCR_HD uint8_t complement_of(uint8_t c) {
+    switch (c) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; case 'U': return 'A';
+        case 'B': return 'V'; case 'D': return 'H'; case 'H': return 'D'; case 'K': return 'M'; case 'M': return 'K';
+        case 'N': return 'N'; case 'R': return 'Y'; case 'S': return 'S'; case 'V': return 'B'; case 'W': return 'W';
+        case 'X': return 'X'; case 'Y': return 'R';
+        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a'; case 'u': return 'a';
+        case 'b': return 'v'; case 'd': return 'h'; case 'h': return 'd'; case 'k': return 'm'; case 'm': return 'k';
+        case 'n': return 'n'; case 'r': return 'y'; case 's': return 's'; case 'v': return 'b'; case 'w': return 'w';
+        case 'x': return 'x'; case 'y': return 'r';
+        default: return 'N';
+    }
+}
+
+// digit reversal: big-endian 2-bit pack (reference) <-> little-endian pack (plane2 order)
+MPCR_HD uint32_t reverse_digits(uint32_t h, int W) {
+    uint32_t r = 0;
+    for (int i = 0; i < W; ++i) { r = (r << 2) | (h & 3u); h >>= 2; }
+    return r;
+}
+
+// engine.py:331-355 _hash_value on an (already upper-cased) primer given as a char accessor.
+// Returns the hash offset or -1; *hash_be gets the reference's value.
+template <class CharAt>
+MPCR_HD int first_clean_word(CharAt at, int len, int W, uint32_t* hash_be) {
+    uint32_t h = 0, mask = wmask_of(W);
+    int run = 0;
+    for (int i = 0; i < len; ++i) {
+        int code = scode_of(at(i));
+        if (code > 3) { run = 0; continue; }
+        h = ((h << 2) | (uint32_t)code) & mask;
+        if (++run >= W) { *hash_be = h; return i - W + 1; }
+    }
+    *hash_be = 0;
+    return -1;
+}
+
+// Encode a primer into nibble words + aux words.  lut[c] = nibble | never_match<<4 | zero_code_char<<5.
+// dst[0..nw) nibbles, dst[nw..2nw) aux (bit0 of nibble i = never match, bit1 = "is the zero-code character").
+template <class CharAt>
+MPCR_HD void encode_primer(CharAt at, int len, const uint8_t* lut, uint64_t* dst) {
+    int nw = (len + 15) >> 4;
+    for (int w = 0; w < nw; ++w) {
+        uint64_t q = 0, aux = 0;
+        int cnt = len - 16 * w; if (cnt > 16) cnt = 16;
+        for (int j = 0; j < cnt; ++j) {
+            uint8_t e = lut[at(16 * w + j)];
+            q |= (uint64_t)(e & 15u) << (4 * j);
+            aux |= (uint64_t)((e >> 4) & 3u) << (4 * j);
+        }
+        dst[w] = q;
+        dst[nw + w] = aux;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Plane access
+// ---------------------------------------------------------------------------------------------------------
+
+// 16 nibbles starting at plane-relative base b (any alignment).  Reads word b/16 and, if unaligned, b/16+1.
+MPCR_HD uint64_t fetch16(const uint64_t* p4, int64_t b) {
+    uint64_t i = (uint64_t)b >> 4;
+    unsigned sh = ((unsigned)b & 15u) * 4u;
+    uint64_t lo = p4[i];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (p4[i + 1] << (64u - sh));
+}
+
+// the W-mer starting at plane-relative base b, little-endian digits
+MPCR_HD uint32_t extract_key(const uint64_t* p2, int64_t b, uint32_t wmask) {
+    uint64_t i = (uint64_t)b >> 5;
+    unsigned sh = ((unsigned)b & 31u) * 2u;
+    uint64_t lo = p2[i];
+    uint64_t v = sh ? ((lo >> sh) | (p2[i + 1] << (64u - sh))) : lo;
+    return (uint32_t)v & wmask;
+}
+
+MPCR_HD uint64_t lanes_below(int n) {  // nibble-LSB mask of lanes [0, n), n in [0,16]
+    return n >= 16 ? kLane1 : (n <= 0 ? 0ull : (((1ull << (4 * n)) - 1ull) & kLane1));
+}
+
+MPCR_HD int popc64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// engine.py:599-642 _compare_seqs on packed data.
+//   genome : 16 bases / uint64 IUPAC-mask nibbles starting at plane-relative base gb
+//   primer : nibble words pw[0..nw) + aux words pw[nw..2nw)
+//   plus   : strand "+" (3' protected zone = last X positions) else "-" (first X positions)   (:609-611)
+// match test (:614-631): non-IUPAC -> identical letter == identical nibble (the nibble code is a bijection on
+// the sequence alphabet); IUPAC -> mask AND != 0, or both are the zero-code letter (X matches only X).
+// A primer letter that can match nothing in the genome carries the never_match aux bit.
+// ---------------------------------------------------------------------------------------------------------
+MPCR_HD bool compare_primer(const uint64_t* p4, int64_t gb, const uint64_t* pw, int len, bool plus,
+                            const SearchParams& prm) {
+    const int nw = (len + 15) >> 4;
+    int prot_lo, prot_hi;  // protected index range [prot_lo, prot_hi)
+    if (plus) { prot_lo = len - prm.X; if (prot_lo < 0) prot_lo = 0; prot_hi = len; }
+    else { prot_lo = 0; prot_hi = prm.X < len ? prm.X : len; }
+    int mism = 0;
+    for (int w = 0; w < nw; ++w) {
+        const uint64_t g = fetch16(p4, gb + 16 * w);
+        const uint64_t q = pw[w], aux = pw[nw + w];
+        uint64_t mis;
+        if (prm.iupac) {
+            uint64_t a = g & q;
+            uint64_t nz = a | (a >> 1) | (a >> 2) | (a >> 3);
+            uint64_t gz = ~(g | (g >> 1) | (g >> 2) | (g >> 3));
+            mis = ~(nz | (gz & (aux >> 1)));
+        } else {
+            uint64_t x = g ^ q;
+            mis = x | (x >> 1) | (x >> 2) | (x >> 3);
+        }
+        mis = (mis | aux) & lanes_below(len - 16 * w);
+        const uint64_t prot = lanes_below(prot_hi - 16 * w) & ~lanes_below(prot_lo - 16 * w);
+        if (mis & prot) return false;                    // :635-636
+        mism += popc64(mis);
+        if (mism > prm.N) return false;                  // :638-640
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// engine.py:486-489 + 507-597: one bucket entry met at hash position p of a contig of true length L.
+// gcontig = plane-relative base index of the contig's first base (may be negative for a shard that starts
+// inside the contig; every base actually touched lies inside the shard + halo).
+// emit(pos1, pos2, rank) is called once per matching delta, in the reference's order.
+// ---------------------------------------------------------------------------------------------------------
+template <class Emit>
+MPCR_HD void verify_record(const uint64_t* p4, int64_t gcontig, int64_t L, int64_t p, const RecMeta& m,
+                           const uint64_t* pwords, const SearchParams& prm, Emit&& emit) {
+    const int l1 = m.len1, l2 = m.len2;
+    const int64_t k = p - (int64_t)m.hash_off;                                   // :486
+    if (k < 0 || k + l1 > L) return;                                              // :487
+    if (!compare_primer(p4, gcontig + k, pwords + m.p1_word, l1, true, prm)) return;   // :515
+    const int64_t avail = L - (k + l1);                                           // :521
+    if (avail < l2) return;                                                       // :524
+    int64_t E = (int64_t)m.pcr_size, hi, lo;
+    if (E > L - k) { E = L - k; hi = 0; }                                         // :531-533 (end clamp, Q5)
+    else { hi = L - k - E; if (hi > prm.M) hi = prm.M; }                          // :535
+    lo = E - l1 - l2; if (lo > prm.M) lo = prm.M; if (lo < 0) lo = 0;             // :538-540
+    const uint64_t* q2 = pwords + m.p2_word;
+    const int64_t p2 = k + E - l2;                                                // :543
+    if (compare_primer(p4, gcontig + p2, q2, l2, false, prm)) emit(k, p2 + l2 - 1, (uint32_t)0);
+    const int64_t mx = lo > hi ? lo : hi;
+    for (int64_t i = 1; i <= mx; ++i) {                                           // :563
+        if (i <= lo && compare_primer(p4, gcontig + p2 - i, q2, l2, false, prm))  // :565-578
+            emit(k, p2 - i + l2 - 1, (uint32_t)(2 * i - 1));
+        if (i <= hi && compare_primer(p4, gcontig + p2 + i, q2, l2, false, prm))  // :581-593
+            emit(k, p2 + i + l2 - 1, (uint32_t)(2 * i));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Table probing
+// ---------------------------------------------------------------------------------------------------------
+
+MPCR_HD uint32_t slot_hash(uint32_t key) {
+    uint32_t h = key * 0x9E3779B1u;
+    return h ^ (h >> 15);
+}
+
+MPCR_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+// bit index of a key in the first-level filter: exact bitmap when 4^W <= filter_bits, else a fold.
+MPCR_HD uint32_t filter_index(uint32_t key, uint32_t filter_bits, int exact) {
+    return exact ? key : mulhi32(key * 0x9E3779B1u, filter_bits);
+}
+
+// slot = key << 32 | start ; empty = all ones.  Returns the bucket start or kEmptySlot.
+MPCR_HD uint32_t find_bucket(const uint64_t* slots, uint32_t slot_mask, uint32_t key) {
+    uint32_t i = slot_hash(key) & slot_mask;
+    for (;;) {
+        uint64_t s = slots[i];
+        uint32_t start = (uint32_t)s;
+        if (start == kEmptySlot) return kEmptySlot;
+        if ((uint32_t)(s >> 32) == key) return start;
+        i = (i + 1) & slot_mask;
+    }
+}
+
+// W-mer validity for the 64 hash positions of a strip: bit j set iff bases j .. j+W-1 are all clean.
+// v0 = valid bits of the strip's 64 bases, v1 = valid bits of the following 64 bases (only W-1 are used).
+MPCR_HD uint64_t window_valid(uint64_t v0, uint64_t v1, int W) {
+    // run-length doubling on the 128-bit pair (lo, hi): a_b[j] = AND of 2^b consecutive bits from j
+    uint64_t lo[5], hi[5];
+    lo[0] = v0; hi[0] = v1;
+    for (int b = 1; b < 5; ++b) {
+        const int s = 1 << (b - 1);
+        uint64_t slo = (lo[b - 1] >> s) | (hi[b - 1] << (64 - s));
+        uint64_t shi = hi[b - 1] >> s;
+        lo[b] = lo[b - 1] & slo;
+        hi[b] = hi[b - 1] & shi;
+    }
+    uint64_t r = ~0ull;
+    int off = 0;
+    for (int b = 4; b >= 0; --b) {
+        if ((W >> b) & 1) {
+            uint64_t x = off == 0 ? lo[b] : ((lo[b] >> off) | (hi[b] << (64 - off)));
+            r &= x;
+            off += 1 << b;
+        }
+    }
+    return r;
+}
+
+}  // namespace mpcr

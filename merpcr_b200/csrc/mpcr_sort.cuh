@@ -1,0 +1,148 @@
+// mpcr_sort.cuh -- stable LSD radix sort of small fixed-size records (hits, table pairs) on the device.
+//
+// Hand-written (no CUB): three kernels per 8-bit digit pass -- per-block histogram, single-block exclusive
+// scan, stable scatter (warp match_any ranking inside a block).  Passes are described by (field, shift,
+// mask) so that callers skip digits that cannot vary (known value bounds), which is what keeps the hit sort
+// at ~9 passes for a human-sized genome.  Replaces `hits.sort(key=pos1)` (core/engine.py:434) together with
+// the discovery-order tie rule.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpcr {
+
+struct PassDesc {
+    uint8_t field;   // index of the uint32 field inside the record
+    uint8_t shift;
+    uint16_t mask;   // <= 255
+};
+
+template <int NF>
+struct Item {
+    uint32_t f[NF];
+};
+
+static constexpr int kSortThreads = 256;
+static constexpr int kSortItemsPerBlock = 2048;
+
+template <int NF>
+__global__ void __launch_bounds__(kSortThreads) rs_hist(const Item<NF>* __restrict__ in, uint64_t n, PassDesc pd,
+                                                        uint32_t* __restrict__ counts, uint32_t nblk) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * kSortItemsPerBlock;
+    for (int i = threadIdx.x; i < kSortItemsPerBlock; i += kSortThreads) {
+        uint64_t idx = base + i;
+        if (idx < n) atomicAdd(&h[(in[idx].f[pd.field] >> pd.shift) & pd.mask], 1u);
+    }
+    __syncthreads();
+    counts[(uint64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of `total` uint32 in place, one block of 1024 threads
+__global__ void __launch_bounds__(1024) rs_scan(uint32_t* __restrict__ a, uint32_t total) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t per = (total + 1023u) / 1024u;
+    const uint32_t lo = min(total, (uint32_t)tid * per), hi = min(total, lo + per);
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; ++i) s += a[i];
+    // block exclusive scan of s
+    uint32_t incl = s;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = warp_sums[lane], wi = w;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        warp_sums[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + incl - s;
+    for (uint32_t i = lo; i < hi; ++i) {
+        uint32_t v = a[i];
+        a[i] = run;
+        run += v;
+    }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(kSortThreads) rs_scatter(const Item<NF>* __restrict__ in, Item<NF>* __restrict__ out,
+                                                           uint64_t n, PassDesc pd, const uint32_t* __restrict__ offsets,
+                                                           uint32_t nblk) {
+    __shared__ uint32_t running[256];
+    __shared__ uint32_t wc[kSortThreads / 32][256];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    running[tid] = offsets[(uint64_t)tid * nblk + blockIdx.x];
+    for (int w = 0; w < kSortThreads / 32; ++w) wc[w][tid] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * kSortItemsPerBlock;
+    for (int c = 0; c < kSortItemsPerBlock; c += kSortThreads) {
+        const uint64_t idx = base + c + tid;
+        const bool act = idx < n;
+        Item<NF> it;
+        uint32_t d = 0x100u + (uint32_t)lane;  // inactive lanes never match an active digit
+        if (act) { it = in[idx]; d = (it.f[pd.field] >> pd.shift) & pd.mask; }
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (act && rank == 0) wc[wid][d] = __popc(peers);
+        __syncthreads();
+        if (act) {
+            uint32_t pre = 0;
+            for (int w = 0; w < wid; ++w) pre += wc[w][d];
+            out[running[d] + pre + rank] = it;
+        }
+        __syncthreads();
+        {
+            uint32_t tot = 0;
+            for (int w = 0; w < kSortThreads / 32; ++w) { tot += wc[w][tid]; wc[w][tid] = 0; }
+            running[tid] += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// Host driver: sorts `n` records in d_a using d_b as the ping-pong buffer; the result ends in d_a.
+// d_counts must hold 256 * ceil(n / kSortItemsPerBlock) uint32.  Returns the number of kernels launched.
+template <int NF>
+inline int radix_sort(Item<NF>* d_a, Item<NF>* d_b, uint64_t n, const PassDesc* passes, int npass, uint32_t* d_counts,
+                      cudaStream_t st) {
+    if (n < 2 || npass == 0) return 0;
+    const uint32_t nblk = (uint32_t)((n + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
+    Item<NF>*src = d_a, *dst = d_b;
+    int launches = 0;
+    for (int p = 0; p < npass; ++p) {
+        rs_hist<NF><<<nblk, kSortThreads, 0, st>>>(src, n, passes[p], d_counts, nblk);
+        rs_scan<<<1, 1024, 0, st>>>(d_counts, 256u * nblk);
+        rs_scatter<NF><<<nblk, kSortThreads, 0, st>>>(src, dst, n, passes[p], d_counts, nblk);
+        launches += 3;
+        Item<NF>* t = src; src = dst; dst = t;
+    }
+    if (src != d_a) cudaMemcpyAsync(d_a, src, n * sizeof(Item<NF>), cudaMemcpyDeviceToDevice, st);
+    return launches;
+}
+
+// append the 8-bit digit passes needed to cover values in [0, max_value] of `field`
+inline int add_passes(PassDesc* out, int np, int field, uint64_t max_value) {
+    int bits = 0;
+    while (bits < 32 && (max_value >> bits)) ++bits;
+    for (int s = 0; s < bits; s += 8) {
+        int w = bits - s < 8 ? bits - s : 8;
+        out[np].field = (uint8_t)field;
+        out[np].shift = (uint8_t)s;
+        out[np].mask = (uint16_t)((1u << w) - 1u);
+        ++np;
+    }
+    return np;
+}
+
+}  // namespace mpcr

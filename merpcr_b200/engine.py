@@ -1,0 +1,543 @@
+"""merpcr_b200 engine: the reference's `MerPCR` class re-hosted on hand-written sm_100a kernels.
+
+Public surface = the reference's (`/root/reference/src/merpcr/core/engine.py:44-451`):
+
+    MerPCR(wordsize=11, margin=50, mismatches=0, three_prime_match=1, iupac_mode=0,
+           default_pcr_size=240, threads=1, max_sts_line_length=1022)
+    .load_sts_file(path) -> bool        .load_fasta_file(path) -> List[FASTARecord]
+    .search(records, output_file=None) -> int
+    attributes: sts_records, sts_table, max_pcr_size, total_hits (+ the constructor arguments)
+    helpers kept for the reference's tests: _hash_value, _reverse_complement, _compare_seqs
+
+What runs where: STS text rules (engine.py:216-251) and output formatting (:437-444) stay in Python; hashing,
+reverse complements, table build, sequence packing, scan, verification, hit compaction and ordering run on
+the GPU through the C ABI in include/merpcr_b200.h.  PyTorch only owns device buffers and streams.
+There is no CPU fallback; without the CUDA library or a device every entry point raises.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import sys
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi
+from .alphabet import genome_exotics, genome_lut, primer_exotics, primer_lut
+from .fasta import FASTALoader
+from .models import FASTARecord, STSHit, STSRecord, ThreadData  # noqa: F401  (re-exported like the reference)
+
+# Constants (engine.py:17-39)
+AMBIG = 100
+MIN_FILESIZE_FOR_THREADING = 100000
+DEFAULT_MARGIN = 50
+DEFAULT_WORDSIZE = 11
+DEFAULT_MISMATCHES = 0
+DEFAULT_THREE_PRIME_MATCH = 1
+DEFAULT_IUPAC_MODE = 0
+DEFAULT_THREADS = 1
+DEFAULT_PCR_SIZE = 240
+MIN_WORDSIZE, MAX_WORDSIZE = 3, 16
+MIN_MISMATCHES, MAX_MISMATCHES = 0, 10
+MIN_MARGIN, MAX_MARGIN = 0, 10000
+MIN_THREE_PRIME_MATCH = 0
+MIN_PCR_SIZE, MAX_PCR_SIZE = 1, 10000
+
+PCR_SIZE_CLAMP = 0x7FFFFFFF   # any expected size >= a contig length behaves identically (engine.py:531-533)
+TILE_BASES = 32768
+PLANE_SLACK_BASES = 1024      # read-ahead of the last strip / last primer window
+
+logger = logging.getLogger("merpcr.core.engine")  # same logger name as the reference module
+
+
+class _Complement(dict):
+    def __missing__(self, key):  # engine.py:359 : unknown -> 'N'
+        return ord("N")
+
+
+_COMPL = _Complement()
+for _a, _b in ("AT", "CG", "GC", "TA", "UA", "BV", "DH", "HD", "KM", "MK", "NN", "RY", "SS", "VB", "WW", "XX", "YR"):
+    _COMPL[ord(_a)] = ord(_b)
+    _COMPL[ord(_a.lower())] = ord(_b.lower())
+
+_IUPAC = {  # engine.py:138-172
+    "A": "A", "C": "C", "G": "G", "T": "TU", "U": "TU", "R": "AGR", "Y": "CTUY", "M": "ACM", "K": "GTUK",
+    "S": "CGS", "W": "ATUW", "B": "CGTUYKSB", "D": "AGTURKWD", "H": "ACTUYMWH", "V": "ACGRMSV",
+    "N": "ACGTURYMKSWBDHVN",
+}
+
+
+def _primer_bytes(p: str) -> bytes:
+    if p.isascii():
+        return p.encode("ascii")
+    return bytes(ord(ch) if ord(ch) < 128 else 0x80 for ch in p)
+
+
+class _Shard:
+    """Device-resident packed genome of one shard (planes + the layout they were built for)."""
+
+    __slots__ = ("device", "origin", "bases", "plane2", "plane4", "valid", "begin", "end", "hits", "count")
+
+
+class MerPCR:
+    """Main merPCR class that handles all the e-PCR functionality (GPU-backed)."""
+
+    def __init__(
+        self,
+        wordsize: int = DEFAULT_WORDSIZE,
+        margin: int = DEFAULT_MARGIN,
+        mismatches: int = DEFAULT_MISMATCHES,
+        three_prime_match: int = DEFAULT_THREE_PRIME_MATCH,
+        iupac_mode: int = DEFAULT_IUPAC_MODE,
+        default_pcr_size: int = DEFAULT_PCR_SIZE,
+        threads: int = DEFAULT_THREADS,
+        max_sts_line_length: int = 1022,
+        *,
+        device: Optional[int] = None,
+        shard: Optional[Sequence[int]] = None,
+    ):
+        """Reference parameters (engine.py:47-57) plus two device knobs:
+
+        device : CUDA device index (default: $LOCAL_RANK or 0).
+        shard  : (rank, world) -- scan only this rank's bp-balanced share of the genome (multi-GPU runs use
+                 one process per GPU; hits are merged by the caller, no collective on the scan path).
+        `threads` (-T) is accepted and stored for compatibility; the GPU path does not use host threads.
+        """
+        self.wordsize = wordsize
+        self.margin = margin
+        self.mismatches = mismatches
+        self.three_prime_match = three_prime_match
+        self.iupac_mode = iupac_mode
+        self.default_pcr_size = default_pcr_size
+        self.threads = threads
+        self.max_sts_line_length = max_sts_line_length
+
+        self.sts_records: List[STSRecord] = []
+        self._sts_table: Optional[Dict[int, List[STSRecord]]] = {}
+        self.max_pcr_size = 0
+        self.total_hits = 0
+
+        self._validate_parameters()
+
+        self._be = _capi.backend()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if self._be.device_kind == "cuda" else 0
+        self.device = device
+        self.shard = (int(shard[0]), int(shard[1])) if shard else (0, 1)
+        if self._be.device_kind == "cuda":
+            if not torch.cuda.is_available():
+                raise RuntimeError("merpcr_b200 needs a CUDA device (none visible); there is no CPU fallback")
+            self._tdev = torch.device("cuda", device)
+        else:
+            self._tdev = torch.device("cpu")
+        self._ctx = None
+        self._create_ctx()
+        # parsed STS lines kept so the table can be re-encoded if a sequence brings an unusual alphabet
+        self._sts_lines = None
+        self._zero_char = "X"
+        self._rec_to_idx = np.zeros(0, dtype=np.int64)
+        self._hashes = np.zeros(0, dtype=np.uint32)
+        self.last_scan_ms = 0.0
+        self.last_timing: Dict[str, float] = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _create_ctx(self):
+        import ctypes as C
+        p = _capi.Params(self.wordsize, self.margin, self.mismatches, self.three_prime_match,
+                         1 if self.iupac_mode else 0)
+        h = C.c_void_p()
+        self._be.check(self._be.lib.mpcr_ctx_create(self.device, C.byref(p), C.byref(h)))
+        self._ctx = h
+
+    def close(self):
+        ctx, self._ctx = getattr(self, "_ctx", None), None
+        if ctx:
+            self._be.lib.mpcr_ctx_destroy(ctx)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _stream(self) -> int:
+        if self._tdev.type == "cuda":
+            return torch.cuda.current_stream(self._tdev).cuda_stream
+        return 0
+
+    def _sync(self):
+        if self._tdev.type == "cuda":
+            torch.cuda.current_stream(self._tdev).synchronize()
+
+    @property
+    def gpu_launches(self) -> int:
+        return int(self._be.lib.mpcr_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------ engine.py:80-97
+    def _validate_parameters(self):
+        if not (MIN_WORDSIZE <= self.wordsize <= MAX_WORDSIZE):
+            raise ValueError(f"Word size must be between {MIN_WORDSIZE} and {MAX_WORDSIZE}")
+        if not (MIN_MISMATCHES <= self.mismatches <= MAX_MISMATCHES):
+            raise ValueError(f"Number of mismatches must be between {MIN_MISMATCHES} and {MAX_MISMATCHES}")
+        if not (MIN_MARGIN <= self.margin <= MAX_MARGIN):
+            raise ValueError(f"Margin must be between {MIN_MARGIN} and {MAX_MARGIN}")
+        if self.three_prime_match < MIN_THREE_PRIME_MATCH:
+            raise ValueError(f"Three prime match must be at least {MIN_THREE_PRIME_MATCH}")
+        if not (MIN_PCR_SIZE <= self.default_pcr_size <= MAX_PCR_SIZE):
+            raise ValueError(f"Default PCR size must be between {MIN_PCR_SIZE} and {MAX_PCR_SIZE}")
+
+    # ------------------------------------------------------------------ STS loading (engine.py:193-322)
+    def load_sts_file(self, filename: str) -> bool:
+        """Load STS records from a tab-delimited file; the word-hash table is built on the device."""
+        start_time = time.time()
+        file_size = os.path.getsize(filename)
+        if file_size == 0:
+            logger.error(f"STS file '{filename}' is empty")
+            return False
+        logger.info(f"Reading STS file: {filename}")
+
+        self.sts_records = []
+        self._sts_table = {}
+        self.max_pcr_size = 0
+        self._sts_lines = None
+        bad_primers_short = 0
+        bad_pcr_size = 0
+
+        ids, aliases, p1s, p2s, sizes, line_nos = [], [], [], [], [], []
+        with open(filename, "r") as file:
+            line_no = 0
+            for line in file:
+                line_no += 1
+                line = line.strip()
+                if not line or line.startswith("#"):
+                    continue
+                fields = line.split("\t")
+                if len(fields) < 4:
+                    logger.error(f"Bad STS file format at line {line_no}. Expected at least 4 fields.")
+                    self.max_pcr_size = 0
+                    return False
+                primer1 = fields[1].upper()
+                primer2 = fields[2].upper()
+                pcr_size = self._parse_pcr_size(fields[3])
+                if len(primer1) < self.wordsize or len(primer2) < self.wordsize:
+                    bad_primers_short += 1
+                    continue
+                if len(primer1) + len(primer2) > pcr_size:
+                    bad_pcr_size += 1
+                    pcr_size = len(primer1) + len(primer2)
+                if pcr_size > self.max_pcr_size:
+                    self.max_pcr_size = pcr_size
+                ids.append(fields[0])
+                aliases.append(fields[4] if len(fields) > 4 else "")
+                p1s.append(primer1)
+                p2s.append(primer2)
+                sizes.append(pcr_size)
+                line_nos.append(line_no)
+
+        self._sts_lines = (ids, aliases, p1s, p2s, sizes, line_nos)
+        self._zero_char = "X"
+        bad_primers_ambig = self._build_table()
+
+        if bad_primers_short > 0:
+            logger.warning(f"{bad_primers_short} STSs have primer shorter than word size ({self.wordsize}): "
+                           "not included in search")
+        if bad_primers_ambig > 0:
+            logger.warning(f"{bad_primers_ambig} primers have ambiguities which prevent computation of a hash "
+                           "value: not included in search")
+        if bad_pcr_size > 0:
+            logger.warning(f"{bad_pcr_size} STSs have a primer length sum greater than the pcr size: "
+                           "expected pcr size adjusted")
+        logger.info(f"Loaded {len(self.sts_records)} STS records in {time.time() - start_time:.2f} seconds")
+        return True
+
+    def _build_table(self) -> int:
+        """Ship the accepted STS lines to the device, build the table there, read back hash offsets."""
+        ids, aliases, p1s, p2s, sizes, line_nos = self._sts_lines
+        n = len(ids)
+        lens = np.empty(2 * n + 1, dtype=np.uint64)
+        lens[0] = 0
+        parts = []
+        for i in range(n):
+            b1, b2 = _primer_bytes(p1s[i]), _primer_bytes(p2s[i])
+            parts.append(b1)
+            parts.append(b2)
+            lens[2 * i + 1] = len(b1)
+            lens[2 * i + 2] = len(b2)
+        off = np.cumsum(lens, dtype=np.uint64)
+        blob = np.frombuffer(b"".join(parts) + b"\0" * 16, dtype=np.uint8)
+        pcr = np.minimum(np.asarray(sizes, dtype=np.int64), PCR_SIZE_CLAMP).astype(np.uint32) if n else \
+            np.zeros(0, dtype=np.uint32)
+        plut = primer_lut(self.iupac_mode, self._zero_char)
+        lib = self._be.lib
+        self._be.check(lib.mpcr_table_build(self._ctx, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
+                                            plut.ctypes.data, self._stream()))
+        ho = np.full(2 * n, -1, dtype=np.int32)
+        hv = np.zeros(2 * n, dtype=np.uint32)
+        self._be.check(lib.mpcr_table_records(self._ctx, ho.ctypes.data, hv.ctypes.data))
+        # host mirror of the records (engine.py:253-281), insertion order == record-slot order
+        self.sts_records = []
+        self._sts_table = None
+        rec_to_idx = np.full(2 * n, -1, dtype=np.int64)
+        bad_ambig = 0
+        for i in range(n):
+            if ho[2 * i] >= 0:
+                rec_to_idx[2 * i] = len(self.sts_records)
+                self.sts_records.append(STSRecord(id=ids[i], primer1=p1s[i], primer2=p2s[i], pcr_size=sizes[i],
+                                                  alias=aliases[i], offset=line_nos[i],
+                                                  hash_offset=int(ho[2 * i]), direct="+"))
+            else:
+                bad_ambig += 1
+            if ho[2 * i + 1] >= 0:
+                rec_to_idx[2 * i + 1] = len(self.sts_records)
+                self.sts_records.append(STSRecord(id=ids[i], primer1=p2s[i],
+                                                  primer2=self._reverse_complement(p1s[i]), pcr_size=sizes[i],
+                                                  alias=aliases[i], offset=line_nos[i],
+                                                  hash_offset=int(ho[2 * i + 1]), direct="-"))
+            else:
+                bad_ambig += 1
+        self._rec_to_idx = rec_to_idx
+        self._hashes = hv
+        return bad_ambig
+
+    @property
+    def sts_table(self) -> Dict[int, List[STSRecord]]:
+        """hash value -> records in insertion order (engine.py:70,324-329), materialised from the device build."""
+        if self._sts_table is None:
+            table: Dict[int, List[STSRecord]] = {}
+            for slot in np.flatnonzero(self._rec_to_idx >= 0).tolist():
+                table.setdefault(int(self._hashes[slot]), []).append(self.sts_records[int(self._rec_to_idx[slot])])
+            self._sts_table = table
+        return self._sts_table
+
+    @sts_table.setter
+    def sts_table(self, value):
+        self._sts_table = value
+
+    def _parse_pcr_size(self, pcr_size_str: str) -> int:
+        """engine.py:304-322."""
+        if "-" in pcr_size_str:
+            try:
+                size_range = pcr_size_str.split("-")
+                if len(size_range) == 2 and size_range[0] and size_range[1]:
+                    return (int(size_range[0]) + int(size_range[1])) // 2
+                return self.default_pcr_size
+            except ValueError:
+                return self.default_pcr_size
+        try:
+            pcr_size = int(pcr_size_str)
+            return pcr_size if pcr_size > 0 else self.default_pcr_size
+        except ValueError:
+            return self.default_pcr_size
+
+    # ------------------------------------------------------------------ helpers the reference's tests call
+    def _hash_value(self, primer: str):
+        """engine.py:331-355 (host mirror; the table itself is hashed on the device)."""
+        primer = primer.upper()
+        W = self.wordsize
+        if len(primer) < W:
+            return -1, 0
+        code = {"A": 0, "C": 1, "G": 2, "T": 3, "U": 3}
+        run, h, mask = 0, 0, (1 << (2 * W)) - 1
+        for i, ch in enumerate(primer):
+            c = code.get(ch)
+            if c is None:
+                run = 0
+                continue
+            h = ((h << 2) | c) & mask
+            run += 1
+            if run >= W:
+                return i - W + 1, h
+        return -1, 0
+
+    def _reverse_complement(self, sequence: str) -> str:
+        """engine.py:357-359."""
+        return sequence[::-1].translate(_COMPL)
+
+    def _compare_seqs(self, seq1: str, seq2: str, strand: str) -> bool:
+        """engine.py:599-642 (host mirror for API users; the search itself compares on the device)."""
+        if len(seq1) != len(seq2):
+            return False
+        n, mism = len(seq1), 0
+        for i in range(n):
+            prot = (strand == "+" and i >= n - self.three_prime_match) or \
+                   (strand == "-" and i < self.three_prime_match)
+            c1, c2 = seq1[i].upper(), seq2[i].upper()
+            if self.iupac_mode and c1 in _IUPAC and c2 in _IUPAC:
+                match = bool(set(_IUPAC[c1]) & set(_IUPAC[c2]))
+            else:
+                match = c1 == c2
+            if not match:
+                if prot:
+                    return False
+                mism += 1
+                if mism > self.mismatches:
+                    return False
+        return True
+
+    def load_fasta_file(self, filename: str) -> List[FASTARecord]:
+        """engine.py:361-363."""
+        return FASTALoader.load_file(filename)
+
+    # ------------------------------------------------------------------ search (engine.py:365-451)
+    def search(self, fasta_records: List[FASTARecord], output_file: str = None) -> int:
+        """Search for STS markers in the provided FASTA sequences; prints one line per hit (engine.py:442)."""
+        total_hits = 0
+        if output_file and output_file.lower() != "stdout":
+            output = open(output_file, "w")
+        else:
+            output = sys.stdout
+        try:
+            hits = self.search_hits(fasta_records) if fasta_records else np.zeros(0, dtype=_capi.HIT_DTYPE)
+            bounds = np.searchsorted(hits["contig"], np.arange(len(fasta_records) + 1))
+            recs = self.sts_records
+            r2i = self._rec_to_idx
+            for ci, record in enumerate(fasta_records):
+                seq_label = record.label
+                logger.info(f"Processing sequence: {seq_label} ({len(record)} bp)")
+                h = hits[bounds[ci]: bounds[ci + 1]]
+                if h.size == 0:
+                    continue
+                p1 = (h["pos1"].astype(np.int64) + 1).tolist()
+                p2 = (h["pos2"].astype(np.int64) + 1).tolist()
+                ri = r2i[h["rec"]].tolist()
+                lines = []
+                for a, b, r in zip(p1, p2, ri):
+                    sts = recs[r]
+                    lines.append(f"{seq_label}\t{a}..{b}\t{sts.id}\t{sts.alias}\t({sts.direct})\n")
+                output.write("".join(lines))
+                total_hits += len(lines)
+        finally:
+            if output is not sys.stdout:
+                output.close()
+        logger.info(f"Total hits found: {total_hits}")
+        self.total_hits = total_hits
+        return total_hits
+
+    def search_hits(self, fasta_records: Sequence[FASTARecord]) -> np.ndarray:
+        """The device path of `search`: returns this shard's hits (structured array, _capi.HIT_DTYPE) in the
+        reference's output order; `contig` indexes `fasta_records`, positions are 0-based inclusive."""
+        t0 = time.perf_counter()
+        if self._sts_lines is None:  # nothing loaded: an empty table, zero hits (like the reference)
+            self._sts_lines = ([], [], [], [], [], [])
+            self._build_table()
+        seqs = [r.sequence_bytes for r in fasta_records]
+        self._check_alphabet(fasta_records, seqs)
+        layout = self.make_layout([int(s.size) for s in seqs])
+        shard = self.upload(layout, seqs)
+        t1 = time.perf_counter()
+        hits = self.scan(layout, shard)
+        t2 = time.perf_counter()
+        self.last_timing = dict(upload_s=t1 - t0, scan_s=t2 - t1)
+        return hits
+
+    # -- alphabet corner cases: sequences built through the API may hold letters FASTA files cannot
+    def _check_alphabet(self, records, seqs):
+        exotic = set()
+        for r, s in zip(records, seqs):
+            if not getattr(r, "_from_loader", False) and s.size:
+                exotic |= genome_exotics(s, self.iupac_mode)
+        if not exotic or exotic == {"X"}:
+            zero = "X"
+        elif len(exotic) == 1:
+            zero = next(iter(exotic))
+        else:
+            pex = primer_exotics(self._sts_lines[2] + self._sts_lines[3], self.iupac_mode) if self._sts_lines else set()
+            if pex & exotic:
+                raise ValueError(
+                    "sequences contain several non-IUPAC characters "
+                    f"({''.join(sorted(exotic))}) that also occur in primers; the 4-bit device alphabet can "
+                    "represent only one such character")
+            zero = ""  # none of them can ever match a primer character
+        if zero != self._zero_char and self._sts_lines is not None:
+            self._zero_char = zero
+            self._build_table()
+
+    # -- layout: padded global coordinate (include/merpcr_b200.h)
+    def make_layout(self, lengths: Sequence[int]) -> dict:
+        n = len(lengths)
+        contigs = np.zeros(n, dtype=_capi.CONTIG_DTYPE)
+        g = 0
+        for i, L in enumerate(lengths):
+            if L >= (1 << 31):
+                raise ValueError("sequences longer than 2^31-1 bases are not supported")
+            contigs[i]["gstart"] = g
+            contigs[i]["length"] = L
+            g = (g + L + 1 + 127) // 128 * 128
+        total = g
+        rank, world = self.shard
+        # bp-balanced shard boundaries on multiples of 128; a tile belongs to the shard holding its first base
+        begin = (total * rank // world) // 128 * 128
+        end = (total * (rank + 1) // world) // 128 * 128 if rank + 1 < world else max(total, 128)
+        return dict(contigs=contigs, total=total, begin=begin, end=end, lengths=list(lengths))
+
+    def upload(self, layout: dict, seqs: Sequence[np.ndarray]) -> _Shard:
+        """H2D + pack (FASTA ingest, device half): builds the planes this shard needs (its range + halos)."""
+        lib = self._be.lib
+        total, begin, end = layout["total"], layout["begin"], layout["end"]
+        halo_l, halo_r = int(lib.mpcr_halo_left(self._ctx)), int(lib.mpcr_halo_right(self._ctx))
+        origin = max(0, begin - halo_l) // 128 * 128
+        stop = min(total, end + halo_r)
+        bases = max(128, (stop - origin + 127) // 128 * 128)
+        alloc = bases + TILE_BASES + PLANE_SLACK_BASES
+        sh = _Shard()
+        sh.device, sh.origin, sh.bases, sh.begin, sh.end = self._tdev, origin, bases, begin, end
+        sh.plane2 = torch.zeros(alloc // 4, dtype=torch.uint8, device=self._tdev)
+        sh.plane4 = torch.zeros(alloc // 2, dtype=torch.uint8, device=self._tdev)
+        sh.valid = torch.zeros(alloc // 8, dtype=torch.uint8, device=self._tdev)
+        sh.hits, sh.count = None, None
+        lut = genome_lut(self.iupac_mode)
+        stream = self._stream()
+        chunk = 1 << 26
+        staging = []
+        for ci, s in enumerate(seqs):
+            g0 = int(layout["contigs"][ci]["gstart"])
+            L = int(s.size)
+            lo, hi = max(g0, origin), min(g0 + L, origin + bases)
+            if hi <= lo:
+                continue
+            for a in range(lo, hi, chunk):
+                b = min(hi, a + chunk)
+                arr = s[a - g0: b - g0]
+                src = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
+                d = src.to(self._tdev, non_blocking=False) if self._tdev.type == "cuda" else src
+                staging.append(d)
+                self._be.check(lib.mpcr_pack_sequence(self._ctx, d.data_ptr(), b - a, a, origin, sh.plane2.data_ptr(),
+                                                      sh.plane4.data_ptr(), sh.valid.data_ptr(), lut.ctypes.data,
+                                                      stream))
+        self._sync()
+        del staging
+        return sh
+
+    def scan(self, layout: dict, sh: _Shard, sort: bool = True) -> np.ndarray:
+        """scanner + verifier + hit emitter + ordering on the resident planes; returns the hits on the host."""
+        hits, n = self.scan_device(layout, sh, sort=sort)
+        self.last_scan_ms = float(self._be.lib.mpcr_last_scan_ms(self._ctx))
+        if n == 0:
+            return np.zeros(0, dtype=_capi.HIT_DTYPE)
+        raw = hits[: n * _capi.HIT_DTYPE.itemsize].cpu().numpy()
+        return raw.view(_capi.HIT_DTYPE).copy()
+
+    def scan_device(self, layout: dict, sh: _Shard, sort: bool = True):
+        """Device-resident scan: returns (uint8 tensor holding mpcr_hit records, n_hits).  Re-runs with a larger
+        buffer if the hit list outgrows it (nothing is ever truncated)."""
+        lib = self._be.lib
+        contigs = layout["contigs"]
+        if sh.count is None:
+            sh.count = torch.zeros(1, dtype=torch.int64, device=self._tdev)
+        cap = 1 << 16 if sh.hits is None else sh.hits.numel() // _capi.HIT_DTYPE.itemsize
+        while True:
+            if sh.hits is None or sh.hits.numel() < cap * _capi.HIT_DTYPE.itemsize:
+                sh.hits = torch.empty(cap * _capi.HIT_DTYPE.itemsize, dtype=torch.uint8, device=self._tdev)
+            self._be.check(lib.mpcr_scan(self._ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
+                                         sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.bases, sh.begin,
+                                         sh.end, sh.hits.data_ptr(), cap, sh.count.data_ptr(), self._stream()))
+            n = int(sh.count.item())  # synchronises the stream
+            if n <= cap:
+                break
+            cap = max(n, 2 * cap)
+        if sort and n > 1:
+            self._be.check(lib.mpcr_sort_hits(self._ctx, sh.hits.data_ptr(), n, self._stream()))
+        return sh.hits, n

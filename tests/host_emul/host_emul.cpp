@@ -1,0 +1,251 @@
+// host_emul.cpp -- TEST INFRASTRUCTURE: a serial CPU emulation of the libmerpcr_b200.so C ABI.
+//
+// It implements include/merpcr_b200.h with "device" pointers being plain host pointers, and runs the SAME
+// per-position semantics as the CUDA kernels because it includes merpcr_b200/csrc/mpcr_core.cuh (all of whose
+// functions are __host__ __device__).  Purpose: let the CPU-only test tier exercise the Python host logic
+// (parsing, layout, sharding, formatting) and the shared verification code against the oracle before any GPU
+// time is spent.  It is injected explicitly by tests (merpcr_b200._capi._inject_backend_for_tests); the product
+// never loads it and has no CPU fallback.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <tuple>
+#include <vector>
+
+#include "../../include/merpcr_b200.h"
+#include "../../merpcr_b200/csrc/mpcr_core.cuh"
+
+using namespace mpcr;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+struct mpcr_ctx {
+    mpcr_params prm{};
+    uint32_t n_rec = 0, n_valid = 0;
+    std::vector<RecMeta> meta;
+    std::vector<uint64_t> pwords;
+    std::vector<uint64_t> slots;
+    uint32_t slot_mask = 0;
+    std::vector<uint32_t> bucket;
+    std::vector<uint32_t> filter;
+    uint32_t filter_bits = 0;
+    int filter_exact = 0;
+    uint32_t max_hash_off = 0, max_len = 0;
+    uint64_t max_pcr = 0;
+    bool table_ready = false;
+    uint64_t launches = 0;
+};
+
+extern "C" {
+
+int mpcr_abi_version(void) { return MPCR_ABI_VERSION; }
+const char* mpcr_last_error(void) { return g_err; }
+
+int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
+    (void)device;
+    if (!p || !out) return fail(MPCR_EINVAL, "null argument");
+    if (p->wordsize < 3 || p->wordsize > 16) return fail(MPCR_EINVAL, "Word size must be between 3 and 16");
+    if (p->mismatches < 0 || p->mismatches > 10) return fail(MPCR_EINVAL, "Number of mismatches must be between 0 and 10");
+    if (p->margin < 0 || p->margin > 10000) return fail(MPCR_EINVAL, "Margin must be between 0 and 10000");
+    if (p->three_prime_match < 0) return fail(MPCR_EINVAL, "Three prime match must be at least 0");
+    mpcr_ctx* c = new mpcr_ctx();
+    c->prm = *p;
+    *out = c;
+    return MPCR_OK;
+}
+void mpcr_ctx_destroy(mpcr_ctx* c) { delete c; }
+int mpcr_ctx_sm_count(const mpcr_ctx*) { return 1; }
+uint64_t mpcr_launch_count(const mpcr_ctx* c) { return c ? c->launches : 0; }
+float mpcr_last_scan_ms(mpcr_ctx*) { return 0.f; }
+
+int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* ascii, uint64_t n, uint64_t dst_base, uint64_t origin, void* plane2,
+                       void* plane4, void* valid, const uint8_t* lut, void*) {
+    if (!c || !plane2 || !plane4 || !valid || !lut) return fail(MPCR_EINVAL, "null argument");
+    if ((dst_base & 63u) || (origin & 127u) || dst_base < origin) return fail(MPCR_EINVAL, "bad alignment");
+    uint64_t *P2 = (uint64_t*)plane2, *P4 = (uint64_t*)plane4, *V = (uint64_t*)valid;
+    const uint64_t rel = dst_base - origin;
+    for (uint64_t s = 0; s * 64 < n; ++s) {
+        uint64_t v = 0, p2[2] = {0, 0}, p4[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 64; ++j) {
+            uint64_t i = s * 64 + j;
+            uint32_t e = lut[i < n ? ascii[i] : 0];
+            p4[j >> 4] |= (uint64_t)(e & 15u) << (4 * (j & 15));
+            p2[j >> 5] |= (uint64_t)((e >> 4) & 3u) << (2 * (j & 31));
+            v |= (uint64_t)((e >> 6) & 1u) << j;
+        }
+        const uint64_t w = rel / 64 + s;
+        V[w] = v; P2[2 * w] = p2[0]; P2[2 * w + 1] = p2[1];
+        for (int k = 0; k < 4; ++k) P4[4 * w + k] = p4[k];
+    }
+    c->launches++;
+    return MPCR_OK;
+}
+
+struct Fwd { const uint8_t* p; uint8_t operator()(int i) const { return p[i]; } };
+struct Rc { const uint8_t* p; int len; uint8_t operator()(int i) const { return complement_of(p[len - 1 - i]); } };
+
+int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, const uint32_t* pcr, uint32_t n_lines,
+                     const uint8_t* plut, void*) {
+    if (!c || !plut) return fail(MPCR_EINVAL, "null argument");
+    const int W = c->prm.wordsize;
+    c->n_rec = 2 * n_lines; c->n_valid = 0; c->max_hash_off = 0; c->max_len = 0; c->max_pcr = 0;
+    c->meta.assign(c->n_rec, RecMeta{});
+    c->pwords.clear();
+    std::vector<std::pair<uint32_t, uint32_t>> pairs;  // (key, rec) of inserted records
+    for (uint32_t l = 0; l < n_lines; ++l) {
+        const uint8_t *pr1 = blob + off[2 * l], *pr2 = blob + off[2 * l + 1];
+        const int n1 = (int)(off[2 * l + 1] - off[2 * l]), n2 = (int)(off[2 * l + 2] - off[2 * l + 1]);
+        if (n1 > 65535 || n2 > 65535) return fail(MPCR_EINVAL, "primer longer than 65535 bases at STS entry %u", l);
+        c->max_len = std::max(c->max_len, (uint32_t)std::max(n1, n2));
+        c->max_pcr = std::max<uint64_t>(c->max_pcr, pcr[l]);
+        for (int minus = 0; minus < 2; ++minus) {
+            const uint32_t r = 2 * l + minus;
+            RecMeta& m = c->meta[r];
+            m.pcr_size = pcr[l];
+            const int l1 = minus ? n2 : n1, l2 = minus ? n1 : n2;
+            m.len1 = (uint16_t)l1; m.len2 = (uint16_t)l2;
+            m.p1_word = (uint32_t)c->pwords.size();
+            c->pwords.resize(c->pwords.size() + 2 * ((l1 + 15) / 16));
+            m.p2_word = (uint32_t)c->pwords.size();
+            c->pwords.resize(c->pwords.size() + 2 * ((l2 + 15) / 16));
+            uint32_t hbe = 0; int ho;
+            if (!minus) {
+                ho = first_clean_word(Fwd{pr1}, n1, W, &hbe);
+                encode_primer(Fwd{pr1}, n1, plut, c->pwords.data() + m.p1_word);
+                encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p2_word);
+            } else {
+                ho = first_clean_word(Fwd{pr2}, n2, W, &hbe);
+                encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p1_word);
+                encode_primer(Rc{pr1, n1}, n1, plut, c->pwords.data() + m.p2_word);
+            }
+            m.hash_be = hbe; m.key = reverse_digits(hbe, W);
+            m.hash_off = (uint16_t)(ho < 0 ? 0 : ho); m.flags = ho >= 0;
+            if (ho >= 0) { pairs.push_back({m.key, r}); c->max_hash_off = std::max(c->max_hash_off, (uint32_t)ho); }
+        }
+    }
+    c->pwords.resize(c->pwords.size() + 2);
+    std::stable_sort(pairs.begin(), pairs.end(), [](auto& a, auto& b) { return a.first < b.first; });
+    c->n_valid = (uint32_t)pairs.size();
+    const uint64_t space = 1ull << (2 * W);
+    uint32_t budget = 1u << 20;
+    if (const char* env = getenv("MPCR_FILTER_BITS")) { long v = atol(env); if (v >= 128) budget = (uint32_t)v & ~127u; }
+    if (space <= budget) { c->filter_exact = 1; c->filter_bits = (uint32_t)std::max<uint64_t>(space, 128); }
+    else { c->filter_exact = 0; c->filter_bits = budget; }
+    c->filter.assign(c->filter_bits / 32, 0);
+    uint32_t nslots = 1024;
+    while (nslots < 2u * c->n_valid + 2u) nslots <<= 1;
+    c->slot_mask = nslots - 1;
+    c->slots.assign(nslots, ~0ull);
+    c->bucket.assign(c->n_valid + 1, 0);
+    for (uint32_t i = 0; i < c->n_valid; ++i) {
+        const uint32_t key = pairs[i].first;
+        const bool head = i == 0 || pairs[i - 1].first != key, last = i + 1 == c->n_valid || pairs[i + 1].first != key;
+        c->bucket[i] = pairs[i].second | (last ? 0x80000000u : 0u);
+        if (head) {
+            uint32_t s = slot_hash(key) & c->slot_mask;
+            while (c->slots[s] != ~0ull) s = (s + 1) & c->slot_mask;
+            c->slots[s] = ((uint64_t)key << 32) | i;
+            const uint32_t fb = filter_index(key, c->filter_bits, c->filter_exact);
+            c->filter[fb >> 5] |= 1u << (fb & 31);
+        }
+    }
+    c->table_ready = true;
+    c->launches++;
+    return MPCR_OK;
+}
+
+int mpcr_table_records(mpcr_ctx* c, int32_t* ho, uint32_t* h) {
+    if (!c || !c->table_ready) return fail(MPCR_ESTATE, "table not built");
+    for (uint32_t r = 0; r < c->n_rec; ++r) {
+        if (ho) ho[r] = (c->meta[r].flags & 1) ? (int32_t)c->meta[r].hash_off : -1;
+        if (h) h[r] = c->meta[r].hash_be;
+    }
+    return MPCR_OK;
+}
+
+int mpcr_table_primer_words(mpcr_ctx* c, uint32_t rec, int which, uint64_t* out, uint32_t max_words, uint32_t* n_words) {
+    if (!c || !c->table_ready) return fail(MPCR_ESTATE, "table not built");
+    if (rec >= c->n_rec || (which != 1 && which != 2)) return fail(MPCR_EINVAL, "bad record / primer index");
+    const RecMeta& m = c->meta[rec];
+    const uint32_t len = which == 1 ? m.len1 : m.len2, nw = 2 * ((len + 15) / 16);
+    if (n_words) *n_words = nw;
+    if (nw > max_words) return fail(MPCR_EINVAL, "buffer too small");
+    memcpy(out, c->pwords.data() + (which == 1 ? m.p1_word : m.p2_word), nw * 8);
+    return MPCR_OK;
+}
+
+static uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+uint64_t mpcr_halo_left(const mpcr_ctx* c) { return c ? round_up((uint64_t)c->max_hash_off + 64, 128) : 0; }
+uint64_t mpcr_halo_right(const mpcr_ctx* c) {
+    return c ? round_up(c->max_pcr + (uint64_t)c->prm.margin + c->max_len + 64 + 128, 128) + kTileBases : 0;
+}
+
+int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const void* plane2, const void* plane4,
+              const void* valid, uint64_t origin, uint64_t plane_bases, uint64_t sb, uint64_t se, mpcr_hit* hits,
+              uint64_t capacity, uint64_t* count, void*) {
+    if (!c || !count) return fail(MPCR_EINVAL, "null argument");
+    if (!c->table_ready) return fail(MPCR_ESTATE, "mpcr_scan called before mpcr_table_build");
+    if ((origin & 127u) || (sb & 127u)) return fail(MPCR_EINVAL, "origin / shard_begin must be multiples of 128");
+    const uint64_t *P2 = (const uint64_t*)plane2, *P4 = (const uint64_t*)plane4, *V = (const uint64_t*)valid;
+    SearchParams prm{c->prm.wordsize, c->prm.margin, c->prm.mismatches, c->prm.three_prime_match, c->prm.iupac_mode ? 1 : 0};
+    const uint32_t wmask = wmask_of(prm.W);
+    uint64_t n = 0;
+    c->launches++;
+    for (uint32_t ci = 0; ci < n_contigs && c->n_valid; ++ci) {
+        const uint64_t L = contigs[ci].length, g0 = contigs[ci].gstart;
+        if (L <= (uint64_t)prm.W) continue;
+        if (g0 & 127u) return fail(MPCR_EINVAL, "contig %u: gstart not a multiple of 128", ci);
+        for (uint64_t ls = 0; ls < L; ls += kTileBases) {
+            const uint64_t g = g0 + ls;
+            if (g < sb || g >= se) continue;
+            const int64_t gbase = (int64_t)(g - origin);
+            const uint32_t nb = (uint32_t)std::min<uint64_t>(L - ls, kTileBases);
+            for (uint32_t lp0 = 0; lp0 < nb; lp0 += 64) {
+                const int64_t gb = gbase + lp0;
+                if ((uint64_t)gb + 128 > plane_bases + 128) return fail(MPCR_EINVAL, "planes too small for the shard");
+                uint64_t cand = window_valid(V[gb >> 6], V[(gb >> 6) + 1], prm.W);
+                for (int j = 0; j < 64 && cand; ++j) {
+                    if (!((cand >> j) & 1)) continue;
+                    const uint32_t key = extract_key(P2, gb + j, wmask);
+                    const uint32_t fb = filter_index(key, c->filter_bits, c->filter_exact);
+                    if (!((c->filter[fb >> 5] >> (fb & 31)) & 1u)) continue;
+                    uint32_t i = find_bucket(c->slots.data(), c->slot_mask, key);
+                    if (i == kEmptySlot) continue;
+                    for (;;) {
+                        const uint32_t e = c->bucket[i], rec = e & 0x7FFFFFFFu;
+                        const RecMeta& m = c->meta[rec];
+                        verify_record(P4, gbase - (int64_t)ls, (int64_t)L, (int64_t)ls + lp0 + j, m, c->pwords.data(), prm,
+                                      [&](int64_t p1, int64_t p2, uint32_t rank) {
+                                          if (n < capacity) hits[n] = mpcr_hit{ci, (uint32_t)p1, (uint32_t)p2, rec, rank, m.hash_off};
+                                          ++n;
+                                      });
+                        if (e & 0x80000000u) break;
+                        ++i;
+                    }
+                }
+            }
+        }
+    }
+    *count = n;
+    return MPCR_OK;
+}
+
+int mpcr_sort_hits(mpcr_ctx* c, mpcr_hit* hits, uint64_t n, void*) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    std::sort(hits, hits + n, [](const mpcr_hit& a, const mpcr_hit& b) {
+        return std::make_tuple(a.contig, a.pos1, a.hash_off, a.rec, a.rank) < std::make_tuple(b.contig, b.pos1, b.hash_off, b.rec, b.rank);
+    });
+    c->launches++;
+    return MPCR_OK;
+}
+
+}  // extern "C"

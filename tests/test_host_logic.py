@@ -1,0 +1,198 @@
+"""CPU tier: the Python host (parsing, alphabet, layout, sharding, formatting, CLI) and the shared per-position
+semantics of merpcr_b200/csrc/mpcr_core.cuh, exercised through tests/host_emul's serial emulation of the C ABI.
+The emulation is test infrastructure (explicitly injected here); the GPU parity tests never use it."""
+import io
+import logging
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import emul
+import goldens
+import parity
+import synth
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _emulated_backend():
+    emul.inject()
+    yield
+    emul.restore()
+
+
+def _engine(**kw):
+    from merpcr_b200 import MerPCR
+    return MerPCR(**kw)
+
+
+def test_fixture_golden_line(tmp_path):
+    eng = _engine()
+    assert eng.load_sts_file(goldens.FIXTURE_STS)
+    assert len(eng.sts_records) == 6 and eng.max_pcr_size == 193        # reference test_comprehensive.py:42
+    assert sorted(eng.sts_table) == sorted([3638181, 3526114, 2555953, 3737721, 2062650, 476488])
+    recs = eng.load_fasta_file(goldens.FIXTURE_FA)
+    assert [(r.label, len(r.sequence)) for r in recs] == [("L78833", 117143)]
+    out = tmp_path / "o.txt"
+    assert eng.search(recs, str(out)) == 1 and eng.total_hits == 1
+    assert out.read_text() == goldens.FIXTURE_LINE
+
+
+def test_fuzz_goldens_through_host_stack():
+    from merpcr_b200 import MerPCR
+    for c in goldens.fuzz_cases():
+        parity.check_fuzz_case(c, MerPCR)
+
+
+def test_constructor_validation_and_attributes():
+    # reference tests/test_engine_internals.py:202-235, test_core_engine_comprehensive.py:20-59
+    from merpcr_b200 import MerPCR
+    e = MerPCR()
+    assert (e.wordsize, e.margin, e.mismatches, e.three_prime_match, e.iupac_mode, e.default_pcr_size, e.threads,
+            e.max_sts_line_length) == (11, 50, 0, 1, 0, 240, 1, 1022)
+    assert e.sts_records == [] and e.sts_table == {} and e.max_pcr_size == 0 and e.total_hits == 0
+    for bad in (dict(wordsize=2), dict(wordsize=17), dict(mismatches=-1), dict(mismatches=11), dict(margin=-1),
+                dict(margin=10001), dict(three_prime_match=-1), dict(default_pcr_size=0), dict(default_pcr_size=10001)):
+        with pytest.raises(ValueError):
+            MerPCR(**bad)
+
+
+def test_private_helpers_known_answers():
+    from merpcr_b200 import MerPCR
+    from merpcr_b200.utils import hash_value, reverse_complement
+    assert MerPCR(wordsize=4)._hash_value("ATCG") == (0, 54) == hash_value("ATCG", 4)
+    assert MerPCR(wordsize=8)._hash_value("TTTTTTTT") == (0, 65535)
+    assert MerPCR(wordsize=8)._hash_value("NNNATCGATCGATCG")[0] == 3
+    assert MerPCR()._hash_value("ACGUACGUACG") == (0, 444102)
+    assert MerPCR(wordsize=8)._hash_value("ACGT") == (-1, 0)
+    e = MerPCR(mismatches=1, three_prime_match=2)
+    assert e._reverse_complement("ACGU-XZ") == "NXNACGT" == reverse_complement("ACGU-XZ")
+    assert e._reverse_complement("RWYS") == "SRWY"
+    assert e._compare_seqs("TTCGATCG", "ATCGATCG", "+") and not e._compare_seqs("ATCGATCA", "ATCGATCG", "+")
+    assert not e._compare_seqs("TTCGATCG", "ATCGATCG", "-") and e._compare_seqs("ATCGATCA", "ATCGATCG", "-")
+    i = MerPCR(iupac_mode=1)
+    assert i._compare_seqs("A", "R", "+") and not i._compare_seqs("C", "R", "+") and i._compare_seqs("N", "A", "+")
+
+
+def test_loader_failure_modes(tmp_path):
+    # reference tests/test_core_engine_comprehensive.py:85-140, test_io_modules.py:110-148
+    e = _engine()
+    empty = tmp_path / "e.sts"
+    empty.write_text("")
+    assert e.load_sts_file(str(empty)) is False
+    assert e.load_fasta_file(str(empty)) == []
+    with pytest.raises(FileNotFoundError):
+        e.load_sts_file(str(tmp_path / "missing.sts"))
+    with pytest.raises(FileNotFoundError):
+        e.load_fasta_file(str(tmp_path / "missing.fa"))
+    bad = tmp_path / "b.sts"
+    bad.write_text("id\tACGTACGTACGT\tACGTACGTACGT\n")
+    assert e.load_sts_file(str(bad)) is False and e.sts_records == []
+    fa = tmp_path / "f.fa"
+    fa.write_text(">seq1\nATCG123NNNN456ATCG\nWXYZ789GCTA\n\n>seq2 only header\n")
+    recs = e.load_fasta_file(str(fa))
+    assert [(r.label, r.sequence) for r in recs] == [("seq1", "ATCGNNNNATCGWXYGCTA"), ("seq2", "")]
+
+
+def test_search_edge_cases(tmp_path, capsys):
+    from merpcr_b200 import FASTARecord, MerPCR
+    e = MerPCR(wordsize=8)
+    assert e.search([]) == 0                                   # nothing loaded, nothing to search
+    sts = tmp_path / "a.sts"
+    p1, p2 = "ACGTTGCAAGGCTA", "TTGACCGGTATCAG"
+    sts.write_text(f"S1\t{p1}\t{p2}\t60\talias one\nS2\t{p1}\t{p2}\t60\n")
+    assert e.load_sts_file(str(sts))
+    filler = "A" * (60 - len(p1) - len(p2))
+    seq = "CCCCC" + p1 + filler + p2 + "GGGGG"
+    recs = [FASTARecord(defline=">c1 test", sequence=seq), FASTARecord(defline=">empty", sequence=""),
+            FASTARecord(defline="noangle x", sequence=seq.lower(), label="given")]
+    n = e.search(recs)                                          # stdout; identical primers list in file order (A.7)
+    out = capsys.readouterr().out
+    assert n == 4 and out == ("c1\t6..65\tS1\talias one\t(+)\nc1\t6..65\tS2\t\t(+)\n"
+                              "given\t6..65\tS1\talias one\t(+)\ngiven\t6..65\tS2\t\t(+)\n")
+    assert e.search(recs, "STDOUT") == 4
+    capsys.readouterr()
+
+
+def test_api_sequences_with_unusual_letters():
+    """Sequences built through the API may carry letters FASTA files cannot: U hashes as T but
+    only equals U outside IUPAC mode; any other letter matches only itself."""
+    from merpcr_b200 import FASTARecord, MerPCR
+    from oracle.oracle import Oracle
+    import tempfile
+    p1, p2 = "ACGUUGCAAGGCTA", "TTGACCGGTATCAG"
+    seq = "CC" + p1 + "A" * 30 + p2 + "GG" + "ACGTTGCAAGGCTA" + "A" * 30 + p2
+    for iupac in (0, 1):
+        with tempfile.NamedTemporaryFile("w", suffix=".sts", delete=False) as f:
+            f.write(f"S1\t{p1}\t{p2}\t58\n")
+        o = Oracle(wordsize=8, iupac_mode=iupac)
+        assert o.load_sts_file(f.name)
+        e = MerPCR(wordsize=8, iupac_mode=iupac)
+        assert e.load_sts_file(f.name)
+        import io as _io, contextlib
+        buf = _io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            e.search([FASTARecord(">u", seq)])
+        assert buf.getvalue() == o.search_text("u", seq)[1] and buf.getvalue().count("\n") == (2 if iupac else 1)
+        os.unlink(f.name)
+
+
+def test_sharded_scan_equals_whole(tmp_path):
+    """bp-balanced shards with halos give, merged, exactly the unsharded hit list."""
+    from merpcr_b200 import FASTARecord, MerPCR
+    rng = synth.Rng(77)
+    contigs = [rng.dna(n) for n in (90000, 70001, 1500, 130000)]
+    sts = synth.make_sts_set(78, 120, 18, 25, 100, 700)
+    expected = synth.plant_amplicons(79, contigs, sts, 50, sub_mode="cfg3")
+    stsf = tmp_path / "s.sts"
+    stsf.write_bytes(synth.sts_lines(sts))
+    params = dict(wordsize=11, margin=50, mismatches=1)
+    recs = [FASTARecord(f">c{i}", c) for i, c in enumerate(contigs)]
+    whole = MerPCR(**params)
+    assert whole.load_sts_file(str(stsf))
+    ref = parity.engine_hits(whole, recs)
+    want = parity.oracle_hits(params, synth.sts_lines(sts).decode(), [c.tobytes() for c in contigs])
+    assert np.array_equal(ref, want) and len(ref) >= len(expected) > 50
+    found = {(r[0], r[1], r[2]) for r in ref.tolist()}
+    assert all((ci, a, b) in found for ci, a, b, _, _ in expected)      # planted truth, independent of the oracle
+    for world in (2, 3, 8):
+        parts = []
+        for rank in range(world):
+            e = MerPCR(**params, shard=(rank, world))
+            assert e.load_sts_file(str(stsf))
+            parts.append(e.search_hits(recs))
+        merged = np.concatenate(parts)
+        order = np.lexsort((merged["rank"], merged["rec"], merged["hash_off"], merged["pos1"], merged["contig"]))
+        assert np.array_equal(merged[order], whole.search_hits(recs)), world
+
+
+def test_cli_in_process(tmp_path, monkeypatch, capsys):
+    # reference tests/test_cli.py, test_cli_enhanced.py:23-156 (flag set, K=V conversion, exit codes)
+    from merpcr_b200 import cli
+    assert cli.convert_mepcr_arguments(["M=50", "N=1", "P=3", "-help", "x.sts", "O=out"]) == \
+        ["-M", "50", "-N", "1", "--help", "x.sts", "-O", "out"]
+    out = tmp_path / "hits.txt"
+    monkeypatch.setattr(sys, "argv", ["merpcr", goldens.FIXTURE_STS, goldens.FIXTURE_FA, "W=11", "-N", "0", "-O", str(out)])
+    assert cli.main() == 0 and out.read_text() == goldens.FIXTURE_LINE
+    monkeypatch.setattr(sys, "argv", ["merpcr", goldens.FIXTURE_STS, goldens.FIXTURE_FA, "-M", "7"])
+    assert cli.main() == 0 and capsys.readouterr().out == ""
+    monkeypatch.setattr(sys, "argv", ["merpcr", str(tmp_path / "nope.sts"), goldens.FIXTURE_FA])
+    assert cli.main() == 1
+    for bad in (["-W", "2"], ["-N", "11"], ["-M", "10001"], ["-Z", "0"], ["-T", "0"], ["-I", "2"]):
+        monkeypatch.setattr(sys, "argv", ["merpcr", goldens.FIXTURE_STS, goldens.FIXTURE_FA] + bad)
+        with pytest.raises(SystemExit) as ei:
+            cli.main()
+        assert ei.value.code == 2
+    capsys.readouterr()
+
+
+def test_verbose_log_lines(tmp_path, caplog):
+    # reference tests/test_cli.py:45-56 greps these strings with -Q 0
+    e = _engine()
+    with caplog.at_level(logging.INFO, logger="merpcr"):
+        e.load_sts_file(goldens.FIXTURE_STS)
+        e.search(e.load_fasta_file(goldens.FIXTURE_FA), str(tmp_path / "o"))
+    text = caplog.text
+    assert "Reading STS file" in text and "Processing sequence: L78833 (117143 bp)" in text
+    assert "Total hits found: 1" in text and "Reading FASTA file" in text
