@@ -1,0 +1,402 @@
+#!/usr/bin/env python3
+"""bench.py -- Gbp/s scanned on BASELINE.json's headline config (cfg3: synthetic 3.1 Gbp, 24 chromosomes,
+100 000 planted STS, -W 11 -N 1 -X 1 -M 50).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # our arm (CUDA, one process per GPU)
+    python bench.py --impl reference [...]                         # the reference's CPU algorithm (C port of it)
+
+One "step" = one pass of the hot path (scan + verify + emit + sort) over the rank's resident genome shard.
+`value` is whole-job throughput with the packed genome and the table resident in HBM; `e2e` repeats the step
+from pinned HOST bytes (H2D + pack + scan + sort + D2H of the hits inside the timed region).
+N > 1: weak scaling -- every rank owns one 3.1 Gbp genome copy ("individual") of a world-sized multi-genome
+layout, selected through the engine's (rank, world) sharding; there is no collective on the scan path.
+
+The CPU baseline is oracle/merpcr_oracle.c (a C restatement of the reference's algorithm; the Python reference
+itself cannot travel to the GPU box), timed on a bounded sample with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+import synth  # noqa: E402
+
+SEED = 1003
+PARAMS = dict(wordsize=11, margin=50, mismatches=1, three_prime_match=1, iupac_mode=0)
+METRIC = "Gbp/s scanned (3.1 Gbp genome, 100k STS, N=1)"
+ALGO_BYTES_PER_BP = 0.75   # plane2 0.25 + plane4 0.5, each read once
+ALGO_BYTES_PER_HIT = 16.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; recorded in config)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(scale: float):
+    lengths = [max(2000, int(L * scale)) for L in synth.GRCH38_LENGTHS]
+    n_sts = max(50, int(round(100000 * scale)))
+    sts = synth.make_sts_set(SEED + 1, n_sts, 18, 25, 100, 1000)
+    return lengths, n_sts, sts
+
+
+def contig_seed(copy: int, ci: int) -> int:
+    return SEED * 1000003 + copy * 1009 + ci
+
+
+def plan_writes(lengths, sts, copy):
+    expected, writes = synth.plant_amplicons(SEED + 2 + 7919 * copy, list(lengths), sts, PARAMS["margin"],
+                                             sub_mode="cfg3")
+    return expected, writes
+
+
+def apply_writes_numpy(arr, ci, writes, lo=0):
+    for c, off, b in writes:
+        if c != ci:
+            continue
+        a, e = off - lo, off - lo + len(b)
+        if e <= 0 or a >= len(arr):
+            continue
+        s = max(a, 0)
+        arr[s: min(e, len(arr))] = b[s - a: min(e, len(arr)) - a]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[2:6]):
+                    if v == "Active":
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference algorithm)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_sample_search(sts_text: bytes, sample: np.ndarray, threads: int, repeats: int = 1):
+    """Time the oracle's search of one in-memory sequence with `threads` host threads. Returns (s/step, hits)."""
+    from oracle.oracle import Oracle
+    o = Oracle(**PARAMS)
+    assert o.load_sts_text(sts_text)
+    best, hits = None, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        hits = o.search_count_buffer(sample.ctypes.data, int(sample.size), threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, hits, o
+
+
+def host_sample(lengths, sts, nbases: int) -> np.ndarray:
+    """First `nbases` of chr1 of copy 0 (same bytes the GPU arm scans), built on the host."""
+    nbases = min(nbases, lengths[0])
+    arr = synth.dna_chunked(contig_seed(0, 0), nbases)
+    _, writes = plan_writes(lengths, sts, 0)
+    apply_writes_numpy(arr, 0, writes)
+    return arr
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    lengths, n_sts, sts = workload(args.scale)
+    sts_text = synth.sts_lines(sts)
+    cores = os.cpu_count() or 1
+    calib = host_sample(lengths, sts, min(lengths[0], 4_000_000))
+    dt, _, _ = cpu_sample_search(sts_text, calib, cores)
+    rate = calib.size / dt
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    nb = int(min(lengths[0], max(calib.size, rate * min(budget, args.cpu_seconds))))
+    sample = host_sample(lengths, sts, nb) if nb != calib.size else calib
+    from oracle.oracle import Oracle
+    o = Oracle(**PARAMS)
+    assert o.load_sts_text(sts_text)
+    for _ in range(args.warmup):
+        o.search_count_buffer(sample.ctypes.data, int(sample.size), cores)
+    t0 = time.perf_counter()
+    hits = 0
+    for _ in range(args.steps):
+        hits = o.search_count_buffer(sample.ctypes.data, int(sample.size), cores)
+    total = time.perf_counter() - t0
+    ms = 1e3 * total / args.steps
+    value = sample.size / (ms * 1e-3) / 1e9
+    line = dict(metric=METRIC, value=value, unit="Gbp/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
+                impl="reference",
+                config=dict(workload="cfg3: 24-chromosome synthetic genome x 100k planted STS, -W 11 -N 1 -X 1 -M 50",
+                            scale=args.scale, n_sts=n_sts, sample_bp=int(sample.size), hits_in_sample=int(hits)),
+                cpu_baseline=dict(value=value, unit="Gbp/s", cores=cores, kind="port",
+                                  sample=f"first {sample.size} bp of chr1 x all {n_sts} STS per step "
+                                         "(oracle/merpcr_oracle.c, pthreads chunking as engine.py:381-419)"),
+                e2e=dict(value=value, unit="Gbp/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from merpcr_b200 import MerPCR, _capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    lengths, n_sts, sts = workload(args.scale)
+    sts_text = synth.sts_lines(sts)
+    ncont = len(lengths)
+    # world-sized layout: copy k of the 24 chromosomes is owned by rank k
+    all_lengths = lengths * world
+    with tempfile.NamedTemporaryFile("wb", suffix=".sts", delete=False) as f:
+        f.write(sts_text)
+        sts_path = f.name
+    eng = MerPCR(**PARAMS, device=local, shard=(rank, world))
+    try:
+        assert eng.load_sts_file(sts_path)
+    finally:
+        os.unlink(sts_path)
+    layout = eng.make_layout(all_lengths)
+
+    # ---- synthetic genome of this rank's copy, generated and planted directly in HBM
+    expected, writes = plan_writes(lengths, sts, rank)
+    dev_contigs = []
+    by_contig = {}
+    for ci, off, b in writes:
+        by_contig.setdefault(ci, []).append((off, b))
+    for ci, L in enumerate(lengths):
+        t = synth.dna_torch(contig_seed(rank, ci), 0, L, dev)
+        w = by_contig.get(ci)
+        if w:
+            idx = np.concatenate([np.arange(off, off + len(b), dtype=np.int64) for off, b in w])
+            val = np.concatenate([b for _, b in w])
+            t[torch.from_numpy(idx).to(dev)] = torch.from_numpy(val).to(dev)
+        dev_contigs.append(t)
+    seqs_dev = [None] * (ncont * world)
+    for ci in range(ncont):
+        seqs_dev[rank * ncont + ci] = dev_contigs[ci]
+    my_bp = int(sum(lengths))
+    shard = eng.upload(layout, seqs_dev)
+    torch.cuda.synchronize()
+
+    # ---- resident (device-timed) region
+    lib, ctx = eng._be.lib, eng._ctx
+    n_hits = 0
+    for _ in range(args.warmup):
+        _, n_hits = eng.scan_device(layout, shard)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.gpu_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms = []
+    ev0.record()
+    for _ in range(args.steps):
+        _, n_hits = eng.scan_device(layout, shard)
+        scan_ms.append(float(lib.mpcr_last_scan_ms(ctx)))
+    ev1.record()
+    torch.cuda.synchronize()
+    t_ms = ev0.elapsed_time(ev1)
+    launches = eng.gpu_launches - launches0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = max_over_ranks(t_ms)
+    ms_per_step = t_ms / args.steps
+    total_bp = sum_over_ranks(float(my_bp))
+    total_hits = sum_over_ranks(float(n_hits))
+    value = total_bp / (ms_per_step * 1e-3) / 1e9
+    kern_ms = float(np.mean(scan_ms))
+
+    # planted truth + ordering sanity on the resident result (not timed)
+    hits_t, n = eng.scan_device(layout, shard)
+    hits = hits_t[: n * _capi.HIT_DTYPE.itemsize].cpu().numpy().view(_capi.HIT_DTYPE)
+    found = set(zip((hits["contig"] - rank * ncont).tolist(), hits["pos1"].tolist(), hits["pos2"].tolist()))
+    planted_ok = all((c, a, b) in found for c, a, b, _, _ in expected)
+    key = np.stack([hits["contig"], hits["pos1"]], axis=1).astype(np.int64)
+    sorted_ok = bool(np.all((key[1:, 0] > key[:-1, 0]) | ((key[1:, 0] == key[:-1, 0]) & (key[1:, 1] >= key[:-1, 1]))))
+
+    # ---- end-to-end from pinned host bytes
+    e2e = None
+    host_contigs = None
+    if not args.no_e2e:
+        host_contigs = [torch.empty(L, dtype=torch.uint8).pin_memory() for L in lengths]
+        for h, d in zip(host_contigs, dev_contigs):
+            h.copy_(d)
+        torch.cuda.synchronize()
+        seqs_host = [None] * (ncont * world)
+        for ci in range(ncont):
+            seqs_host[rank * ncont + ci] = host_contigs[ci]
+        del dev_contigs, seqs_dev
+        e2e_steps = max(2, min(args.steps, 5))
+        sh2 = None
+        d2h = 0
+        for it in range(1 + e2e_steps):            # 1 warm-up
+            if it == 1:
+                barrier()
+                t0 = time.perf_counter()
+            sh2 = eng.upload(layout, seqs_host, shard=sh2)
+            out = eng.scan(layout, sh2)
+            d2h = out.nbytes + 8
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        e2e = dict(value=total_bp / dt / 1e9, unit="Gbp/s", h2d_bytes_per_step=int(sum_over_ranks(float(my_bp))),
+                   d2h_bytes_per_step=int(sum_over_ranks(float(d2h))), ms_per_step=dt * 1e3, steps=e2e_steps,
+                   hits=int(sum_over_ranks(float(len(out)))))
+        assert len(out) == n_hits, "e2e and resident hit counts differ"
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        chr1 = host_contigs[0].numpy() if host_contigs is not None else dev_contigs[0].cpu().numpy()
+        calib_n = min(len(chr1), 4_000_000)
+        dt, _, _ = cpu_sample_search(sts_text, chr1[:calib_n], cores)
+        nb = int(min(len(chr1), max(calib_n, calib_n / dt * args.cpu_seconds)))
+        dt, cpu_hits, orc = cpu_sample_search(sts_text, chr1[:nb], cores)
+        # bit-exact check of a sub-sample against the GPU result (single-thread oracle == reference -T 1)
+        sub = min(nb, 8_000_000)
+        oh = orc.search_hits(chr1[:sub].tobytes(), threads=1)
+        safe = sub - (int(sts["size"].max()) + PARAMS["margin"] + 64)
+        oh = oh[oh[:, 1] < safe]
+        g = hits[(hits["contig"] == 0) & (hits["pos2"] < safe)]
+        parity_ok = len(oh) == len(g) and bool(np.array_equal(oh[:, 0], g["pos1"]) and np.array_equal(oh[:, 1], g["pos2"]))
+        cpu = dict(value=nb / dt / 1e9, unit="Gbp/s", cores=cores, kind="port",
+                   sample=f"first {nb} bp of chr1 x all {n_sts} STS, one pass, {cores} threads "
+                          "(oracle/merpcr_oracle.c)", seconds=dt, hits=int(cpu_hits), parity_vs_gpu_first_8Mbp=parity_ok)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        algo_bytes = ALGO_BYTES_PER_BP * my_bp + ALGO_BYTES_PER_HIT * n_hits
+        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        line = dict(
+            metric=METRIC, value=value, unit="Gbp/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8",
+            data="synthetic", impl="b200",
+            config=dict(workload="cfg3: 24-chromosome synthetic genome (GRCh38 lengths) x 100k planted STS, "
+                                 "-W 11 -N 1 -X 1 -M 50; one genome copy per GPU",
+                        scale=args.scale, bp_per_gpu=my_bp, n_sts=n_sts, hits_per_gpu=int(n_hits),
+                        l2="inputs (2.7 GB of planes per GPU) exceed the 126 MB L2; no flush needed",
+                        planted_found=planted_ok, sorted=sorted_ok),
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,
+                          traffic=None, kernel="scan_kernel", kernel_ms=kern_ms,
+                          algorithmic_bytes_per_launch=algo_bytes,
+                          peak_source="MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650"),
+            cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
+        )
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -141,6 +141,7 @@ class MerPCR:
         self._rec_to_idx = np.zeros(0, dtype=np.int64)
         self._hashes = np.zeros(0, dtype=np.uint32)
         self.last_scan_ms = 0.0
+        self.last_h2d_bytes = 0
         self.last_timing: Dict[str, float] = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -473,8 +474,11 @@ class MerPCR:
         end = (total * (rank + 1) // world) // 128 * 128 if rank + 1 < world else max(total, 128)
         return dict(contigs=contigs, total=total, begin=begin, end=end, lengths=list(lengths))
 
-    def upload(self, layout: dict, seqs: Sequence[np.ndarray]) -> _Shard:
-        """H2D + pack (FASTA ingest, device half): builds the planes this shard needs (its range + halos)."""
+    def upload(self, layout: dict, seqs: Sequence, shard: Optional[_Shard] = None) -> _Shard:
+        """FASTA ingest, device half: copy the bases this shard needs (its range + halos) to the GPU and pack them
+        into the planes.  seqs[i] is the i-th contig as a uint8 numpy array, a torch uint8 tensor (pinned host or
+        already on the device) or None for a contig this shard never touches.  Passing the previous `shard`
+        re-uses its buffers (steady-state re-upload)."""
         lib = self._be.lib
         total, begin, end = layout["total"], layout["begin"], layout["end"]
         halo_l, halo_r = int(lib.mpcr_halo_left(self._ctx)), int(lib.mpcr_halo_right(self._ctx))
@@ -482,33 +486,48 @@ class MerPCR:
         stop = min(total, end + halo_r)
         bases = max(128, (stop - origin + 127) // 128 * 128)
         alloc = bases + TILE_BASES + PLANE_SLACK_BASES
-        sh = _Shard()
-        sh.device, sh.origin, sh.bases, sh.begin, sh.end = self._tdev, origin, bases, begin, end
-        sh.plane2 = torch.zeros(alloc // 4, dtype=torch.uint8, device=self._tdev)
-        sh.plane4 = torch.zeros(alloc // 2, dtype=torch.uint8, device=self._tdev)
-        sh.valid = torch.zeros(alloc // 8, dtype=torch.uint8, device=self._tdev)
-        sh.hits, sh.count = None, None
+        sh = shard
+        if sh is not None and (sh.origin, sh.bases, sh.begin, sh.end) == (origin, bases, begin, end):
+            sh.plane2.zero_()
+            sh.plane4.zero_()
+            sh.valid.zero_()
+        else:
+            sh = _Shard()
+            sh.device, sh.origin, sh.bases, sh.begin, sh.end = self._tdev, origin, bases, begin, end
+            sh.plane2 = torch.zeros(alloc // 4, dtype=torch.uint8, device=self._tdev)
+            sh.plane4 = torch.zeros(alloc // 2, dtype=torch.uint8, device=self._tdev)
+            sh.valid = torch.zeros(alloc // 8, dtype=torch.uint8, device=self._tdev)
+            sh.hits, sh.count = None, None
         lut = genome_lut(self.iupac_mode)
         stream = self._stream()
         chunk = 1 << 26
         staging = []
+        h2d = 0
         for ci, s in enumerate(seqs):
+            if s is None:
+                continue
             g0 = int(layout["contigs"][ci]["gstart"])
-            L = int(s.size)
+            L = int(layout["contigs"][ci]["length"])
             lo, hi = max(g0, origin), min(g0 + L, origin + bases)
             if hi <= lo:
                 continue
             for a in range(lo, hi, chunk):
                 b = min(hi, a + chunk)
-                arr = s[a - g0: b - g0]
-                src = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
-                d = src.to(self._tdev, non_blocking=False) if self._tdev.type == "cuda" else src
-                staging.append(d)
-                self._be.check(lib.mpcr_pack_sequence(self._ctx, d.data_ptr(), b - a, a, origin, sh.plane2.data_ptr(),
-                                                      sh.plane4.data_ptr(), sh.valid.data_ptr(), lut.ctypes.data,
-                                                      stream))
+                if isinstance(s, torch.Tensor):
+                    src = s[a - g0: b - g0]
+                else:
+                    arr = s[a - g0: b - g0]
+                    src = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
+                if src.device != self._tdev:
+                    h2d += b - a
+                    src = src.to(self._tdev, non_blocking=True)
+                    staging.append(src)
+                self._be.check(lib.mpcr_pack_sequence(self._ctx, src.data_ptr(), b - a, a, origin,
+                                                      sh.plane2.data_ptr(), sh.plane4.data_ptr(), sh.valid.data_ptr(),
+                                                      lut.ctypes.data, stream))
         self._sync()
         del staging
+        self.last_h2d_bytes = h2d
         return sh
 
     def scan(self, layout: dict, sh: _Shard, sort: bool = True) -> np.ndarray:

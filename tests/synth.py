@@ -121,25 +121,34 @@ def sts_lines(sts, id_fmt: str = "STS%06d", ranged: bool = False) -> bytes:
     return "".join(out).encode()
 
 
-def plant_amplicons(seed: int, contigs, sts, margin: int, sub_mode: str = "none", x_protect: int = 1):
+def plant_amplicons(seed: int, contigs, sts, margin: int, sub_mode: str = "none", x_protect: int = 1,
+                    plant_count=None):
     """Plant each STS once, in place, at non-overlapping slots spread over the contigs.
 
     contigs: list of writable uint8 arrays.  sub_mode:
       "none"  : exact primers; product = size + d, d in [-margin, margin] (90%) or +-[margin+1, margin+20] (10%, negatives)
       "cfg3"  : d as above for all; primers 45% exact, 45% one substitution outside the protected 3' base,
                 5% one substitution ON the protected base (negative), 5% two substitutions (negative at N=1)
+    If `contigs` is a list of LENGTHS the genome is not touched and (expected, writes) is returned, writes being
+    (contig_index, offset, bytes) triples to apply in order (used to plant into device-resident genomes).
     Returns a list of expected hits (contig_index, pos1, pos2, sts_index, strand) for plants that must be
     found at the given margin (and N>=1 for cfg3), as a cross-check independent of any implementation.
     """
+    writes = None
+    if contigs and not hasattr(contigs[0], "__len__"):
+        # planning mode: `contigs` is a list of lengths; the writes are returned instead of applied
+        lengths, writes = [int(x) for x in contigs], []
+    else:
+        lengths = [len(c) for c in contigs]
     r = Rng(seed)
-    n = len(sts["l1"])
-    total = sum(len(c) for c in contigs)
+    n = len(sts["l1"]) if plant_count is None else min(int(plant_count), len(sts["l1"]))   # plant the first n STS
+    total = sum(lengths)
     slot = total // max(n, 1)
-    max_span = int(sts["size"].max()) + margin + 64 if n else 0
+    max_span = int(sts["size"][:n].max()) + margin + 64 if n else 0
     if slot < max_span + 8:
         raise ValueError("genome too small for non-overlapping plants")
     # global slot start -> (contig, offset); skip slots that straddle a contig end
-    starts = np.cumsum([0] + [len(c) for c in contigs])
+    starts = np.cumsum([0] + lengths)
     jitter = r.ints(0, slot - max_span - 1, n)
     strand = r.u64(n) & np.uint64(1)
     d_in = r.ints(-margin, margin, n)
@@ -159,7 +168,7 @@ def plant_amplicons(seed: int, contigs, sts, margin: int, sub_mode: str = "none"
         prod = size + d
         if prod < L1 + L2:
             prod, d = L1 + L2, L1 + L2 - size
-        if off + prod > len(contigs[ci]):
+        if off + prod > lengths[ci]:
             continue
         a = sts["p1"][i, :L1].copy()
         b = sts["p2"][i, :L2].copy()
@@ -190,9 +199,46 @@ def plant_amplicons(seed: int, contigs, sts, margin: int, sub_mode: str = "none"
                 j0 = int(subpos[i] >> np.uint64(8)) % len(free_idx)
                 j1 = (j0 + 1 + int(subpos[i] >> np.uint64(20)) % (len(free_idx) - 1)) % len(free_idx)
                 sub(free_idx[j0]); sub(free_idx[j1]); found = False
-        seq = contigs[ci]
-        seq[off: off + len(left)] = left
-        seq[off + prod - len(right): off + prod] = right
+        if writes is None:
+            seq = contigs[ci]
+            seq[off: off + len(left)] = left
+            seq[off + prod - len(right): off + prod] = right
+        else:
+            writes.append((ci, off, left))
+            writes.append((ci, off + prod - len(right), right))
         if found:
             expected.append((ci, off, off + prod - 1, i, "+" if left_is_p1 else "-"))
-    return expected
+    return expected if writes is None else (expected, writes)
+
+
+# ---------------------------------------------------------------------------------------------
+# The same generator on a torch device (bench.py builds the 3.1 Gbp genome directly in HBM)
+# ---------------------------------------------------------------------------------------------
+
+def _i64(x: int) -> int:
+    x &= 0xFFFFFFFFFFFFFFFF
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def dna_torch(seed: int, start: int, n: int, device, chunk: int = 1 << 26):
+    """Bases [start, start+n) of the stream dna_chunked(seed, ...) as a uint8 tensor on `device`
+    (bit-identical to the numpy generator; int64 arithmetic wraps like uint64)."""
+    import torch
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    shifts = (torch.arange(32, dtype=torch.int64, device=device) * 2)[None, :]
+
+    def lsr(z, s):
+        return (z >> s) & ((1 << (64 - s)) - 1)
+
+    for s in range(start, start + n, chunk):
+        e = min(start + n, s + chunk)
+        w0, w1 = s // 32, (e + 31) // 32
+        idx = torch.arange(w0 + 1, w1 + 1, dtype=torch.int64, device=device)
+        z = idx * _i64(0x9E3779B97F4A7C15) + _i64(seed)
+        z = (z ^ lsr(z, 30)) * _i64(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * _i64(0x94D049BB133111EB)
+        z = z ^ lsr(z, 31)
+        codes = ((z[:, None] >> shifts) & 3).reshape(-1)
+        out[s - start: e - start] = lut[codes[s - w0 * 32: e - w0 * 32]]
+    return out

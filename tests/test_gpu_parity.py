@@ -1,0 +1,263 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI by the Python host, against
+  * the reference's fixture golden line and the reference-generated fuzz goldens (bit-exact text),
+  * the CPU oracle on seeded synthetic workloads shaped like BASELINE.json's configs (bit-exact hit lists in order),
+  * planted-amplicon truth and size-independent properties at larger sizes.
+Nothing here reads /root/reference; nothing uses the host emulation."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import goldens
+import parity
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _real_backend():
+    import torch
+    from merpcr_b200 import _capi
+    _capi._inject_backend_for_tests("", "cpu")          # drop any emulation a CPU-tier module left behind
+    be = _capi.backend()
+    assert be.device_kind == "cuda" and os.path.basename(_capi.LIB_PATH) == "libmerpcr_b200.so"
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    yield
+
+
+def _records(contigs, names=None):
+    from merpcr_b200 import FASTARecord
+    out = []
+    for i, c in enumerate(contigs):
+        r = FASTARecord(f">{names[i] if names else 'c%d' % i}", c)
+        r._from_loader = True
+        out.append(r)
+    return out
+
+
+def _write(tmp_path, name, data):
+    p = tmp_path / name
+    p.write_bytes(data)
+    return str(p)
+
+
+def test_fixture_golden_line(tmp_path):
+    from merpcr_b200 import MerPCR
+    eng = MerPCR()
+    assert eng.load_sts_file(goldens.FIXTURE_STS)
+    assert [r.hash_offset for r in eng.sts_records] == [0] * 6
+    assert sorted(eng.sts_table) == sorted([3638181, 3526114, 2555953, 3737721, 2062650, 476488])
+    out = tmp_path / "o.txt"
+    assert eng.search(eng.load_fasta_file(goldens.FIXTURE_FA), str(out)) == 1
+    assert out.read_text() == goldens.FIXTURE_LINE
+    assert eng.gpu_launches >= 4
+
+
+@pytest.mark.parametrize("flags,expect_hit", [
+    (dict(mismatches=1), True), (dict(mismatches=2), True), (dict(wordsize=3), True),
+    (dict(wordsize=8, mismatches=2, margin=500, three_prime_match=0), True), (dict(iupac_mode=1), True),
+    (dict(margin=8), True), (dict(margin=7), False), (dict(wordsize=16), True), (dict(wordsize=12), True),
+])
+def test_fixture_flag_sweep(tmp_path, flags, expect_hit):
+    from merpcr_b200 import MerPCR
+    eng = MerPCR(**flags)
+    assert eng.load_sts_file(goldens.FIXTURE_STS)
+    out = tmp_path / "o.txt"
+    eng.search(eng.load_fasta_file(goldens.FIXTURE_FA), str(out))
+    assert out.read_text() == (goldens.FIXTURE_LINE if expect_hit else "")
+
+
+def test_fuzz_goldens_bit_exact():
+    from merpcr_b200 import MerPCR
+    cases = goldens.fuzz_cases()
+    for c in cases:
+        parity.check_fuzz_case(c, MerPCR)
+
+
+def test_pack_planes_match_numpy():
+    """mpcr_pack_sequence against a numpy restatement of the plane layout (include/merpcr_b200.h)."""
+    import torch
+    from merpcr_b200 import MerPCR
+    from merpcr_b200.alphabet import genome_lut
+    rng = synth.Rng(5)
+    n = 100000 + 37
+    seq = rng.dna(n)
+    letters = np.frombuffer(b"NRYKMSWBDHVXnacgtu", dtype=np.uint8)
+    pos = rng.ints(0, n - 1, 4000)
+    seq[pos] = letters[rng.ints(0, len(letters) - 1, 4000)]
+    for iupac in (0, 1):
+        eng = MerPCR(iupac_mode=iupac)
+        eng.load_sts_file(goldens.FIXTURE_STS)
+        lay = eng.make_layout([n])
+        sh = eng.upload(lay, [seq])
+        lut = genome_lut(iupac)[seq].astype(np.uint64)
+        pad = (-n) % 64
+        e = np.concatenate([lut, np.zeros(pad, dtype=np.uint64)])
+        nib = (e & 15).reshape(-1, 16)
+        p4 = (nib << (np.arange(16, dtype=np.uint64) * 4)).sum(axis=1).astype(np.uint64)
+        c2 = ((e >> 4) & 3).reshape(-1, 32)
+        p2 = (c2 << (np.arange(32, dtype=np.uint64) * 2)).sum(axis=1).astype(np.uint64)
+        vb = ((e >> 6) & 1).reshape(-1, 64)
+        v = (vb << np.arange(64, dtype=np.uint64)).sum(axis=1).astype(np.uint64)
+        got4 = sh.plane4.cpu().numpy().view(np.uint64)[: len(p4)]
+        got2 = sh.plane2.cpu().numpy().view(np.uint64)[: len(p2)]
+        gotv = sh.valid.cpu().numpy().view(np.uint64)[: len(v)]
+        assert np.array_equal(got4, p4) and np.array_equal(got2, p2) and np.array_equal(gotv, v)
+        assert not sh.plane4.cpu().numpy().view(np.uint64)[len(p4):].any()     # padding stays zero / invalid
+
+
+def test_device_table_matches_oracle(tmp_path):
+    """Device-built records (hash offsets, hash values, reverse complements) vs the oracle's load (engine.py:253-281)."""
+    from merpcr_b200 import MerPCR
+    from oracle.oracle import Oracle
+    rng = synth.Rng(11)
+    lines = []
+    for i in range(3000):
+        a = rng.dna(rng.randint(11, 40)).tobytes().decode()
+        b = rng.dna(rng.randint(11, 40)).tobytes().decode()
+        if i % 7 == 0:
+            j = rng.randint(0, len(a) - 1)
+            a = a[:j] + rng.choice("NRYKMSWBDHVXU") + a[j + 1:]
+        if i % 11 == 0:
+            j = rng.randint(0, len(b) - 1)
+            b = b[:j] + rng.choice("NRYKMSWBDHVXZ") + b[j + 1:]
+        lines.append(f"ID{i}\t{a}\t{b}\t{rng.randint(30, 900)}\tal {i}\n")
+    text = "".join(lines)
+    path = _write(tmp_path, "t.sts", text.encode())
+    for W in (8, 11, 16):
+        o = Oracle(wordsize=W)
+        assert o.load_sts_text(text)
+        eng = MerPCR(wordsize=W)
+        assert eng.load_sts_file(path)
+        want = o.records()
+        assert len(eng.sts_records) == len(want)
+        for g, w in zip(eng.sts_records, want):
+            assert (g.id, g.direct, g.hash_offset, g.primer1, g.primer2, g.pcr_size) == \
+                (w["id"], w["direct"], w["hash_offset"], w["primer1"], w["primer2"], w["pcr_size"])
+        table = eng.sts_table
+        assert sorted(table) == sorted({w["hash"] for w in want})
+        # the device's encoded reverse-complement primer of every '-' record decodes back to the host string
+        from merpcr_b200.alphabet import IUPAC_MASK
+        inv = {v: k for k, v in IUPAC_MASK.items()}
+        lib, words, nw = eng._be.lib, (C.c_uint64 * 16)(), C.c_uint32(0)
+        slots = np.flatnonzero(eng._rec_to_idx >= 0)
+        for slot in slots[:400].tolist():
+            rec = eng.sts_records[int(eng._rec_to_idx[slot])]
+            eng._be.check(lib.mpcr_table_primer_words(eng._ctx, slot, 2, words, 16, C.byref(nw)))
+            half = nw.value // 2
+            dec = ""
+            for i, ch in enumerate(rec.primer2):
+                nib = (words[i // 16] >> (4 * (i % 16))) & 15
+                aux = (words[half + i // 16] >> (4 * (i % 16))) & 3
+                dec += inv.get(nib, "X" if aux == 2 else "?") if not (aux & 1) else "?"
+            expect = "".join(c if (c in IUPAC_MASK or c == "X") else "?" for c in rec.primer2)
+            assert dec == expect, (slot, rec.primer2, dec)
+
+
+CASES = [
+    # (name, contig lengths, n_sts, params, sub_mode, decorate, ranged)
+    ("cfg2-like", [3_000_000], 1500, dict(wordsize=11, margin=50, mismatches=0), "none", False, False),
+    ("cfg3-like", [1_300_000, 900_001, 450_000, 77, 11, 250_000], 2500,
+     dict(wordsize=11, margin=50, mismatches=1, three_prime_match=1), "cfg3", False, False),
+    ("cfg4-like", [1_500_000, 800_000], 2000,
+     dict(wordsize=11, margin=50, mismatches=2, three_prime_match=1, iupac_mode=1), "cfg3", True, False),
+    ("cfg5-like", [400_000, 150_000], 20000, dict(wordsize=8, margin=500, mismatches=0), "none", False, True),
+    ("w16", [600_000], 800, dict(wordsize=16, margin=20, mismatches=3, three_prime_match=0), "cfg3", False, False),
+]
+
+
+def _make_workload(seed, lengths, n_sts, params, sub_mode, decorate, ranged):
+    rng = synth.Rng(seed)
+    contigs = [rng.dna(n) for n in lengths]
+    sts = synth.make_sts_set(seed + 1, n_sts, 18, 25, 100, 1000)
+    big = [c for c in contigs if len(c) > 100000]
+    expected = synth.plant_amplicons(seed + 2, big, sts, params["margin"], sub_mode=sub_mode,
+                                     plant_count=min(n_sts, sum(len(c) for c in big) // 2200))
+    if decorate:
+        # N runs (some abutting / inside amplicons), scattered IUPAC letters, degenerate primers
+        for c in big:
+            for _ in range(40):
+                a = rng.randint(0, len(c) - 1)
+                c[a: a + rng.choice([1, 3, 10, 200, 5000])] = ord("N")
+            pos = rng.ints(0, len(c) - 1, len(c) // 5000)
+            c[pos] = np.frombuffer(b"RYKMSWBDHVNX", dtype=np.uint8)[rng.ints(0, 11, len(pos))]
+        for i in range(0, n_sts, 5):
+            j = rng.randint(12, int(sts["l1"][i]) - 2)
+            sts["p1"][i, j] = ord(rng.choice("RYMKSWBDHVN"))
+            j = rng.randint(1, int(sts["l2"][i]) - 2)
+            sts["p2"][i, j] = ord(rng.choice("RYMKSWBDHVN"))
+    return contigs, synth.sts_lines(sts, ranged=ranged), expected
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_synthetic_configs_bit_exact_vs_oracle(tmp_path, case):
+    from merpcr_b200 import MerPCR
+    name, lengths, n_sts, params, sub_mode, decorate, ranged = case
+    contigs, sts_text, expected = _make_workload(hash(name) % 1000 + 3000 if False else len(name) * 131 + n_sts,
+                                                 lengths, n_sts, params, sub_mode, decorate, ranged)
+    path = _write(tmp_path, "w.sts", sts_text)
+    eng = MerPCR(**params)
+    assert eng.load_sts_file(path)
+    got = parity.engine_hits(eng, _records(contigs))
+    want = parity.oracle_hits(params, sts_text.decode(), [c.tobytes() for c in contigs])
+    assert got.shape == want.shape and np.array_equal(got, want), name
+    if not decorate and name != "w16":     # (w16 substitutions may land inside the 16-base seed word)
+        found = {(r[0], r[1], r[2]) for r in got.tolist()}
+        big_index = [i for i, c in enumerate(contigs) if len(c) > 100000]
+        assert all((big_index[ci], a, b) in found for ci, a, b, _, _ in expected)
+    assert len(got) > 100 and len(expected) > 100
+
+
+def test_hit_buffer_regrows_and_sort_is_total(tmp_path):
+    """More hits than the initial 65 536-entry buffer: nothing is truncated, order key is exact
+    (repeat-rich sequence, duplicate STS lines, multi-delta hits)."""
+    from merpcr_b200 import MerPCR
+    unit = "ACGGTCATTGCAGT" + "TTGACCGGTATCAG" + "CATGCATGAACC"      # 40-mer tandem repeat
+    seq = np.frombuffer((unit * 9000).encode(), dtype=np.uint8).copy()
+    sts_text = "".join(f"R{i}\tACGGTCATTGCAGT\tTTGACCGGTATCAG\t{68 + (i % 3)}\trep\n" for i in range(4)).encode()
+    path = _write(tmp_path, "r.sts", sts_text)
+    params = dict(wordsize=8, margin=45, mismatches=0)
+    eng = MerPCR(**params)
+    assert eng.load_sts_file(path)
+    got = parity.engine_hits(eng, _records([seq]))
+    want = parity.oracle_hits(params, sts_text.decode(), [seq.tobytes()])
+    assert len(want) > 65536 and np.array_equal(got, want)
+
+
+def test_sharded_equals_whole_on_device(tmp_path):
+    from merpcr_b200 import MerPCR
+    contigs, sts_text, _ = _make_workload(901, [700_000, 300_000, 64, 500_001], 1200,
+                                          dict(margin=50), "cfg3", False, False)
+    path = _write(tmp_path, "s.sts", sts_text)
+    params = dict(wordsize=11, margin=50, mismatches=1)
+    recs = _records(contigs)
+    whole = MerPCR(**params)
+    assert whole.load_sts_file(path)
+    ref = whole.search_hits(recs)
+    for world in (2, 8):
+        parts = []
+        for rank in range(world):
+            e = MerPCR(**params, shard=(rank, world))
+            assert e.load_sts_file(path)
+            parts.append(e.search_hits(recs))
+            e.close()
+        merged = np.concatenate(parts)
+        order = np.lexsort((merged["rank"], merged["rec"], merged["hash_off"], merged["pos1"], merged["contig"]))
+        assert np.array_equal(merged[order], ref), world
+
+
+def test_idempotent_rescan_on_resident_planes(tmp_path):
+    """Scanning the same resident planes twice gives the same sorted list (no state leaks between launches)."""
+    from merpcr_b200 import MerPCR
+    contigs, sts_text, _ = _make_workload(902, [2_000_000], 1000, dict(margin=50), "none", False, False)
+    path = _write(tmp_path, "i.sts", sts_text)
+    eng = MerPCR()
+    assert eng.load_sts_file(path)
+    lay = eng.make_layout([len(c) for c in contigs])
+    sh = eng.upload(lay, contigs)
+    a = eng.scan(lay, sh)
+    b = eng.scan(lay, sh)
+    assert len(a) > 500 and np.array_equal(a, b)
+    assert eng.last_scan_ms > 0
