@@ -253,6 +253,7 @@ struct ScanArgs {
     unsigned long long capacity;
     unsigned long long* count;
     uint32_t* tile_counter;
+    int debug;  // MPCR_DEBUG bit0: hash/filter phase only (candidates are counted, not verified)
 };
 
 struct HitEmitter {
@@ -330,6 +331,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const ScanArgs a) {
             if (j < 32) pass_lo |= bit << j; else pass_hi |= bit << (j - 32);
         }
         uint64_t cand = wv & (((uint64_t)pass_hi << 32) | pass_lo);
+        if (a.debug & 1) {
+            if (cand) atomicAdd(a.count, (unsigned long long)__popcll(cand));
+            continue;
+        }
         while (cand) {
             const int j = __ffsll((long long)cand) - 1;
             cand &= cand - 1;
@@ -649,6 +654,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.filter = c->d_filter; a.filter_bits = c->filter_bits; a.filter_words = c->filter_words; a.filter_exact = c->filter_exact;
     a.prm.W = c->prm.wordsize; a.prm.M = c->prm.margin; a.prm.N = c->prm.mismatches; a.prm.X = c->prm.three_prime_match;
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
+    a.debug = getenv("MPCR_DEBUG") ? atoi(getenv("MPCR_DEBUG")) : 0;
     a.hits = d_hits; a.capacity = capacity; a.count = (unsigned long long*)d_count; a.tile_counter = c->d_tile_counter;
     const size_t smem = (size_t)c->filter_words * 4;
     CU(cudaFuncSetAttribute(scan_kernel<kScanThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
