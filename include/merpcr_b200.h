@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 1
+#define MPCR_ABI_VERSION 2
 
 enum {
     MPCR_OK = 0,
@@ -126,6 +126,9 @@ int mpcr_scan(mpcr_ctx *ctx, const mpcr_contig *h_contigs, uint32_t n_contigs, c
               uint64_t shard_begin, uint64_t shard_end, mpcr_hit *d_hits, uint64_t capacity,
               uint64_t *d_count, void *stream);
 uint64_t mpcr_halo_left(const mpcr_ctx *ctx);
+/* Hash positions per scanner tile; the planes must be allocated with at least this many bases (+1024) of zeroed
+ * slack behind the last base a shard can touch (tiles are staged whole). */
+uint64_t mpcr_tile_bases(void);
 uint64_t mpcr_halo_right(const mpcr_ctx *ctx);
 
 /* Replaces the sort of MerPCR.search (core/engine.py:434) including its tie order: orders n hits by
@@ -136,6 +139,8 @@ int mpcr_sort_hits(mpcr_ctx *ctx, mpcr_hit *d_hits, uint64_t n, void *stream);
 uint64_t mpcr_launch_count(const mpcr_ctx *ctx);
 /* Name / elapsed-ms of the most recent scan kernel as timed by CUDA events on its stream (0 if none). */
 float mpcr_last_scan_ms(mpcr_ctx *ctx);
+/* Same for the verify kernel that follows it (primer compare + mate search of the surviving seed positions). */
+float mpcr_last_verify_ms(mpcr_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -13,13 +13,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmerpcr_b200.so")
 
 MPCR_OK, MPCR_EINVAL, MPCR_ECUDA, MPCR_ENOMEM, MPCR_ESTATE, MPCR_EOVERFLOW = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/merpcr_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_sm_count",
     "mpcr_pack_sequence", "mpcr_table_build", "mpcr_table_records", "mpcr_table_primer_words", "mpcr_scan",
-    "mpcr_halo_left", "mpcr_halo_right", "mpcr_sort_hits", "mpcr_launch_count", "mpcr_last_scan_ms",
+    "mpcr_halo_left", "mpcr_halo_right", "mpcr_tile_bases", "mpcr_sort_hits", "mpcr_launch_count", "mpcr_last_scan_ms", "mpcr_last_verify_ms",
 ]
 
 HIT_DTYPE = np.dtype([("contig", "<u4"), ("pos1", "<u4"), ("pos2", "<u4"), ("rec", "<u4"), ("rank", "<u4"),
@@ -60,12 +60,16 @@ class Backend:
         lib.mpcr_halo_left.argtypes = [vp]
         lib.mpcr_halo_right.restype = u64
         lib.mpcr_halo_right.argtypes = [vp]
+        lib.mpcr_tile_bases.restype = u64
+        lib.mpcr_tile_bases.argtypes = []
         lib.mpcr_sort_hits.restype = i32
         lib.mpcr_sort_hits.argtypes = [vp, vp, u64, vp]
         lib.mpcr_launch_count.restype = u64
         lib.mpcr_launch_count.argtypes = [vp]
         lib.mpcr_last_scan_ms.restype = C.c_float
         lib.mpcr_last_scan_ms.argtypes = [vp]
+        lib.mpcr_last_verify_ms.restype = C.c_float
+        lib.mpcr_last_verify_ms.argtypes = [vp]
         if lib.mpcr_abi_version() != ABI_VERSION:
             raise RuntimeError("libmerpcr_b200.so ABI version mismatch; rebuild with `python -m merpcr_b200.build`")
 

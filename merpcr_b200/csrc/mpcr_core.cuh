@@ -19,8 +19,10 @@ namespace mpcr {
 // ---------------------------------------------------------------------------------------------------------
 
 static constexpr uint64_t kLane1 = 0x1111111111111111ull;  // LSB of every nibble
-static constexpr int kTileBases = 32768;                   // hash positions per tile (multiple of 128)
-static constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
+static constexpr int kScanThreads = 512;                   // threads of one scanner CTA (one CTA per SM)
+static constexpr int kPosPerThread = 64;                   // hash positions per thread and tile
+static constexpr int kTileBases = kScanThreads * kPosPerThread;  // hash positions per tile (multiple of 128)
+static constexpr int kTagBases = 8;                        // bases after the seed carried inline in the table
 
 // One record = one strand of one STS line (core/models.py:17-29 + engine.py:253-281).
 struct RecMeta {
@@ -32,7 +34,7 @@ struct RecMeta {
     uint16_t len1, len2;
     uint16_t hash_off;  // engine.py:339-353
     uint16_t flags;     // bit0: inserted in the table
-    uint32_t pad;
+    uint32_t tag;       // primer1 bases right after the seed: 2-bit codes in bits [0,16), their count in [16,24)
 };
 static_assert(sizeof(RecMeta) == 32, "RecMeta layout");
 
@@ -229,12 +231,15 @@ MPCR_HD void verify_record(const uint64_t* p4, int64_t gcontig, int64_t L, int64
 
 // ---------------------------------------------------------------------------------------------------------
 // Table probing
+//
+// Level 1 (shared memory): a blocked Bloom filter over the seed keys, TWO bits per key inside ONE 32-bit word
+//   word index = mulhi(key * cw, n_words), cw = golden-ratio constant << (32 - 2W)  (so garbage above the key's
+//   2W bits cancels and the scanner never has to mask the funnel-shifted register), bit positions taken from
+//   two disjoint 5-bit fields of the key so that a left shift by the raw register brings each to the MSB.
+// Level 2 (L2-resident, one 16-byte gather): open-addressed slot table keyed by the exact seed, carrying the
+//   record (or bucket start) and the inline tag of the single record.
+// Level 3: CSR bucket entries {record | last << 31, tag} for seeds shared by several records.
 // ---------------------------------------------------------------------------------------------------------
-
-MPCR_HD uint32_t slot_hash(uint32_t key) {
-    uint32_t h = key * 0x9E3779B1u;
-    return h ^ (h >> 15);
-}
 
 MPCR_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
@@ -244,20 +249,133 @@ MPCR_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-// bit index of a key in the first-level filter: exact bitmap when 4^W <= filter_bits, else a fold.
-MPCR_HD uint32_t filter_index(uint32_t key, uint32_t filter_bits, int exact) {
-    return exact ? key : mulhi32(key * 0x9E3779B1u, filter_bits);
+MPCR_HD uint32_t filter_mul(int W) { return 0x9E3779B1u << (32 - 2 * W); }
+MPCR_HD uint32_t filter_word(uint32_t key_raw, uint32_t cw, uint32_t n_words) { return mulhi32(key_raw * cw, n_words); }
+// bit positions: 31 - (key & 31) and, when the key has at least 11 bits (W >= 6), 31 - ((key >> 6) & 31).
+// (key >> 6) is the raw register of the hash position three bases further on, so the scanner gets the second
+// shift amount for free.)
+MPCR_HD uint32_t filter_bits_of(uint32_t key, int W) {
+    const uint32_t s1 = key & 31u, s2 = W >= 6 ? ((key >> 6) & 31u) : s1;
+    return (0x80000000u >> s1) | (0x80000000u >> s2);
+}
+MPCR_HD bool filter_pass(uint32_t word, uint32_t key, int W) {
+    const uint32_t m = filter_bits_of(key, W);
+    return (word & m) == m;
 }
 
-// slot = key << 32 | start ; empty = all ones.  Returns the bucket start or kEmptySlot.
-MPCR_HD uint32_t find_bucket(const uint64_t* slots, uint32_t slot_mask, uint32_t key) {
-    uint32_t i = slot_hash(key) & slot_mask;
+struct Slot {          // 16 bytes, one 128-bit gather
+    uint32_t key;      // exact seed key (little-endian digits); checked only in hashed mode
+    uint32_t val;      // n == 1: record index; n >= 2: index of the first bucket entry
+    uint32_t tag_n;    // tag of the first record in bits [0,24), n in [24,32): kSlotEmpty, 1, 2 or 3 (= 3 or more)
+    uint32_t tag_b;    // n == 2: tag of the second record
+};
+static_assert(sizeof(Slot) == 16, "Slot layout");
+static constexpr uint32_t kSlotEmpty = 0xFFu;         // cudaMemset(0xFF) == all slots empty
+static constexpr uint32_t kWalkBucket = 0x80000000u;  // survivor code flag: "val is a bucket start, walk it"
+
+struct BucketEntry {
+    uint32_t rec_last;  // record index | last-of-bucket << 31
+    uint32_t tag;
+};
+
+// Slot addressing: 4^W slots indexed by the key itself while that stays L2-sized (W <= 11: 64 MiB), otherwise
+// open addressing with linear probing at load <= 1/8.
+struct SlotMap {
+    uint32_t mask;    // n_slots - 1
+    uint32_t direct;  // 1: index = key
+};
+
+MPCR_HD uint32_t slot_hash(uint32_t key) {
+    uint32_t h = key * 0x9E3779B1u;
+    return h ^ (h >> 15);
+}
+MPCR_HD uint32_t slot_index(uint32_t key, SlotMap sm) { return sm.direct ? key : (slot_hash(key) & sm.mask); }
+
+// engine.py:614-640 restricted to the tag: true iff the full primer-1 compare is CERTAIN to fail because the
+// bases right after the seed already carry more than N mismatches.  tag holds only A/C/G/T primer letters;
+// gcodes / gvalid are the 2-bit codes / clean flags of the genome bases following the seed.  A clean genome
+// base whose code differs from an A/C/G/T primer letter mismatches in both compare modes; anything not clean
+// is left to the full compare.
+MPCR_HD bool tag_rejects(uint32_t tag, uint32_t gcodes, uint32_t gvalid, int N) {
+    const uint32_t len = (tag >> 16) & 0xFFu;
+    if (len == 0) return false;
+    const uint32_t vm = (1u << len) - 1u;
+    if ((gvalid & vm) != vm) return false;
+    uint32_t d = (tag ^ gcodes) & ((1u << (2 * len)) - 1u);
+    d = (d | (d >> 1)) & 0x5555u;
+#ifdef __CUDA_ARCH__
+    return __popc(d) > N;
+#else
+    return __builtin_popcount(d) > N;
+#endif
+}
+
+// the tag of a primer: up to kTagBases A/C/G/T letters following the seed [ho+W, ...)
+template <class CharAt>
+MPCR_HD uint32_t make_tag(CharAt at, int len, int ho, int W) {
+    uint32_t codes = 0, n = 0;
+    for (int i = ho + W; i < len && n < (uint32_t)kTagBases; ++i) {
+        const uint8_t c = at(i);
+        uint32_t code;
+        if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3;
+        else break;
+        codes |= code << (2 * n);
+        ++n;
+    }
+    return codes | (n << 16);
+}
+
+// n bits of a little-endian bit plane starting at bit index b (n <= 32)
+MPCR_HD uint32_t fetch_bits(const uint64_t* plane, int64_t b, int n) {
+    const uint64_t i = (uint64_t)b >> 6;
+    const unsigned sh = (unsigned)b & 63u;
+    uint64_t v = plane[i] >> sh;
+    if (sh) v |= plane[i + 1] << (64u - sh);
+    return (uint32_t)v & (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u));
+}
+
+MPCR_HD Slot load_slot(const Slot* p) {
+#ifdef __CUDA_ARCH__
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    return Slot{v.x, v.y, v.z, v.w};
+#else
+    return *p;
+#endif
+}
+
+// Does a (non-empty, key-matching) slot leave anything to verify at this position?  *any = false if every record
+// of the seed is ruled out by its inline tag.  Returns the survivor code: the record index (n == 1) or
+// kWalkBucket | first bucket entry.
+MPCR_HD uint32_t slot_survivor(const Slot& s, uint32_t gcodes, uint32_t gvalid, int N, bool* any) {
+    const uint32_t n = s.tag_n >> 24;
+    bool pass = n >= 3u || !tag_rejects(s.tag_n & 0xFFFFFFu, gcodes, gvalid, N);
+    if (n == 2u && !pass) pass = !tag_rejects(s.tag_b & 0xFFFFFFu, gcodes, gvalid, N);
+    *any = pass;
+    return n == 1u ? s.val : (kWalkBucket | s.val);
+}
+
+// Find the slot of a key: returns false when the key is not in the table.  (The scanner issues the first probe
+// itself as an async gather and only comes here for hashed-mode collisions.)
+MPCR_HD bool find_slot(const Slot* slots, SlotMap sm, uint32_t key, Slot* out) {
+    uint32_t i = slot_index(key, sm);
     for (;;) {
-        uint64_t s = slots[i];
-        uint32_t start = (uint32_t)s;
-        if (start == kEmptySlot) return kEmptySlot;
-        if ((uint32_t)(s >> 32) == key) return start;
-        i = (i + 1) & slot_mask;
+        const Slot s = load_slot(slots + i);
+        if ((s.tag_n >> 24) == kSlotEmpty) return false;
+        if (sm.direct || s.key == key) { *out = s; return true; }
+        i = (i + 1) & sm.mask;
+    }
+}
+
+// engine.py:483-484 for one survivor code: visit, in bucket (= insertion) order, every record whose inline tag
+// does not already rule out a primer-1 match at this position.
+template <class OnRec>
+MPCR_HD void for_each_survivor_record(const BucketEntry* bucket, uint32_t code, uint32_t gcodes, uint32_t gvalid, int N,
+                                      OnRec&& on_rec) {
+    if (!(code & kWalkBucket)) { on_rec(code); return; }
+    for (uint32_t e = code & ~kWalkBucket;; ++e) {
+        const BucketEntry b = bucket[e];
+        if (!tag_rejects(b.tag, gcodes, gvalid, N)) on_rec(b.rec_last & 0x7FFFFFFFu);
+        if (b.rec_last >> 31) return;
     }
 }
 

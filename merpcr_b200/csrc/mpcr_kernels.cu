@@ -40,6 +40,7 @@ static int fail(int code, const char* fmt, ...) {
                                            __FILE__, __LINE__);                                           \
     } while (0)
 
+struct Survivor;
 struct mpcr_ctx {
     int device = 0;
     mpcr_params prm{};
@@ -50,12 +51,12 @@ struct mpcr_ctx {
     RecMeta* d_meta = nullptr;
     uint64_t* d_pwords = nullptr;
     uint64_t total_pwords = 0;
-    uint64_t* d_slots = nullptr;
-    uint32_t slot_mask = 0;
-    uint32_t* d_bucket = nullptr;
+    Slot* d_slots = nullptr;
+    SlotMap smap{1023u, 0u};
+    BucketEntry* d_bucket = nullptr;
     uint32_t* d_filter = nullptr;
-    uint32_t filter_bits = 0, filter_words = 0;
-    int filter_exact = 0;
+    uint32_t filter_words = 0;
+    uint32_t n_keys = 0;
     uint32_t max_hash_off = 0, max_len = 0;
     uint64_t max_pcr = 0;
     bool table_ready = false;
@@ -65,7 +66,9 @@ struct mpcr_ctx {
     uint32_t n_tiles = 0;
     uint64_t tiles_sig = 0;
     uint32_t lay_contigs = 0, lay_max_len = 0;  // bounds of the last scanned layout (sort digit counts)
-    uint32_t* d_tile_counter = nullptr;
+    uint32_t* d_tile_counter = nullptr;  // [0] tile counter, [1..2] survivor count / verify cursor
+    Survivor* d_surv = nullptr;
+    size_t surv_bytes = 0;
     // sort scratch
     void* d_sort_tmp = nullptr;
     size_t sort_tmp_cap = 0;
@@ -73,7 +76,7 @@ struct mpcr_ctx {
     size_t counts_cap = 0;
     uint8_t* d_lut = nullptr;  // 256 B genome LUT for pack
     uint64_t launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     bool scan_timed = false;
 };
 
@@ -180,17 +183,19 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
     m.pcr_size = pcr[line];
     m.p1_word = word_off[2 * r];
     m.p2_word = word_off[2 * r + 1];
-    m.pad = 0;
+    m.tag = 0;
     uint32_t hbe = 0;
     int ho;
     if (!minus) {
         m.len1 = (uint16_t)n1; m.len2 = (uint16_t)n2;
         ho = first_clean_word(BlobFwd{pr1}, n1, W, &hbe);
+        if (ho >= 0) m.tag = make_tag(BlobFwd{pr1}, n1, ho, W);
         encode_primer(BlobFwd{pr1}, n1, plut, pwords + m.p1_word);
         encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p2_word);
     } else {
         m.len1 = (uint16_t)n2; m.len2 = (uint16_t)n1;
         ho = first_clean_word(BlobFwd{pr2}, n2, W, &hbe);
+        if (ho >= 0) m.tag = make_tag(BlobFwd{pr2}, n2, ho, W);
         encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p1_word);
         encode_primer(BlobRc{pr1, n1}, n1, plut, pwords + m.p2_word);
     }
@@ -207,138 +212,415 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
     }
 }
 
-// After the pairs are sorted by (invalid, key, record): CSR bucket array + open-addressed slot table + filter.
+// After the pairs are sorted by (invalid, key, record): CSR bucket entries (with inline tags), the 16-byte slot
+// table (direct-indexed or open-addressed) and the two-bit-per-key blocked Bloom filter.
 __global__ void __launch_bounds__(256) build_buckets(const Item<2>* __restrict__ pairs, uint32_t n_valid,
-                                                     uint32_t* __restrict__ bucket, uint64_t* __restrict__ slots,
-                                                     uint32_t slot_mask, uint32_t* __restrict__ filter,
-                                                     uint32_t filter_bits, int filter_exact) {
+                                                     const RecMeta* __restrict__ meta, BucketEntry* __restrict__ bucket,
+                                                     Slot* __restrict__ slots, SlotMap sm,
+                                                     uint32_t* __restrict__ filter, uint32_t filter_words, uint32_t cw,
+                                                     int W, uint32_t* __restrict__ n_keys) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_valid) return;
     const uint32_t key = pairs[i].f[0];
+    const uint32_t rec = pairs[i].f[1] & 0x7FFFFFFFu;
     const bool head = (i == 0) || (pairs[i - 1].f[0] != key);
     const bool last = (i + 1 == n_valid) || (pairs[i + 1].f[0] != key);
-    bucket[i] = (pairs[i].f[1] & 0x7FFFFFFFu) | (last ? 0x80000000u : 0u);
+    const uint32_t tag = meta[rec].tag;
+    bucket[i] = BucketEntry{rec | (last ? 0x80000000u : 0u), tag};
     if (head) {
-        const unsigned long long val = ((unsigned long long)key << 32) | i;
-        uint32_t s = slot_hash(key) & slot_mask;
-        for (;;) {
-            unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(slots + s), ~0ull, val);
-            if (prev == ~0ull) break;
-            s = (s + 1) & slot_mask;
+        // bucket size, capped at 3, and the second record's tag
+        uint32_t n = 1, tag_b = 0;
+        if (!last) {
+            n = 2;
+            tag_b = meta[pairs[i + 1].f[1] & 0x7FFFFFFFu].tag;
+            if (i + 2 < n_valid && pairs[i + 2].f[0] == key) n = 3;
         }
-        const uint32_t fb = filter_index(key, filter_bits, filter_exact);
-        atomicOr(&filter[fb >> 5], 1u << (fb & 31));
+        const unsigned long long lo = (unsigned long long)key | ((unsigned long long)(n == 1 ? rec : i) << 32);
+        const unsigned long long hi = (unsigned long long)((tag & 0xFFFFFFu) | (n << 24)) | ((unsigned long long)tag_b << 32);
+        uint32_t s = slot_index(key, sm);
+        if (!sm.direct) {
+            for (;;) {  // claim on the (tag_n, tag_b) half -- n == kSlotEmpty marks an empty slot
+                unsigned long long* h = reinterpret_cast<unsigned long long*>(slots + s) + 1;
+                if (atomicCAS(h, ~0ull, hi) == ~0ull) break;
+                s = (s + 1) & sm.mask;
+            }
+        } else {
+            reinterpret_cast<unsigned long long*>(slots + s)[1] = hi;
+        }
+        reinterpret_cast<unsigned long long*>(slots + s)[0] = lo;
+        atomicOr(&filter[filter_word(key, cw, filter_words)], filter_bits_of(key, W));
+        atomicAdd(n_keys, 1u);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // (3)(4)(5) scan
 // ---------------------------------------------------------------------------------------------------------
+// A seed position that survived the Bloom filter, the exact table probe and the inline tag: (tile, offset, record).
+struct Survivor {
+    uint32_t tile, lp, code, pad;  // code: record index, or kWalkBucket | first bucket entry
+};
+
 struct ScanArgs {
     const uint64_t* p2;
     const uint64_t* p4;
     const uint64_t* valid;
     const TileDesc* tiles;
     uint32_t n_tiles;
-    const uint64_t* slots;
-    uint32_t slot_mask;
-    const uint32_t* bucket;
+    const Slot* slots;
+    SlotMap smap;
+    const BucketEntry* bucket;
     const RecMeta* meta;
     const uint64_t* pwords;
     const uint32_t* filter;
-    uint32_t filter_bits, filter_words;
-    int filter_exact;
+    uint32_t filter_words;
+    uint32_t cw;  // filter_mul(W)
     SearchParams prm;
     mpcr_hit* hits;
     unsigned long long capacity;
     unsigned long long* count;
     uint32_t* tile_counter;
-    int debug;  // MPCR_DEBUG bit0: hash/filter phase only (candidates are counted, not verified)
+    Survivor* surv;
+    uint32_t surv_cap;
+    uint32_t* surv_count;  // [0] = survivors appended (may exceed surv_cap), [1] = verify work counter
+    int debug;  // MPCR_DEBUG bit0: stop after the filter stage; bit1: probe the table but drop the survivors
 };
 
+// shared-memory plan of the scanner CTA (dynamic shared memory): one private block per warp, then the filter
+struct ScanSmem {
+    static constexpr int kWarps = kScanThreads / 32;
+    static constexpr int kUnitBases = 32 * kPosPerThread;    // hash positions one warp scans per step (2048)
+    static constexpr int kUnitsPerTile = kTileBases / kUnitBases;
+    static constexpr int kP2Bytes = kUnitBases / 4 + 32;     // plane2 of a unit + 128-base read-ahead
+    static constexpr int kVBytes = kUnitBases / 8 + 16;      // valid bits of a unit + 128-base read-ahead
+    static constexpr int kQCap = 256;                        // candidate queue entries
+    static constexpr int kIlp = 4;                           // slot gathers in flight per lane
+    struct Warp {
+        alignas(16) uint8_t p2[2][kP2Bytes];
+        alignas(16) uint8_t v[2][kVBytes];
+        alignas(16) uint4 landing[kIlp][32];                 // cp.async targets of the slot gathers
+        uint16_t queue[kQCap];
+        unsigned long long mbar[2];
+    };
+    static constexpr int kFilterOff = (int)((sizeof(Warp) * kWarps + 127) / 128 * 128);
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.b32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 16-byte asynchronous gather global -> shared that bypasses L1 (LDGSTS.BYPASS): unlike a plain load it does not
+// need an L1 line while in flight, which is what keeps ~0.75 gathers/clk/SM alive next to a 160 KB filter.
+__device__ __forceinline__ void gather16_async(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gather_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void gather_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct HitEmitter {
-    const ScanArgs& a;
+    mpcr_hit* hits;
+    unsigned long long capacity;
+    unsigned long long* count;
     uint32_t contig, rec, hash_off;
     __device__ void operator()(int64_t pos1, int64_t pos2, uint32_t rank) const {
-        unsigned long long i = atomicAdd(a.count, 1ull);
-        if (i < a.capacity) {
+        unsigned long long i = atomicAdd(count, 1ull);
+        if (i < capacity) {
             mpcr_hit h;
             h.contig = contig; h.pos1 = (uint32_t)pos1; h.pos2 = (uint32_t)pos2; h.rec = rec; h.rank = rank;
             h.hash_off = hash_off;
-            a.hits[i] = h;
+            hits[i] = h;
         }
     }
 };
 
-// engine.py:483-489: probe the table with the key at tile-local offset lp and dispatch every bucket entry.
-__device__ __noinline__ void process_candidate(const ScanArgs& a, const TileDesc& td, uint32_t lp, uint32_t wmask) {
-    const int64_t gpos = td.gbase + lp;
-    const uint32_t key = extract_key(a.p2, gpos, wmask);
-    uint32_t i = find_bucket(a.slots, a.slot_mask, key);
-    if (i == kEmptySlot) return;
-    const int64_t gcontig = td.gbase - (int64_t)td.lstart;
-    const int64_t p = (int64_t)td.lstart + lp;
-    for (;;) {
-        const uint32_t e = a.bucket[i];
-        const uint32_t rec = e & 0x7FFFFFFFu;
+// engine.py:483-489 + 507-597 for one survivor, serially in one thread (overflow path of the survivor list).
+__device__ __noinline__ void verify_serial(const ScanArgs& a, uint32_t tile, uint32_t lp, uint32_t code) {
+    const TileDesc td = a.tiles[tile];
+    const int64_t gb = td.gbase + lp + a.prm.W;
+    const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
+    for_each_survivor_record(a.bucket, code, gcodes, gvalid, a.prm.N, [&](uint32_t rec) {
         const RecMeta m = a.meta[rec];
-        verify_record(a.p4, gcontig, (int64_t)td.length, p, m, a.pwords, a.prm,
-                      HitEmitter{a, td.contig, rec, (uint32_t)m.hash_off});
-        if (e & 0x80000000u) break;
-        ++i;
-    }
+        verify_record(a.p4, td.gbase - (int64_t)td.lstart, (int64_t)td.length, (int64_t)td.lstart + lp, m, a.pwords,
+                      a.prm, HitEmitter{a.hits, a.capacity, a.count, td.contig, rec, (uint32_t)m.hash_off});
+    });
 }
 
-// Persistent CTAs; each pulls 32 768-base tiles from a global counter.  Thread t owns the 64 hash positions
-// [64t, 64t+64) of the tile: one 128-bit load of plane2 (+ the next word for the W-1 overhang), rolling keys by
-// funnel shift, one shared-memory filter probe per position, then the surviving positions are verified.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) scan_kernel(const ScanArgs a) {
-    extern __shared__ uint32_t s_filter[];
-    __shared__ uint32_t s_tile;
+// A seed position matched a table entry whose tags did not rule it out: hand it to verify_kernel.
+__device__ __noinline__ void push_survivor(const ScanArgs& a, uint32_t tile, uint32_t lp, uint32_t code) {
+    const uint32_t k = atomicAdd(a.surv_count, 1u);
+    if (k < a.surv_cap) a.surv[k] = Survivor{tile, lp, code, 0u};
+    else verify_serial(a, tile, lp, code);
+}
+
+// Hashed mode only: the first probe hit another key's slot -- continue the probe sequence with plain loads.
+__device__ __noinline__ void probe_collision(const ScanArgs& a, uint32_t key, uint32_t gcodes, uint32_t gvalid,
+                                             uint32_t tile, uint32_t lp) {
+    Slot s;
+    if (!find_slot(a.slots, a.smap, key, &s)) return;
+    bool any;
+    const uint32_t code = slot_survivor(s, gcodes, gvalid, a.prm.N, &any);
+    if (any) push_survivor(a, tile, lp, code);
+}
+
+// One filter probe: returns a word whose MSB is set iff both Bloom bits of the key are set.
+// x holds the key in its low 2W bits (anything above cancels in the multiply by cw); x3 is the raw register of
+// the position three bases further on, i.e. x >> 6 in its low bits (WIDE: W >= 6, else the second bit == the first).
+template <bool WIDE>
+__device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ s_filter, uint32_t x, uint32_t x3,
+                                                 uint32_t cw, uint32_t n_words) {
+    const uint32_t word = s_filter[__umulhi(x * cw, n_words)];
+    const uint32_t t1 = __funnelshift_l(0u, word, x);  // word << (x & 31)
+    if (!WIDE) return t1;
+    return t1 & __funnelshift_l(0u, word, x3);
+}
+
+// Persistent CTAs, one per SM, made of AUTONOMOUS warps: there is no CTA-wide barrier after the prologue, so
+// the warps drift apart and the ALU/shared-memory work of stage 1 overlaps the gather latency of stage 2.
+// Each warp walks units of 2048 hash positions (unit u of tile u/16), strided over all warps of the grid.
+//   staging : plane2 + valid bits of a unit (+128 bases read-ahead) arrive by two TMA bulk copies on the warp's
+//             own mbarrier, double buffered (the next unit loads while this one is scanned).
+//   stage 1 : lane l owns positions [64l, 64l+64) -- rolling keys by funnel shift out of five registers, one
+//             shared-memory Bloom probe (two bits of one word) per position.
+//   stage 2 : surviving positions are compacted into the warp's queue and processed with full lanes, kIlp
+//             16-byte L1-bypassing async gathers of the slot table in flight per lane; key + tag window come
+//             from the staged unit; inline tag check.
+//   What is left (about one position in 10^4) goes to the survivor list for verify_kernel.
+template <bool WIDE>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    ScanSmem::Warp& ws = reinterpret_cast<ScanSmem::Warp*>(smem)[warp];
+    uint32_t* s_filter = reinterpret_cast<uint32_t*>(smem + ScanSmem::kFilterOff);
+
+    const uint32_t n_units = a.n_tiles * ScanSmem::kUnitsPerTile;
+    const uint32_t stride = gridDim.x * ScanSmem::kWarps;
+    // interleave: consecutive units go to different CTAs first, so neighbouring tiles spread over the SMs
+    uint32_t unit = (uint32_t)warp * gridDim.x + blockIdx.x;
+
+    // lane 0 fetches the descriptor of a unit and starts its two bulk copies
+    auto issue_unit = [&](uint32_t u, int buf) {
+        const TileDesc td = a.tiles[u / ScanSmem::kUnitsPerTile];
+        const int64_t gb = td.gbase + (int64_t)(u % ScanSmem::kUnitsPerTile) * ScanSmem::kUnitBases;
+        mbar_expect_tx(&ws.mbar[buf], ScanSmem::kP2Bytes + ScanSmem::kVBytes);
+        tma_load_1d(ws.p2[buf], reinterpret_cast<const uint8_t*>(a.p2) + (gb >> 2), ScanSmem::kP2Bytes, &ws.mbar[buf]);
+        tma_load_1d(ws.v[buf], reinterpret_cast<const uint8_t*>(a.valid) + (gb >> 3), ScanSmem::kVBytes, &ws.mbar[buf]);
+    };
+
+    if (lane == 0) {
+        mbar_init(&ws.mbar[0], 1);
+        mbar_init(&ws.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (unit < n_units) issue_unit(unit, 0);
+    }
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.filter);
         uint4* dst = reinterpret_cast<uint4*>(s_filter);
-        for (uint32_t i = threadIdx.x; i < a.filter_words / 4; i += THREADS) dst[i] = src[i];
+        for (uint32_t i = tid; i < a.filter_words / 4; i += kScanThreads) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    const uint32_t wmask = wmask_of(a.prm.W);
-    const uint32_t fbits = a.filter_bits;
-    const int fexact = a.filter_exact;
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(a.tile_counter, 1u);
-        __syncthreads();
-        const uint32_t t = s_tile;
-        __syncthreads();
-        if (t >= a.n_tiles) break;
-        const TileDesc td = a.tiles[t];
-        const uint32_t lp0 = threadIdx.x * 64u;
-        if (lp0 >= td.nbases) continue;
-        const int64_t gb = td.gbase + lp0;
-        const uint64_t* vw = a.valid + (gb >> 6);
-        const uint64_t wv = window_valid(vw[0], vw[1], a.prm.W);
-        if (wv == 0) continue;
-        const uint64_t* w = a.p2 + (gb >> 5);
-        const uint4 q = *reinterpret_cast<const uint4*>(w);
-        const uint64_t w2 = w[2];
-        const uint32_t r[6] = {q.x, q.y, q.z, q.w, (uint32_t)w2, (uint32_t)(w2 >> 32)};
-        uint32_t pass_lo = 0, pass_hi = 0;
+
+    const int W = a.prm.W;
+    const uint32_t wmask = wmask_of(W);
+    const uint32_t cw = a.cw, fw = a.filter_words;
+    unsigned long long n_dbg = 0;
+
+    for (uint32_t it = 0; unit < n_units; ++it, unit += stride) {
+        const int buf = it & 1;
+        if (lane == 0 && unit + stride < n_units) issue_unit(unit + stride, buf ^ 1);
+        const uint32_t tile = unit / ScanSmem::kUnitsPerTile;
+        const uint32_t ubase = (unit % ScanSmem::kUnitsPerTile) * ScanSmem::kUnitBases;  // tile-local offset of the unit
+        const uint32_t tile_nbases = __ldg(&a.tiles[tile].nbases);
+        while (!mbar_try_wait(&ws.mbar[buf], (it >> 1) & 1u)) {}
+        if (ubase >= tile_nbases) { __syncwarp(); continue; }
+        const uint32_t unit_nbases = min(tile_nbases - ubase, (uint32_t)ScanSmem::kUnitBases);
+        const uint32_t* s_p2 = reinterpret_cast<const uint32_t*>(ws.p2[buf]);
+        const uint32_t* s_v = reinterpret_cast<const uint32_t*>(ws.v[buf]);
+
+        // ---------------- stage 1: rolling keys + Bloom probe ----------------
+        const uint32_t lp0 = (uint32_t)lane * kPosPerThread;  // unit-local
+        uint32_t c_lo = 0, c_hi = 0;
+        if (lp0 < unit_nbases) {
+            const uint2 v0 = *reinterpret_cast<const uint2*>(s_v + 2 * lane);
+            const uint2 v1 = *reinterpret_cast<const uint2*>(s_v + 2 * lane + 2);
+            uint64_t wv = window_valid(((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v1.y << 32) | v1.x, W);
+            const uint32_t left = unit_nbases - lp0;
+            if (left < 64u) wv &= (1ull << left) - 1ull;
+            if (wv) {
+                const uint4 q = *reinterpret_cast<const uint4*>(s_p2 + 4 * lane);
+                const uint32_t r[6] = {q.x, q.y, q.z, q.w, s_p2[4 * lane + 4], 0u};
+                // raw register of position j (its low 2W bits are the key); positions 64..66 only feed shift amounts
+                auto raw = [&](int j) -> uint32_t {
+                    return (j & 15) ? __funnelshift_r(r[j >> 4], r[(j >> 4) + 1], 2 * (j & 15)) : r[j >> 4];
+                };
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            const uint32_t key = __funnelshift_r(r[(2 * j) >> 5], r[((2 * j) >> 5) + 1], (2 * j) & 31) & wmask;
-            const uint32_t fb = filter_index(key, fbits, fexact);
-            const uint32_t bit = (s_filter[fb >> 5] >> (fb & 31)) & 1u;
-            if (j < 32) pass_lo |= bit << j; else pass_hi |= bit << (j - 32);
+                for (int j = 31; j >= 0; --j)
+                    c_lo = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_lo, 1);
+#pragma unroll
+                for (int j = 63; j >= 32; --j)
+                    c_hi = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_hi, 1);
+                c_lo &= (uint32_t)wv;
+                c_hi &= (uint32_t)(wv >> 32);
+            }
         }
-        uint64_t cand = wv & (((uint64_t)pass_hi << 32) | pass_lo);
         if (a.debug & 1) {
-            if (cand) atomicAdd(a.count, (unsigned long long)__popcll(cand));
+            n_dbg += __popc(c_lo) + __popc(c_hi);
+            __syncwarp();
             continue;
         }
-        while (cand) {
-            const int j = __ffsll((long long)cand) - 1;
-            cand &= cand - 1;
-            process_candidate(a, td, lp0 + (uint32_t)j, wmask);
+
+        // ---------------- stage 2: warp queue, async slot gathers, tag check ----------------
+        for (;;) {
+            const uint32_t n = __popc(c_lo) + __popc(c_hi);
+            uint32_t incl = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) break;
+            const bool fits = incl <= (uint32_t)ScanSmem::kQCap;
+            if (fits && n) {
+                uint32_t pos = incl - n;
+                while (c_lo) {
+                    const int j = __ffs(c_lo) - 1;
+                    c_lo &= c_lo - 1;
+                    ws.queue[pos++] = (uint16_t)(lp0 + j);
+                }
+                while (c_hi) {
+                    const int j = __ffs(c_hi) - 1;
+                    c_hi &= c_hi - 1;
+                    ws.queue[pos++] = (uint16_t)(lp0 + 32 + j);
+                }
+            }
+            const uint32_t fit_mask = __ballot_sync(0xffffffffu, fits);
+            const uint32_t cnt = __shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));  // lane 0 always fits
+            __syncwarp();
+            constexpr int kIlp = ScanSmem::kIlp;
+            for (uint32_t base = 0; base < cnt; base += 32 * kIlp) {
+                uint32_t lpv[kIlp], key[kIlp], gcodes[kIlp], gvalid[kIlp];
+#pragma unroll
+                for (int u = 0; u < kIlp; ++u) {
+                    const uint32_t qi = base + 32 * u + lane;
+                    lpv[u] = 0xFFFFFFFFu;
+                    if (qi < cnt) {
+                        const uint32_t lp = ws.queue[qi];
+                        lpv[u] = lp;
+                        // key (2W bits) and the 8-base tag window (16 bits) out of three staged words
+                        const uint32_t wi = lp >> 4, sh = (lp & 15u) * 2u;
+                        const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1], w2 = s_p2[wi + 2];
+                        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+                        key[u] = x0 & wmask;
+                        gcodes[u] = __funnelshift_rc(x0, x1, 2 * W) & 0xFFFFu;  // clamped: 2W == 32 -> x1
+                        const uint32_t vb = lp + (uint32_t)W, vi = vb >> 5, vs = vb & 31u;
+                        gvalid[u] = __funnelshift_r(s_v[vi], s_v[vi + 1], vs) & 0xFFu;
+                        gather16_async(&ws.landing[u][lane], a.slots + slot_index(key[u], a.smap));
+                    }
+                    gather_commit();
+                }
+#pragma unroll
+                for (int u = 0; u < kIlp; ++u) {
+                    if (u == 0) gather_wait<kIlp - 1>();
+                    else if (u == 1) gather_wait<(kIlp > 2 ? kIlp - 2 : 0)>();
+                    else if (u == 2) gather_wait<(kIlp > 3 ? kIlp - 3 : 0)>();
+                    else gather_wait<0>();
+                    if (lpv[u] != 0xFFFFFFFFu) {
+                        const uint4 v = ws.landing[u][lane];
+                        if ((v.z >> 24) != kSlotEmpty) {
+                            if (!a.smap.direct && v.x != key[u]) {
+                                if (!(a.debug & 2)) probe_collision(a, key[u], gcodes[u], gvalid[u], tile, ubase + lpv[u]);
+                            } else {
+                                bool any;
+                                const uint32_t code = slot_survivor(Slot{v.x, v.y, v.z, v.w}, gcodes[u], gvalid[u], a.prm.N, &any);
+                                if (any) {
+                                    if (a.debug & 2) ++n_dbg; else push_survivor(a, tile, ubase + lpv[u], code);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (fit_mask == 0xffffffffu) break;
+        }
+        __syncwarp();  // every lane is done with this buffer before lane 0 refills it two steps from now
+    }
+    if (a.debug) {
+        for (int d = 16; d; d >>= 1) n_dbg += __shfl_xor_sync(0xffffffffu, n_dbg, d);
+        if (lane == 0 && n_dbg) atomicAdd(a.count, n_dbg);
+    }
+}
+
+// (4)(5) verifier + hit emitter: one warp per survivor.  Primer 1 is compared by every lane (same addresses,
+// broadcast loads); the mate search of engine.py:543-593 is spread over the lanes, one delta per lane and round,
+// so the 2M+1 window costs ceil((2M+1)/32) rounds of coalesced loads.
+__device__ __forceinline__ void verify_warp(const ScanArgs& a, const TileDesc& td, uint32_t lp, uint32_t rec, int lane) {
+    const RecMeta m = a.meta[rec];
+    const int64_t gcontig = td.gbase - (int64_t)td.lstart, L = td.length;
+    const int l1 = m.len1, l2 = m.len2;
+    const int64_t k = (int64_t)td.lstart + lp - (int64_t)m.hash_off;                         // engine.py:486
+    if (k < 0 || k + l1 > L) return;                                                          // :487
+    if (!compare_primer(a.p4, gcontig + k, a.pwords + m.p1_word, l1, true, a.prm)) return;    // :515
+    if (L - (k + l1) < l2) return;                                                            // :521-524
+    int64_t E = (int64_t)m.pcr_size, hi, lo;
+    if (E > L - k) { E = L - k; hi = 0; }                                                     // :531-533
+    else { hi = L - k - E; if (hi > a.prm.M) hi = a.prm.M; }                                  // :535
+    lo = E - l1 - l2; if (lo > a.prm.M) lo = a.prm.M; if (lo < 0) lo = 0;                     // :538-540
+    const int64_t p2 = k + E - l2;                                                            // :543
+    const uint32_t n_rank = 2u * (uint32_t)(lo > hi ? lo : hi) + 1u;
+    const uint64_t* q2 = a.pwords + m.p2_word;
+    const HitEmitter emit{a.hits, a.capacity, a.count, td.contig, rec, (uint32_t)m.hash_off};
+    for (uint32_t r0 = 0; r0 < n_rank; r0 += 32) {
+        const uint32_t rank = r0 + lane;              // 0: delta 0, 2i-1: -i, 2i: +i   (:545-593)
+        const int64_t i = (rank + 1) >> 1;
+        const bool neg = rank & 1u;
+        if (rank < n_rank && (rank == 0 || (neg ? i <= lo : i <= hi))) {
+            const int64_t q = p2 + (neg ? -i : i);
+            if (compare_primer(a.p4, gcontig + q, q2, l2, false, a.prm)) emit(k, q + l2 - 1, rank);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = min(a.surv_count[0], a.surv_cap);
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(a.surv_count + 1, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n) return;
+        const Survivor sv = a.surv[idx];
+        const TileDesc td = a.tiles[sv.tile];
+        if (!(sv.code & kWalkBucket)) {
+            verify_warp(a, td, sv.lp, sv.code, lane);
+        } else {  // a seed shared by several records: bucket order, each entry behind its own tag
+            const int64_t gb = td.gbase + sv.lp + a.prm.W;
+            const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
+            for (uint32_t e = sv.code & ~kWalkBucket;; ++e) {
+                const BucketEntry b = a.bucket[e];
+                if (!tag_rejects(b.tag, gcodes, gvalid, a.prm.N)) verify_warp(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, lane);
+                if (b.rec_last >> 31) break;
+            }
         }
     }
 }
@@ -374,6 +656,7 @@ int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
     CU(cudaMalloc(&c->d_lut, 256));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    CU(cudaEventCreate(&c->ev2));
     *out = c;
     return MPCR_OK;
 }
@@ -391,6 +674,8 @@ void mpcr_ctx_destroy(mpcr_ctx* c) {
     cudaFree(c->d_tiles); cudaFree(c->d_tile_counter); cudaFree(c->d_sort_tmp); cudaFree(c->d_counts); cudaFree(c->d_lut);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    cudaFree(c->d_surv);
     delete c;
 }
 
@@ -453,26 +738,23 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
     word_off[2 * (size_t)n_rec] = (uint32_t)acc;
     c->total_pwords = acc;
 
-    // first-level filter geometry: exact bitmap if it fits the shared-memory budget, else a fold
-    const uint64_t space = 1ull << (2 * W);
-    uint32_t budget_bits = 1u << 20;  // 128 KiB of shared memory
-    if (const char* env = getenv("MPCR_FILTER_BITS")) {
-        long v = atol(env);
-        if (v >= 128) budget_bits = (uint32_t)v;
+    // first-level filter: as many words as the scanner CTA's shared memory leaves (a multiple of 4 words)
+    {
+        long words = ((long)c->max_smem_optin - ScanSmem::kFilterOff) / 4;
+        if (const char* env = getenv("MPCR_FILTER_WORDS")) {
+            long v = atol(env);
+            if (v >= 4 && v < words) words = v;
+        }
+        if (words < 64) return fail(MPCR_ECUDA, "device shared memory too small for the scanner (%d bytes opt-in)", c->max_smem_optin);
+        c->filter_words = (uint32_t)words & ~3u;
     }
-    const uint32_t max_bits = (uint32_t)(((size_t)c->max_smem_optin - 2048) * 8);
-    if (budget_bits > max_bits) budget_bits = max_bits;
-    budget_bits &= ~127u;
-    if (space <= budget_bits) { c->filter_exact = 1; c->filter_bits = (uint32_t)(space < 128 ? 128 : space); }
-    else { c->filter_exact = 0; c->filter_bits = budget_bits; }
-    c->filter_words = c->filter_bits / 32;
-
+    c->n_keys = 0;
     CU(cudaMalloc(&c->d_filter, (size_t)c->filter_words * 4));
     CU(cudaMemsetAsync(c->d_filter, 0, (size_t)c->filter_words * 4, st));
     if (n_lines == 0) {
-        c->slot_mask = 1023;
-        CU(cudaMalloc(&c->d_slots, 1024 * sizeof(uint64_t)));
-        CU(cudaMemsetAsync(c->d_slots, 0xFF, 1024 * sizeof(uint64_t), st));
+        c->smap = SlotMap{1023u, 0u};
+        CU(cudaMalloc(&c->d_slots, 1024 * sizeof(Slot)));
+        CU(cudaMemsetAsync(c->d_slots, 0xFF, 1024 * sizeof(Slot), st));
         CU(cudaStreamSynchronize(st));
         c->table_ready = true;
         return MPCR_OK;
@@ -526,20 +808,33 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         if (rc) goto done;
         c->launches += radix_sort<2>(d_pairs, d_pairs2, n_rec, passes, np, c->d_counts, st);
         CUG(cudaGetLastError());
-        uint32_t nslots = 1024;
-        while (nslots < 2u * c->n_valid + 2u) nslots <<= 1;
-        c->slot_mask = nslots - 1;
-        CUG(cudaMalloc(&c->d_slots, (size_t)nslots * sizeof(uint64_t)));
-        CUG(cudaMemsetAsync(c->d_slots, 0xFF, (size_t)nslots * sizeof(uint64_t), st));
-        CUG(cudaMalloc(&c->d_bucket, ((size_t)c->n_valid + 1) * 4));
+        // slot table: direct-indexed by the key while 4^W slots stay L2-sized (W <= 11 -> 64 MiB), else open
+        // addressing at load <= 1/8 (distinct seeds <= min(records, 4^W))
+        uint32_t nslots;
+        if (W <= 11) {
+            nslots = 1u << (2 * W);
+            c->smap.direct = 1;
+        } else {
+            nslots = 1024;
+            while (nslots < 8ull * c->n_valid && nslots < (1u << 25)) nslots <<= 1;
+            while (nslots < 2ull * c->n_valid + 2) nslots <<= 1;
+            c->smap.direct = 0;
+        }
+        c->smap.mask = nslots - 1;
+        CUG(cudaMalloc(&c->d_slots, (size_t)nslots * sizeof(Slot)));
+        CUG(cudaMemsetAsync(c->d_slots, 0xFF, (size_t)nslots * sizeof(Slot), st));
+        CUG(cudaMalloc(&c->d_bucket, ((size_t)c->n_valid + 1) * sizeof(BucketEntry)));
         if (c->n_valid) {
-            build_buckets<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_pairs, c->n_valid, c->d_bucket, c->d_slots,
-                                                                     c->slot_mask, c->d_filter, c->filter_bits,
-                                                                     c->filter_exact);
+            CUG(cudaMemsetAsync(d_stats, 0, 16, st));
+            build_buckets<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_pairs, c->n_valid, c->d_meta, c->d_bucket,
+                                                                     c->d_slots, c->smap, c->d_filter,
+                                                                     c->filter_words, filter_mul(W), W, d_stats);
             c->launches++;
             CUG(cudaGetLastError());
+            CUG(cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, st));
         }
         CUG(cudaStreamSynchronize(st));
+        c->n_keys = stats[0];
         c->table_ready = true;
     }
 done:
@@ -579,6 +874,7 @@ int mpcr_table_primer_words(mpcr_ctx* c, uint32_t rec, int which, uint64_t* h_wo
 
 static uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
+uint64_t mpcr_tile_bases(void) { return (uint64_t)kTileBases; }
 uint64_t mpcr_halo_left(const mpcr_ctx* c) { return c ? round_up((uint64_t)c->max_hash_off + 64, 128) : 0; }
 uint64_t mpcr_halo_right(const mpcr_ctx* c) {
     if (!c) return 0;
@@ -628,8 +924,6 @@ static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_conti
     return MPCR_OK;
 }
 
-static constexpr int kScanThreads = kTileBases / 64;  // 512
-
 int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, const void* d_plane2, const void* d_plane4,
               const void* d_valid, uint64_t plane_origin, uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end,
               mpcr_hit* d_hits, uint64_t capacity, uint64_t* d_count, void* stream) {
@@ -646,26 +940,49 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     CU(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     c->scan_timed = false;
     if (c->n_tiles == 0 || c->n_valid == 0) return MPCR_OK;
-    CU(cudaMemsetAsync(c->d_tile_counter, 0, 4, st));
+    CU(cudaMemsetAsync(c->d_tile_counter, 0, 16, st));
+    // survivor list: ~1 position in 10^4 survives on random sequence; overflow falls back to in-kernel serial verify
+    {
+        uint64_t scanned = 0;
+        for (uint32_t i = 0; i < n_contigs; ++i) scanned += h_contigs[i].length;
+        size_t want = (size_t)(scanned / 64 + (1u << 16)) * sizeof(Survivor);
+        if (want > ((size_t)1 << 30)) want = (size_t)1 << 30;
+        if (c->surv_bytes < want) {
+            int rc2 = ensure((void**)&c->d_surv, &c->surv_bytes, want);
+            if (rc2) return rc2;
+        }
+    }
     ScanArgs a;
     a.p2 = (const uint64_t*)d_plane2; a.p4 = (const uint64_t*)d_plane4; a.valid = (const uint64_t*)d_valid;
     a.tiles = c->d_tiles; a.n_tiles = c->n_tiles;
-    a.slots = c->d_slots; a.slot_mask = c->slot_mask; a.bucket = c->d_bucket; a.meta = c->d_meta; a.pwords = c->d_pwords;
-    a.filter = c->d_filter; a.filter_bits = c->filter_bits; a.filter_words = c->filter_words; a.filter_exact = c->filter_exact;
+    a.slots = c->d_slots; a.smap = c->smap; a.bucket = c->d_bucket; a.meta = c->d_meta; a.pwords = c->d_pwords;
+    a.filter = c->d_filter; a.filter_words = c->filter_words; a.cw = filter_mul(c->prm.wordsize);
     a.prm.W = c->prm.wordsize; a.prm.M = c->prm.margin; a.prm.N = c->prm.mismatches; a.prm.X = c->prm.three_prime_match;
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
     a.debug = getenv("MPCR_DEBUG") ? atoi(getenv("MPCR_DEBUG")) : 0;
     a.hits = d_hits; a.capacity = capacity; a.count = (unsigned long long*)d_count; a.tile_counter = c->d_tile_counter;
-    const size_t smem = (size_t)c->filter_words * 4;
-    CU(cudaFuncSetAttribute(scan_kernel<kScanThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.surv = c->d_surv; a.surv_cap = (uint32_t)(c->surv_bytes / sizeof(Survivor)); a.surv_count = c->d_tile_counter + 1;
+    const size_t smem = (size_t)ScanSmem::kFilterOff + (size_t)c->filter_words * 4;
     uint32_t grid = (uint32_t)c->sm_count;
     if (grid > c->n_tiles) grid = c->n_tiles;
     CU(cudaEventRecord(c->ev0, st));
-    scan_kernel<kScanThreads><<<grid, kScanThreads, smem, st>>>(a);
+    if (a.prm.W >= 6) {
+        CU(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        scan_kernel<true><<<grid, kScanThreads, smem, st>>>(a);
+    } else {
+        CU(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        scan_kernel<false><<<grid, kScanThreads, smem, st>>>(a);
+    }
     CU(cudaEventRecord(c->ev1, st));
     c->launches++;
-    c->scan_timed = true;
     CU(cudaGetLastError());
+    if (!a.debug) {
+        verify_kernel<<<c->sm_count * 8, 256, 0, st>>>(a);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(c->ev2, st));
+    c->scan_timed = true;
     return MPCR_OK;
 }
 
@@ -674,6 +991,13 @@ float mpcr_last_scan_ms(mpcr_ctx* c) {
     float ms = 0.f;
     if (cudaEventSynchronize(c->ev1) != cudaSuccess) return 0.f;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return 0.f;
+    return ms;
+}
+float mpcr_last_verify_ms(mpcr_ctx* c) {
+    if (!c || !c->scan_timed) return 0.f;
+    float ms = 0.f;
+    if (cudaEventSynchronize(c->ev2) != cudaSuccess) return 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev1, c->ev2) != cudaSuccess) return 0.f;
     return ms;
 }
 

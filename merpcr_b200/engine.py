@@ -47,7 +47,6 @@ MIN_THREE_PRIME_MATCH = 0
 MIN_PCR_SIZE, MAX_PCR_SIZE = 1, 10000
 
 PCR_SIZE_CLAMP = 0x7FFFFFFF   # any expected size >= a contig length behaves identically (engine.py:531-533)
-TILE_BASES = 32768
 PLANE_SLACK_BASES = 1024      # read-ahead of the last strip / last primer window
 
 logger = logging.getLogger("merpcr.core.engine")  # same logger name as the reference module
@@ -485,7 +484,7 @@ class MerPCR:
         origin = max(0, begin - halo_l) // 128 * 128
         stop = min(total, end + halo_r)
         bases = max(128, (stop - origin + 127) // 128 * 128)
-        alloc = bases + TILE_BASES + PLANE_SLACK_BASES
+        alloc = bases + int(lib.mpcr_tile_bases()) + PLANE_SLACK_BASES
         sh = shard
         if sh is not None and (sh.origin, sh.bases, sh.begin, sh.end) == (origin, bases, begin, end):
             sh.plane2.zero_()

@@ -92,6 +92,75 @@ __global__ void dsmem_lookup(uint32_t* out, int words, int iters, int local_only
 
 static float time_it(cudaEvent_t a, cudaEvent_t b) { float ms; CK(cudaEventSynchronize(b)); CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
 
+// gathers with a cache operator, run under a large dynamic-smem carve-out (what the scanner CTA looks like)
+template <int MODE, int ILP>
+__global__ void gmem_gather_mode(const uint4* __restrict__ tab, uint32_t n, uint32_t* out, int iters) {
+    extern __shared__ uint4 sbuf[];
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u, acc = 0;
+    if (MODE == 5) {
+        unsigned long long* bar = reinterpret_cast<unsigned long long*>(sbuf + blockDim.x * ILP) + (threadIdx.x >> 5);
+        if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
+    for (int it = 0; it < iters; ++it) {
+        uint4 v[ILP];
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            x = x * 1664525u + 1013904223u;
+            const uint4* p = tab + __umulhi(x, n);
+            if (MODE == 0) v[k] = *p;
+            else if (MODE == 1) v[k] = __ldg(p);
+            else if (MODE == 2) v[k] = __ldcg(p);
+            else if (MODE == 3) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w) : "l"(p));
+            else if (MODE == 4) {
+                uint32_t d = (uint32_t)__cvta_generic_to_shared(&sbuf[threadIdx.x * ILP + k]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(p) : "memory");
+            } else if (MODE == 5) {  // per-lane TMA bulk copy, one mbarrier per warp
+                unsigned long long* bar = reinterpret_cast<unsigned long long*>(sbuf + blockDim.x * ILP) + (threadIdx.x >> 5);
+                uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+                uint32_t d = (uint32_t)__cvta_generic_to_shared(&sbuf[threadIdx.x * ILP + k]);
+                if (k == 0) {
+                    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(32 * ILP * 16) : "memory");
+                    __syncwarp();
+                }
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];" ::"r"(d), "l"(p), "r"(b) : "memory");
+            } else if (MODE == 6) {  // 64-bit atomic OR with 0: served by L2, no L1 line
+                unsigned long long r = atomicOr((unsigned long long*)p, 0ull);
+                v[k].x = (uint32_t)r; v[k].w = (uint32_t)(r >> 32); v[k].y = v[k].z = 0;
+            }
+        }
+        if (MODE == 5) {
+            unsigned long long* bar = reinterpret_cast<unsigned long long*>(sbuf + blockDim.x * ILP) + (threadIdx.x >> 5);
+            uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), ok = 0;
+            while (!ok) asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.b32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(b), "r"(it & 1) : "memory");
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) v[k] = sbuf[threadIdx.x * ILP + k];
+            __syncwarp();
+        }
+        if (MODE == 4) {
+            asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) v[k] = sbuf[threadIdx.x * ILP + k];
+        }
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) acc += v[k].x + v[k].w;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+template <int MODE>
+static void run_mode(const char* name, const uint4* tab, uint32_t n16, uint32_t* out, int sms, cudaEvent_t e0, cudaEvent_t e1) {
+    for (int kb : {100, 132, 164, 196, 224}) for (int threads : {512, 1024}) {
+        int iters = 100;
+        CK(cudaFuncSetAttribute(gmem_gather_mode<MODE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024));
+        gmem_gather_mode<MODE, 4><<<sms, threads, kb * 1024>>>(tab, n16, out, 3);
+        CK(cudaEventRecord(e0)); gmem_gather_mode<MODE, 4><<<sms, threads, kb * 1024>>>(tab, n16, out, iters); CK(cudaEventRecord(e1));
+        float ms = time_it(e0, e1); double n = (double)sms * threads * iters * 4;
+        printf("gather16 %-14s smem %3d KB %4d thr ILP4: %.3f ms  %.1f G/s (%.2f /clk/SM)\n", name, kb, threads, ms, n / ms / 1e6, n / ms / 1e6 / sms / 1.965);
+    }
+}
+
+
 int main() {
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
     const int sms = pr.multiProcessorCount;
@@ -99,6 +168,16 @@ int main() {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     uint32_t* out; CK(cudaMalloc(&out, 64 << 20));
 
+    if (getenv("UB_MODES")) {
+        uint32_t n16 = (uint32_t)(((size_t)32 << 20) / 16);
+        uint4* tab; CK(cudaMalloc(&tab, (size_t)32 << 20)); CK(cudaMemset(tab, 1, (size_t)32 << 20));
+        run_mode<0>("ld", tab, n16, out, sms, e0, e1);
+        run_mode<4>("cp.async.cg", tab, n16, out, sms, e0, e1);
+        run_mode<5>("tma.bulk16", tab, n16, out, sms, e0, e1);
+        run_mode<6>("atom.or.b64", tab, n16, out, sms, e0, e1);
+        printf("done\n");
+        return 0;
+    }
     // 1. smem
     for (int kb : {64, 128, 192}) for (int threads : {512, 1024}) {
         int words = kb * 256, iters = 2000;

@@ -33,12 +33,10 @@ struct mpcr_ctx {
     uint32_t n_rec = 0, n_valid = 0;
     std::vector<RecMeta> meta;
     std::vector<uint64_t> pwords;
-    std::vector<uint64_t> slots;
-    uint32_t slot_mask = 0;
-    std::vector<uint32_t> bucket;
+    std::vector<Slot> slots;
+    SlotMap smap{1023u, 0u};
+    std::vector<BucketEntry> bucket;
     std::vector<uint32_t> filter;
-    uint32_t filter_bits = 0;
-    int filter_exact = 0;
     uint32_t max_hash_off = 0, max_len = 0;
     uint64_t max_pcr = 0;
     bool table_ready = false;
@@ -66,6 +64,7 @@ void mpcr_ctx_destroy(mpcr_ctx* c) { delete c; }
 int mpcr_ctx_sm_count(const mpcr_ctx*) { return 1; }
 uint64_t mpcr_launch_count(const mpcr_ctx* c) { return c ? c->launches : 0; }
 float mpcr_last_scan_ms(mpcr_ctx*) { return 0.f; }
+float mpcr_last_verify_ms(mpcr_ctx*) { return 0.f; }
 
 int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* ascii, uint64_t n, uint64_t dst_base, uint64_t origin, void* plane2,
                        void* plane4, void* valid, const uint8_t* lut, void*) {
@@ -120,10 +119,12 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
             uint32_t hbe = 0; int ho;
             if (!minus) {
                 ho = first_clean_word(Fwd{pr1}, n1, W, &hbe);
+                if (ho >= 0) m.tag = make_tag(Fwd{pr1}, n1, ho, W);
                 encode_primer(Fwd{pr1}, n1, plut, c->pwords.data() + m.p1_word);
                 encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p2_word);
             } else {
                 ho = first_clean_word(Fwd{pr2}, n2, W, &hbe);
+                if (ho >= 0) m.tag = make_tag(Fwd{pr2}, n2, ho, W);
                 encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p1_word);
                 encode_primer(Rc{pr1, n1}, n1, plut, c->pwords.data() + m.p2_word);
             }
@@ -135,27 +136,32 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
     c->pwords.resize(c->pwords.size() + 2);
     std::stable_sort(pairs.begin(), pairs.end(), [](auto& a, auto& b) { return a.first < b.first; });
     c->n_valid = (uint32_t)pairs.size();
-    const uint64_t space = 1ull << (2 * W);
-    uint32_t budget = 1u << 20;
-    if (const char* env = getenv("MPCR_FILTER_BITS")) { long v = atol(env); if (v >= 128) budget = (uint32_t)v & ~127u; }
-    if (space <= budget) { c->filter_exact = 1; c->filter_bits = (uint32_t)std::max<uint64_t>(space, 128); }
-    else { c->filter_exact = 0; c->filter_bits = budget; }
-    c->filter.assign(c->filter_bits / 32, 0);
+    uint32_t words = 39616;  // what a B200 scanner CTA has room for; any multiple of 4 works
+    if (const char* env = getenv("MPCR_FILTER_WORDS")) { long v = atol(env); if (v >= 4) words = (uint32_t)v & ~3u; }
+    c->filter.assign(words, 0);
+    const uint32_t cw = filter_mul(W);
     uint32_t nslots = 1024;
-    while (nslots < 2u * c->n_valid + 2u) nslots <<= 1;
-    c->slot_mask = nslots - 1;
-    c->slots.assign(nslots, ~0ull);
-    c->bucket.assign(c->n_valid + 1, 0);
+    const bool direct = getenv("MPCR_EMUL_HASHED") ? false : W <= 11;  // the env switch lets CPU tests cover both modes
+    if (direct) nslots = 1u << (2 * W);
+    else while (nslots < 2u * c->n_valid + 2u) nslots <<= 1;
+    c->smap = SlotMap{nslots - 1, direct ? 1u : 0u};
+    c->slots.assign(nslots, Slot{~0u, ~0u, ~0u, ~0u});
+    c->bucket.assign(c->n_valid + 1, BucketEntry{0, 0});
     for (uint32_t i = 0; i < c->n_valid; ++i) {
-        const uint32_t key = pairs[i].first;
+        const uint32_t key = pairs[i].first, rec = pairs[i].second;
         const bool head = i == 0 || pairs[i - 1].first != key, last = i + 1 == c->n_valid || pairs[i + 1].first != key;
-        c->bucket[i] = pairs[i].second | (last ? 0x80000000u : 0u);
+        c->bucket[i] = BucketEntry{rec | (last ? 0x80000000u : 0u), c->meta[rec].tag};
         if (head) {
-            uint32_t s = slot_hash(key) & c->slot_mask;
-            while (c->slots[s] != ~0ull) s = (s + 1) & c->slot_mask;
-            c->slots[s] = ((uint64_t)key << 32) | i;
-            const uint32_t fb = filter_index(key, c->filter_bits, c->filter_exact);
-            c->filter[fb >> 5] |= 1u << (fb & 31);
+            uint32_t n = 1, tag_b = 0;
+            if (!last) {
+                n = 2;
+                tag_b = c->meta[pairs[i + 1].second].tag;
+                if (i + 2 < c->n_valid && pairs[i + 2].first == key) n = 3;
+            }
+            uint32_t s = slot_index(key, c->smap);
+            if (!direct) while ((c->slots[s].tag_n >> 24) != kSlotEmpty) s = (s + 1) & c->smap.mask;
+            c->slots[s] = Slot{key, n == 1 ? rec : i, (c->meta[rec].tag & 0xFFFFFFu) | (n << 24), tag_b};
+            c->filter[filter_word(key, cw, words)] |= filter_bits_of(key, W);
         }
     }
     c->table_ready = true;
@@ -184,6 +190,7 @@ int mpcr_table_primer_words(mpcr_ctx* c, uint32_t rec, int which, uint64_t* out,
 }
 
 static uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+uint64_t mpcr_tile_bases(void) { return (uint64_t)kTileBases; }
 uint64_t mpcr_halo_left(const mpcr_ctx* c) { return c ? round_up((uint64_t)c->max_hash_off + 64, 128) : 0; }
 uint64_t mpcr_halo_right(const mpcr_ctx* c) {
     return c ? round_up(c->max_pcr + (uint64_t)c->prm.margin + c->max_len + 64 + 128, 128) + kTileBases : 0;
@@ -197,7 +204,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
     if ((origin & 127u) || (sb & 127u)) return fail(MPCR_EINVAL, "origin / shard_begin must be multiples of 128");
     const uint64_t *P2 = (const uint64_t*)plane2, *P4 = (const uint64_t*)plane4, *V = (const uint64_t*)valid;
     SearchParams prm{c->prm.wordsize, c->prm.margin, c->prm.mismatches, c->prm.three_prime_match, c->prm.iupac_mode ? 1 : 0};
-    const uint32_t wmask = wmask_of(prm.W);
+    const uint32_t wmask = wmask_of(prm.W), cw = filter_mul(prm.W);
     uint64_t n = 0;
     c->launches++;
     for (uint32_t ci = 0; ci < n_contigs && c->n_valid; ++ci) {
@@ -216,21 +223,22 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
                 for (int j = 0; j < 64 && cand; ++j) {
                     if (!((cand >> j) & 1)) continue;
                     const uint32_t key = extract_key(P2, gb + j, wmask);
-                    const uint32_t fb = filter_index(key, c->filter_bits, c->filter_exact);
-                    if (!((c->filter[fb >> 5] >> (fb & 31)) & 1u)) continue;
-                    uint32_t i = find_bucket(c->slots.data(), c->slot_mask, key);
-                    if (i == kEmptySlot) continue;
-                    for (;;) {
-                        const uint32_t e = c->bucket[i], rec = e & 0x7FFFFFFFu;
+                    if (!filter_pass(c->filter[filter_word(key, cw, (uint32_t)c->filter.size())], key, prm.W)) continue;
+                    const uint32_t gcodes = fetch_bits(P2, 2 * (gb + j + prm.W), 2 * kTagBases);
+                    const uint32_t gvalid = fetch_bits(V, gb + j + prm.W, kTagBases);
+                    Slot sl;
+                    if (!find_slot(c->slots.data(), c->smap, key, &sl)) continue;
+                    bool any;
+                    const uint32_t code = slot_survivor(sl, gcodes, gvalid, prm.N, &any);
+                    if (!any) continue;
+                    for_each_survivor_record(c->bucket.data(), code, gcodes, gvalid, prm.N, [&](uint32_t rec) {
                         const RecMeta& m = c->meta[rec];
                         verify_record(P4, gbase - (int64_t)ls, (int64_t)L, (int64_t)ls + lp0 + j, m, c->pwords.data(), prm,
                                       [&](int64_t p1, int64_t p2, uint32_t rank) {
                                           if (n < capacity) hits[n] = mpcr_hit{ci, (uint32_t)p1, (uint32_t)p2, rec, rank, m.hash_off};
                                           ++n;
                                       });
-                        if (e & 0x80000000u) break;
-                        ++i;
-                    }
+                    });
                 }
             }
         }
