@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmerpcr_b200.so")
+# $MPCR_B200_LIB selects a tuning build of the same CUDA library (merpcr_b200/build.py --variant=...)
+LIB_PATH = os.environ.get("MPCR_B200_LIB") or os.path.join(_HERE, "lib", "libmerpcr_b200.so")
 
 MPCR_OK, MPCR_EINVAL, MPCR_ECUDA, MPCR_ENOMEM, MPCR_ESTATE, MPCR_EOVERFLOW = 0, -1, -2, -3, -4, -5
 ABI_VERSION = 2

@@ -24,14 +24,21 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found; cannot build libmerpcr_b200.so")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """variant/defines: tuning builds (lib/libmerpcr_b200_<variant>.so with -D overrides), selected at run time with
+    $MPCR_B200_LIB; the product is the default build."""
+    out = OUT if not variant else OUT.replace(".so", f"_{variant}.so")
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", out] + SRC
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    args = [a for a in sys.argv[1:] if not a.startswith("-D") and not a.startswith("--variant=")]
+    variant = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--variant=")), "")
+    print(build(force="--force" in args or bool(variant), verbose="-v" in args, variant=variant,
+                defines=[a[2:] for a in sys.argv[1:] if a.startswith("-D")]))

@@ -19,9 +19,18 @@ namespace mpcr {
 // ---------------------------------------------------------------------------------------------------------
 
 static constexpr uint64_t kLane1 = 0x1111111111111111ull;  // LSB of every nibble
-static constexpr int kScanThreads = 512;                   // threads of one scanner CTA (one CTA per SM)
-static constexpr int kPosPerThread = 64;                   // hash positions per thread and tile
-static constexpr int kTileBases = kScanThreads * kPosPerThread;  // hash positions per tile (multiple of 128)
+#ifndef MPCR_SCAN_THREADS
+#define MPCR_SCAN_THREADS 512
+#endif
+#ifndef MPCR_SCAN_ILP
+#define MPCR_SCAN_ILP 4
+#endif
+#ifndef MPCR_SCAN_QCAP
+#define MPCR_SCAN_QCAP 256
+#endif
+static constexpr int kScanThreads = MPCR_SCAN_THREADS;     // threads of one scanner CTA (one CTA per SM)
+static constexpr int kPosPerThread = 64;                   // hash positions per lane and unit
+static constexpr int kTileBases = 32768;                   // hash positions per tile descriptor (multiple of 2048)
 static constexpr int kTagBases = 8;                        // bases after the seed carried inline in the table
 
 // One record = one strand of one STS line (core/models.py:17-29 + engine.py:253-281).
@@ -34,7 +43,7 @@ struct RecMeta {
     uint16_t len1, len2;
     uint16_t hash_off;  // engine.py:339-353
     uint16_t flags;     // bit0: inserted in the table
-    uint32_t tag;       // primer1 bases right after the seed: 2-bit codes in bits [0,16), their count in [16,24)
+    uint32_t tag;       // primer1 bases right after the seed: 2-bit codes in bits [0,16), compare mask in [16,32)
 };
 static_assert(sizeof(RecMeta) == 32, "RecMeta layout");
 
@@ -265,13 +274,13 @@ MPCR_HD bool filter_pass(uint32_t word, uint32_t key, int W) {
 
 struct Slot {          // 16 bytes, one 128-bit gather
     uint32_t key;      // exact seed key (little-endian digits); checked only in hashed mode
-    uint32_t val;      // n == 1: record index; n >= 2: index of the first bucket entry
-    uint32_t tag_n;    // tag of the first record in bits [0,24), n in [24,32): kSlotEmpty, 1, 2 or 3 (= 3 or more)
-    uint32_t tag_b;    // n == 2: tag of the second record
+    uint32_t code;     // survivor code: record index (one record) or kWalkBucket | first bucket entry; kSlotEmpty = free
+    uint32_t tag_a;    // tag of the first record  (one record: tag_b == tag_a; three or more: both tags have mask 0,
+    uint32_t tag_b;    // tag of the second record  i.e. they never reject)
 };
 static_assert(sizeof(Slot) == 16, "Slot layout");
-static constexpr uint32_t kSlotEmpty = 0xFFu;         // cudaMemset(0xFF) == all slots empty
-static constexpr uint32_t kWalkBucket = 0x80000000u;  // survivor code flag: "val is a bucket start, walk it"
+static constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu;   // cudaMemset(0xFF) == all slots empty
+static constexpr uint32_t kWalkBucket = 0x80000000u;  // survivor code flag: "walk the bucket starting at code & ~flag"
 
 struct BucketEntry {
     uint32_t rec_last;  // record index | last-of-bucket << 31
@@ -292,16 +301,13 @@ MPCR_HD uint32_t slot_hash(uint32_t key) {
 MPCR_HD uint32_t slot_index(uint32_t key, SlotMap sm) { return sm.direct ? key : (slot_hash(key) & sm.mask); }
 
 // engine.py:614-640 restricted to the tag: true iff the full primer-1 compare is CERTAIN to fail because the
-// bases right after the seed already carry more than N mismatches.  tag holds only A/C/G/T primer letters;
-// gcodes / gvalid are the 2-bit codes / clean flags of the genome bases following the seed.  A clean genome
-// base whose code differs from an A/C/G/T primer letter mismatches in both compare modes; anything not clean
-// is left to the full compare.
-MPCR_HD bool tag_rejects(uint32_t tag, uint32_t gcodes, uint32_t gvalid, int N) {
-    const uint32_t len = (tag >> 16) & 0xFFu;
-    if (len == 0) return false;
-    const uint32_t vm = (1u << len) - 1u;
-    if ((gvalid & vm) != vm) return false;
-    uint32_t d = (tag ^ gcodes) & ((1u << (2 * len)) - 1u);
+// bases right after the seed already carry more than N mismatches.  tag = 2-bit codes of up to kTagBases
+// A/C/G/T primer letters (bits [0,16)) and the mask of the 2-bit lanes that hold one (bits [16,32)); gcodes are
+// the 2-bit codes of the genome bases following the seed.  A clean genome base whose code differs from an
+// A/C/G/T primer letter mismatches in both compare modes; the caller must not use the verdict when one of the
+// kTagBases genome bases is not clean (tag_window_clean) -- those positions go to the full compare.
+MPCR_HD bool tag_rejects(uint32_t tag, uint32_t gcodes, int N) {
+    uint32_t d = (tag ^ gcodes) & (tag >> 16);
     d = (d | (d >> 1)) & 0x5555u;
 #ifdef __CUDA_ARCH__
     return __popc(d) > N;
@@ -309,20 +315,22 @@ MPCR_HD bool tag_rejects(uint32_t tag, uint32_t gcodes, uint32_t gvalid, int N) 
     return __builtin_popcount(d) > N;
 #endif
 }
+MPCR_HD bool tag_window_clean(uint32_t gvalid) { return (gvalid & 0xFFu) == 0xFFu; }
 
 // the tag of a primer: up to kTagBases A/C/G/T letters following the seed [ho+W, ...)
 template <class CharAt>
 MPCR_HD uint32_t make_tag(CharAt at, int len, int ho, int W) {
-    uint32_t codes = 0, n = 0;
+    uint32_t codes = 0, mask = 0, n = 0;
     for (int i = ho + W; i < len && n < (uint32_t)kTagBases; ++i) {
         const uint8_t c = at(i);
         uint32_t code;
         if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3;
         else break;
         codes |= code << (2 * n);
+        mask |= 3u << (2 * n);
         ++n;
     }
-    return codes | (n << 16);
+    return codes | (mask << 16);
 }
 
 // n bits of a little-endian bit plane starting at bit index b (n <= 32)
@@ -343,15 +351,11 @@ MPCR_HD Slot load_slot(const Slot* p) {
 #endif
 }
 
-// Does a (non-empty, key-matching) slot leave anything to verify at this position?  *any = false if every record
-// of the seed is ruled out by its inline tag.  Returns the survivor code: the record index (n == 1) or
-// kWalkBucket | first bucket entry.
-MPCR_HD uint32_t slot_survivor(const Slot& s, uint32_t gcodes, uint32_t gvalid, int N, bool* any) {
-    const uint32_t n = s.tag_n >> 24;
-    bool pass = n >= 3u || !tag_rejects(s.tag_n & 0xFFFFFFu, gcodes, gvalid, N);
-    if (n == 2u && !pass) pass = !tag_rejects(s.tag_b & 0xFFFFFFu, gcodes, gvalid, N);
-    *any = pass;
-    return n == 1u ? s.val : (kWalkBucket | s.val);
+// Does a (non-empty, key-matching) slot leave anything to verify at this position?  False iff every record of the
+// seed is ruled out by its inline tag.
+MPCR_HD bool slot_survives(const Slot& s, uint32_t gcodes, uint32_t gvalid, int N) {
+    if (!tag_window_clean(gvalid)) return true;
+    return !(tag_rejects(s.tag_a, gcodes, N) && tag_rejects(s.tag_b, gcodes, N));
 }
 
 // Find the slot of a key: returns false when the key is not in the table.  (The scanner issues the first probe
@@ -360,7 +364,7 @@ MPCR_HD bool find_slot(const Slot* slots, SlotMap sm, uint32_t key, Slot* out) {
     uint32_t i = slot_index(key, sm);
     for (;;) {
         const Slot s = load_slot(slots + i);
-        if ((s.tag_n >> 24) == kSlotEmpty) return false;
+        if (s.code == kSlotEmpty) return false;
         if (sm.direct || s.key == key) { *out = s; return true; }
         i = (i + 1) & sm.mask;
     }
@@ -372,9 +376,10 @@ template <class OnRec>
 MPCR_HD void for_each_survivor_record(const BucketEntry* bucket, uint32_t code, uint32_t gcodes, uint32_t gvalid, int N,
                                       OnRec&& on_rec) {
     if (!(code & kWalkBucket)) { on_rec(code); return; }
+    const bool clean = tag_window_clean(gvalid);
     for (uint32_t e = code & ~kWalkBucket;; ++e) {
         const BucketEntry b = bucket[e];
-        if (!tag_rejects(b.tag, gcodes, gvalid, N)) on_rec(b.rec_last & 0x7FFFFFFFu);
+        if (!clean || !tag_rejects(b.tag, gcodes, N)) on_rec(b.rec_last & 0x7FFFFFFFu);
         if (b.rec_last >> 31) return;
     }
 }

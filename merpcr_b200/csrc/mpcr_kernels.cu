@@ -235,19 +235,22 @@ __global__ void __launch_bounds__(256) build_buckets(const Item<2>* __restrict__
             tag_b = meta[pairs[i + 1].f[1] & 0x7FFFFFFFu].tag;
             if (i + 2 < n_valid && pairs[i + 2].f[0] == key) n = 3;
         }
-        const unsigned long long lo = (unsigned long long)key | ((unsigned long long)(n == 1 ? rec : i) << 32);
-        const unsigned long long hi = (unsigned long long)((tag & 0xFFFFFFu) | (n << 24)) | ((unsigned long long)tag_b << 32);
+        // one record: both tags are its tag; two: one tag each; three or more: mask 0 = never reject
+        const uint32_t code = n == 1 ? rec : (kWalkBucket | i);
+        const uint32_t ta = n >= 3 ? 0u : tag, tb = n == 1 ? tag : (n == 2 ? tag_b : 0u);
+        const unsigned long long lo = (unsigned long long)key | ((unsigned long long)code << 32);
+        const unsigned long long hi = (unsigned long long)ta | ((unsigned long long)tb << 32);
         uint32_t s = slot_index(key, sm);
         if (!sm.direct) {
-            for (;;) {  // claim on the (tag_n, tag_b) half -- n == kSlotEmpty marks an empty slot
-                unsigned long long* h = reinterpret_cast<unsigned long long*>(slots + s) + 1;
-                if (atomicCAS(h, ~0ull, hi) == ~0ull) break;
+            for (;;) {  // claim on the (key, code) half -- code == kSlotEmpty marks a free slot
+                unsigned long long* h = reinterpret_cast<unsigned long long*>(slots + s);
+                if (atomicCAS(h, ~0ull, lo) == ~0ull) break;
                 s = (s + 1) & sm.mask;
             }
         } else {
-            reinterpret_cast<unsigned long long*>(slots + s)[1] = hi;
+            reinterpret_cast<unsigned long long*>(slots + s)[0] = lo;
         }
-        reinterpret_cast<unsigned long long*>(slots + s)[0] = lo;
+        reinterpret_cast<unsigned long long*>(slots + s)[1] = hi;
         atomicOr(&filter[filter_word(key, cw, filter_words)], filter_bits_of(key, W));
         atomicAdd(n_keys, 1u);
     }
@@ -293,8 +296,8 @@ struct ScanSmem {
     static constexpr int kUnitsPerTile = kTileBases / kUnitBases;
     static constexpr int kP2Bytes = kUnitBases / 4 + 32;     // plane2 of a unit + 128-base read-ahead
     static constexpr int kVBytes = kUnitBases / 8 + 16;      // valid bits of a unit + 128-base read-ahead
-    static constexpr int kQCap = 256;                        // candidate queue entries
-    static constexpr int kIlp = 4;                           // slot gathers in flight per lane
+    static constexpr int kQCap = MPCR_SCAN_QCAP;             // candidate queue entries
+    static constexpr int kIlp = MPCR_SCAN_ILP;               // slot gathers in flight per lane
     struct Warp {
         alignas(16) uint8_t p2[2][kP2Bytes];
         alignas(16) uint8_t v[2][kVBytes];
@@ -377,9 +380,7 @@ __device__ __noinline__ void probe_collision(const ScanArgs& a, uint32_t key, ui
                                              uint32_t tile, uint32_t lp) {
     Slot s;
     if (!find_slot(a.slots, a.smap, key, &s)) return;
-    bool any;
-    const uint32_t code = slot_survivor(s, gcodes, gvalid, a.prm.N, &any);
-    if (any) push_survivor(a, tile, lp, code);
+    if (slot_survives(s, gcodes, gvalid, a.prm.N)) push_survivor(a, tile, lp, s.code);
 }
 
 // One filter probe: returns a word whose MSB is set iff both Bloom bits of the key are set.
@@ -392,6 +393,60 @@ __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ s_
     const uint32_t t1 = __funnelshift_l(0u, word, x);  // word << (x & 31)
     if (!WIDE) return t1;
     return t1 & __funnelshift_l(0u, word, x3);
+}
+
+// Stage 2 for the cnt (> 0) queued positions of a warp: kIlp rounds of 32 async slot gathers in flight, then the
+// tag check on what came back.  Straight-line code: lanes past the end of the queue re-probe entry 0 and are
+// masked out, so the kIlp rounds interleave freely.  CLEAN: every base of the unit (and its read-ahead) is
+// A/C/G/T, so the tag verdict can be used without looking at the valid bits.
+template <bool CLEAN>
+__device__ __forceinline__ void probe_queue(const ScanArgs& a, ScanSmem::Warp& ws, const uint32_t* __restrict__ s_p2,
+                                            const uint32_t* __restrict__ s_v, uint32_t cnt, int lane, uint32_t tile,
+                                            uint32_t ubase, unsigned long long& n_dbg) {
+    constexpr int kIlp = ScanSmem::kIlp;
+    const int W = a.prm.W, N = a.prm.N;
+    const uint32_t wmask = wmask_of(W);
+    const bool hashed = !a.smap.direct;
+    for (uint32_t base = 0; base < cnt; base += 32 * kIlp) {
+        uint32_t lpv[kIlp], key[kIlp], gcodes[kIlp];
+        bool ok[kIlp], dirty[kIlp];
+#pragma unroll
+        for (int u = 0; u < kIlp; ++u) {
+            const uint32_t qi = base + 32 * u + lane;
+            ok[u] = qi < cnt;
+            const uint32_t lp = ws.queue[ok[u] ? qi : 0u];
+            // key (2W bits) and the 8-base tag window (16 bits) out of three staged words
+            const uint32_t wi = lp >> 4, sh = (lp & 15u) * 2u;
+            const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1], w2 = s_p2[wi + 2];
+            const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+            key[u] = x0 & wmask;
+            gcodes[u] = __funnelshift_rc(x0, x1, 2 * W);  // clamped: 2W == 32 -> x1; only the low 16 bits are used
+            lpv[u] = lp;
+            dirty[u] = false;
+            if (!CLEAN) {
+                const uint32_t vb = lp + (uint32_t)W, vi = vb >> 5, vs = vb & 31u;
+                dirty[u] = !tag_window_clean(__funnelshift_r(s_v[vi], s_v[vi + 1], vs));
+            }
+            gather16_async(&ws.landing[u][lane], a.slots + slot_index(key[u], a.smap));
+            gather_commit();
+        }
+#pragma unroll
+        for (int u = 0; u < kIlp; ++u) {
+            if (u == 0) gather_wait<kIlp - 1>();
+            else if (u == 1) gather_wait<(kIlp > 2 ? kIlp - 2 : 0)>();
+            else if (u == 2) gather_wait<(kIlp > 3 ? kIlp - 3 : 0)>();
+            else gather_wait<0>();
+            const uint4 v = ws.landing[u][lane];
+            const bool collide = hashed && v.x != key[u];
+            const bool pass = dirty[u] || !(tag_rejects(v.z, gcodes[u], N) && tag_rejects(v.w, gcodes[u], N));
+            if (ok[u] && v.y != kSlotEmpty && (collide || pass)) {  // about one queued position in a thousand
+                const uint32_t lp = ubase + lpv[u];
+                if (a.debug & 2) ++n_dbg;
+                else if (collide) probe_collision(a, key[u], gcodes[u] & 0xFFFFu, dirty[u] ? 0u : 0xFFu, tile, lp);
+                else push_survivor(a, tile, lp, v.y);
+            }
+        }
+    }
 }
 
 // Persistent CTAs, one per SM, made of AUTONOMOUS warps: there is no CTA-wide barrier after the prologue, so
@@ -412,26 +467,43 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     ScanSmem::Warp& ws = reinterpret_cast<ScanSmem::Warp*>(smem)[warp];
     uint32_t* s_filter = reinterpret_cast<uint32_t*>(smem + ScanSmem::kFilterOff);
 
-    const uint32_t n_units = a.n_tiles * ScanSmem::kUnitsPerTile;
+    // Warp gw walks tiles gw, gw + stride, ... and inside a tile its units of 2048 positions in order.  Two cursors
+    // run over that sequence: the load cursor (l_*) is one unit ahead of the process cursor (p_*).
     const uint32_t stride = gridDim.x * ScanSmem::kWarps;
-    // interleave: consecutive units go to different CTAs first, so neighbouring tiles spread over the SMs
-    uint32_t unit = (uint32_t)warp * gridDim.x + blockIdx.x;
-
-    // lane 0 fetches the descriptor of a unit and starts its two bulk copies
-    auto issue_unit = [&](uint32_t u, int buf) {
-        const TileDesc td = a.tiles[u / ScanSmem::kUnitsPerTile];
-        const int64_t gb = td.gbase + (int64_t)(u % ScanSmem::kUnitsPerTile) * ScanSmem::kUnitBases;
-        mbar_expect_tx(&ws.mbar[buf], ScanSmem::kP2Bytes + ScanSmem::kVBytes);
-        tma_load_1d(ws.p2[buf], reinterpret_cast<const uint8_t*>(a.p2) + (gb >> 2), ScanSmem::kP2Bytes, &ws.mbar[buf]);
-        tma_load_1d(ws.v[buf], reinterpret_cast<const uint8_t*>(a.valid) + (gb >> 3), ScanSmem::kVBytes, &ws.mbar[buf]);
+    const uint32_t gw = (uint32_t)warp * gridDim.x + blockIdx.x;  // neighbouring tiles spread over the SMs
+    uint32_t l_tile = gw, l_sub = 0, l_nsub = 0, p_tile = gw, p_sub = 0, p_nbases = 0;
+    int64_t l_gbase = 0;
+    if (gw < a.n_tiles) {
+        const TileDesc td = a.tiles[gw];
+        l_gbase = td.gbase;
+        p_nbases = td.nbases;
+        l_nsub = (td.nbases + ScanSmem::kUnitBases - 1) / ScanSmem::kUnitBases;
+    }
+    // lane 0 starts the two bulk copies of the load cursor's unit; then every lane advances the cursor
+    auto issue_next = [&](int buf) {
+        if (lane == 0) {
+            const int64_t gb = l_gbase + (int64_t)l_sub * ScanSmem::kUnitBases;
+            mbar_expect_tx(&ws.mbar[buf], ScanSmem::kP2Bytes + ScanSmem::kVBytes);
+            tma_load_1d(ws.p2[buf], reinterpret_cast<const uint8_t*>(a.p2) + (gb >> 2), ScanSmem::kP2Bytes, &ws.mbar[buf]);
+            tma_load_1d(ws.v[buf], reinterpret_cast<const uint8_t*>(a.valid) + (gb >> 3), ScanSmem::kVBytes, &ws.mbar[buf]);
+        }
+        if (++l_sub >= l_nsub) {
+            l_tile += stride;
+            l_sub = 0;
+            if (l_tile < a.n_tiles) {
+                l_gbase = __ldg(&a.tiles[l_tile].gbase);
+                l_nsub = (__ldg(&a.tiles[l_tile].nbases) + ScanSmem::kUnitBases - 1) / ScanSmem::kUnitBases;
+            }
+        }
     };
 
     if (lane == 0) {
         mbar_init(&ws.mbar[0], 1);
         mbar_init(&ws.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (unit < n_units) issue_unit(unit, 0);
     }
+    __syncwarp();
+    if (l_tile < a.n_tiles) issue_next(0);
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.filter);
         uint4* dst = reinterpret_cast<uint4*>(s_filter);
@@ -440,28 +512,34 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     __syncthreads();
 
     const int W = a.prm.W;
-    const uint32_t wmask = wmask_of(W);
     const uint32_t cw = a.cw, fw = a.filter_words;
     unsigned long long n_dbg = 0;
 
-    for (uint32_t it = 0; unit < n_units; ++it, unit += stride) {
+    for (uint32_t it = 0; p_tile < a.n_tiles; ++it) {
         const int buf = it & 1;
-        if (lane == 0 && unit + stride < n_units) issue_unit(unit + stride, buf ^ 1);
-        const uint32_t tile = unit / ScanSmem::kUnitsPerTile;
-        const uint32_t ubase = (unit % ScanSmem::kUnitsPerTile) * ScanSmem::kUnitBases;  // tile-local offset of the unit
-        const uint32_t tile_nbases = __ldg(&a.tiles[tile].nbases);
+        if (l_tile < a.n_tiles) issue_next(buf ^ 1);
+        const uint32_t tile = p_tile;
+        const uint32_t ubase = p_sub * ScanSmem::kUnitBases;  // tile-local offset of the unit
+        const uint32_t unit_nbases = min(p_nbases - ubase, (uint32_t)ScanSmem::kUnitBases);
+        if (ubase + ScanSmem::kUnitBases >= p_nbases) {  // last unit of the tile: move the process cursor on
+            p_tile += stride;
+            p_sub = 0;
+            if (p_tile < a.n_tiles) p_nbases = __ldg(&a.tiles[p_tile].nbases);
+        } else {
+            ++p_sub;
+        }
         while (!mbar_try_wait(&ws.mbar[buf], (it >> 1) & 1u)) {}
-        if (ubase >= tile_nbases) { __syncwarp(); continue; }
-        const uint32_t unit_nbases = min(tile_nbases - ubase, (uint32_t)ScanSmem::kUnitBases);
         const uint32_t* s_p2 = reinterpret_cast<const uint32_t*>(ws.p2[buf]);
         const uint32_t* s_v = reinterpret_cast<const uint32_t*>(ws.v[buf]);
 
         // ---------------- stage 1: rolling keys + Bloom probe ----------------
         const uint32_t lp0 = (uint32_t)lane * kPosPerThread;  // unit-local
         uint32_t c_lo = 0, c_hi = 0;
+        bool my_clean = false;
         if (lp0 < unit_nbases) {
             const uint2 v0 = *reinterpret_cast<const uint2*>(s_v + 2 * lane);
             const uint2 v1 = *reinterpret_cast<const uint2*>(s_v + 2 * lane + 2);
+            my_clean = (v0.x & v0.y & v1.x) == 0xFFFFFFFFu;  // own 64 bases + the 32 behind them (W + tag <= 24)
             uint64_t wv = window_valid(((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v1.y << 32) | v1.x, W);
             const uint32_t left = unit_nbases - lp0;
             if (left < 64u) wv &= (1ull << left) - 1ull;
@@ -472,12 +550,19 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
                 auto raw = [&](int j) -> uint32_t {
                     return (j & 15) ? __funnelshift_r(r[j >> 4], r[(j >> 4) + 1], 2 * (j & 15)) : r[j >> 4];
                 };
+#ifndef MPCR_ACC_FORM
+#define MPCR_ACC_FORM 0
+#endif
+                // collect the MSB of each probe result as bit j of the pass mask
+                auto collect = [&](uint32_t& c, uint32_t u, int j) {
+                    if (MPCR_ACC_FORM == 0) c = __funnelshift_l(u, c, 1);          // ALU pipe
+                    else if (MPCR_ACC_FORM == 1) c = c * 2u + __umulhi(u, 2u);     // FMA pipe
+                    else if ((int32_t)u < 0) c |= 1u << (j & 31);                  // predicate
+                };
 #pragma unroll
-                for (int j = 31; j >= 0; --j)
-                    c_lo = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_lo, 1);
+                for (int j = 31; j >= 0; --j) collect(c_lo, filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), j);
 #pragma unroll
-                for (int j = 63; j >= 32; --j)
-                    c_hi = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_hi, 1);
+                for (int j = 63; j >= 32; --j) collect(c_hi, filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), j);
                 c_lo &= (uint32_t)wv;
                 c_hi &= (uint32_t)(wv >> 32);
             }
@@ -489,6 +574,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         }
 
         // ---------------- stage 2: warp queue, async slot gathers, tag check ----------------
+        const bool all_clean = __all_sync(0xffffffffu, my_clean);
         for (;;) {
             const uint32_t n = __popc(c_lo) + __popc(c_hi);
             uint32_t incl = n;
@@ -516,50 +602,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
             const uint32_t fit_mask = __ballot_sync(0xffffffffu, fits);
             const uint32_t cnt = __shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));  // lane 0 always fits
             __syncwarp();
-            constexpr int kIlp = ScanSmem::kIlp;
-            for (uint32_t base = 0; base < cnt; base += 32 * kIlp) {
-                uint32_t lpv[kIlp], key[kIlp], gcodes[kIlp], gvalid[kIlp];
-#pragma unroll
-                for (int u = 0; u < kIlp; ++u) {
-                    const uint32_t qi = base + 32 * u + lane;
-                    lpv[u] = 0xFFFFFFFFu;
-                    if (qi < cnt) {
-                        const uint32_t lp = ws.queue[qi];
-                        lpv[u] = lp;
-                        // key (2W bits) and the 8-base tag window (16 bits) out of three staged words
-                        const uint32_t wi = lp >> 4, sh = (lp & 15u) * 2u;
-                        const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1], w2 = s_p2[wi + 2];
-                        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
-                        key[u] = x0 & wmask;
-                        gcodes[u] = __funnelshift_rc(x0, x1, 2 * W) & 0xFFFFu;  // clamped: 2W == 32 -> x1
-                        const uint32_t vb = lp + (uint32_t)W, vi = vb >> 5, vs = vb & 31u;
-                        gvalid[u] = __funnelshift_r(s_v[vi], s_v[vi + 1], vs) & 0xFFu;
-                        gather16_async(&ws.landing[u][lane], a.slots + slot_index(key[u], a.smap));
-                    }
-                    gather_commit();
-                }
-#pragma unroll
-                for (int u = 0; u < kIlp; ++u) {
-                    if (u == 0) gather_wait<kIlp - 1>();
-                    else if (u == 1) gather_wait<(kIlp > 2 ? kIlp - 2 : 0)>();
-                    else if (u == 2) gather_wait<(kIlp > 3 ? kIlp - 3 : 0)>();
-                    else gather_wait<0>();
-                    if (lpv[u] != 0xFFFFFFFFu) {
-                        const uint4 v = ws.landing[u][lane];
-                        if ((v.z >> 24) != kSlotEmpty) {
-                            if (!a.smap.direct && v.x != key[u]) {
-                                if (!(a.debug & 2)) probe_collision(a, key[u], gcodes[u], gvalid[u], tile, ubase + lpv[u]);
-                            } else {
-                                bool any;
-                                const uint32_t code = slot_survivor(Slot{v.x, v.y, v.z, v.w}, gcodes[u], gvalid[u], a.prm.N, &any);
-                                if (any) {
-                                    if (a.debug & 2) ++n_dbg; else push_survivor(a, tile, ubase + lpv[u], code);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
+            if (all_clean) probe_queue<true>(a, ws, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
+            else probe_queue<false>(a, ws, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
             __syncwarp();
             if (fit_mask == 0xffffffffu) break;
         }
@@ -616,9 +660,10 @@ __global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
         } else {  // a seed shared by several records: bucket order, each entry behind its own tag
             const int64_t gb = td.gbase + sv.lp + a.prm.W;
             const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
+            const bool clean = tag_window_clean(gvalid);
             for (uint32_t e = sv.code & ~kWalkBucket;; ++e) {
                 const BucketEntry b = a.bucket[e];
-                if (!tag_rejects(b.tag, gcodes, gvalid, a.prm.N)) verify_warp(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, lane);
+                if (!clean || !tag_rejects(b.tag, gcodes, a.prm.N)) verify_warp(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, lane);
                 if (b.rec_last >> 31) break;
             }
         }
@@ -705,7 +750,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
                      const uint8_t* h_plut, void* stream) {
     if (!c || !h_plut) return fail(MPCR_EINVAL, "null argument");
     if (n_lines && (!h_blob || !h_off || !h_pcr)) return fail(MPCR_EINVAL, "null argument");
-    if (n_lines >= (1u << 30)) return fail(MPCR_EINVAL, "too many STS lines");
+    if (n_lines >= (1u << 29)) return fail(MPCR_EINVAL, "too many STS lines");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c->device));
     free_table(c);
@@ -892,13 +937,24 @@ static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_conti
     mix(n_contigs); mix(origin); mix(sb); mix(se); mix((uint64_t)c->prm.wordsize);
     for (uint32_t i = 0; i < n_contigs; ++i) { mix(contigs[i].gstart); mix(contigs[i].length); }
     if (sig == c->tiles_sig && c->d_tiles) return MPCR_OK;
+    // tile size: kTileBases for big inputs; halved (down to one 2048-position unit) while the scanner's warps would
+    // get fewer than ~8 tiles each, so small inputs still spread over the whole GPU
+    uint64_t span = 0;
+    for (uint32_t i = 0; i < n_contigs; ++i) {
+        const uint64_t g0 = contigs[i].gstart, g1 = g0 + contigs[i].length;
+        const uint64_t a0 = g0 > sb ? g0 : sb, a1 = g1 < se ? g1 : se;
+        if (a1 > a0) span += a1 - a0;
+    }
+    uint64_t tb = kTileBases;
+    const uint64_t want_tiles = 8ull * (uint64_t)c->sm_count * (kScanThreads / 32);
+    while (tb > 2048 && span / tb < want_tiles) tb >>= 1;
     std::vector<TileDesc> tiles;
     for (uint32_t i = 0; i < n_contigs; ++i) {
         const uint64_t L = contigs[i].length, g0 = contigs[i].gstart;
         if (L <= (uint64_t)c->prm.wordsize) continue;  // engine.py:458 (Q3: len <= W is skipped)
         if (g0 & 127u) return fail(MPCR_EINVAL, "contig %u: gstart not a multiple of 128", i);
         if (L >= (1ull << 31)) return fail(MPCR_EINVAL, "contig %u longer than 2^31-1 bases", i);
-        for (uint64_t ls = 0; ls < L; ls += kTileBases) {
+        for (uint64_t ls = 0; ls < L; ls += tb) {
             const uint64_t g = g0 + ls;
             if (g < sb || g >= se) continue;  // tile ownership by first base (tiles never straddle shards)
             TileDesc t;
@@ -906,7 +962,7 @@ static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_conti
             t.contig = i;
             t.lstart = (uint32_t)ls;
             t.length = (uint32_t)L;
-            t.nbases = (uint32_t)(L - ls < (uint64_t)kTileBases ? L - ls : (uint64_t)kTileBases);
+            t.nbases = (uint32_t)(L - ls < tb ? L - ls : tb);
             tiles.push_back(t);
         }
     }

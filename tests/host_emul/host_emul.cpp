@@ -159,8 +159,10 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
                 if (i + 2 < c->n_valid && pairs[i + 2].first == key) n = 3;
             }
             uint32_t s = slot_index(key, c->smap);
-            if (!direct) while ((c->slots[s].tag_n >> 24) != kSlotEmpty) s = (s + 1) & c->smap.mask;
-            c->slots[s] = Slot{key, n == 1 ? rec : i, (c->meta[rec].tag & 0xFFFFFFu) | (n << 24), tag_b};
+            if (!direct) while (c->slots[s].code != kSlotEmpty) s = (s + 1) & c->smap.mask;
+            const uint32_t tag_a = c->meta[rec].tag;
+            c->slots[s] = n == 1 ? Slot{key, rec, tag_a, tag_a}
+                          : n == 2 ? Slot{key, kWalkBucket | i, tag_a, tag_b} : Slot{key, kWalkBucket | i, 0u, 0u};
             c->filter[filter_word(key, cw, words)] |= filter_bits_of(key, W);
         }
     }
@@ -228,10 +230,8 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
                     const uint32_t gvalid = fetch_bits(V, gb + j + prm.W, kTagBases);
                     Slot sl;
                     if (!find_slot(c->slots.data(), c->smap, key, &sl)) continue;
-                    bool any;
-                    const uint32_t code = slot_survivor(sl, gcodes, gvalid, prm.N, &any);
-                    if (!any) continue;
-                    for_each_survivor_record(c->bucket.data(), code, gcodes, gvalid, prm.N, [&](uint32_t rec) {
+                    if (!slot_survives(sl, gcodes, gvalid, prm.N)) continue;
+                    for_each_survivor_record(c->bucket.data(), sl.code, gcodes, gvalid, prm.N, [&](uint32_t rec) {
                         const RecMeta& m = c->meta[rec];
                         verify_record(P4, gbase - (int64_t)ls, (int64_t)L, (int64_t)ls + lp0 + j, m, c->pwords.data(), prm,
                                       [&](int64_t p1, int64_t p2, uint32_t rank) {
