@@ -286,11 +286,12 @@ def run_b200(args):
         sampler.start()
     launches0 = eng.gpu_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scan_ms = []
+    scan_ms, verify_ms = [], []
     ev0.record()
     for _ in range(args.steps):
         _, n_hits = eng.scan_device(layout, shard)
         scan_ms.append(float(lib.mpcr_last_scan_ms(ctx)))
+        verify_ms.append(float(lib.mpcr_last_verify_ms(ctx)))
     ev1.record()
     torch.cuda.synchronize()
     t_ms = ev0.elapsed_time(ev1)
@@ -370,6 +371,14 @@ def run_b200(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         algo_bytes = ALGO_BYTES_PER_BP * my_bp + ALGO_BYTES_PER_HIT * n_hits
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same workload)
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "scan_kernel_ncu.json")))
+            if abs(args.scale - float(prof.get("scale", 1.0))) < 1e-9:
+                traffic = float(prof["dram_bytes_read"]) + float(prof["dram_bytes_write"])
+        except Exception:  # noqa: BLE001
+            pass
         line = dict(
             metric=METRIC, value=value, unit="Gbp/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8",
@@ -380,7 +389,8 @@ def run_b200(args):
                         l2="inputs (2.7 GB of planes per GPU) exceed the 126 MB L2; no flush needed",
                         planted_found=planted_ok, sorted=sorted_ok),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,
-                          traffic=None, kernel="scan_kernel", kernel_ms=kern_ms,
+                          traffic=traffic, kernel="scan_kernel", kernel_ms=kern_ms,
+                          verify_kernel_ms=float(np.mean(verify_ms)),
                           algorithmic_bytes_per_launch=algo_bytes,
                           peak_source="MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650"),
             cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
