@@ -395,58 +395,71 @@ __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ s_
     return t1 & __funnelshift_l(0u, word, x3);
 }
 
-// Stage 2 for the cnt (> 0) queued positions of a warp: kIlp rounds of 32 async slot gathers in flight, then the
-// tag check on what came back.  Straight-line code: lanes past the end of the queue re-probe entry 0 and are
-// masked out, so the kIlp rounds interleave freely.  CLEAN: every base of the unit (and its read-ahead) is
-// A/C/G/T, so the tag verdict can be used without looking at the valid bits.
+// Stage 2 for up to 32*R queued positions of a warp starting at queue index base (R rounds of 32 async slot
+// gathers in flight, then the tag check on what came back).  Straight-line code: lanes past the end of the queue
+// re-probe entry 0 and are masked out, so the R rounds interleave freely.  CLEAN: every base of the unit (and its
+// read-ahead) is A/C/G/T, so the tag verdict can be used without looking at the valid bits.
+template <bool CLEAN, int R>
+__device__ __forceinline__ void probe_rounds(const ScanArgs& a, ScanSmem::Warp& ws, const uint32_t* __restrict__ s_p2,
+                                             const uint32_t* __restrict__ s_v, uint32_t base, uint32_t cnt, int lane,
+                                             uint32_t tile, uint32_t ubase, unsigned long long& n_dbg) {
+    const int W = a.prm.W, N = a.prm.N;
+    const uint32_t wmask = wmask_of(W);
+    const bool hashed = !a.smap.direct;
+    uint32_t lpv[R], key[R], gcodes[R];
+    bool ok[R], dirty[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        const uint32_t qi = base + 32 * u + lane;
+        ok[u] = qi < cnt;
+        const uint32_t lp = ws.queue[ok[u] ? qi : 0u];
+        // key (2W bits) and the 8-base tag window (16 bits) out of three staged words
+        const uint32_t wi = lp >> 4, sh = (lp & 15u) * 2u;
+        const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1], w2 = s_p2[wi + 2];
+        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+        key[u] = x0 & wmask;
+        gcodes[u] = __funnelshift_rc(x0, x1, 2 * W);  // clamped: 2W == 32 -> x1; only the low 16 bits are used
+        lpv[u] = lp;
+        dirty[u] = false;
+        if (!CLEAN) {
+            const uint32_t vb = lp + (uint32_t)W, vi = vb >> 5, vs = vb & 31u;
+            dirty[u] = !tag_window_clean(__funnelshift_r(s_v[vi], s_v[vi + 1], vs));
+        }
+        gather16_async(&ws.landing[u][lane], a.slots + slot_index(key[u], a.smap));
+        gather_commit();
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        if (u == 0) gather_wait<R - 1>();
+        else if (u == 1) gather_wait<(R > 2 ? R - 2 : 0)>();
+        else if (u == 2) gather_wait<(R > 3 ? R - 3 : 0)>();
+        else gather_wait<0>();
+        const uint4 v = ws.landing[u][lane];
+        const bool collide = hashed && v.x != key[u];
+        const bool pass = dirty[u] || !(tag_rejects(v.z, gcodes[u], N) && tag_rejects(v.w, gcodes[u], N));
+        if (ok[u] && v.y != kSlotEmpty && (collide || pass)) {  // about one queued position in a thousand
+            const uint32_t lp = ubase + lpv[u];
+            if (a.debug & 2) ++n_dbg;
+            else if (collide) probe_collision(a, key[u], gcodes[u] & 0xFFFFu, dirty[u] ? 0u : 0xFFu, tile, lp);
+            else push_survivor(a, tile, lp, v.y);
+        }
+    }
+}
+
 template <bool CLEAN>
 __device__ __forceinline__ void probe_queue(const ScanArgs& a, ScanSmem::Warp& ws, const uint32_t* __restrict__ s_p2,
                                             const uint32_t* __restrict__ s_v, uint32_t cnt, int lane, uint32_t tile,
                                             uint32_t ubase, unsigned long long& n_dbg) {
     constexpr int kIlp = ScanSmem::kIlp;
-    const int W = a.prm.W, N = a.prm.N;
-    const uint32_t wmask = wmask_of(W);
-    const bool hashed = !a.smap.direct;
-    for (uint32_t base = 0; base < cnt; base += 32 * kIlp) {
-        uint32_t lpv[kIlp], key[kIlp], gcodes[kIlp];
-        bool ok[kIlp], dirty[kIlp];
-#pragma unroll
-        for (int u = 0; u < kIlp; ++u) {
-            const uint32_t qi = base + 32 * u + lane;
-            ok[u] = qi < cnt;
-            const uint32_t lp = ws.queue[ok[u] ? qi : 0u];
-            // key (2W bits) and the 8-base tag window (16 bits) out of three staged words
-            const uint32_t wi = lp >> 4, sh = (lp & 15u) * 2u;
-            const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1], w2 = s_p2[wi + 2];
-            const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
-            key[u] = x0 & wmask;
-            gcodes[u] = __funnelshift_rc(x0, x1, 2 * W);  // clamped: 2W == 32 -> x1; only the low 16 bits are used
-            lpv[u] = lp;
-            dirty[u] = false;
-            if (!CLEAN) {
-                const uint32_t vb = lp + (uint32_t)W, vi = vb >> 5, vs = vb & 31u;
-                dirty[u] = !tag_window_clean(__funnelshift_r(s_v[vi], s_v[vi + 1], vs));
-            }
-            gather16_async(&ws.landing[u][lane], a.slots + slot_index(key[u], a.smap));
-            gather_commit();
-        }
-#pragma unroll
-        for (int u = 0; u < kIlp; ++u) {
-            if (u == 0) gather_wait<kIlp - 1>();
-            else if (u == 1) gather_wait<(kIlp > 2 ? kIlp - 2 : 0)>();
-            else if (u == 2) gather_wait<(kIlp > 3 ? kIlp - 3 : 0)>();
-            else gather_wait<0>();
-            const uint4 v = ws.landing[u][lane];
-            const bool collide = hashed && v.x != key[u];
-            const bool pass = dirty[u] || !(tag_rejects(v.z, gcodes[u], N) && tag_rejects(v.w, gcodes[u], N));
-            if (ok[u] && v.y != kSlotEmpty && (collide || pass)) {  // about one queued position in a thousand
-                const uint32_t lp = ubase + lpv[u];
-                if (a.debug & 2) ++n_dbg;
-                else if (collide) probe_collision(a, key[u], gcodes[u] & 0xFFFFu, dirty[u] ? 0u : 0xFFu, tile, lp);
-                else push_survivor(a, tile, lp, v.y);
-            }
-        }
-    }
+    static_assert(kIlp >= 1 && kIlp <= 4, "kIlp");
+    uint32_t base = 0;
+    for (; base + 32 * kIlp <= cnt; base += 32 * kIlp)
+        probe_rounds<CLEAN, kIlp>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    const uint32_t rounds = (cnt - base + 31) >> 5;  // tail: only the rounds that hold something
+    if (rounds == 1) probe_rounds<CLEAN, 1>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 2) probe_rounds<CLEAN, (kIlp >= 2 ? 2 : 1)>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 3) probe_rounds<CLEAN, (kIlp >= 3 ? 3 : 1)>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 4) probe_rounds<CLEAN, (kIlp >= 4 ? 4 : 1)>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
 }
 
 // Persistent CTAs, one per SM, made of AUTONOMOUS warps: there is no CTA-wide barrier after the prologue, so
@@ -540,7 +553,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
             const uint2 v0 = *reinterpret_cast<const uint2*>(s_v + 2 * lane);
             const uint2 v1 = *reinterpret_cast<const uint2*>(s_v + 2 * lane + 2);
             my_clean = (v0.x & v0.y & v1.x) == 0xFFFFFFFFu;  // own 64 bases + the 32 behind them (W + tag <= 24)
-            uint64_t wv = window_valid(((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v1.y << 32) | v1.x, W);
+            // W-mer validity of the 64 positions: all ones on clean sequence, else log-doubling over the valid bits
+            uint64_t wv = ~0ull;
+            if (!my_clean) wv = window_valid(((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v1.y << 32) | v1.x, W);
             const uint32_t left = unit_nbases - lp0;
             if (left < 64u) wv &= (1ull << left) - 1ull;
             if (wv) {
@@ -576,6 +591,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         // ---------------- stage 2: warp queue, async slot gathers, tag check ----------------
         const bool all_clean = __all_sync(0xffffffffu, my_clean);
         for (;;) {
+            // reserve queue space: lanes take their share in lane order while it fits (a lane has <= 64 <= kQCap)
             const uint32_t n = __popc(c_lo) + __popc(c_hi);
             uint32_t incl = n;
 #pragma unroll
@@ -587,20 +603,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
             if (total == 0) break;
             const bool fits = incl <= (uint32_t)ScanSmem::kQCap;
             if (fits && n) {
-                uint32_t pos = incl - n;
+                uint16_t* q = ws.queue + (incl - n);
                 while (c_lo) {
-                    const int j = __ffs(c_lo) - 1;
+                    *q++ = (uint16_t)(lp0 + __ffs(c_lo) - 1);
                     c_lo &= c_lo - 1;
-                    ws.queue[pos++] = (uint16_t)(lp0 + j);
                 }
                 while (c_hi) {
-                    const int j = __ffs(c_hi) - 1;
+                    *q++ = (uint16_t)(lp0 + 31 + __ffs(c_hi));
                     c_hi &= c_hi - 1;
-                    ws.queue[pos++] = (uint16_t)(lp0 + 32 + j);
                 }
             }
             const uint32_t fit_mask = __ballot_sync(0xffffffffu, fits);
-            const uint32_t cnt = __shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));  // lane 0 always fits
+            const uint32_t cnt = total <= (uint32_t)ScanSmem::kQCap
+                                     ? total
+                                     : __shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));  // lane 0 always fits
             __syncwarp();
             if (all_clean) probe_queue<true>(a, ws, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
             else probe_queue<false>(a, ws, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
