@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 2
+#define MPCR_ABI_VERSION 3
 
 enum {
     MPCR_OK = 0,
@@ -95,7 +95,24 @@ int mpcr_pack_sequence(mpcr_ctx *ctx, const uint8_t *d_ascii, uint64_t n, uint64
                        uint64_t plane_origin, void *d_plane2, void *d_plane4, void *d_valid,
                        const uint8_t *h_lut, void *stream);
 
-/* Device-side FASTA text ingest (io/fasta.py:43-66 on raw file bytes): see mpcr_fasta_* in a later ABI rev. */
+/* Device-side FASTA text ingest: replaces the whole of FASTALoader.load_file (io/fasta.py:43-66) for ASCII files.
+ * d_text holds the raw file bytes (device memory, n bytes).  mpcr_fasta_index finds the header lines ('>' as the
+ * first non-blank character of a line; lines end at \n, \r or \r\n), blanks them and everything before the first
+ * header IN PLACE, and returns per record the byte range of its header line in the file and where its filtered
+ * sequence (characters of ACGTBDHKMNRSVWXY in either case, case preserved) will sit in the compacted stream.
+ * *flags bit0 = the file has bytes >= 128 (nothing else is computed then; the host applies the locale rules).
+ * MPCR_EOVERFLOW: more than max_records headers, *n_records holds the count.  Synchronous.
+ * mpcr_fasta_compact then writes the kept bytes of all records, contiguous and in file order, to d_seq
+ * (sum of seq_length bytes); d_ws is the workspace mpcr_fasta_index filled (mpcr_fasta_workspace_bytes). */
+typedef struct mpcr_fasta_record {
+    uint64_t header_begin, header_end;  /* file bytes [begin, end) = the header line from '>' to its terminator */
+    uint64_t seq_offset, seq_length;    /* position and size of the record's sequence in the compacted stream   */
+} mpcr_fasta_record;
+uint64_t mpcr_fasta_workspace_bytes(uint64_t n, uint32_t max_records);
+int mpcr_fasta_index(mpcr_ctx *ctx, uint8_t *d_text, uint64_t n, mpcr_fasta_record *h_records, uint32_t max_records,
+                     uint32_t *n_records, uint32_t *flags, void *d_ws, uint64_t ws_bytes, void *stream);
+int mpcr_fasta_compact(mpcr_ctx *ctx, const uint8_t *d_text, uint64_t n, const void *d_ws, uint8_t *d_seq,
+                       void *stream);
 
 /* ---- (2) primer word-hash table ----------------------------------------------------------------- */
 /* Replaces the hashing half of MerPCR.load_sts_file + _hash_value + _reverse_complement + _insert_sts

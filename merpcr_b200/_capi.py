@@ -14,18 +14,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPCR_B200_LIB") or os.path.join(_HERE, "lib", "libmerpcr_b200.so")
 
 MPCR_OK, MPCR_EINVAL, MPCR_ECUDA, MPCR_ENOMEM, MPCR_ESTATE, MPCR_EOVERFLOW = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/merpcr_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_sm_count",
-    "mpcr_pack_sequence", "mpcr_table_build", "mpcr_table_records", "mpcr_table_primer_words", "mpcr_scan",
+    "mpcr_pack_sequence", "mpcr_fasta_workspace_bytes", "mpcr_fasta_index", "mpcr_fasta_compact",
+    "mpcr_table_build", "mpcr_table_records", "mpcr_table_primer_words", "mpcr_scan",
     "mpcr_halo_left", "mpcr_halo_right", "mpcr_tile_bases", "mpcr_sort_hits", "mpcr_launch_count", "mpcr_last_scan_ms", "mpcr_last_verify_ms",
 ]
 
 HIT_DTYPE = np.dtype([("contig", "<u4"), ("pos1", "<u4"), ("pos2", "<u4"), ("rec", "<u4"), ("rank", "<u4"),
                       ("hash_off", "<u4")])
 CONTIG_DTYPE = np.dtype([("gstart", "<u8"), ("length", "<u4"), ("reserved", "<u4")])
+FASTA_RECORD_DTYPE = np.dtype([("header_begin", "<u8"), ("header_end", "<u8"), ("seq_offset", "<u8"),
+                               ("seq_length", "<u8")])
 
 
 class Params(C.Structure):
@@ -49,6 +52,12 @@ class Backend:
         lib.mpcr_ctx_sm_count.argtypes = [vp]
         lib.mpcr_pack_sequence.restype = i32
         lib.mpcr_pack_sequence.argtypes = [vp, vp, u64, u64, u64, vp, vp, vp, vp, vp]
+        lib.mpcr_fasta_workspace_bytes.restype = u64
+        lib.mpcr_fasta_workspace_bytes.argtypes = [u64, u32]
+        lib.mpcr_fasta_index.restype = i32
+        lib.mpcr_fasta_index.argtypes = [vp, vp, u64, vp, u32, C.POINTER(u32), C.POINTER(u32), vp, u64, vp]
+        lib.mpcr_fasta_compact.restype = i32
+        lib.mpcr_fasta_compact.argtypes = [vp, vp, u64, vp, vp, vp]
         lib.mpcr_table_build.restype = i32
         lib.mpcr_table_build.argtypes = [vp, vp, vp, vp, u32, vp, vp]
         lib.mpcr_table_records.restype = i32

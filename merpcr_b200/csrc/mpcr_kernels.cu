@@ -14,11 +14,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/merpcr_b200.h"
 #include "mpcr_core.cuh"
 #include "mpcr_sort.cuh"
+#include "mpcr_fasta.cuh"
 
 using namespace mpcr;
 
@@ -390,9 +392,15 @@ template <bool WIDE>
 __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ s_filter, uint32_t x, uint32_t x3,
                                                  uint32_t cw, uint32_t n_words) {
     const uint32_t word = s_filter[__umulhi(x * cw, n_words)];
+#if MPCR_ACC_FORM == 3
+    const uint32_t t1 = __funnelshift_r(word, 0u, x);  // word >> (x & 31): the bit of interest at the LSB
+    if (!WIDE) return t1 & 1u;
+    return t1 & __funnelshift_r(word, 0u, x3) & 1u;
+#else
     const uint32_t t1 = __funnelshift_l(0u, word, x);  // word << (x & 31)
     if (!WIDE) return t1;
     return t1 & __funnelshift_l(0u, word, x3);
+#endif
 }
 
 // Stage 2 for up to 32*R queued positions of a warp starting at queue index base (R rounds of 32 async slot
@@ -565,13 +573,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
                 auto raw = [&](int j) -> uint32_t {
                     return (j & 15) ? __funnelshift_r(r[j >> 4], r[(j >> 4) + 1], 2 * (j & 15)) : r[j >> 4];
                 };
-#ifndef MPCR_ACC_FORM
-#define MPCR_ACC_FORM 0
-#endif
-                // collect the MSB of each probe result as bit j of the pass mask
+                // collect the probe results (MSB, or LSB in form 3) as bit j of the pass mask
                 auto collect = [&](uint32_t& c, uint32_t u, int j) {
                     if (MPCR_ACC_FORM == 0) c = __funnelshift_l(u, c, 1);          // ALU pipe
-                    else if (MPCR_ACC_FORM == 1) c = c * 2u + __umulhi(u, 2u);     // FMA pipe
+                    else if (MPCR_ACC_FORM == 1) c = c * 2u + __umulhi(u, 2u);     // FMA pipe (two ops)
+                    else if (MPCR_ACC_FORM == 3) c = c * 2u + u;                   // FMA pipe (one IMAD)
                     else if ((int32_t)u < 0) c |= 1u << (j & 31);                  // predicate
                 };
 #pragma unroll
@@ -742,6 +748,10 @@ void mpcr_ctx_destroy(mpcr_ctx* c) {
 
 int mpcr_ctx_sm_count(const mpcr_ctx* c) { return c ? c->sm_count : 0; }
 uint64_t mpcr_launch_count(const mpcr_ctx* c) { return c ? c->launches : 0; }
+uint64_t mpcr_fasta_workspace_bytes(uint64_t n, uint32_t max_records) {
+    const uint64_t n_blk = (n + kFastaBlock - 1) / kFastaBlock, m = max_records ? max_records : 1;
+    return (n_blk + 1) * 8 + ((n_blk + 1) & ~1ull) * 4 + 8 + m * (sizeof(FastaHeader) + 32) + 64;
+}
 
 int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* d_ascii, uint64_t n, uint64_t dst_base, uint64_t plane_origin,
                        void* d_plane2, void* d_plane4, void* d_valid, const uint8_t* h_lut, void* stream) {
@@ -757,6 +767,86 @@ int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* d_ascii, uint64_t n, uint64_t
     const uint32_t blocks = (uint32_t)((strips + 255) / 256);
     pack_kernel<<<blocks, 256, 0, st>>>(d_ascii, n, dst_base - plane_origin, (uint64_t*)d_plane2, (uint64_t*)d_plane4,
                                         (uint64_t*)d_valid, c->d_lut);
+    c->launches++;
+    CU(cudaGetLastError());
+    return MPCR_OK;
+}
+
+// ---- device-side FASTA text ingest (io/fasta.py:43-66) -------------------------------------------------------
+int mpcr_fasta_index(mpcr_ctx* c, uint8_t* d_text, uint64_t n, mpcr_fasta_record* h_records, uint32_t max_records,
+                     uint32_t* n_records, uint32_t* flags, void* d_ws, uint64_t ws_bytes, void* stream) {
+    if (!c || !n_records || !flags) return fail(MPCR_EINVAL, "null argument");
+    if (n && !d_text) return fail(MPCR_EINVAL, "null text pointer");
+    if (max_records && !h_records) return fail(MPCR_EINVAL, "null record buffer");
+    *n_records = 0;
+    *flags = 0;
+    if (n == 0) return MPCR_OK;
+    if (mpcr_fasta_workspace_bytes(n, max_records) > ws_bytes || !d_ws)
+        return fail(MPCR_EINVAL, "workspace too small (need %llu bytes)", (unsigned long long)mpcr_fasta_workspace_bytes(n, max_records));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->device));
+    // workspace: [block offsets u64 (n_blk+1)] [block counts u32 n_blk] [headers max_records] [positions/offsets 4*max] [ctr]
+    const uint64_t n_blk = (n + kFastaBlock - 1) / kFastaBlock;
+    uint8_t* w = (uint8_t*)d_ws;
+    uint64_t* d_off = (uint64_t*)w;                 w += (n_blk + 1) * 8;
+    uint32_t* d_cnt = (uint32_t*)w;                 w += ((n_blk + 1) & ~1ull) * 4 + 8;
+    FastaHeader* d_hdr = (FastaHeader*)w;           w += (size_t)(max_records ? max_records : 1) * sizeof(FastaHeader);
+    uint64_t* d_pos = (uint64_t*)w;                 w += (size_t)(max_records ? max_records : 1) * 16;
+    uint64_t* d_posoff = (uint64_t*)w;              w += (size_t)(max_records ? max_records : 1) * 16;
+    uint32_t* d_ctr = (uint32_t*)w;
+    CU(cudaMemsetAsync(d_ctr, 0, 8, st));
+    const uint64_t n_thr = (n + 15) / 16;
+    fasta_find_headers<<<(uint32_t)((n_thr + 255) / 256), 256, 0, st>>>(d_text, n, d_hdr, max_records, d_ctr, d_ctr + 1);
+    c->launches++;
+    CU(cudaGetLastError());
+    uint32_t ctr[2] = {0, 0};
+    CU(cudaMemcpyAsync(ctr, d_ctr, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_records = ctr[0];
+    *flags = ctr[1];
+    if (ctr[1] & 1u) return MPCR_OK;                      // non-ASCII: the host applies the locale rules itself
+    if (ctr[0] > max_records) return MPCR_EOVERFLOW;      // *n_records holds the required capacity
+    const uint32_t nh = ctr[0];
+    if (nh == 0) return MPCR_OK;                          // no header: no records (everything is "before the first header")
+    std::vector<FastaHeader> hdr(nh);
+    CU(cudaMemcpy(hdr.data(), d_hdr, (size_t)nh * sizeof(FastaHeader), cudaMemcpyDeviceToHost));
+    std::sort(hdr.begin(), hdr.end(), [](const FastaHeader& a, const FastaHeader& b) { return a.begin < b.begin; });
+    CU(cudaMemcpyAsync(d_hdr, hdr.data(), (size_t)nh * sizeof(FastaHeader), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_text, '\n', (size_t)hdr[0].begin, st));   // data before the first header is discarded
+    fasta_blank_headers<<<(nh + 127) / 128, 128, 0, st>>>(d_text, d_hdr, nh);
+    fasta_count<<<(uint32_t)n_blk, kFastaThreads, 0, st>>>(d_text, n, d_cnt);
+    fasta_scan_blocks<<<1, 1024, 0, st>>>(d_cnt, n_blk, d_off);
+    c->launches += 3;
+    // kept-byte offsets at every record boundary: end of header r, start of header r+1 (or n)
+    std::vector<uint64_t> pos(2 * (size_t)nh);
+    for (uint32_t r = 0; r < nh; ++r) {
+        pos[2 * r] = hdr[r].end;
+        pos[2 * r + 1] = r + 1 < nh ? hdr[r + 1].begin : n;
+    }
+    CU(cudaMemcpyAsync(d_pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice, st));
+    fasta_offsets_at<<<(2 * nh + 127) / 128, 128, 0, st>>>(d_text, n, d_off, d_pos, 2 * nh, d_posoff);
+    c->launches++;
+    CU(cudaGetLastError());
+    std::vector<uint64_t> po(2 * (size_t)nh);
+    CU(cudaMemcpyAsync(po.data(), d_posoff, po.size() * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (uint32_t r = 0; r < nh; ++r) {
+        h_records[r].header_begin = hdr[r].begin;
+        h_records[r].header_end = hdr[r].end;
+        h_records[r].seq_offset = po[2 * r];
+        h_records[r].seq_length = po[2 * r + 1] - po[2 * r];
+    }
+    return MPCR_OK;
+}
+
+int mpcr_fasta_compact(mpcr_ctx* c, const uint8_t* d_text, uint64_t n, const void* d_ws, uint8_t* d_seq, void* stream) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (n == 0) return MPCR_OK;
+    if (!d_text || !d_ws || !d_seq) return fail(MPCR_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->device));
+    const uint64_t n_blk = (n + kFastaBlock - 1) / kFastaBlock;
+    fasta_compact<<<(uint32_t)n_blk, kFastaThreads, 0, st>>>(d_text, n, (const uint64_t*)d_ws, d_seq);
     c->launches++;
     CU(cudaGetLastError());
     return MPCR_OK;

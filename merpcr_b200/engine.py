@@ -379,7 +379,7 @@ class MerPCR:
 
     def load_fasta_file(self, filename: str) -> List[FASTARecord]:
         """engine.py:361-363."""
-        return FASTALoader.load_file(filename)
+        return FASTALoader.load_file(filename, engine=self)
 
     # ------------------------------------------------------------------ search (engine.py:365-451)
     def search(self, fasta_records: List[FASTARecord], output_file: str = None) -> int:
@@ -423,9 +423,11 @@ class MerPCR:
         if self._sts_lines is None:  # nothing loaded: an empty table, zero hits (like the reference)
             self._sts_lines = ([], [], [], [], [], [])
             self._build_table()
-        seqs = [r.sequence_bytes for r in fasta_records]
+        # sequences the device-side ingest left in HBM are used in place; everything else is host bytes
+        seqs = [r.sequence_device if getattr(r, "sequence_device", None) is not None and
+                r.sequence_device.device == self._tdev else r.sequence_bytes for r in fasta_records]
         self._check_alphabet(fasta_records, seqs)
-        layout = self.make_layout([int(s.size) for s in seqs])
+        layout = self.make_layout([len(r) for r in fasta_records])
         shard = self.upload(layout, seqs)
         t1 = time.perf_counter()
         hits = self.scan(layout, shard)
@@ -437,8 +439,8 @@ class MerPCR:
     def _check_alphabet(self, records, seqs):
         exotic = set()
         for r, s in zip(records, seqs):
-            if not getattr(r, "_from_loader", False) and s.size:
-                exotic |= genome_exotics(s, self.iupac_mode)
+            if not getattr(r, "_from_loader", False) and len(r):
+                exotic |= genome_exotics(s if isinstance(s, np.ndarray) else r.sequence_bytes, self.iupac_mode)
         if not exotic or exotic == {"X"}:
             zero = "X"
         elif len(exotic) == 1:

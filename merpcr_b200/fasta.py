@@ -91,20 +91,86 @@ def _parse_text(text: str) -> List[FASTARecord]:
     return records
 
 
+DEVICE_INGEST_MIN_BYTES = 1 << 20   # below this the host parser is as fast as the round trip
+
+
+def _device_ingest(filename: str, size: int, engine) -> List[FASTARecord] | None:
+    """FASTA text ingest on the GPU (mpcr_fasta_index / mpcr_fasta_compact): file bytes -> pinned host buffer -> HBM ->
+    header table + filtered bases, which stay in device memory.  Returns None for a non-ASCII file (the host parser
+    applies the locale rules)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _capi
+    lib, be, ctx, dev = engine._be.lib, engine._be, engine._ctx, engine._tdev
+    pinned = dev.type == "cuda"
+    host = torch.empty(size, dtype=torch.uint8, pin_memory=pinned)
+    with open(filename, "rb", buffering=0) as f:
+        view = memoryview(host.numpy())
+        got = 0
+        while got < size:
+            k = f.readinto(view[got:])
+            if not k:
+                break
+            got += k
+    size = got
+    text = host[:size].to(dev, non_blocking=True) if pinned else host[:size].clone()
+    stream = engine._stream()
+    cap = 1 << 16
+    while True:
+        ws = torch.empty(int(lib.mpcr_fasta_workspace_bytes(size, cap)), dtype=torch.uint8, device=dev)
+        recs = np.zeros(cap, dtype=_capi.FASTA_RECORD_DTYPE)
+        n_rec, flags = C.c_uint32(0), C.c_uint32(0)
+        rc = lib.mpcr_fasta_index(ctx, text.data_ptr(), size, recs.ctypes.data, cap, C.byref(n_rec), C.byref(flags),
+                                  ws.data_ptr(), ws.numel(), stream)
+        if rc == _capi.MPCR_EOVERFLOW:
+            # header lines are not blanked yet at this point, so the call can simply be repeated with room for all
+            cap = int(n_rec.value) + 16
+            continue
+        be.check(rc)
+        break
+    if flags.value & 1:
+        return None
+    n = int(n_rec.value)
+    recs = recs[:n]
+    total = int(recs["seq_offset"][-1] + recs["seq_length"][-1]) if n else 0
+    seq = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    be.check(lib.mpcr_fasta_compact(ctx, text.data_ptr(), size, ws.data_ptr(), seq.data_ptr(), stream))
+    engine._sync()
+    raw = host.numpy()
+    out = []
+    for r in recs:
+        defline = raw[int(r["header_begin"]): int(r["header_end"])].tobytes().decode("ascii").strip()
+        a, b = int(r["seq_offset"]), int(r["seq_offset"] + r["seq_length"])
+        rec = FASTARecord(defline=defline, sequence=seq[a:b])
+        rec._from_loader = True
+        out.append(rec)
+    return out
+
+
 class FASTALoader:
     """Class for loading FASTA files (mirror of io/fasta.py:15)."""
 
     @staticmethod
-    def load_file(filename: str) -> List[FASTARecord]:
+    def load_file(filename: str, engine=None) -> List[FASTARecord]:
+        """`engine` (a MerPCR bound to a CUDA device) enables the device-side ingest for files >= 1 MiB; the
+        records then keep their sequences in HBM (`FASTARecord.sequence` still reads back as `str`)."""
         start = time.time()
-        if os.path.getsize(filename) == 0:
+        size = os.path.getsize(filename)
+        if size == 0:
             logger.error(f"FASTA file '{filename}' is empty")
             return []
         logger.info(f"Reading FASTA file: {filename}")
-        a = np.fromfile(filename, dtype=np.uint8)
-        if a.size and int(a.max()) < 128:
-            records = _parse_ascii(a)
-        else:
-            records = _parse_text(a.tobytes().decode(locale.getpreferredencoding(False)))
+        records = None
+        min_bytes = int(os.environ.get("MPCR_DEVICE_INGEST_MIN_BYTES", DEVICE_INGEST_MIN_BYTES))
+        if engine is not None and getattr(engine, "_ctx", None) and size >= min_bytes:
+            records = _device_ingest(filename, size, engine)
+        if records is None:
+            a = np.fromfile(filename, dtype=np.uint8)
+            if a.size and int(a.max()) < 128:
+                records = _parse_ascii(a)
+            else:
+                records = _parse_text(a.tobytes().decode(locale.getpreferredencoding(False)))
         logger.info(f"Loaded {len(records)} sequences in {time.time() - start:.2f} seconds")
         return records

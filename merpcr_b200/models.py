@@ -41,12 +41,19 @@ class FASTARecord:
     `.sequence` always reads back as `str`, `.sequence_bytes` as a uint8 array, each converted lazily.
     """
 
-    __slots__ = ("defline", "label", "_seq_str", "_seq_bytes", "_from_loader")
+    __slots__ = ("defline", "label", "_seq_str", "_seq_bytes", "_seq_dev", "_from_loader")
 
     def __init__(self, defline: str, sequence, label: str = ""):
         self.defline = defline
         self._from_loader = False
-        if isinstance(sequence, str):
+        self._seq_dev = None
+        if hasattr(sequence, "data_ptr") and hasattr(sequence, "device"):
+            # a torch uint8 tensor (the device-side FASTA ingest leaves the filtered bases in HBM); host views
+            # are materialised lazily
+            self._seq_str = None
+            self._seq_bytes = None
+            self._seq_dev = sequence
+        elif isinstance(sequence, str):
             self._seq_str: Optional[str] = sequence
             self._seq_bytes: Optional[np.ndarray] = None
         else:
@@ -64,7 +71,7 @@ class FASTARecord:
     @property
     def sequence(self) -> str:
         if self._seq_str is None:
-            self._seq_str = self._seq_bytes.tobytes().decode("latin-1")
+            self._seq_str = self.sequence_bytes.tobytes().decode("latin-1")
         return self._seq_str
 
     @sequence.setter
@@ -74,6 +81,8 @@ class FASTARecord:
     @property
     def sequence_bytes(self) -> np.ndarray:
         """uint8 view of the sequence; raises ValueError for non-ASCII text (not encodable on the device)."""
+        if self._seq_bytes is None and self._seq_dev is not None:
+            self._seq_bytes = self._seq_dev.cpu().numpy()
         if self._seq_bytes is None:
             try:
                 self._seq_bytes = np.frombuffer(self._seq_str.encode("ascii"), dtype=np.uint8)
@@ -81,8 +90,17 @@ class FASTARecord:
                 raise ValueError(f"sequence '{self.label}' contains non-ASCII characters") from e
         return self._seq_bytes
 
+    @property
+    def sequence_device(self):
+        """The torch uint8 tensor holding the sequence in device memory, or None."""
+        return self._seq_dev
+
     def __len__(self) -> int:
-        return len(self._seq_str) if self._seq_str is not None else int(self._seq_bytes.size)
+        if self._seq_str is not None:
+            return len(self._seq_str)
+        if self._seq_bytes is not None:
+            return int(self._seq_bytes.size)
+        return int(self._seq_dev.numel())
 
     def __eq__(self, other) -> bool:
         if not isinstance(other, FASTARecord):

@@ -89,6 +89,55 @@ int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* ascii, uint64_t n, uint64_t d
     return MPCR_OK;
 }
 
+// ---- FASTA text ingest, serial restatement of io/fasta.py:43-66 for ASCII bytes ------------------------------------
+static bool f_term(uint8_t c) { return c == 10 || c == 13; }
+static bool f_blank(uint8_t c) { return c == 32 || c == 9 || c == 11 || c == 12 || (c >= 28 && c <= 31); }
+static bool f_keep(uint8_t c) {
+    static const char* K = "ACGTBDHKMNRSVWXYacgtbdhkmnrsvwxy";
+    return c && strchr(K, c) != nullptr;
+}
+uint64_t mpcr_fasta_workspace_bytes(uint64_t n, uint32_t max_records) { return 64 + n / 512 + (uint64_t)max_records; }
+int mpcr_fasta_index(mpcr_ctx* c, uint8_t* text, uint64_t n, mpcr_fasta_record* recs, uint32_t max_records,
+                     uint32_t* n_records, uint32_t* flags, void* ws, uint64_t ws_bytes, void*) {
+    if (!c || !n_records || !flags) return fail(MPCR_EINVAL, "null argument");
+    *n_records = 0; *flags = 0;
+    if (n == 0) return MPCR_OK;
+    if (!ws || ws_bytes < mpcr_fasta_workspace_bytes(n, max_records)) return fail(MPCR_EINVAL, "workspace too small");
+    for (uint64_t i = 0; i < n; ++i) if (text[i] >= 128) { *flags = 1; return MPCR_OK; }
+    std::vector<std::pair<uint64_t, uint64_t>> hdr;
+    uint64_t line = 0;
+    while (line < n) {
+        uint64_t e = line;
+        while (e < n && !f_term(text[e])) ++e;
+        uint64_t a = line;
+        while (a < e && f_blank(text[a])) ++a;
+        if (a < e && text[a] == '>') hdr.push_back({a, e});
+        line = e + 1;   // "\r\n" yields an empty line in between, which changes nothing
+    }
+    c->launches++;
+    *n_records = (uint32_t)hdr.size();
+    if (hdr.size() > max_records) return MPCR_EOVERFLOW;
+    if (hdr.empty()) return MPCR_OK;
+    memset(text, '\n', hdr[0].first);
+    for (auto& h : hdr) memset(text + h.first, '\n', h.second - h.first);
+    uint64_t kept = 0, pos = 0;
+    for (size_t r = 0; r < hdr.size(); ++r) {
+        const uint64_t stop = r + 1 < hdr.size() ? hdr[r + 1].first : n;
+        for (; pos < hdr[r].second; ++pos) kept += f_keep(text[pos]);
+        recs[r].header_begin = hdr[r].first; recs[r].header_end = hdr[r].second; recs[r].seq_offset = kept;
+        for (; pos < stop; ++pos) kept += f_keep(text[pos]);
+        recs[r].seq_length = kept - recs[r].seq_offset;
+    }
+    return MPCR_OK;
+}
+int mpcr_fasta_compact(mpcr_ctx* c, const uint8_t* text, uint64_t n, const void*, uint8_t* seq, void*) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n; ++i) if (f_keep(text[i])) seq[k++] = text[i];
+    c->launches++;
+    return MPCR_OK;
+}
+
 struct Fwd { const uint8_t* p; uint8_t operator()(int i) const { return p[i]; } };
 struct Rc { const uint8_t* p; int len; uint8_t operator()(int i) const { return complement_of(p[len - 1 - i]); } };
 

@@ -261,3 +261,76 @@ def test_idempotent_rescan_on_resident_planes(tmp_path):
     b = eng.scan(lay, sh)
     assert len(a) > 500 and np.array_equal(a, b)
     assert eng.last_scan_ms > 0
+
+
+def _random_fasta(seed: int, n_records: int, approx_len: int) -> bytes:
+    """FASTA text with everything the loader rules care about: mixed newlines, blank lines, junk characters, '>' inside
+    lines, indented headers, lower case, IUPAC letters, U (dropped), data before the first header."""
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTacgtNnRYKMSWBDHVXUu-*1 >\t", dtype=np.uint8)
+    weights = np.array([20, 20, 20, 20, 3, 3, 3, 3, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0.3, 0.3])
+    weights = weights / weights.sum()
+    nl = [b"\n", b"\r\n", b"\r"]
+    parts = [b"leading junk ACGT\n"]
+    for r in range(n_records):
+        parts.append(b" " * int(rng.integers(0, 3)) + b">rec%d some text > more" % r + nl[int(rng.integers(0, 3))])
+        total = int(rng.integers(approx_len // 2, approx_len * 2))
+        while total > 0:
+            k = int(min(total, rng.integers(1, 120)))
+            line = rng.choice(alphabet, size=k, p=weights).tobytes()
+            if line.lstrip(b" \t").startswith(b">"):
+                line = b"A" + line
+            parts.append(line + nl[int(rng.integers(0, 3))])
+            if rng.random() < 0.05:
+                parts.append(nl[int(rng.integers(0, 3))])
+            total -= k
+    return b"".join(parts)
+
+
+@pytest.mark.parametrize("seed,n_records,approx_len", [(1, 3, 2000), (2, 40, 30000), (3, 1, 3_000_000), (4, 300, 500)])
+def test_device_fasta_ingest_equals_host_parser(tmp_path, monkeypatch, seed, n_records, approx_len):
+    """mpcr_fasta_index + mpcr_fasta_compact on the GPU == the host parser (pinned to the reference by the goldens)."""
+    from merpcr_b200 import MerPCR
+    from merpcr_b200.fasta import FASTALoader
+    monkeypatch.setenv("MPCR_DEVICE_INGEST_MIN_BYTES", "1")
+    p = tmp_path / "x.fa"
+    p.write_bytes(_random_fasta(seed, n_records, approx_len))
+    eng = MerPCR()
+    host = FASTALoader.load_file(str(p))
+    dev = eng.load_fasta_file(str(p))
+    assert len(dev) == len(host) == n_records
+    assert all(r.sequence_device is not None and r.sequence_device.is_cuda for r in dev)
+    for a, b in zip(dev, host):
+        assert (a.defline, a.label, len(a)) == (b.defline, b.label, len(b))
+        assert np.array_equal(a.sequence_bytes, b.sequence_bytes)
+
+
+def test_fuzz_goldens_bit_exact_with_device_ingest(monkeypatch):
+    """The reference-generated goldens once more, with every FASTA file going through the device-side ingest."""
+    from merpcr_b200 import MerPCR
+    monkeypatch.setenv("MPCR_DEVICE_INGEST_MIN_BYTES", "1")
+    for c in goldens.fuzz_cases():
+        parity.check_fuzz_case(c, MerPCR)
+
+
+def test_search_from_device_resident_records(tmp_path, monkeypatch):
+    """load_fasta_file (device ingest) -> search: the planes are packed straight from HBM, same hits as from host bytes."""
+    from merpcr_b200 import MerPCR
+    monkeypatch.setenv("MPCR_DEVICE_INGEST_MIN_BYTES", "1")
+    rng = synth.Rng(901)
+    contigs = [rng.dna(n) for n in (150000, 80000)]
+    sts = synth.make_sts_set(902, 100, 18, 25, 100, 700)
+    synth.plant_amplicons(903, contigs, sts, 50, sub_mode="cfg3")
+    stsf = _write(tmp_path, "s.sts", synth.sts_lines(sts))
+    fa = b"".join(b">c%d\n" % i + b"\n".join(c[j:j + 60].tobytes() for j in range(0, len(c), 60)) + b"\n"
+                  for i, c in enumerate(contigs))
+    faf = _write(tmp_path, "g.fa", fa)
+    eng = MerPCR(mismatches=1)
+    assert eng.load_sts_file(stsf)
+    recs = eng.load_fasta_file(faf)
+    assert all(r.sequence_device is not None for r in recs)
+    got = parity.engine_hits(eng, recs)
+    want = parity.oracle_hits(dict(wordsize=11, margin=50, mismatches=1), synth.sts_lines(sts).decode(),
+                              [c.tobytes() for c in contigs])
+    assert np.array_equal(got, want) and len(got) > 50
+    assert eng.last_h2d_bytes == 0

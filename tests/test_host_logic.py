@@ -196,3 +196,34 @@ def test_verbose_log_lines(tmp_path, caplog):
     text = caplog.text
     assert "Reading STS file" in text and "Processing sequence: L78833 (117143 bp)" in text
     assert "Total hits found: 1" in text and "Reading FASTA file" in text
+
+
+FASTA_TEXTS = [
+    b">a desc\nACGT\nacgtn\n>b\n\nNNNN\n",
+    b"junk before\nACGT\n>first\r\nAC GT\r\n  >second  \r\nTTTT>AAAA\r\n>third",
+    b"\n\n  \t>x\rACGTRYKM\r\rBDHVSWX\r>y\rUUUU1234acgu\r",
+    b"no header at all\nACGT\n",
+    b">only header\n",
+    b">\x1f>odd\nAC\x0bGT\n\x0c>z\nGG-GG*\n",
+    b">h1\nACGT\n>h2 > not a header marker\nAAAA >CCCC\n>h3\n" + b"ACGTN" * 3000 + b"\n",
+]
+
+
+@pytest.mark.parametrize("i", range(len(FASTA_TEXTS)))
+def test_device_ingest_protocol_equals_host_parser(tmp_path, monkeypatch, i):
+    """The mpcr_fasta_index / mpcr_fasta_compact protocol (driven by merpcr_b200/fasta.py) gives exactly what the host
+    parser gives -- which test_fuzz_goldens pins to the reference's FASTALoader."""
+    from merpcr_b200.fasta import FASTALoader
+    monkeypatch.setenv("MPCR_DEVICE_INGEST_MIN_BYTES", "1")
+    p = tmp_path / "x.fa"
+    p.write_bytes(FASTA_TEXTS[i])
+    eng = _engine()
+    host = FASTALoader.load_file(str(p))
+    try:
+        dev = FASTALoader.load_file(str(p), engine=eng)
+    except IndexError:   # a bare '>' header raises in FASTARecord (models.py:43-49) on both paths
+        with pytest.raises(IndexError):
+            FASTALoader.load_file(str(p))
+        return
+    assert [(r.defline, r.label, r.sequence) for r in dev] == [(r.defline, r.label, r.sequence) for r in host]
+    assert all(r.sequence_device is not None for r in dev)
