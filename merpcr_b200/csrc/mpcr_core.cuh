@@ -207,6 +207,51 @@ MPCR_HD bool compare_primer(const uint64_t* p4, int64_t gb, const uint64_t* pw, 
     return true;
 }
 
+// The same compare for primers of up to 32 bases with everything that does not depend on the genome position
+// hoisted: the verifier compares ONE primer at up to 2M+1 positions (engine.py:543-593).
+struct PrimerView {
+    uint64_t q[2], aux[2], lanes[2], prot[2];
+    int nw;  // words in use (1 or 2); 0 = primer longer than 32 bases, use compare_primer
+};
+MPCR_HD PrimerView make_primer_view(const uint64_t* pw, int len, bool plus, const SearchParams& prm) {
+    PrimerView v;
+    v.nw = len <= 32 ? ((len + 15) >> 4) : 0;
+    int prot_lo, prot_hi;
+    if (plus) { prot_lo = len - prm.X; if (prot_lo < 0) prot_lo = 0; prot_hi = len; }
+    else { prot_lo = 0; prot_hi = prm.X < len ? prm.X : len; }
+    for (int w = 0; w < 2; ++w) {
+        const bool on = w < v.nw;
+        v.q[w] = on ? pw[w] : 0ull;
+        v.aux[w] = on ? pw[v.nw + w] : 0ull;
+        v.lanes[w] = on ? lanes_below(len - 16 * w) : 0ull;
+        v.prot[w] = on ? (lanes_below(prot_hi - 16 * w) & ~lanes_below(prot_lo - 16 * w)) : 0ull;
+    }
+    return v;
+}
+MPCR_HD uint64_t mismatch_lanes(uint64_t g, uint64_t q, uint64_t aux, uint64_t lanes, int iupac) {
+    uint64_t mis;
+    if (iupac) {
+        const uint64_t a = g & q;
+        const uint64_t nz = a | (a >> 1) | (a >> 2) | (a >> 3);
+        const uint64_t gz = ~(g | (g >> 1) | (g >> 2) | (g >> 3));
+        mis = ~(nz | (gz & (aux >> 1)));
+    } else {
+        const uint64_t x = g ^ q;
+        mis = x | (x >> 1) | (x >> 2) | (x >> 3);
+    }
+    return (mis | aux) & lanes;
+}
+MPCR_HD bool compare_view(const uint64_t* p4, int64_t gb, const PrimerView& v, const SearchParams& prm) {
+    // first 16 bases decide almost every position of the mate window: leave as early as the reference does
+    const uint64_t m0 = mismatch_lanes(fetch16(p4, gb), v.q[0], v.aux[0], v.lanes[0], prm.iupac);
+    const int n0 = popc64(m0);
+    if ((m0 & v.prot[0]) || n0 > prm.N) return false;           // :635-640
+    if (v.nw < 2) return true;
+    const uint64_t m1 = mismatch_lanes(fetch16(p4, gb + 16), v.q[1], v.aux[1], v.lanes[1], prm.iupac);
+    if (m1 & v.prot[1]) return false;
+    return n0 + popc64(m1) <= prm.N;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // engine.py:486-489 + 507-597: one bucket entry met at hash position p of a contig of true length L.
 // gcontig = plane-relative base index of the contig's first base (may be negative for a shard that starts
@@ -227,14 +272,16 @@ MPCR_HD void verify_record(const uint64_t* p4, int64_t gcontig, int64_t L, int64
     else { hi = L - k - E; if (hi > prm.M) hi = prm.M; }                          // :535
     lo = E - l1 - l2; if (lo > prm.M) lo = prm.M; if (lo < 0) lo = 0;             // :538-540
     const uint64_t* q2 = pwords + m.p2_word;
+    const PrimerView v2 = make_primer_view(q2, l2, false, prm);
+    auto mate = [&](int64_t q) {
+        return v2.nw ? compare_view(p4, gcontig + q, v2, prm) : compare_primer(p4, gcontig + q, q2, l2, false, prm);
+    };
     const int64_t p2 = k + E - l2;                                                // :543
-    if (compare_primer(p4, gcontig + p2, q2, l2, false, prm)) emit(k, p2 + l2 - 1, (uint32_t)0);
+    if (mate(p2)) emit(k, p2 + l2 - 1, (uint32_t)0);
     const int64_t mx = lo > hi ? lo : hi;
     for (int64_t i = 1; i <= mx; ++i) {                                           // :563
-        if (i <= lo && compare_primer(p4, gcontig + p2 - i, q2, l2, false, prm))  // :565-578
-            emit(k, p2 - i + l2 - 1, (uint32_t)(2 * i - 1));
-        if (i <= hi && compare_primer(p4, gcontig + p2 + i, q2, l2, false, prm))  // :581-593
-            emit(k, p2 + i + l2 - 1, (uint32_t)(2 * i));
+        if (i <= lo && mate(p2 - i)) emit(k, p2 - i + l2 - 1, (uint32_t)(2 * i - 1));   // :565-578
+        if (i <= hi && mate(p2 + i)) emit(k, p2 + i + l2 - 1, (uint32_t)(2 * i));       // :581-593
     }
 }
 

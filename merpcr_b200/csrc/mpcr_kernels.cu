@@ -637,10 +637,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     }
 }
 
-// (4)(5) verifier + hit emitter: one warp per survivor.  Primer 1 is compared by every lane (same addresses,
-// broadcast loads); the mate search of engine.py:543-593 is spread over the lanes, one delta per lane and round,
-// so the 2M+1 window costs ceil((2M+1)/32) rounds of coalesced loads.
-__device__ __forceinline__ void verify_warp(const ScanArgs& a, const TileDesc& td, uint32_t lp, uint32_t rec, int lane) {
+// (4)(5) verifier + hit emitter: one group of kVerifyLanes lanes per survivor (four survivors per warp: the work is
+// a chain of dependent loads, so narrow groups keep more of them in flight).  Primer 1 is compared by every lane of
+// the group (same addresses, broadcast loads); the mate search of engine.py:543-593 is spread over the lanes, one
+// delta per lane and round (rank 0: delta 0, 2i-1: -i, 2i: +i), neighbouring lanes touching neighbouring plane4 words.
+static constexpr int kVerifyLanes = 8;
+
+__device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& td, uint32_t lp, uint32_t rec, int gl) {
     const RecMeta m = a.meta[rec];
     const int64_t gcontig = td.gbase - (int64_t)td.lstart, L = td.length;
     const int l1 = m.len1, l2 = m.len2;
@@ -655,37 +658,41 @@ __device__ __forceinline__ void verify_warp(const ScanArgs& a, const TileDesc& t
     const int64_t p2 = k + E - l2;                                                            // :543
     const uint32_t n_rank = 2u * (uint32_t)(lo > hi ? lo : hi) + 1u;
     const uint64_t* q2 = a.pwords + m.p2_word;
+    const PrimerView v2 = make_primer_view(q2, l2, false, a.prm);   // hoisted out of the delta loop
     const HitEmitter emit{a.hits, a.capacity, a.count, td.contig, rec, (uint32_t)m.hash_off};
-    for (uint32_t r0 = 0; r0 < n_rank; r0 += 32) {
-        const uint32_t rank = r0 + lane;              // 0: delta 0, 2i-1: -i, 2i: +i   (:545-593)
+    for (uint32_t rank = (uint32_t)gl; rank < n_rank; rank += kVerifyLanes) {                 // :545-593
         const int64_t i = (rank + 1) >> 1;
         const bool neg = rank & 1u;
-        if (rank < n_rank && (rank == 0 || (neg ? i <= lo : i <= hi))) {
+        if (rank == 0 || (neg ? i <= lo : i <= hi)) {
             const int64_t q = p2 + (neg ? -i : i);
-            if (compare_primer(a.p4, gcontig + q, q2, l2, false, a.prm)) emit(k, q + l2 - 1, rank);
+            const bool ok = v2.nw ? compare_view(a.p4, gcontig + q, v2, a.prm)
+                                  : compare_primer(a.p4, gcontig + q, q2, l2, false, a.prm);
+            if (ok) emit(k, q + l2 - 1, rank);
         }
     }
 }
 
 __global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
-    const int lane = threadIdx.x & 31;
+    constexpr int kGroups = 32 / kVerifyLanes;
+    const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
     const uint32_t n = min(a.surv_count[0], a.surv_cap);
     for (;;) {
         uint32_t idx = 0;
-        if (lane == 0) idx = atomicAdd(a.surv_count + 1, 1u);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= n) return;
+        if (lane == 0) idx = atomicAdd(a.surv_count + 1, (uint32_t)kGroups);
+        idx = __shfl_sync(0xffffffffu, idx, 0) + group;
+        if (idx - group >= n) return;
+        if (idx >= n) continue;   // the tail of the last batch (the whole warp leaves on the next round)
         const Survivor sv = a.surv[idx];
         const TileDesc td = a.tiles[sv.tile];
         if (!(sv.code & kWalkBucket)) {
-            verify_warp(a, td, sv.lp, sv.code, lane);
+            verify_group(a, td, sv.lp, sv.code, gl);
         } else {  // a seed shared by several records: bucket order, each entry behind its own tag
             const int64_t gb = td.gbase + sv.lp + a.prm.W;
             const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
             const bool clean = tag_window_clean(gvalid);
             for (uint32_t e = sv.code & ~kWalkBucket;; ++e) {
                 const BucketEntry b = a.bucket[e];
-                if (!clean || !tag_rejects(b.tag, gcodes, a.prm.N)) verify_warp(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, lane);
+                if (!clean || !tag_rejects(b.tag, gcodes, a.prm.N)) verify_group(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, gl);
                 if (b.rec_last >> 31) break;
             }
         }

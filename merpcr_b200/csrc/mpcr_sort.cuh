@@ -6,6 +6,7 @@
 // at ~9 passes for a human-sized genome.  Replaces `hits.sort(key=pos1)` (core/engine.py:434) together with
 // the discovery-order tie rule.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -111,6 +112,90 @@ __global__ void __launch_bounds__(kSortThreads) rs_scatter(const Item<NF>* __res
     }
 }
 
+// All passes in ONE cooperative launch for small inputs (n_blk <= kFusedMaxBlocks chunks of 2048 records, one CTA
+// each): per pass a block histogram, a grid barrier, every CTA derives its own 256 scatter offsets from the
+// histograms of all CTAs, the same stable match_any scatter as rs_scatter, a grid barrier.  This is what orders
+// the ~10^5 hits of a human-sized scan: 9 passes in one launch instead of 27 launches.
+static constexpr int kFusedMaxBlocks = 128;
+static constexpr int kMaxPasses = 24;
+struct PassList {
+    PassDesc p[kMaxPasses];
+    int n;
+};
+
+template <int NF>
+__global__ void __launch_bounds__(kSortThreads) rs_sort_fused(Item<NF>* a, Item<NF>* b, uint32_t n, PassList pl,
+                                                              uint32_t* __restrict__ counts /* 256 * gridDim.x */) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t running[256];
+    __shared__ uint32_t wc[kSortThreads / 32][256];
+    __shared__ uint32_t warp_sums[kSortThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nblk = gridDim.x, blk = blockIdx.x;
+    const uint32_t base = blk * kSortItemsPerBlock;
+    Item<NF>*src = a, *dst = b;
+    for (int p = 0; p < pl.n; ++p) {
+        const PassDesc pd = pl.p[p];
+        hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < kSortItemsPerBlock; i += kSortThreads) {
+            const uint32_t idx = base + i;
+            if (idx < n) atomicAdd(&hist[(src[idx].f[pd.field] >> pd.shift) & pd.mask], 1u);
+        }
+        __syncthreads();
+        counts[(uint32_t)tid * nblk + blk] = hist[tid];
+        __threadfence();
+        grid.sync();
+        // offset of (digit tid, this CTA) = records with a smaller digit + records with this digit in earlier CTAs
+        uint32_t total = 0, before = 0;
+        for (uint32_t bb = 0; bb < nblk; ++bb) {
+            const uint32_t v = counts[(uint32_t)tid * nblk + bb];
+            total += v;
+            if (bb < blk) before += v;
+        }
+        uint32_t incl = total;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < wid; ++w) wbase += warp_sums[w];
+        running[tid] = wbase + incl - total + before;
+        for (int w = 0; w < kSortThreads / 32; ++w) wc[w][tid] = 0;
+        __syncthreads();
+        for (int c = 0; c < kSortItemsPerBlock; c += kSortThreads) {
+            const uint32_t idx = base + c + tid;
+            const bool act = idx < n;
+            Item<NF> it;
+            uint32_t d = 0x100u + (uint32_t)lane;  // inactive lanes never match an active digit
+            if (act) { it = src[idx]; d = (it.f[pd.field] >> pd.shift) & pd.mask; }
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            if (act && rank == 0) wc[wid][d] = __popc(peers);
+            __syncthreads();
+            if (act) {
+                uint32_t pre = 0;
+                for (int w = 0; w < wid; ++w) pre += wc[w][d];
+                dst[running[d] + pre + rank] = it;
+            }
+            __syncthreads();
+            {
+                uint32_t tot = 0;
+                for (int w = 0; w < kSortThreads / 32; ++w) { tot += wc[w][tid]; wc[w][tid] = 0; }
+                running[tid] += tot;
+            }
+            __syncthreads();
+        }
+        __threadfence();
+        grid.sync();
+        Item<NF>* t = src; src = dst; dst = t;
+    }
+}
+
 // Host driver: sorts `n` records in d_a using d_b as the ping-pong buffer; the result ends in d_a.
 // d_counts must hold 256 * ceil(n / kSortItemsPerBlock) uint32.  Returns the number of kernels launched.
 template <int NF>
@@ -118,6 +203,19 @@ inline int radix_sort(Item<NF>* d_a, Item<NF>* d_b, uint64_t n, const PassDesc* 
                       cudaStream_t st) {
     if (n < 2 || npass == 0) return 0;
     const uint32_t nblk = (uint32_t)((n + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
+    if (nblk <= (uint32_t)kFusedMaxBlocks && npass <= kMaxPasses) {
+        PassList pl;
+        pl.n = npass;
+        for (int p = 0; p < npass; ++p) pl.p[p] = passes[p];
+        uint32_t n32 = (uint32_t)n;
+        void* args[] = {&d_a, &d_b, &n32, &pl, &d_counts};
+        if (cudaLaunchCooperativeKernel((const void*)rs_sort_fused<NF>, dim3(nblk), dim3(kSortThreads), args, 0, st) ==
+            cudaSuccess) {
+            if (npass & 1) cudaMemcpyAsync(d_a, d_b, n * sizeof(Item<NF>), cudaMemcpyDeviceToDevice, st);
+            return 1;
+        }
+        (void)cudaGetLastError();  // not launchable cooperatively here: fall through to the three-kernel passes
+    }
     Item<NF>*src = d_a, *dst = d_b;
     int launches = 0;
     for (int p = 0; p < npass; ++p) {
