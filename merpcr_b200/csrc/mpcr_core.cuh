@@ -62,6 +62,7 @@ struct SearchParams {
 };
 
 MPCR_HD uint32_t wmask_of(int W) { return W >= 16 ? 0xFFFFFFFFu : ((1u << (2 * W)) - 1u); }
+MPCR_HD uint32_t wmask_bits(int W) { return (1u << W) - 1u; }  // W one-bits (W <= 16)
 
 // ---------------------------------------------------------------------------------------------------------
 // Alphabet (engine.py:99-172).  The genome-side LUT is built by the host (merpcr_b200/alphabet.py) because it

@@ -59,6 +59,7 @@ struct mpcr_ctx {
     uint32_t* d_filter = nullptr;
     uint32_t filter_words = 0;
     uint32_t n_keys = 0;
+    bool dense = false;
     uint32_t max_hash_off = 0, max_len = 0;
     uint64_t max_pcr = 0;
     bool table_ready = false;
@@ -637,6 +638,67 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     }
 }
 
+// Dense tables: when a large share of all 4^W words are seeds (W = 8 with 10^5..10^6 STS, or W = 11 with 10^6) a
+// Bloom filter cannot reject anything, so this scanner skips it.  A warp takes 32 consecutive hash positions:
+//   phase A, one position per lane: key + tag window straight from the planes (coalesced, L1-resident), one slot
+//            load (no shared-memory carve-out here, so plain loads run at full rate), inline tags for seeds with
+//            one or two records;
+//   phase B, one position at a time: seeds shared by three or more records are walked by the whole warp, 32 bucket
+//            entries per coalesced 256-byte load, each entry behind its own tag.
+// Same survivor list and verify_kernel as the sparse path.
+__global__ void __launch_bounds__(256, 3) dense_scan_kernel(const ScanArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int W = a.prm.W, N = a.prm.N;
+    const uint32_t wmask = wmask_of(W);
+    const uint32_t need = (W + kTagBases) >= 32 ? 0xFFFFFFFFu : ((1u << (W + kTagBases)) - 1u);
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= a.n_tiles) return;
+        const TileDesc td = a.tiles[tile];
+        for (uint32_t lp0 = 0; lp0 < td.nbases; lp0 += 32) {
+            const uint32_t lp = lp0 + lane;
+            const int64_t gpos = td.gbase + lp;
+            bool walk = false, clean = false;
+            uint32_t gcodes = 0, start = 0;
+            if (lp < td.nbases) {
+                const uint32_t vb = fetch_bits(a.valid, gpos, W + kTagBases);
+                if ((vb & wmask_bits(W)) == wmask_bits(W)) {          // all W bases of the window hashable (engine.py:483)
+                    clean = (vb & need) == need;                       // ... and the tag window as well
+                    const uint32_t key = extract_key(a.p2, gpos, wmask);
+                    gcodes = fetch_bits(a.p2, 2 * (gpos + W), 2 * kTagBases);
+                    Slot s;
+                    if (find_slot(a.slots, a.smap, key, &s)) {
+                        if (!(s.code & kWalkBucket) || ((s.tag_a | s.tag_b) >> 16)) {
+                            // one or two records: their tags are inline
+                            if (slot_survives(s, gcodes, clean ? 0xFFu : 0u, N)) push_survivor(a, tile, lp, s.code);
+                        } else {
+                            walk = true;                                // three or more (or untagged): phase B
+                            start = s.code & ~kWalkBucket;
+                        }
+                    }
+                }
+            }
+            uint32_t todo = __ballot_sync(0xffffffffu, walk);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t gj = __shfl_sync(0xffffffffu, gcodes, j);
+                const bool cj = __shfl_sync(0xffffffffu, (uint32_t)clean, j) != 0;
+                for (uint32_t e = __shfl_sync(0xffffffffu, start, j);; e += 32) {   // the entry array is padded by 32
+                    const BucketEntry b = a.bucket[e + lane];
+                    const uint32_t last = __ballot_sync(0xffffffffu, (b.rec_last >> 31) != 0);
+                    const int n_in = last ? __ffs(last) : 32;
+                    if (lane < n_in && (!cj || !tag_rejects(b.tag, gj, N)))
+                        push_survivor(a, tile, lp0 + j, b.rec_last & 0x7FFFFFFFu);
+                    if (last) break;
+                }
+            }
+        }
+    }
+}
+
 // (4)(5) verifier + hit emitter: one group of kVerifyLanes lanes per survivor (four survivors per warp: the work is
 // a chain of dependent loads, so narrow groups keep more of them in flight).  Primer 1 is compared by every lane of
 // the group (same addresses, broadcast loads); the mate search of engine.py:543-593 is spread over the lanes, one
@@ -981,7 +1043,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         c->smap.mask = nslots - 1;
         CUG(cudaMalloc(&c->d_slots, (size_t)nslots * sizeof(Slot)));
         CUG(cudaMemsetAsync(c->d_slots, 0xFF, (size_t)nslots * sizeof(Slot), st));
-        CUG(cudaMalloc(&c->d_bucket, ((size_t)c->n_valid + 1) * sizeof(BucketEntry)));
+        CUG(cudaMalloc(&c->d_bucket, ((size_t)c->n_valid + 33) * sizeof(BucketEntry)));   // +32: dense walks read whole warps
+        CUG(cudaMemsetAsync(c->d_bucket, 0, ((size_t)c->n_valid + 33) * sizeof(BucketEntry), st));
         if (c->n_valid) {
             CUG(cudaMemsetAsync(d_stats, 0, 16, st));
             build_buckets<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_pairs, c->n_valid, c->d_meta, c->d_bucket,
@@ -993,6 +1056,11 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         }
         CUG(cudaStreamSynchronize(st));
         c->n_keys = stats[0];
+        // a quarter of all words are seeds (or seeds are shared by several records on average): no filter can help,
+        // use the dense scanner
+        c->dense = c->n_keys && (c->n_valid >= 3ull * c->n_keys ||
+                                 (2 * W < 32 && 4ull * c->n_keys >= (1ull << (2 * W))));
+        if (const char* env = getenv("MPCR_DENSE")) c->dense = atoi(env) != 0;
         c->table_ready = true;
     }
 done:
@@ -1135,7 +1203,9 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     uint32_t grid = (uint32_t)c->sm_count;
     if (grid > c->n_tiles) grid = c->n_tiles;
     CU(cudaEventRecord(c->ev0, st));
-    if (a.prm.W >= 6) {
+    if (c->dense) {
+        dense_scan_kernel<<<c->sm_count * 8, 256, 0, st>>>(a);
+    } else if (a.prm.W >= 6) {
         CU(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         scan_kernel<true><<<grid, kScanThreads, smem, st>>>(a);
     } else {

@@ -165,6 +165,10 @@ CASES = [
      dict(wordsize=11, margin=50, mismatches=2, three_prime_match=1, iupac_mode=1), "cfg3", True, False),
     ("cfg5-like", [400_000, 150_000], 20000, dict(wordsize=8, margin=500, mismatches=0), "none", False, True),
     ("w16", [600_000], 800, dict(wordsize=16, margin=20, mismatches=3, three_prime_match=0), "cfg3", False, False),
+    # several records per seed on average -> the bucket-parallel dense scanner
+    ("dense-w8", [300_000, 120_000], 150000, dict(wordsize=8, margin=100, mismatches=0), "none", False, True),
+    ("dense-w6-iupac", [250_000, 101_000], 20000,
+     dict(wordsize=6, margin=30, mismatches=1, three_prime_match=2, iupac_mode=1), "cfg3", True, False),
 ]
 
 
