@@ -375,7 +375,7 @@ __device__ __noinline__ void verify_serial(const ScanArgs& a, uint32_t tile, uin
 __device__ __noinline__ void push_survivor(const ScanArgs& a, uint32_t tile, uint32_t lp, uint32_t code) {
     const uint32_t k = atomicAdd(a.surv_count, 1u);
     if (k < a.surv_cap) a.surv[k] = Survivor{tile, lp, code, 0u};
-    else verify_serial(a, tile, lp, code);
+    else verify_serial(a, tile, lp, code);   // list full: verify right here
 }
 
 // Hashed mode only: the first probe hit another key's slot -- continue the probe sequence with plain loads.
@@ -682,17 +682,34 @@ __global__ void __launch_bounds__(256, 3) dense_scan_kernel(const ScanArgs a) {
             }
             uint32_t todo = __ballot_sync(0xffffffffu, walk);
             while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t gj = __shfl_sync(0xffffffffu, gcodes, j);
-                const bool cj = __shfl_sync(0xffffffffu, (uint32_t)clean, j) != 0;
-                for (uint32_t e = __shfl_sync(0xffffffffu, start, j);; e += 32) {   // the entry array is padded by 32
-                    const BucketEntry b = a.bucket[e + lane];
-                    const uint32_t last = __ballot_sync(0xffffffffu, (b.rec_last >> 31) != 0);
-                    const int n_in = last ? __ffs(last) : 32;
-                    if (lane < n_in && (!cj || !tag_rejects(b.tag, gj, N)))
-                        push_survivor(a, tile, lp0 + j, b.rec_last & 0x7FFFFFFFu);
-                    if (last) break;
+                // four positions per round: their first 32 entries are loaded together (the walk is latency-bound)
+                constexpr int kBatch = 4;
+                int js[kBatch];
+                uint32_t es[kBatch];
+                BucketEntry bs[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const bool on = todo != 0;
+                    js[u] = on ? __ffs(todo) - 1 : -1;
+                    todo &= todo - 1;                                   // 0 stays 0
+                    es[u] = __shfl_sync(0xffffffffu, start, js[u] & 31);
+                    bs[u] = on ? a.bucket[es[u] + lane] : BucketEntry{0x80000000u, 0u};   // the entry array is padded by 32
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const int j = js[u] & 31;
+                    const uint32_t gj = __shfl_sync(0xffffffffu, gcodes, j);
+                    const bool cj = __shfl_sync(0xffffffffu, (uint32_t)clean, j) != 0;
+                    BucketEntry b = bs[u];
+                    for (uint32_t e = es[u];;) {
+                        const uint32_t last = __ballot_sync(0xffffffffu, (b.rec_last >> 31) != 0);
+                        const int n_in = last ? __ffs(last) : 32;
+                        if (js[u] >= 0 && lane < n_in && (!cj || !tag_rejects(b.tag, gj, N)))
+                            push_survivor(a, tile, lp0 + j, b.rec_last & 0x7FFFFFFFu);
+                        if (last) break;
+                        e += 32;
+                        b = a.bucket[e + lane];
+                    }
                 }
             }
         }
