@@ -72,6 +72,7 @@ struct mpcr_ctx {
     uint32_t* d_tile_counter = nullptr;  // [0] tile counter, [1..2] survivor count / verify cursor
     Survivor* d_surv = nullptr;
     size_t surv_bytes = 0;
+    uint32_t* d_surv_ctl = nullptr;
     // sort scratch
     void* d_sort_tmp = nullptr;
     size_t sort_tmp_cap = 0;
@@ -286,9 +287,9 @@ struct ScanArgs {
     unsigned long long capacity;
     unsigned long long* count;
     uint32_t* tile_counter;
-    Survivor* surv;
+    Survivor* surv;        // kSurvLists sub-lists of surv_cap entries each
     uint32_t surv_cap;
-    uint32_t* surv_count;  // [0] = survivors appended (may exceed surv_cap), [1] = verify work counter
+    uint32_t* surv_ctl;    // per sub-list, 128 bytes apart: [0] entries appended (may exceed surv_cap), [1] verify cursor
     int debug;  // MPCR_DEBUG bit0: stop after the filter stage; bit1: probe the table but drop the survivors
 };
 
@@ -371,11 +372,16 @@ __device__ __noinline__ void verify_serial(const ScanArgs& a, uint32_t tile, uin
     });
 }
 
-// A seed position matched a table entry whose tags did not rule it out: hand it to verify_kernel.
+// A seed position matched a table entry whose tags did not rule it out: hand it to verify_kernel.  The survivor list
+// is split into kSurvLists sub-lists (one counter each, on its own 128-byte line) chosen by the warp, because with
+// N = 2 or ambiguity-rich sequence a human-sized scan appends 10^7 survivors and one hot counter would serialise them.
+static constexpr uint32_t kSurvLists = 256;
+static constexpr uint32_t kSurvCtlStride = 32;   // uint32 units = 128 bytes
 __device__ __noinline__ void push_survivor(const ScanArgs& a, uint32_t tile, uint32_t lp, uint32_t code) {
-    const uint32_t k = atomicAdd(a.surv_count, 1u);
-    if (k < a.surv_cap) a.surv[k] = Survivor{tile, lp, code, 0u};
-    else verify_serial(a, tile, lp, code);   // list full: verify right here
+    const uint32_t list = (blockIdx.x + (threadIdx.x >> 5) * gridDim.x) & (kSurvLists - 1u);
+    const uint32_t k = atomicAdd(a.surv_ctl + list * kSurvCtlStride, 1u);
+    if (k < a.surv_cap) a.surv[(size_t)list * a.surv_cap + k] = Survivor{tile, lp, code, 0u};
+    else verify_serial(a, tile, lp, code);   // sub-list full: verify right here
 }
 
 // Hashed mode only: the first probe hit another key's slot -- continue the probe sequence with plain loads.
@@ -754,27 +760,42 @@ __device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& 
 __global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
     constexpr int kGroups = 32 / kVerifyLanes;
     const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
-    const uint32_t n = min(a.surv_count[0], a.surv_cap);
-    for (;;) {
-        uint32_t idx = 0;
-        if (lane == 0) idx = atomicAdd(a.surv_count + 1, (uint32_t)kGroups);
-        idx = __shfl_sync(0xffffffffu, idx, 0) + group;
-        if (idx - group >= n) return;
-        if (idx >= n) continue;   // the tail of the last batch (the whole warp leaves on the next round)
-        const Survivor sv = a.surv[idx];
-        const TileDesc td = a.tiles[sv.tile];
-        if (!(sv.code & kWalkBucket)) {
-            verify_group(a, td, sv.lp, sv.code, gl);
-        } else {  // a seed shared by several records: bucket order, each entry behind its own tag
-            const int64_t gb = td.gbase + sv.lp + a.prm.W;
-            const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
-            const bool clean = tag_window_clean(gvalid);
-            for (uint32_t e = sv.code & ~kWalkBucket;; ++e) {
-                const BucketEntry b = a.bucket[e];
-                if (!clean || !tag_rejects(b.tag, gcodes, a.prm.N)) verify_group(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, gl);
-                if (b.rec_last >> 31) break;
+    const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // every warp starts at its own sub-list and moves on when that one is drained, until it has seen them all;
+    // 32 sub-lists are looked at per round (one per lane) so that drained ones cost nothing
+    for (uint32_t round = 0; round < kSurvLists / 32; ++round) {
+      const uint32_t my_list = (warp_id + 32 * round + lane) & (kSurvLists - 1u);
+      const uint32_t* my_ctl = a.surv_ctl + my_list * kSurvCtlStride;
+      uint32_t open = __ballot_sync(0xffffffffu, __ldcg(my_ctl + 1) < min(__ldcg(my_ctl), a.surv_cap));
+      while (open) {
+        const int l = __ffs(open) - 1;
+        open &= open - 1;
+        const uint32_t list = (warp_id + 32 * round + l) & (kSurvLists - 1u);
+        uint32_t* ctl = a.surv_ctl + list * kSurvCtlStride;
+        const uint32_t n = min(ctl[0], a.surv_cap);
+        const Survivor* surv = a.surv + (size_t)list * a.surv_cap;
+        for (;;) {
+            uint32_t idx = 0;
+            if (lane == 0) idx = atomicAdd(ctl + 1, (uint32_t)kGroups);
+            idx = __shfl_sync(0xffffffffu, idx, 0) + group;
+            if (idx - group >= n) break;
+            if (idx >= n) continue;   // the tail of the last batch (the whole warp leaves the list on the next round)
+            const Survivor sv = surv[idx];
+            const TileDesc td = a.tiles[sv.tile];
+            if (!(sv.code & kWalkBucket)) {
+                verify_group(a, td, sv.lp, sv.code, gl);
+            } else {  // a seed shared by several records: bucket order, each entry behind its own tag
+                const int64_t gb = td.gbase + sv.lp + a.prm.W;
+                const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
+                const bool clean = tag_window_clean(gvalid);
+                for (uint32_t e = sv.code & ~kWalkBucket;; ++e) {
+                    const BucketEntry b = a.bucket[e];
+                    if (!clean || !tag_rejects(b.tag, gcodes, a.prm.N)) verify_group(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, gl);
+                    if (b.rec_last >> 31) break;
+                }
             }
         }
+      }
     }
 }
 
@@ -806,6 +827,7 @@ int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CU(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CU(cudaMalloc(&c->d_tile_counter, 256));
+    CU(cudaMalloc(&c->d_surv_ctl, 256 * 128));   // kSurvLists control lines
     CU(cudaMalloc(&c->d_lut, 256));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
@@ -829,6 +851,7 @@ void mpcr_ctx_destroy(mpcr_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
     cudaFree(c->d_surv);
+    cudaFree(c->d_surv_ctl);
     delete c;
 }
 
@@ -1195,11 +1218,13 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     c->scan_timed = false;
     if (c->n_tiles == 0 || c->n_valid == 0) return MPCR_OK;
     CU(cudaMemsetAsync(c->d_tile_counter, 0, 16, st));
+    CU(cudaMemsetAsync(c->d_surv_ctl, 0, (size_t)kSurvLists * kSurvCtlStride * 4, st));
     // survivor list: ~1 position in 10^4 survives on random sequence; overflow falls back to in-kernel serial verify
     {
         uint64_t scanned = 0;
         for (uint32_t i = 0; i < n_contigs; ++i) scanned += h_contigs[i].length;
-        size_t want = (size_t)(scanned / 64 + (1u << 16)) * sizeof(Survivor);
+        // entries per sub-list: room for one survivor per 64 scanned positions overall
+        size_t want = (size_t)(scanned / 64 / kSurvLists + 1024) * kSurvLists * sizeof(Survivor);
         if (want > ((size_t)1 << 30)) want = (size_t)1 << 30;
         if (c->surv_bytes < want) {
             int rc2 = ensure((void**)&c->d_surv, &c->surv_bytes, want);
@@ -1215,7 +1240,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
     a.debug = getenv("MPCR_DEBUG") ? atoi(getenv("MPCR_DEBUG")) : 0;
     a.hits = d_hits; a.capacity = capacity; a.count = (unsigned long long*)d_count; a.tile_counter = c->d_tile_counter;
-    a.surv = c->d_surv; a.surv_cap = (uint32_t)(c->surv_bytes / sizeof(Survivor)); a.surv_count = c->d_tile_counter + 1;
+    a.surv = c->d_surv; a.surv_cap = (uint32_t)(c->surv_bytes / sizeof(Survivor) / kSurvLists); a.surv_ctl = c->d_surv_ctl;
     const size_t smem = (size_t)ScanSmem::kFilterOff + (size_t)c->filter_words * 4;
     uint32_t grid = (uint32_t)c->sm_count;
     if (grid > c->n_tiles) grid = c->n_tiles;
