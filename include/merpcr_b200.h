@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 3
+#define MPCR_ABI_VERSION 4
 
 enum {
     MPCR_OK = 0,
@@ -82,6 +82,17 @@ const char *mpcr_last_error(void);
 /* Replaces MerPCR.__init__/_validate_parameters (core/engine.py:47-97). MPCR_EINVAL <-> ValueError. */
 int mpcr_ctx_create(int device, const mpcr_params *params, mpcr_ctx **out);
 void mpcr_ctx_destroy(mpcr_ctx *ctx);
+/* Seed extension for EXACT searches (mismatches 0, no IUPAC mode; MPCR_EINVAL otherwise).  With no mismatch
+ * allowed, a record can only match where the letters following its seed word match too, so a table may be keyed on
+ * a longer word w_ext (wordsize < w_ext <= 16) taken at the SAME hash offset the reference computes -- which is what
+ * keeps candidate-heavy searches (small -W, 10^5..10^6 STS) off the bucket walk.  Records whose primer has no w_ext
+ * plain A/C/G/T letters from that offset cannot be keyed that way, hence two tables (two contexts):
+ *   which = 1 : this context's next table holds only the records that can NOT be extended, keyed by wordsize;
+ *   which = 2 : only the records that can, keyed by w_ext (mpcr_scan then hashes w_ext-mers);
+ *   which = 0 : back to one table with every record (default).
+ * Scanning both tables over the same planes and sorting the concatenated hits gives exactly the one-table result.
+ * Call before mpcr_table_build; drops the current table. */
+int mpcr_ctx_set_seed_extension(mpcr_ctx *ctx, int w_ext, int which);
 /* Multiprocessor count of the context's device (grid sizing is a multiple of this). */
 int mpcr_ctx_sm_count(const mpcr_ctx *ctx);
 

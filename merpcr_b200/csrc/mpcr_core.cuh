@@ -42,7 +42,7 @@ struct RecMeta {
     uint32_t p2_word;
     uint16_t len1, len2;
     uint16_t hash_off;  // engine.py:339-353
-    uint16_t flags;     // bit0: inserted in the table
+    uint16_t flags;     // bit0: the reference inserts the record (it has a clean W-mer); bit1: it is in THIS table
     uint32_t tag;       // primer1 bases right after the seed: 2-bit codes in bits [0,16), compare mask in [16,32)
 };
 static_assert(sizeof(RecMeta) == 32, "RecMeta layout");
@@ -116,6 +116,23 @@ MPCR_HD int first_clean_word(CharAt at, int len, int W, uint32_t* hash_be) {
     }
     *hash_be = 0;
     return -1;
+}
+
+// Seed extension (exact-match searches only, see mpcr_ctx_set_seed_extension): can the seed at offset ho be
+// lengthened to w_ext plain A/C/G/T letters inside the primer?  Returns the extended word (little-endian digits).
+template <class CharAt>
+MPCR_HD bool extended_seed(CharAt at, int len, int ho, int w_ext, uint32_t* key_le) {
+    if (ho < 0 || ho + w_ext > len) return false;
+    uint32_t k = 0;
+    for (int i = 0; i < w_ext; ++i) {
+        const uint8_t c = at(ho + i);
+        uint32_t code;
+        if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3;
+        else return false;
+        k |= code << (2 * i);
+    }
+    *key_le = k;
+    return true;
 }
 
 // Encode a primer into nibble words + aux words.  lut[c] = nibble | never_match<<4 | zero_code_char<<5.

@@ -60,6 +60,8 @@ struct mpcr_ctx {
     uint32_t filter_words = 0;
     uint32_t n_keys = 0;
     bool dense = false;
+    int ext_w = 0, ext_which = 0;   // seed extension (mpcr_ctx_set_seed_extension)
+    int scan_w = 0;                 // word width the scanner keys on: ext_w for an extended table, else wordsize
     uint32_t max_hash_off = 0, max_len = 0;
     uint64_t max_pcr = 0;
     bool table_ready = false;
@@ -173,8 +175,9 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
                                                       const uint32_t* __restrict__ pcr, uint32_t n_lines,
                                                       const uint8_t* __restrict__ plut,
                                                       const uint32_t* __restrict__ word_off,  // 2*n_rec+1 prefix
-                                                      int W, RecMeta* __restrict__ meta, uint64_t* __restrict__ pwords,
-                                                      Item<2>* __restrict__ pairs, uint32_t* __restrict__ stats) {
+                                                      int W, int w_scan, int which, RecMeta* __restrict__ meta,
+                                                      uint64_t* __restrict__ pwords, Item<2>* __restrict__ pairs,
+                                                      uint32_t* __restrict__ stats) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= 2 * n_lines) return;
     const uint32_t line = r >> 1;
@@ -188,28 +191,35 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
     m.p1_word = word_off[2 * r];
     m.p2_word = word_off[2 * r + 1];
     m.tag = 0;
-    uint32_t hbe = 0;
+    uint32_t hbe = 0, kext = 0;
     int ho;
+    bool ext;
+    // which: 0 = every record keyed by its W-mer; 1 = only records whose seed cannot be lengthened to w_scan letters;
+    //        2 = only those that can, keyed by the lengthened word (mpcr_ctx_set_seed_extension)
     if (!minus) {
         m.len1 = (uint16_t)n1; m.len2 = (uint16_t)n2;
         ho = first_clean_word(BlobFwd{pr1}, n1, W, &hbe);
-        if (ho >= 0) m.tag = make_tag(BlobFwd{pr1}, n1, ho, W);
+        ext = which != 0 && extended_seed(BlobFwd{pr1}, n1, ho, w_scan, &kext);
+        if (ho >= 0) m.tag = make_tag(BlobFwd{pr1}, n1, ho, which == 2 ? w_scan : W);
         encode_primer(BlobFwd{pr1}, n1, plut, pwords + m.p1_word);
         encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p2_word);
     } else {
         m.len1 = (uint16_t)n2; m.len2 = (uint16_t)n1;
         ho = first_clean_word(BlobFwd{pr2}, n2, W, &hbe);
-        if (ho >= 0) m.tag = make_tag(BlobFwd{pr2}, n2, ho, W);
+        ext = which != 0 && extended_seed(BlobFwd{pr2}, n2, ho, w_scan, &kext);
+        if (ho >= 0) m.tag = make_tag(BlobFwd{pr2}, n2, ho, which == 2 ? w_scan : W);
         encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p1_word);
         encode_primer(BlobRc{pr1, n1}, n1, plut, pwords + m.p2_word);
     }
+    const bool here = ho >= 0 && (which == 0 || (which == 1 ? !ext : ext));
     m.hash_be = hbe;
-    m.key = reverse_digits(hbe, W);
+    m.key = which == 2 ? kext : reverse_digits(hbe, W);
     m.hash_off = (uint16_t)(ho < 0 ? 0 : ho);
-    m.flags = ho >= 0 ? 1u : 0u;
+    m.flags = (ho >= 0 ? 1u : 0u) | (here ? 2u : 0u);
     meta[r] = m;
     pairs[r].f[0] = m.key;
-    pairs[r].f[1] = r | (ho >= 0 ? 0u : 0x80000000u);
+    pairs[r].f[1] = r | (here ? 0u : 0x80000000u);
+    if (here) atomicAdd(&stats[2], 1u);
     if (ho >= 0) {
         atomicAdd(&stats[0], 1u);
         atomicMax(&stats[1], (uint32_t)ho);
@@ -855,6 +865,19 @@ void mpcr_ctx_destroy(mpcr_ctx* c) {
     delete c;
 }
 
+int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (which < 0 || which > 2) return fail(MPCR_EINVAL, "which must be 0, 1 or 2");
+    if (which != 0) {
+        if (c->prm.mismatches != 0 || c->prm.iupac_mode != 0)
+            return fail(MPCR_EINVAL, "seed extension needs an exact search (mismatches 0, no IUPAC mode)");
+        if (w_ext <= c->prm.wordsize || w_ext > 16) return fail(MPCR_EINVAL, "extended word must be in (wordsize, 16]");
+    }
+    c->ext_w = which ? w_ext : 0;
+    c->ext_which = which;
+    free_table(c);
+    return MPCR_OK;
+}
 int mpcr_ctx_sm_count(const mpcr_ctx* c) { return c ? c->sm_count : 0; }
 uint64_t mpcr_launch_count(const mpcr_ctx* c) { return c ? c->launches : 0; }
 uint64_t mpcr_fasta_workspace_bytes(uint64_t n, uint32_t max_records) {
@@ -970,6 +993,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
     CU(cudaSetDevice(c->device));
     free_table(c);
     const int W = c->prm.wordsize;
+    const int WS = c->ext_which == 2 ? c->ext_w : W;   // key width of THIS table
+    c->scan_w = WS;
     const uint32_t n_rec = 2 * n_lines;
     c->n_rec = n_rec;
     c->n_valid = 0;
@@ -1050,18 +1075,19 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         CUG(cudaMemcpyAsync(d_pcr, h_pcr, (size_t)n_lines * 4, cudaMemcpyHostToDevice, st));
         CUG(cudaMemcpyAsync(d_woff, word_off.data(), word_off.size() * 4, cudaMemcpyHostToDevice, st));
         CUG(cudaMemsetAsync(d_stats, 0, 16, st));
-        encode_records<<<(n_rec + 127) / 128, 128, 0, st>>>(d_blob, d_off, d_pcr, n_lines, d_plut, d_woff, W, c->d_meta,
+        encode_records<<<(n_rec + 127) / 128, 128, 0, st>>>(d_blob, d_off, d_pcr, n_lines, d_plut, d_woff, W,
+                                                             c->ext_which ? c->ext_w : W, c->ext_which, c->d_meta,
                                                              c->d_pwords, d_pairs, d_stats);
         c->launches++;
         CUG(cudaGetLastError());
         uint32_t stats[4] = {0, 0, 0, 0};
         CUG(cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, st));
         CUG(cudaStreamSynchronize(st));
-        c->n_valid = stats[0];
+        c->n_valid = stats[2];        // records in this table (stats[0] = records the reference inserts)
         c->max_hash_off = stats[1];
         // stable sort by (invalid flag, key): LSD passes over the key digits, then the flag bit
         PassDesc passes[8];
-        int np = add_passes(passes, 0, 0, wmask_of(W));
+        int np = add_passes(passes, 0, 0, wmask_of(WS));
         passes[np].field = 1; passes[np].shift = 31; passes[np].mask = 1; ++np;
         const uint32_t nblk = (n_rec + kSortItemsPerBlock - 1) / kSortItemsPerBlock;
         rc = ensure((void**)&c->d_counts, &c->counts_cap, (size_t)256 * nblk * 4);
@@ -1071,8 +1097,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         // slot table: direct-indexed by the key while 4^W slots stay L2-sized (W <= 11 -> 64 MiB), else open
         // addressing at load <= 1/8 (distinct seeds <= min(records, 4^W))
         uint32_t nslots;
-        if (W <= 11) {
-            nslots = 1u << (2 * W);
+        if (WS <= 11) {
+            nslots = 1u << (2 * WS);
             c->smap.direct = 1;
         } else {
             nslots = 1024;
@@ -1089,7 +1115,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
             CUG(cudaMemsetAsync(d_stats, 0, 16, st));
             build_buckets<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_pairs, c->n_valid, c->d_meta, c->d_bucket,
                                                                      c->d_slots, c->smap, c->d_filter,
-                                                                     c->filter_words, filter_mul(W), W, d_stats);
+                                                                     c->filter_words, filter_mul(WS), WS, d_stats);
             c->launches++;
             CUG(cudaGetLastError());
             CUG(cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, st));
@@ -1099,7 +1125,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         // a quarter of all words are seeds (or seeds are shared by several records on average): no filter can help,
         // use the dense scanner
         c->dense = c->n_keys && (c->n_valid >= 3ull * c->n_keys ||
-                                 (2 * W < 32 && 4ull * c->n_keys >= (1ull << (2 * W))));
+                                 (2 * WS < 32 && 4ull * c->n_keys >= (1ull << (2 * WS))));
         if (const char* env = getenv("MPCR_DENSE")) c->dense = atoi(env) != 0;
         c->table_ready = true;
     }
@@ -1235,8 +1261,8 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.p2 = (const uint64_t*)d_plane2; a.p4 = (const uint64_t*)d_plane4; a.valid = (const uint64_t*)d_valid;
     a.tiles = c->d_tiles; a.n_tiles = c->n_tiles;
     a.slots = c->d_slots; a.smap = c->smap; a.bucket = c->d_bucket; a.meta = c->d_meta; a.pwords = c->d_pwords;
-    a.filter = c->d_filter; a.filter_words = c->filter_words; a.cw = filter_mul(c->prm.wordsize);
-    a.prm.W = c->prm.wordsize; a.prm.M = c->prm.margin; a.prm.N = c->prm.mismatches; a.prm.X = c->prm.three_prime_match;
+    a.filter = c->d_filter; a.filter_words = c->filter_words; a.cw = filter_mul(c->scan_w);
+    a.prm.W = c->scan_w; a.prm.M = c->prm.margin; a.prm.N = c->prm.mismatches; a.prm.X = c->prm.three_prime_match;
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
     a.debug = getenv("MPCR_DEBUG") ? atoi(getenv("MPCR_DEBUG")) : 0;
     a.hits = d_hits; a.capacity = capacity; a.count = (unsigned long long*)d_count; a.tile_counter = c->d_tile_counter;

@@ -46,6 +46,7 @@ MIN_MARGIN, MAX_MARGIN = 0, 10000
 MIN_THREE_PRIME_MATCH = 0
 MIN_PCR_SIZE, MAX_PCR_SIZE = 1, 10000
 
+EXTENDED_WORDSIZE = 11        # key width of the second table of exact, candidate-heavy searches
 PCR_SIZE_CLAMP = 0x7FFFFFFF   # any expected size >= a contig length behaves identically (engine.py:531-533)
 PLANE_SLACK_BASES = 1024      # read-ahead of the last strip / last primer window
 
@@ -133,6 +134,7 @@ class MerPCR:
         else:
             self._tdev = torch.device("cpu")
         self._ctx = None
+        self._ctx_ext = None      # second table for exact, candidate-heavy searches (mpcr_ctx_set_seed_extension)
         self._create_ctx()
         # parsed STS lines kept so the table can be re-encoded if a sequence brings an unusual alphabet
         self._sts_lines = None
@@ -144,18 +146,23 @@ class MerPCR:
         self.last_timing: Dict[str, float] = {}
 
     # ------------------------------------------------------------------ plumbing
-    def _create_ctx(self):
+    def _new_ctx(self):
         import ctypes as C
         p = _capi.Params(self.wordsize, self.margin, self.mismatches, self.three_prime_match,
                          1 if self.iupac_mode else 0)
         h = C.c_void_p()
         self._be.check(self._be.lib.mpcr_ctx_create(self.device, C.byref(p), C.byref(h)))
-        self._ctx = h
+        return h
+
+    def _create_ctx(self):
+        self._ctx = self._new_ctx()
 
     def close(self):
-        ctx, self._ctx = getattr(self, "_ctx", None), None
-        if ctx:
-            self._be.lib.mpcr_ctx_destroy(ctx)
+        for name in ("_ctx", "_ctx_ext"):
+            ctx = getattr(self, name, None)
+            setattr(self, name, None)
+            if ctx:
+                self._be.lib.mpcr_ctx_destroy(ctx)
 
     def __del__(self):
         try:
@@ -174,7 +181,10 @@ class MerPCR:
 
     @property
     def gpu_launches(self) -> int:
-        return int(self._be.lib.mpcr_launch_count(self._ctx))
+        n = int(self._be.lib.mpcr_launch_count(self._ctx))
+        if self._ctx_ext:
+            n += int(self._be.lib.mpcr_launch_count(self._ctx_ext))
+        return n
 
     # ------------------------------------------------------------------ engine.py:80-97
     def _validate_parameters(self):
@@ -272,8 +282,26 @@ class MerPCR:
             np.zeros(0, dtype=np.uint32)
         plut = primer_lut(self.iupac_mode, self._zero_char)
         lib = self._be.lib
+        # Exact searches whose seed words cover a quarter or more of all 4^W words (small -W, many STS) are keyed on
+        # 11-letter words instead: two tables -- the records whose seed extends to 11 plain letters, and the rest.
+        w_ext = EXTENDED_WORDSIZE
+        extend = (self.mismatches == 0 and not self.iupac_mode and self.wordsize < w_ext and
+                  8 * n >= 4 ** self.wordsize)
+        env = os.environ.get("MPCR_SEED_EXTENSION")
+        if env is not None and self.mismatches == 0 and not self.iupac_mode and self.wordsize < w_ext:
+            extend = env not in ("0", "")
+        self._be.check(lib.mpcr_ctx_set_seed_extension(self._ctx, w_ext if extend else 0, 1 if extend else 0))
         self._be.check(lib.mpcr_table_build(self._ctx, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
                                             plut.ctypes.data, self._stream()))
+        if extend:
+            if not self._ctx_ext:
+                self._ctx_ext = self._new_ctx()
+            self._be.check(lib.mpcr_ctx_set_seed_extension(self._ctx_ext, w_ext, 2))
+            self._be.check(lib.mpcr_table_build(self._ctx_ext, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
+                                                plut.ctypes.data, self._stream()))
+        elif self._ctx_ext:
+            lib.mpcr_ctx_destroy(self._ctx_ext)
+            self._ctx_ext = None
         ho = np.full(2 * n, -1, dtype=np.int32)
         hv = np.zeros(2 * n, dtype=np.uint32)
         self._be.check(lib.mpcr_table_records(self._ctx, ho.ctypes.data, hv.ctypes.data))
@@ -534,7 +562,6 @@ class MerPCR:
     def scan(self, layout: dict, sh: _Shard, sort: bool = True) -> np.ndarray:
         """scanner + verifier + hit emitter + ordering on the resident planes; returns the hits on the host."""
         hits, n = self.scan_device(layout, sh, sort=sort)
-        self.last_scan_ms = float(self._be.lib.mpcr_last_scan_ms(self._ctx))
         if n == 0:
             return np.zeros(0, dtype=_capi.HIT_DTYPE)
         raw = hits[: n * _capi.HIT_DTYPE.itemsize].cpu().numpy()
@@ -547,17 +574,27 @@ class MerPCR:
         contigs = layout["contigs"]
         if sh.count is None:
             sh.count = torch.zeros(1, dtype=torch.int64, device=self._tdev)
-        cap = 1 << 16 if sh.hits is None else sh.hits.numel() // _capi.HIT_DTYPE.itemsize
+        isz = _capi.HIT_DTYPE.itemsize
+        cap = 1 << 16 if sh.hits is None else sh.hits.numel() // isz
+        ctxs = [self._ctx] + ([self._ctx_ext] if self._ctx_ext else [])
         while True:
-            if sh.hits is None or sh.hits.numel() < cap * _capi.HIT_DTYPE.itemsize:
-                sh.hits = torch.empty(cap * _capi.HIT_DTYPE.itemsize, dtype=torch.uint8, device=self._tdev)
-            self._be.check(lib.mpcr_scan(self._ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
-                                         sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.bases, sh.begin,
-                                         sh.end, sh.hits.data_ptr(), cap, sh.count.data_ptr(), self._stream()))
-            n = int(sh.count.item())  # synchronises the stream
-            if n <= cap:
+            if sh.hits is None or sh.hits.numel() < cap * isz:
+                sh.hits = torch.empty(cap * isz, dtype=torch.uint8, device=self._tdev)
+            n, need = 0, 0
+            self.last_scan_ms = 0.0
+            for ctx in ctxs:   # every table appends behind the previous one's hits
+                room = max(cap - n, 0)
+                self._be.check(lib.mpcr_scan(ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
+                                             sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.bases, sh.begin,
+                                             sh.end, sh.hits.data_ptr() + n * isz if room else 0, room,
+                                             sh.count.data_ptr(), self._stream()))
+                k = int(sh.count.item())  # synchronises the stream
+                self.last_scan_ms += float(lib.mpcr_last_scan_ms(ctx))
+                need += k
+                n += min(k, room)
+            if need <= cap:
                 break
-            cap = max(n, 2 * cap)
+            cap = max(need, 2 * cap)
         if sort and n > 1:
             self._be.check(lib.mpcr_sort_hits(self._ctx, sh.hits.data_ptr(), n, self._stream()))
         return sh.hits, n

@@ -41,6 +41,7 @@ struct mpcr_ctx {
     uint64_t max_pcr = 0;
     bool table_ready = false;
     uint64_t launches = 0;
+    int ext_w = 0, ext_which = 0, scan_w = 0;
 };
 
 extern "C" {
@@ -61,6 +62,17 @@ int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
     return MPCR_OK;
 }
 void mpcr_ctx_destroy(mpcr_ctx* c) { delete c; }
+int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (which < 0 || which > 2) return fail(MPCR_EINVAL, "which must be 0, 1 or 2");
+    if (which != 0) {
+        if (c->prm.mismatches != 0 || c->prm.iupac_mode != 0)
+            return fail(MPCR_EINVAL, "seed extension needs an exact search (mismatches 0, no IUPAC mode)");
+        if (w_ext <= c->prm.wordsize || w_ext > 16) return fail(MPCR_EINVAL, "extended word must be in (wordsize, 16]");
+    }
+    c->ext_w = which ? w_ext : 0; c->ext_which = which; c->table_ready = false;
+    return MPCR_OK;
+}
 int mpcr_ctx_sm_count(const mpcr_ctx*) { return 1; }
 uint64_t mpcr_launch_count(const mpcr_ctx* c) { return c ? c->launches : 0; }
 float mpcr_last_scan_ms(mpcr_ctx*) { return 0.f; }
@@ -145,6 +157,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
                      const uint8_t* plut, void*) {
     if (!c || !plut) return fail(MPCR_EINVAL, "null argument");
     const int W = c->prm.wordsize;
+    const int WS = c->ext_which == 2 ? c->ext_w : W;
+    c->scan_w = WS;
     c->n_rec = 2 * n_lines; c->n_valid = 0; c->max_hash_off = 0; c->max_len = 0; c->max_pcr = 0;
     c->meta.assign(c->n_rec, RecMeta{});
     c->pwords.clear();
@@ -165,21 +179,25 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
             c->pwords.resize(c->pwords.size() + 2 * ((l1 + 15) / 16));
             m.p2_word = (uint32_t)c->pwords.size();
             c->pwords.resize(c->pwords.size() + 2 * ((l2 + 15) / 16));
-            uint32_t hbe = 0; int ho;
+            uint32_t hbe = 0, kext = 0; int ho; bool ext;
             if (!minus) {
                 ho = first_clean_word(Fwd{pr1}, n1, W, &hbe);
-                if (ho >= 0) m.tag = make_tag(Fwd{pr1}, n1, ho, W);
+                ext = c->ext_which != 0 && extended_seed(Fwd{pr1}, n1, ho, c->ext_w, &kext);
+                if (ho >= 0) m.tag = make_tag(Fwd{pr1}, n1, ho, WS);
                 encode_primer(Fwd{pr1}, n1, plut, c->pwords.data() + m.p1_word);
                 encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p2_word);
             } else {
                 ho = first_clean_word(Fwd{pr2}, n2, W, &hbe);
-                if (ho >= 0) m.tag = make_tag(Fwd{pr2}, n2, ho, W);
+                ext = c->ext_which != 0 && extended_seed(Fwd{pr2}, n2, ho, c->ext_w, &kext);
+                if (ho >= 0) m.tag = make_tag(Fwd{pr2}, n2, ho, WS);
                 encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p1_word);
                 encode_primer(Rc{pr1, n1}, n1, plut, c->pwords.data() + m.p2_word);
             }
-            m.hash_be = hbe; m.key = reverse_digits(hbe, W);
-            m.hash_off = (uint16_t)(ho < 0 ? 0 : ho); m.flags = ho >= 0;
-            if (ho >= 0) { pairs.push_back({m.key, r}); c->max_hash_off = std::max(c->max_hash_off, (uint32_t)ho); }
+            const bool here = ho >= 0 && (c->ext_which == 0 || (c->ext_which == 1 ? !ext : ext));
+            m.hash_be = hbe; m.key = c->ext_which == 2 ? kext : reverse_digits(hbe, W);
+            m.hash_off = (uint16_t)(ho < 0 ? 0 : ho); m.flags = (ho >= 0 ? 1 : 0) | (here ? 2 : 0);
+            if (ho >= 0) c->max_hash_off = std::max(c->max_hash_off, (uint32_t)ho);
+            if (here) pairs.push_back({m.key, r});
         }
     }
     c->pwords.resize(c->pwords.size() + 2);
@@ -188,10 +206,10 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
     uint32_t words = 39616;  // what a B200 scanner CTA has room for; any multiple of 4 works
     if (const char* env = getenv("MPCR_FILTER_WORDS")) { long v = atol(env); if (v >= 4) words = (uint32_t)v & ~3u; }
     c->filter.assign(words, 0);
-    const uint32_t cw = filter_mul(W);
+    const uint32_t cw = filter_mul(WS);
     uint32_t nslots = 1024;
-    const bool direct = getenv("MPCR_EMUL_HASHED") ? false : W <= 11;  // the env switch lets CPU tests cover both modes
-    if (direct) nslots = 1u << (2 * W);
+    const bool direct = getenv("MPCR_EMUL_HASHED") ? false : WS <= 11;  // the env switch lets CPU tests cover both modes
+    if (direct) nslots = 1u << (2 * WS);
     else while (nslots < 2u * c->n_valid + 2u) nslots <<= 1;
     c->smap = SlotMap{nslots - 1, direct ? 1u : 0u};
     c->slots.assign(nslots, Slot{~0u, ~0u, ~0u, ~0u});
@@ -212,7 +230,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
             const uint32_t tag_a = c->meta[rec].tag;
             c->slots[s] = n == 1 ? Slot{key, rec, tag_a, tag_a}
                           : n == 2 ? Slot{key, kWalkBucket | i, tag_a, tag_b} : Slot{key, kWalkBucket | i, 0u, 0u};
-            c->filter[filter_word(key, cw, words)] |= filter_bits_of(key, W);
+            c->filter[filter_word(key, cw, words)] |= filter_bits_of(key, WS);
         }
     }
     c->table_ready = true;
@@ -254,13 +272,14 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
     if (!c->table_ready) return fail(MPCR_ESTATE, "mpcr_scan called before mpcr_table_build");
     if ((origin & 127u) || (sb & 127u)) return fail(MPCR_EINVAL, "origin / shard_begin must be multiples of 128");
     const uint64_t *P2 = (const uint64_t*)plane2, *P4 = (const uint64_t*)plane4, *V = (const uint64_t*)valid;
-    SearchParams prm{c->prm.wordsize, c->prm.margin, c->prm.mismatches, c->prm.three_prime_match, c->prm.iupac_mode ? 1 : 0};
+    SearchParams prm{c->scan_w, c->prm.margin, c->prm.mismatches, c->prm.three_prime_match, c->prm.iupac_mode ? 1 : 0};
+    const int W_ref = c->prm.wordsize;   // the contig-length rule of engine.py:458 uses the reference's word size
     const uint32_t wmask = wmask_of(prm.W), cw = filter_mul(prm.W);
     uint64_t n = 0;
     c->launches++;
     for (uint32_t ci = 0; ci < n_contigs && c->n_valid; ++ci) {
         const uint64_t L = contigs[ci].length, g0 = contigs[ci].gstart;
-        if (L <= (uint64_t)prm.W) continue;
+        if (L <= (uint64_t)W_ref) continue;
         if (g0 & 127u) return fail(MPCR_EINVAL, "contig %u: gstart not a multiple of 128", ci);
         for (uint64_t ls = 0; ls < L; ls += kTileBases) {
             const uint64_t g = g0 + ls;

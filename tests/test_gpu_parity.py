@@ -338,3 +338,38 @@ def test_search_from_device_resident_records(tmp_path, monkeypatch):
                               [c.tobytes() for c in contigs])
     assert np.array_equal(got, want) and len(got) > 50
     assert eng.last_h2d_bytes == 0
+
+
+def test_seed_extension_two_tables_equal_one_on_device(tmp_path, monkeypatch):
+    """mpcr_ctx_set_seed_extension on the GPU: exact search keyed on 11-letter words (+ the table of records that cannot
+    be extended) == the plain one-table search == the oracle."""
+    from merpcr_b200 import MerPCR
+    rng = synth.Rng(711)
+    contigs = [rng.dna(n) for n in (400_000, 150_000, 9)]
+    sts = synth.make_sts_set(712, 30000, 9, 25, 60, 400)
+    sts["p1"][::7, 9] = ord("N")
+    expected = synth.plant_amplicons(713, contigs[:2], sts, 30, plant_count=200)
+    text = synth.sts_lines(sts)
+    stsf = _write(tmp_path, "s.sts", text)
+    params = dict(wordsize=8, margin=30, mismatches=0)
+    want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MPCR_SEED_EXTENSION", flag)
+        eng = MerPCR(**params)
+        assert eng.load_sts_file(stsf)
+        assert (eng._ctx_ext is not None) == (flag == "1")
+        got = parity.engine_hits(eng, _records(contigs))
+        assert np.array_equal(got, want), flag
+        eng.close()
+    assert len(want) >= len(expected) > 100
+
+
+def test_fuzz_goldens_with_seed_extension_on_device(monkeypatch):
+    from merpcr_b200 import MerPCR
+    monkeypatch.setenv("MPCR_SEED_EXTENSION", "1")
+    n = 0
+    for c in goldens.fuzz_cases():
+        if c["params"].get("mismatches", 0) == 0 and not c["params"].get("iupac_mode", 0):
+            parity.check_fuzz_case(c, MerPCR)
+            n += 1
+    assert n > 5

@@ -227,3 +227,37 @@ def test_device_ingest_protocol_equals_host_parser(tmp_path, monkeypatch, i):
         return
     assert [(r.defline, r.label, r.sequence) for r in dev] == [(r.defline, r.label, r.sequence) for r in host]
     assert all(r.sequence_device is not None for r in dev)
+
+
+def test_seed_extension_two_tables_equal_one(tmp_path, monkeypatch):
+    """Exact searches may be keyed on 11-letter words (mpcr_ctx_set_seed_extension): records that extend + records
+    that do not, scanned separately and merged, must give the one-table result (== the oracle)."""
+    from merpcr_b200 import FASTARecord, MerPCR
+    rng = synth.Rng(611)
+    contigs = [rng.dna(n) for n in (60000, 25000, 9)]
+    sts = synth.make_sts_set(612, 4000, 9, 25, 60, 400)       # short primers: many cannot be extended to 11
+    sts["p1"][::7, 9] = ord("N")                                # ... and some have an ambiguity right after the seed
+    expected = synth.plant_amplicons(613, contigs[:2], sts, 30, plant_count=60)
+    text = synth.sts_lines(sts)
+    stsf = tmp_path / "s.sts"
+    stsf.write_bytes(text)
+    params = dict(wordsize=8, margin=30, mismatches=0)
+    recs = [FASTARecord(f">c{i}", c) for i, c in enumerate(contigs)]
+    want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MPCR_SEED_EXTENSION", flag)
+        eng = MerPCR(**params)
+        assert eng.load_sts_file(str(stsf))
+        assert (eng._ctx_ext is not None) == (flag == "1")
+        got = parity.engine_hits(eng, recs)
+        assert np.array_equal(got, want), flag
+        eng.close()
+    assert len(want) >= len(expected) > 20
+
+
+def test_fuzz_goldens_with_seed_extension(monkeypatch):
+    monkeypatch.setenv("MPCR_SEED_EXTENSION", "1")
+    from merpcr_b200 import MerPCR
+    for c in goldens.fuzz_cases():
+        if c["params"].get("mismatches", 0) == 0 and not c["params"].get("iupac_mode", 0):
+            parity.check_fuzz_case(c, MerPCR)
