@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 4
+#define MPCR_ABI_VERSION 5
 
 enum {
     MPCR_OK = 0,
@@ -124,6 +124,31 @@ int mpcr_fasta_index(mpcr_ctx *ctx, uint8_t *d_text, uint64_t n, mpcr_fasta_reco
                      uint32_t *n_records, uint32_t *flags, void *d_ws, uint64_t ws_bytes, void *stream);
 int mpcr_fasta_compact(mpcr_ctx *ctx, const uint8_t *d_text, uint64_t n, const void *d_ws, uint8_t *d_seq,
                        void *stream);
+
+/* ---- host-side text helpers (no device work) ---------------------------------------------------- */
+/* One accepted STS line: byte ranges of its fields inside the file text, its 1-based line number, and the expected
+ * size when the field is a plain "123" or "100-200" (-1: the host must apply int() itself, engine.py:304-322). */
+typedef struct mpcr_sts_line {
+    uint32_t line_no;
+    uint32_t id_off, id_len, p1_off, p1_len, p2_off, p2_len, size_off, size_len, alias_off, alias_len;
+    int32_t pcr_size;
+} mpcr_sts_line;
+/* Replaces the line loop of MerPCR.load_sts_file (core/engine.py:216-243) for ASCII files: universal newlines, strip(),
+ * blank / '#' lines skipped, split on tabs, lines whose primers are shorter than wordsize counted in *short_primers
+ * and dropped.  *bad_line != 0: 1-based number of the first line with fewer than 4 fields (the load fails there).
+ * *flags bit0: the text has bytes >= 128 (nothing parsed; the host applies the locale rules).
+ * MPCR_EOVERFLOW: more than max_lines accepted lines, *n_lines holds the count. */
+int mpcr_sts_parse(const uint8_t *text, uint64_t n, int32_t wordsize, int32_t default_pcr_size, mpcr_sts_line *lines,
+                   uint32_t max_lines, uint32_t *n_lines, uint32_t *bad_line, uint32_t *short_primers, uint32_t *flags);
+/* Upper-cased primers of the accepted lines back to back (primer1, primer2 per line) + 2*n_lines+1 offsets: the
+ * h_blob / h_off arguments of mpcr_table_build. */
+int mpcr_sts_blob(const uint8_t *text, const mpcr_sts_line *lines, uint32_t n_lines, uint8_t *blob, uint64_t *off);
+/* Replaces the formatting loop of MerPCR.search (core/engine.py:437-444): one line
+ * "label\tpos1+1..pos2+1\tid\talias\t(+|-)\n" per hit, in the given order.  hits are host memory; rec >> 1 indexes
+ * `lines`; labels[label_off[c] .. label_off[c+1]) is the label of contig c.  Returns the bytes needed; the text is
+ * written only when it fits out_cap. */
+uint64_t mpcr_format_hits(const mpcr_hit *hits, uint64_t n, const uint8_t *text, const mpcr_sts_line *lines,
+                          const uint8_t *labels, const uint64_t *label_off, uint8_t *out, uint64_t out_cap);
 
 /* ---- (2) primer word-hash table ----------------------------------------------------------------- */
 /* Replaces the hashing half of MerPCR.load_sts_file + _hash_value + _reverse_complement + _insert_sts

@@ -14,19 +14,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPCR_B200_LIB") or os.path.join(_HERE, "lib", "libmerpcr_b200.so")
 
 MPCR_OK, MPCR_EINVAL, MPCR_ECUDA, MPCR_ENOMEM, MPCR_ESTATE, MPCR_EOVERFLOW = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # every symbol include/merpcr_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_set_seed_extension", "mpcr_ctx_sm_count",
     "mpcr_pack_sequence", "mpcr_fasta_workspace_bytes", "mpcr_fasta_index", "mpcr_fasta_compact",
-    "mpcr_table_build", "mpcr_table_records", "mpcr_table_primer_words", "mpcr_scan",
+    "mpcr_sts_parse", "mpcr_sts_blob", "mpcr_format_hits", "mpcr_table_build", "mpcr_table_records", "mpcr_table_primer_words", "mpcr_scan",
     "mpcr_halo_left", "mpcr_halo_right", "mpcr_tile_bases", "mpcr_sort_hits", "mpcr_launch_count", "mpcr_last_scan_ms", "mpcr_last_verify_ms",
 ]
 
 HIT_DTYPE = np.dtype([("contig", "<u4"), ("pos1", "<u4"), ("pos2", "<u4"), ("rec", "<u4"), ("rank", "<u4"),
                       ("hash_off", "<u4")])
 CONTIG_DTYPE = np.dtype([("gstart", "<u8"), ("length", "<u4"), ("reserved", "<u4")])
+STS_LINE_DTYPE = np.dtype([(k, "<u4") for k in ("line_no", "id_off", "id_len", "p1_off", "p1_len", "p2_off", "p2_len",
+                                                "size_off", "size_len", "alias_off", "alias_len")] + [("pcr_size", "<i4")])
 FASTA_RECORD_DTYPE = np.dtype([("header_begin", "<u8"), ("header_end", "<u8"), ("seq_offset", "<u8"),
                                ("seq_length", "<u8")])
 
@@ -60,6 +62,13 @@ class Backend:
         lib.mpcr_fasta_index.argtypes = [vp, vp, u64, vp, u32, C.POINTER(u32), C.POINTER(u32), vp, u64, vp]
         lib.mpcr_fasta_compact.restype = i32
         lib.mpcr_fasta_compact.argtypes = [vp, vp, u64, vp, vp, vp]
+        lib.mpcr_sts_parse.restype = i32
+        lib.mpcr_sts_parse.argtypes = [vp, u64, C.c_int32, C.c_int32, vp, u32, C.POINTER(u32), C.POINTER(u32),
+                                       C.POINTER(u32), C.POINTER(u32)]
+        lib.mpcr_sts_blob.restype = i32
+        lib.mpcr_sts_blob.argtypes = [vp, vp, u32, vp, vp]
+        lib.mpcr_format_hits.restype = u64
+        lib.mpcr_format_hits.argtypes = [vp, u64, vp, vp, vp, vp, vp, u64]
         lib.mpcr_table_build.restype = i32
         lib.mpcr_table_build.argtypes = [vp, vp, vp, vp, u32, vp, vp]
         lib.mpcr_table_records.restype = i32

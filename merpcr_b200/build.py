@@ -10,7 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "mpcr_kernels.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("mpcr_core.cuh", "mpcr_sort.cuh", "mpcr_fasta.cuh")] + \
+DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("mpcr_core.cuh", "mpcr_sort.cuh", "mpcr_fasta.cuh", "mpcr_hostio.h")] + \
     [os.path.join(os.path.dirname(HERE), "include", "merpcr_b200.h")]
 OUT = os.path.join(HERE, "lib", "libmerpcr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -21,6 +21,7 @@
 #include "mpcr_core.cuh"
 #include "mpcr_sort.cuh"
 #include "mpcr_fasta.cuh"
+#include "mpcr_hostio.h"
 
 using namespace mpcr;
 
@@ -902,6 +903,25 @@ int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* d_ascii, uint64_t n, uint64_t
     c->launches++;
     CU(cudaGetLastError());
     return MPCR_OK;
+}
+
+// ---- host-side text helpers (mpcr_hostio.h) ------------------------------------------------------------------
+int mpcr_sts_parse(const uint8_t* text, uint64_t n, int32_t wordsize, int32_t default_pcr_size, mpcr_sts_line* lines,
+                   uint32_t max_lines, uint32_t* n_lines, uint32_t* bad_line, uint32_t* short_primers, uint32_t* flags) {
+    if (!n_lines || !bad_line || !short_primers || !flags || (n && !text) || (max_lines && !lines))
+        return fail(MPCR_EINVAL, "null argument");
+    const int rc = sts_parse_impl(text, n, wordsize, default_pcr_size, lines, max_lines, n_lines, bad_line, short_primers, flags);
+    if (rc == MPCR_EINVAL) return fail(MPCR_EINVAL, "STS text of 4 GiB or more is not supported");
+    return rc;
+}
+int mpcr_sts_blob(const uint8_t* text, const mpcr_sts_line* lines, uint32_t n_lines, uint8_t* blob, uint64_t* off) {
+    if (!off || (n_lines && (!text || !lines || !blob))) return fail(MPCR_EINVAL, "null argument");
+    sts_blob_impl(text, lines, n_lines, blob, off);
+    return MPCR_OK;
+}
+uint64_t mpcr_format_hits(const mpcr_hit* hits, uint64_t n, const uint8_t* text, const mpcr_sts_line* lines,
+                          const uint8_t* labels, const uint64_t* label_off, uint8_t* out, uint64_t out_cap) {
+    return format_hits_impl(hits, n, text, lines, labels, label_off, out, out_cap);
 }
 
 // ---- device-side FASTA text ingest (io/fasta.py:43-66) -------------------------------------------------------

@@ -76,6 +76,52 @@ def _primer_bytes(p: str) -> bytes:
     return bytes(ord(ch) if ord(ch) < 128 else 0x80 for ch in p)
 
 
+class _STSLines:
+    """The accepted STS lines of one file (after the text rules of engine.py:216-247), in file order.
+
+    Two producers: the native parser (`mpcr_sts_parse`: field byte ranges into the file text, nothing decoded until
+    somebody asks) and the Python line loop kept for non-ASCII files."""
+
+    def __init__(self, n, sizes, line_nos, *, raw=None, lines=None, ids=None, aliases=None, p1s=None, p2s=None):
+        self.n = n
+        self.sizes = sizes          # adjusted expected sizes (Python ints or an int64 array)
+        self.line_nos = line_nos
+        self.raw, self.lines = raw, lines
+        self._ids, self._aliases, self._p1s, self._p2s = ids, aliases, p1s, p2s
+
+    def _field(self, off_key, len_key, upper=False):
+        raw, L = self.raw, self.lines
+        out = []
+        for a, k in zip(L[off_key].tolist(), L[len_key].tolist()):
+            t = raw[a: a + k].tobytes().decode("ascii")
+            out.append(t.upper() if upper else t)
+        return out
+
+    @property
+    def ids(self):
+        if self._ids is None:
+            self._ids = self._field("id_off", "id_len")
+        return self._ids
+
+    @property
+    def aliases(self):
+        if self._aliases is None:
+            self._aliases = self._field("alias_off", "alias_len")
+        return self._aliases
+
+    @property
+    def p1s(self):
+        if self._p1s is None:
+            self._p1s = self._field("p1_off", "p1_len", upper=True)
+        return self._p1s
+
+    @property
+    def p2s(self):
+        if self._p2s is None:
+            self._p2s = self._field("p2_off", "p2_len", upper=True)
+        return self._p2s
+
+
 class _Shard:
     """Device-resident packed genome of one shard (planes + the layout they were built for)."""
 
@@ -115,7 +161,8 @@ class MerPCR:
         self.threads = threads
         self.max_sts_line_length = max_sts_line_length
 
-        self.sts_records: List[STSRecord] = []
+        self._sts_records: Optional[List[STSRecord]] = []
+        self._hash_offsets = np.zeros(0, dtype=np.int32)
         self._sts_table: Optional[Dict[int, List[STSRecord]]] = {}
         self.max_pcr_size = 0
         self.total_hits = 0
@@ -213,41 +260,16 @@ class MerPCR:
         self._sts_table = {}
         self.max_pcr_size = 0
         self._sts_lines = None
-        bad_primers_short = 0
-        bad_pcr_size = 0
 
-        ids, aliases, p1s, p2s, sizes, line_nos = [], [], [], [], [], []
-        with open(filename, "r") as file:
-            line_no = 0
-            for line in file:
-                line_no += 1
-                line = line.strip()
-                if not line or line.startswith("#"):
-                    continue
-                fields = line.split("\t")
-                if len(fields) < 4:
-                    logger.error(f"Bad STS file format at line {line_no}. Expected at least 4 fields.")
-                    self.max_pcr_size = 0
-                    return False
-                primer1 = fields[1].upper()
-                primer2 = fields[2].upper()
-                pcr_size = self._parse_pcr_size(fields[3])
-                if len(primer1) < self.wordsize or len(primer2) < self.wordsize:
-                    bad_primers_short += 1
-                    continue
-                if len(primer1) + len(primer2) > pcr_size:
-                    bad_pcr_size += 1
-                    pcr_size = len(primer1) + len(primer2)
-                if pcr_size > self.max_pcr_size:
-                    self.max_pcr_size = pcr_size
-                ids.append(fields[0])
-                aliases.append(fields[4] if len(fields) > 4 else "")
-                p1s.append(primer1)
-                p2s.append(primer2)
-                sizes.append(pcr_size)
-                line_nos.append(line_no)
-
-        self._sts_lines = (ids, aliases, p1s, p2s, sizes, line_nos)
+        raw = np.fromfile(filename, dtype=np.uint8)
+        parsed = self._parse_sts_native(raw)
+        if parsed is None:                      # non-ASCII text: the Python line loop with the locale's decoding
+            parsed = self._parse_sts_python(filename)
+        if parsed is False:
+            self.max_pcr_size = 0
+            return False
+        self._sts_lines, bad_primers_short, bad_pcr_size = parsed
+        self.max_pcr_size = int(max(self._sts_lines.sizes)) if self._sts_lines.n else 0
         self._zero_char = "X"
         bad_primers_ambig = self._build_table()
 
@@ -260,28 +282,101 @@ class MerPCR:
         if bad_pcr_size > 0:
             logger.warning(f"{bad_pcr_size} STSs have a primer length sum greater than the pcr size: "
                            "expected pcr size adjusted")
-        logger.info(f"Loaded {len(self.sts_records)} STS records in {time.time() - start_time:.2f} seconds")
+        n_records = int(np.count_nonzero(self._hash_offsets >= 0))
+        logger.info(f"Loaded {n_records} STS records in {time.time() - start_time:.2f} seconds")
         return True
+
+    def _parse_sts_native(self, raw: np.ndarray):
+        """engine.py:216-251 through mpcr_sts_parse.  Returns (lines, n_short, n_adjusted), False for a malformed file,
+        None when the text is not ASCII."""
+        import ctypes as C
+        lib = self._be.lib
+        cap = int(np.count_nonzero((raw == 10) | (raw == 13))) + 1
+        lines = np.zeros(cap, dtype=_capi.STS_LINE_DTYPE)
+        n, bad, short, flags = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        self._be.check(lib.mpcr_sts_parse(raw.ctypes.data, raw.size, self.wordsize, self.default_pcr_size,
+                                          lines.ctypes.data, cap, C.byref(n), C.byref(bad), C.byref(short), C.byref(flags)))
+        if flags.value & 1:
+            return None
+        if bad.value:
+            logger.error(f"Bad STS file format at line {bad.value}. Expected at least 4 fields.")
+            return False
+        lines = lines[: n.value]
+        sizes = lines["pcr_size"].astype(np.int64)
+        slow = np.flatnonzero(sizes < 0)        # fields that are not a plain "123" / "100-200": Python's own int()
+        if slow.size:
+            sizes = sizes.astype(object)
+            for i in slow.tolist():
+                a, k = int(lines["size_off"][i]), int(lines["size_len"][i])
+                sizes[i] = self._parse_pcr_size(raw[a: a + k].tobytes().decode("ascii"))
+        l12 = lines["p1_len"].astype(np.int64) + lines["p2_len"].astype(np.int64)
+        adjust = l12 > sizes                    # engine.py:245-247
+        n_adjusted = int(np.count_nonzero(adjust))
+        if n_adjusted:
+            sizes = np.where(adjust, l12, sizes)
+        src = _STSLines(int(n.value), sizes, lines["line_no"], raw=raw, lines=lines)
+        return src, int(short.value), n_adjusted
+
+    def _parse_sts_python(self, filename: str):
+        """The reference's line loop (engine.py:216-251), for files the native parser hands back."""
+        bad_primers_short = bad_pcr_size = 0
+        ids, aliases, p1s, p2s, sizes, line_nos = [], [], [], [], [], []
+        with open(filename, "r") as file:
+            line_no = 0
+            for line in file:
+                line_no += 1
+                line = line.strip()
+                if not line or line.startswith("#"):
+                    continue
+                fields = line.split("\t")
+                if len(fields) < 4:
+                    logger.error(f"Bad STS file format at line {line_no}. Expected at least 4 fields.")
+                    return False
+                primer1 = fields[1].upper()
+                primer2 = fields[2].upper()
+                pcr_size = self._parse_pcr_size(fields[3])
+                if len(primer1) < self.wordsize or len(primer2) < self.wordsize:
+                    bad_primers_short += 1
+                    continue
+                if len(primer1) + len(primer2) > pcr_size:
+                    bad_pcr_size += 1
+                    pcr_size = len(primer1) + len(primer2)
+                ids.append(fields[0])
+                aliases.append(fields[4] if len(fields) > 4 else "")
+                p1s.append(primer1)
+                p2s.append(primer2)
+                sizes.append(pcr_size)
+                line_nos.append(line_no)
+        src = _STSLines(len(ids), sizes, line_nos, ids=ids, aliases=aliases, p1s=p1s, p2s=p2s)
+        return src, bad_primers_short, bad_pcr_size
 
     def _build_table(self) -> int:
         """Ship the accepted STS lines to the device, build the table there, read back hash offsets."""
-        ids, aliases, p1s, p2s, sizes, line_nos = self._sts_lines
-        n = len(ids)
-        lens = np.empty(2 * n + 1, dtype=np.uint64)
-        lens[0] = 0
-        parts = []
-        for i in range(n):
-            b1, b2 = _primer_bytes(p1s[i]), _primer_bytes(p2s[i])
-            parts.append(b1)
-            parts.append(b2)
-            lens[2 * i + 1] = len(b1)
-            lens[2 * i + 2] = len(b2)
-        off = np.cumsum(lens, dtype=np.uint64)
-        blob = np.frombuffer(b"".join(parts) + b"\0" * 16, dtype=np.uint8)
-        pcr = np.minimum(np.asarray(sizes, dtype=np.int64), PCR_SIZE_CLAMP).astype(np.uint32) if n else \
-            np.zeros(0, dtype=np.uint32)
-        plut = primer_lut(self.iupac_mode, self._zero_char)
+        src = self._sts_lines
+        n = src.n
         lib = self._be.lib
+        if src.lines is not None:               # native source: upper-cased primer blob straight from the file text
+            blob = np.zeros(int(src.lines["p1_len"].sum(dtype=np.int64) + src.lines["p2_len"].sum(dtype=np.int64)) + 16,
+                            dtype=np.uint8)
+            off = np.zeros(2 * n + 1, dtype=np.uint64)
+            self._be.check(lib.mpcr_sts_blob(src.raw.ctypes.data, src.lines.ctypes.data, n, blob.ctypes.data,
+                                             off.ctypes.data))
+        else:
+            lens = np.empty(2 * n + 1, dtype=np.uint64)
+            lens[0] = 0
+            parts = []
+            for i in range(n):
+                b1, b2 = _primer_bytes(src.p1s[i]), _primer_bytes(src.p2s[i])
+                parts.append(b1)
+                parts.append(b2)
+                lens[2 * i + 1] = len(b1)
+                lens[2 * i + 2] = len(b2)
+            off = np.cumsum(lens, dtype=np.uint64)
+            blob = np.frombuffer(b"".join(parts) + b"\0" * 16, dtype=np.uint8)
+        pcr = np.array([min(int(x), PCR_SIZE_CLAMP) for x in src.sizes], dtype=np.uint32) \
+            if isinstance(src.sizes, list) or getattr(src.sizes, "dtype", None) == object else \
+            np.minimum(np.asarray(src.sizes, dtype=np.int64), PCR_SIZE_CLAMP).astype(np.uint32)
+        plut = primer_lut(self.iupac_mode, self._zero_char)
         # Exact searches whose seed words cover a quarter or more of all 4^W words (small -W, many STS) are keyed on
         # 11-letter words instead: two tables -- the records whose seed extends to 11 plain letters, and the rest.
         w_ext = EXTENDED_WORDSIZE
@@ -305,30 +400,43 @@ class MerPCR:
         ho = np.full(2 * n, -1, dtype=np.int32)
         hv = np.zeros(2 * n, dtype=np.uint32)
         self._be.check(lib.mpcr_table_records(self._ctx, ho.ctypes.data, hv.ctypes.data))
-        # host mirror of the records (engine.py:253-281), insertion order == record-slot order
-        self.sts_records = []
-        self._sts_table = None
+        # insertion order == record-slot order ("+" then "-" of each line, engine.py:265-281)
+        inserted = ho >= 0
         rec_to_idx = np.full(2 * n, -1, dtype=np.int64)
-        bad_ambig = 0
-        for i in range(n):
-            if ho[2 * i] >= 0:
-                rec_to_idx[2 * i] = len(self.sts_records)
-                self.sts_records.append(STSRecord(id=ids[i], primer1=p1s[i], primer2=p2s[i], pcr_size=sizes[i],
-                                                  alias=aliases[i], offset=line_nos[i],
-                                                  hash_offset=int(ho[2 * i]), direct="+"))
-            else:
-                bad_ambig += 1
-            if ho[2 * i + 1] >= 0:
-                rec_to_idx[2 * i + 1] = len(self.sts_records)
-                self.sts_records.append(STSRecord(id=ids[i], primer1=p2s[i],
-                                                  primer2=self._reverse_complement(p1s[i]), pcr_size=sizes[i],
-                                                  alias=aliases[i], offset=line_nos[i],
-                                                  hash_offset=int(ho[2 * i + 1]), direct="-"))
-            else:
-                bad_ambig += 1
+        rec_to_idx[inserted] = np.arange(int(np.count_nonzero(inserted)), dtype=np.int64)
         self._rec_to_idx = rec_to_idx
+        self._hash_offsets = ho
         self._hashes = hv
-        return bad_ambig
+        self._sts_records = None                # host mirror of the records: built when somebody looks at it
+        self._sts_table = None
+        return int(2 * n - np.count_nonzero(inserted))
+
+    @property
+    def sts_records(self) -> List[STSRecord]:
+        """The reference's record list (engine.py:253-281, insertion order), materialised lazily from the parsed lines
+        and the hash offsets the device computed."""
+        if self._sts_records is None:
+            src, ho = self._sts_lines, self._hash_offsets
+            recs: List[STSRecord] = []
+            if src is not None and src.n:
+                ids, aliases, p1s, p2s = src.ids, src.aliases, src.p1s, src.p2s
+                sizes = [int(x) for x in src.sizes]
+                line_nos = [int(x) for x in src.line_nos]
+                hol = ho.tolist()
+                for i in range(src.n):
+                    if hol[2 * i] >= 0:
+                        recs.append(STSRecord(id=ids[i], primer1=p1s[i], primer2=p2s[i], pcr_size=sizes[i],
+                                              alias=aliases[i], offset=line_nos[i], hash_offset=hol[2 * i], direct="+"))
+                    if hol[2 * i + 1] >= 0:
+                        recs.append(STSRecord(id=ids[i], primer1=p2s[i], primer2=self._reverse_complement(p1s[i]),
+                                              pcr_size=sizes[i], alias=aliases[i], offset=line_nos[i],
+                                              hash_offset=hol[2 * i + 1], direct="-"))
+            self._sts_records = recs
+        return self._sts_records
+
+    @sts_records.setter
+    def sts_records(self, value):
+        self._sts_records = value
 
     @property
     def sts_table(self) -> Dict[int, List[STSRecord]]:
@@ -419,24 +527,41 @@ class MerPCR:
             output = sys.stdout
         try:
             hits = self.search_hits(fasta_records) if fasta_records else np.zeros(0, dtype=_capi.HIT_DTYPE)
-            bounds = np.searchsorted(hits["contig"], np.arange(len(fasta_records) + 1))
-            recs = self.sts_records
-            r2i = self._rec_to_idx
-            for ci, record in enumerate(fasta_records):
-                seq_label = record.label
-                logger.info(f"Processing sequence: {seq_label} ({len(record)} bp)")
-                h = hits[bounds[ci]: bounds[ci + 1]]
-                if h.size == 0:
-                    continue
-                p1 = (h["pos1"].astype(np.int64) + 1).tolist()
-                p2 = (h["pos2"].astype(np.int64) + 1).tolist()
-                ri = r2i[h["rec"]].tolist()
-                lines = []
-                for a, b, r in zip(p1, p2, ri):
-                    sts = recs[r]
-                    lines.append(f"{seq_label}\t{a}..{b}\t{sts.id}\t{sts.alias}\t({sts.direct})\n")
-                output.write("".join(lines))
-                total_hits += len(lines)
+            for record in fasta_records:
+                logger.info(f"Processing sequence: {record.label} ({len(record)} bp)")
+            total_hits = int(hits.size)
+            src = self._sts_lines
+            labels = [r.label for r in fasta_records]
+            if hits.size and src is not None and src.lines is not None and all(lb.isascii() for lb in labels):
+                # engine.py:437-444 in one native pass over the hit array (ids / aliases straight from the file text)
+                lb = [x.encode("ascii") for x in labels]
+                label_off = np.zeros(len(lb) + 1, dtype=np.uint64)
+                label_off[1:] = np.cumsum([len(x) for x in lb])
+                label_blob = np.frombuffer(b"".join(lb) + b"\0", dtype=np.uint8)
+                hits = np.ascontiguousarray(hits)
+                fmt = self._be.lib.mpcr_format_hits
+                args = (hits.ctypes.data, hits.size, src.raw.ctypes.data, src.lines.ctypes.data, label_blob.ctypes.data,
+                        label_off.ctypes.data)
+                need = int(fmt(*args, None, 0))
+                buf = np.empty(need, dtype=np.uint8)
+                used = int(fmt(*args, buf.ctypes.data, need))
+                output.write(buf[:used].tobytes().decode("ascii"))
+            elif hits.size:
+                bounds = np.searchsorted(hits["contig"], np.arange(len(fasta_records) + 1))
+                recs = self.sts_records
+                r2i = self._rec_to_idx
+                for ci, record in enumerate(fasta_records):
+                    h = hits[bounds[ci]: bounds[ci + 1]]
+                    if h.size == 0:
+                        continue
+                    p1 = (h["pos1"].astype(np.int64) + 1).tolist()
+                    p2 = (h["pos2"].astype(np.int64) + 1).tolist()
+                    ri = r2i[h["rec"]].tolist()
+                    lines = []
+                    for a, b, r in zip(p1, p2, ri):
+                        sts = recs[r]
+                        lines.append(f"{record.label}\t{a}..{b}\t{sts.id}\t{sts.alias}\t({sts.direct})\n")
+                    output.write("".join(lines))
         finally:
             if output is not sys.stdout:
                 output.close()
@@ -449,7 +574,7 @@ class MerPCR:
         reference's output order; `contig` indexes `fasta_records`, positions are 0-based inclusive."""
         t0 = time.perf_counter()
         if self._sts_lines is None:  # nothing loaded: an empty table, zero hits (like the reference)
-            self._sts_lines = ([], [], [], [], [], [])
+            self._sts_lines = _STSLines(0, [], [], ids=[], aliases=[], p1s=[], p2s=[])
             self._build_table()
         # sequences the device-side ingest left in HBM are used in place; everything else is host bytes
         seqs = [r.sequence_device if getattr(r, "sequence_device", None) is not None and
@@ -474,7 +599,7 @@ class MerPCR:
         elif len(exotic) == 1:
             zero = next(iter(exotic))
         else:
-            pex = primer_exotics(self._sts_lines[2] + self._sts_lines[3], self.iupac_mode) if self._sts_lines else set()
+            pex = primer_exotics(self._sts_lines.p1s + self._sts_lines.p2s, self.iupac_mode) if self._sts_lines else set()
             if pex & exotic:
                 raise ValueError(
                     "sequences contain several non-IUPAC characters "

@@ -6,6 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emul", "host_emul.cpp")
 OUT = os.path.join(HERE, "host_emul", "_build", "libmerpcr_emul.so")
 DEPS = [SRC, os.path.join(HERE, "..", "merpcr_b200", "csrc", "mpcr_core.cuh"),
+        os.path.join(HERE, "..", "merpcr_b200", "csrc", "mpcr_hostio.h"),
         os.path.join(HERE, "..", "include", "merpcr_b200.h")]
 
 

@@ -16,6 +16,7 @@
 
 #include "../../include/merpcr_b200.h"
 #include "../../merpcr_b200/csrc/mpcr_core.cuh"
+#include "../../merpcr_b200/csrc/mpcr_hostio.h"
 
 using namespace mpcr;
 
@@ -99,6 +100,19 @@ int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* ascii, uint64_t n, uint64_t d
     }
     c->launches++;
     return MPCR_OK;
+}
+
+int mpcr_sts_parse(const uint8_t* text, uint64_t n, int32_t wordsize, int32_t default_pcr_size, mpcr_sts_line* lines,
+                   uint32_t max_lines, uint32_t* n_lines, uint32_t* bad_line, uint32_t* short_primers, uint32_t* flags) {
+    return sts_parse_impl(text, n, wordsize, default_pcr_size, lines, max_lines, n_lines, bad_line, short_primers, flags);
+}
+int mpcr_sts_blob(const uint8_t* text, const mpcr_sts_line* lines, uint32_t n_lines, uint8_t* blob, uint64_t* off) {
+    sts_blob_impl(text, lines, n_lines, blob, off);
+    return MPCR_OK;
+}
+uint64_t mpcr_format_hits(const mpcr_hit* hits, uint64_t n, const uint8_t* text, const mpcr_sts_line* lines,
+                          const uint8_t* labels, const uint64_t* label_off, uint8_t* out, uint64_t out_cap) {
+    return format_hits_impl(hits, n, text, lines, labels, label_off, out, out_cap);
 }
 
 // ---- FASTA text ingest, serial restatement of io/fasta.py:43-66 for ASCII bytes ------------------------------------

@@ -261,3 +261,65 @@ def test_fuzz_goldens_with_seed_extension(monkeypatch):
     for c in goldens.fuzz_cases():
         if c["params"].get("mismatches", 0) == 0 and not c["params"].get("iupac_mode", 0):
             parity.check_fuzz_case(c, MerPCR)
+
+
+def _weird_sts_text(seed: int) -> bytes:
+    rng = np.random.default_rng(seed)
+    sizes = ["100", "0", "007", " 12", "12 ", "+5", "-5", "5-", "1_000", "100-200", "100-200-300", "a-b", "-", "",
+             "999999999", "12345678901234567890", "50-60 ", "1e3", "٣", "100--200", "3-2", "0-0"]
+    nl = ["\n", "\r\n", "\r"]
+    letters = list("ACGTacgtNRYnU-*")
+    w = np.array([20, 20, 20, 20, 3, 3, 3, 3, 1, 1, 1, 1, 1, .5, .5])
+    prim = lambda k: "".join(rng.choice(letters, size=k, p=w / w.sum()))
+    out = []
+    for i in range(300):
+        kind = rng.integers(0, 20)
+        if kind == 0:
+            out.append("# comment\tx\ty\tz")
+        elif kind == 1:
+            out.append("   ")
+        elif kind == 2:
+            out.append(f"\tSTS{i}\t{prim(20)}\t{prim(20)}\t100\talias")           # leading tab is stripped away
+        else:
+            size = sizes[int(rng.integers(0, len(sizes)))]
+            if not size.isascii():
+                size = "77"
+            fields = [f"id {i}", prim(int(rng.integers(5, 30))), prim(int(rng.integers(5, 30))), size]
+            if rng.random() < 0.6 or size.strip() == "":
+                fields.append(f"alias {i}  x")
+            if rng.random() < 0.2:
+                fields += ["extra", "more"]
+            if rng.random() < 0.1:
+                fields[-1] += "\t"                                              # trailing tab
+            out.append(("  " if rng.random() < 0.1 else "") + "\t".join(fields))
+        out[-1] += nl[int(rng.integers(0, 3))]
+    return "".join(out).encode("ascii")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_native_sts_parser_equals_python_loop(tmp_path, seed):
+    """mpcr_sts_parse + the vectorised size rules == the reference's line loop kept in _parse_sts_python."""
+    p = tmp_path / "w.sts"
+    p.write_bytes(_weird_sts_text(seed))
+    for W in (8, 11):
+        eng = _engine(wordsize=W)
+        nat = eng._parse_sts_native(np.fromfile(str(p), dtype=np.uint8))
+        py = eng._parse_sts_python(str(p))
+        assert nat is not None and nat is not False and py is not False
+        a, b = nat[0], py[0]
+        assert (nat[1], nat[2]) == (py[1], py[2])
+        assert a.n == b.n and [int(x) for x in a.sizes] == [int(x) for x in b.sizes]
+        assert [int(x) for x in a.line_nos] == b.line_nos
+        assert (a.ids, a.aliases, a.p1s, a.p2s) == (b.ids, b.aliases, b.p1s, b.p2s)
+
+
+def test_native_sts_parser_malformed_and_non_ascii(tmp_path):
+    eng = _engine()
+    bad = tmp_path / "bad.sts"
+    bad.write_bytes(b"ok\tACGTACGTACGTA\tACGTACGTACGTA\t100\nbroken line\tonly two\n")
+    assert eng._parse_sts_native(np.fromfile(str(bad), dtype=np.uint8)) is False
+    assert eng.load_sts_file(str(bad)) is False
+    na = tmp_path / "na.sts"
+    na.write_bytes("id\tACGTACGTACGTA\tACGTACGTACGTA\t100\tnaïve alias\n".encode("utf-8"))
+    assert eng._parse_sts_native(np.fromfile(str(na), dtype=np.uint8)) is None
+    assert eng.load_sts_file(str(na)) and eng.sts_records[0].alias == "naïve alias"
