@@ -328,16 +328,9 @@ MPCR_HD uint32_t filter_word(uint32_t key_raw, uint32_t cw, uint32_t n_words) { 
 // bit positions: 31 - (key & 31) and, when the key has at least 11 bits (W >= 6), 31 - ((key >> 6) & 31).
 // (key >> 6) is the raw register of the hash position three bases further on, so the scanner gets the second
 // shift amount for free.)
-#ifndef MPCR_ACC_FORM
-#define MPCR_ACC_FORM 0
-#endif
 MPCR_HD uint32_t filter_bits_of(uint32_t key, int W) {
     const uint32_t s1 = key & 31u, s2 = W >= 6 ? ((key >> 6) & 31u) : s1;
-#if MPCR_ACC_FORM == 3
-    return (1u << s1) | (1u << s2);
-#else
     return (0x80000000u >> s1) | (0x80000000u >> s2);
-#endif
 }
 MPCR_HD bool filter_pass(uint32_t word, uint32_t key, int W) {
     const uint32_t m = filter_bits_of(key, W);

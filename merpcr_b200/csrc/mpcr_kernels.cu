@@ -410,15 +410,9 @@ template <bool WIDE>
 __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ s_filter, uint32_t x, uint32_t x3,
                                                  uint32_t cw, uint32_t n_words) {
     const uint32_t word = s_filter[__umulhi(x * cw, n_words)];
-#if MPCR_ACC_FORM == 3
-    const uint32_t t1 = __funnelshift_r(word, 0u, x);  // word >> (x & 31): the bit of interest at the LSB
-    if (!WIDE) return t1 & 1u;
-    return t1 & __funnelshift_r(word, 0u, x3) & 1u;
-#else
     const uint32_t t1 = __funnelshift_l(0u, word, x);  // word << (x & 31)
     if (!WIDE) return t1;
     return t1 & __funnelshift_l(0u, word, x3);
-#endif
 }
 
 // Stage 2 for up to 32*R queued positions of a warp starting at queue index base (R rounds of 32 async slot
@@ -591,17 +585,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
                 auto raw = [&](int j) -> uint32_t {
                     return (j & 15) ? __funnelshift_r(r[j >> 4], r[(j >> 4) + 1], 2 * (j & 15)) : r[j >> 4];
                 };
-                // collect the probe results (MSB, or LSB in form 3) as bit j of the pass mask
-                auto collect = [&](uint32_t& c, uint32_t u, int j) {
-                    if (MPCR_ACC_FORM == 0) c = __funnelshift_l(u, c, 1);          // ALU pipe
-                    else if (MPCR_ACC_FORM == 1) c = c * 2u + __umulhi(u, 2u);     // FMA pipe (two ops)
-                    else if (MPCR_ACC_FORM == 3) c = c * 2u + u;                   // FMA pipe (one IMAD)
-                    else if ((int32_t)u < 0) c |= 1u << (j & 31);                  // predicate
-                };
+                // collect the MSB of each probe result as bit j of the pass mask (descending j: one funnel shift each)
 #pragma unroll
-                for (int j = 31; j >= 0; --j) collect(c_lo, filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), j);
+                for (int j = 31; j >= 0; --j)
+                    c_lo = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_lo, 1);
 #pragma unroll
-                for (int j = 63; j >= 32; --j) collect(c_hi, filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), j);
+                for (int j = 63; j >= 32; --j)
+                    c_hi = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_hi, 1);
                 c_lo &= (uint32_t)wv;
                 c_hi &= (uint32_t)(wv >> 32);
             }

@@ -373,3 +373,25 @@ def test_fuzz_goldens_with_seed_extension_on_device(monkeypatch):
             parity.check_fuzz_case(c, MerPCR)
             n += 1
     assert n > 5
+
+
+def test_cli_subprocess_on_the_fixture(tmp_path):
+    """`python -m merpcr_b200 <sts> <fasta>` -- the reference's CLI surface end to end on the GPU (cli.py:217-266)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "hits.txt"
+    env = dict(os.environ, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-m", "merpcr_b200", goldens.FIXTURE_STS, goldens.FIXTURE_FA, "-W", "11", "-N", "0",
+                        "-M", "50", "-X", "1", "-T", "1", "-Q", "0", "-O", str(out)], capture_output=True, text=True, env=env,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == goldens.FIXTURE_LINE
+    assert "Reading STS file" in r.stderr and "Total hits found: 1" in r.stderr
+    # me-PCR style K=V arguments and stdout output (cli.py:19-62)
+    r = subprocess.run([sys.executable, "-m", "merpcr_b200", goldens.FIXTURE_STS, goldens.FIXTURE_FA, "W=11", "M=50", "N=0"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout == goldens.FIXTURE_LINE
+    r = subprocess.run([sys.executable, "-m", "merpcr_b200", goldens.FIXTURE_STS, goldens.FIXTURE_FA, "-W", "2"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 2
