@@ -93,6 +93,8 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.path = None
+        self.offset = 0
+        self.end = None
 
     def start(self):
         try:
@@ -100,9 +102,33 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
+
+    def mark(self):
+        """Samples after this point are the ones taken under load (the timed region starts now)."""
+        try:
+            self.offset = os.path.getsize(self.path)
+        except OSError:
+            self.offset = 0
+
+    def mark_end(self):
+        try:
+            self.end = os.path.getsize(self.path)
+        except OSError:
+            self.end = None
+
+    def wait_first_sample(self, timeout: float = 3.0):
+        """nvidia-smi needs a moment to start; the timed region (tens of ms) must not begin before it samples."""
+        t0 = time.time()
+        while self.proc and time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.01)
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
@@ -117,7 +143,11 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
-            for line in open(self.path):
+            text = open(self.path).read()
+            lines = text[self.offset: self.end].splitlines()
+            if not any(len(x.split(",")) >= 6 for x in lines):      # region shorter than a sampling period
+                lines = text.splitlines()
+            for line in lines:
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 6:
                     continue
@@ -280,12 +310,18 @@ def run_b200(args):
     # ---- resident (device-timed) region
     lib, ctx = eng._be.lib, eng._ctx
     n_hits = 0
-    for _ in range(args.warmup):
-        _, n_hits = eng.scan_device(layout, shard)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # samples every 20 ms from the warm-up to the end of the timed region (GPU under load)
+    for _ in range(args.warmup):
+        _, n_hits = eng.scan_device(layout, shard)
+    if rank == 0:
+        sampler.wait_first_sample()
+        for _ in range(2):       # keep the GPU busy while the sampler gets going (untimed)
+            eng.scan_device(layout, shard)
+    barrier()
+    if rank == 0:
+        sampler.mark()
     launches0 = eng.gpu_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, verify_ms = [], []
@@ -296,6 +332,8 @@ def run_b200(args):
         verify_ms.append(float(lib.mpcr_last_verify_ms(ctx)))
     ev1.record()
     torch.cuda.synchronize()
+    if rank == 0:
+        sampler.mark_end()
     t_ms = ev0.elapsed_time(ev1)
     launches = eng.gpu_launches - launches0
     barrier()

@@ -125,7 +125,8 @@ class _STSLines:
 class _Shard:
     """Device-resident packed genome of one shard (planes + the layout they were built for)."""
 
-    __slots__ = ("device", "origin", "bases", "plane2", "plane4", "valid", "begin", "end", "hits", "count")
+    __slots__ = ("device", "origin", "bases", "plane2", "plane4", "valid", "begin", "end", "hits", "count", "staging",
+                 "contig_sig")
 
 
 class MerPCR:
@@ -641,21 +642,24 @@ class MerPCR:
         bases = max(128, (stop - origin + 127) // 128 * 128)
         alloc = bases + int(lib.mpcr_tile_bases()) + PLANE_SLACK_BASES
         sh = shard
+        contig_sig = layout["contigs"].tobytes()
         if sh is not None and (sh.origin, sh.bases, sh.begin, sh.end) == (origin, bases, begin, end):
-            sh.plane2.zero_()
-            sh.plane4.zero_()
-            sh.valid.zero_()
+            if sh.contig_sig != contig_sig:     # same extent, other contig boundaries: the gaps must be zero again
+                sh.plane2.zero_()
+                sh.plane4.zero_()
+                sh.valid.zero_()
+            # identical layout: every word that holds a base is overwritten below, the gaps are still zero
         else:
             sh = _Shard()
             sh.device, sh.origin, sh.bases, sh.begin, sh.end = self._tdev, origin, bases, begin, end
             sh.plane2 = torch.zeros(alloc // 4, dtype=torch.uint8, device=self._tdev)
             sh.plane4 = torch.zeros(alloc // 2, dtype=torch.uint8, device=self._tdev)
             sh.valid = torch.zeros(alloc // 8, dtype=torch.uint8, device=self._tdev)
-            sh.hits, sh.count = None, None
+            sh.hits, sh.count, sh.staging = None, None, None
+        sh.contig_sig = contig_sig
         lut = genome_lut(self.iupac_mode)
         stream = self._stream()
-        chunk = 1 << 26
-        staging = []
+        chunk = 1 << 28
         h2d = 0
         for ci, s in enumerate(seqs):
             if s is None:
@@ -673,14 +677,17 @@ class MerPCR:
                     arr = s[a - g0: b - g0]
                     src = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
                 if src.device != self._tdev:
+                    # one device staging buffer, reused: copy and pack are ordered on the same stream
                     h2d += b - a
-                    src = src.to(self._tdev, non_blocking=True)
-                    staging.append(src)
+                    if sh.staging is None or sh.staging.numel() < b - a:
+                        sh.staging = torch.empty(min(chunk, max(b - a, 1 << 24)), dtype=torch.uint8, device=self._tdev)
+                    dst = sh.staging[: b - a]
+                    dst.copy_(src, non_blocking=True)
+                    src = dst
                 self._be.check(lib.mpcr_pack_sequence(self._ctx, src.data_ptr(), b - a, a, origin,
                                                       sh.plane2.data_ptr(), sh.plane4.data_ptr(), sh.valid.data_ptr(),
                                                       lut.ctypes.data, stream))
         self._sync()
-        del staging
         self.last_h2d_bytes = h2d
         return sh
 
