@@ -44,7 +44,7 @@ ALGO_BYTES_PER_HIT = 16.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; recorded in config)")

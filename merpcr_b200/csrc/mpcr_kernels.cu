@@ -1277,6 +1277,10 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.debug = getenv("MPCR_DEBUG") ? atoi(getenv("MPCR_DEBUG")) : 0;
     a.hits = d_hits; a.capacity = capacity; a.count = (unsigned long long*)d_count; a.tile_counter = c->d_tile_counter;
     a.surv = c->d_surv; a.surv_cap = (uint32_t)(c->surv_bytes / sizeof(Survivor) / kSurvLists); a.surv_ctl = c->d_surv_ctl;
+    if (const char* env = getenv("MPCR_SURVIVOR_CAP")) {   // test hook: force the list-full path (in-kernel verify)
+        const long v = atol(env);
+        if (v >= 0 && (uint32_t)v < a.surv_cap) a.surv_cap = (uint32_t)v;
+    }
     const size_t smem = (size_t)ScanSmem::kFilterOff + (size_t)c->filter_words * 4;
     uint32_t grid = (uint32_t)c->sm_count;
     if (grid > c->n_tiles) grid = c->n_tiles;

@@ -395,3 +395,18 @@ def test_cli_subprocess_on_the_fixture(tmp_path):
     r = subprocess.run([sys.executable, "-m", "merpcr_b200", goldens.FIXTURE_STS, goldens.FIXTURE_FA, "-W", "2"],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 2
+
+
+@pytest.mark.parametrize("cap", ["0", "3"])
+def test_survivor_list_overflow_verifies_in_place(tmp_path, monkeypatch, cap):
+    """A full survivor list must not lose anything: the scanner verifies the overflow itself (verify_serial)."""
+    from merpcr_b200 import MerPCR
+    monkeypatch.setenv("MPCR_SURVIVOR_CAP", cap)
+    name, lengths, n_sts, params, sub_mode, decorate, ranged = CASES[1]
+    contigs, sts_text, expected = _make_workload(4242, lengths, n_sts, params, sub_mode, decorate, ranged)
+    path = _write(tmp_path, "w.sts", sts_text)
+    eng = MerPCR(**params)
+    assert eng.load_sts_file(path)
+    got = parity.engine_hits(eng, _records(contigs))
+    want = parity.oracle_hits(params, sts_text.decode(), [c.tobytes() for c in contigs])
+    assert np.array_equal(got, want) and len(got) > 100
