@@ -235,6 +235,29 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local: int):
+    """Run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off: with 8 ranks pulling
+    3 GB each per end-to-end step, cross-socket traffic is what the host side can least afford."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -247,6 +270,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local)   # pinned host buffers then live next to this GPU's PCIe root
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
@@ -427,6 +451,7 @@ def run_b200(args):
                                  "-W 11 -N 1 -X 1 -M 50; one genome copy per GPU",
                         scale=args.scale, bp_per_gpu=my_bp, n_sts=n_sts, hits_per_gpu=int(n_hits),
                         l2="inputs (2.7 GB of planes per GPU) exceed the 126 MB L2; no flush needed",
+                        numa_node=numa,
                         planted_found=planted_ok, sorted=sorted_ok),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,
                           traffic=traffic, kernel="scan_kernel", kernel_ms=kern_ms,
