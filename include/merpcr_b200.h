@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 5
+#define MPCR_ABI_VERSION 6
 
 enum {
     MPCR_OK = 0,
@@ -93,6 +93,10 @@ void mpcr_ctx_destroy(mpcr_ctx *ctx);
  * Scanning both tables over the same planes and sorting the concatenated hits gives exactly the one-table result.
  * Call before mpcr_table_build; drops the current table. */
 int mpcr_ctx_set_seed_extension(mpcr_ctx *ctx, int w_ext, int which);
+/* NOT reference behaviour, off by default: with on != 0 the "+" record of an STS line looks for
+ * primer1 ... revcomp(primer2) -- a biologically normal forward amplicon, as NCBI me-PCR does -- instead of the
+ * reference's primer1 ... primer2 (core/engine.py:267).  "-" records are unchanged.  Call before mpcr_table_build. */
+int mpcr_ctx_set_true_strands(mpcr_ctx *ctx, int on);
 /* Multiprocessor count of the context's device (grid sizing is a multiple of this). */
 int mpcr_ctx_sm_count(const mpcr_ctx *ctx);
 

@@ -86,6 +86,9 @@ def create_parser() -> argparse.ArgumentParser:
                         help=f"Max. line length for the STS file (default: {DEFAULT_MAX_STS_LINE_LENGTH})")
     parser.add_argument("-v", "--version", action="version", version="merPCR version 1.0.0")
     parser.add_argument("--debug", action="store_true", help="Enable debug logging")
+    parser.add_argument("--true-strands", action="store_true",
+                        help="NOT reference behaviour: report forward amplicons primer1 ... revcomp(primer2) as (+), "
+                             "like NCBI me-PCR, instead of the reference's primer1 ... primer2")
     return parser
 
 
@@ -98,7 +101,7 @@ def main() -> int:
         mer_pcr = MerPCR(wordsize=args.wordsize, margin=args.margin, mismatches=args.mismatches,
                          three_prime_match=args.three_prime_match, iupac_mode=args.iupac,
                          default_pcr_size=args.default_pcr_size, threads=args.threads,
-                         max_sts_line_length=args.max_sts_line_length)
+                         max_sts_line_length=args.max_sts_line_length, true_strands=args.true_strands)
         if not mer_pcr.load_sts_file(args.sts_file):
             logger.error(f"Failed to load STS file: {args.sts_file}")
             return 1

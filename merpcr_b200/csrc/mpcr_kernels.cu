@@ -62,6 +62,7 @@ struct mpcr_ctx {
     uint32_t n_keys = 0;
     bool dense = false;
     int ext_w = 0, ext_which = 0;   // seed extension (mpcr_ctx_set_seed_extension)
+    int true_strands = 0;           // mpcr_ctx_set_true_strands
     int scan_w = 0;                 // word width the scanner keys on: ext_w for an extended table, else wordsize
     uint32_t max_hash_off = 0, max_len = 0;
     uint64_t max_pcr = 0;
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
                                                       const uint32_t* __restrict__ pcr, uint32_t n_lines,
                                                       const uint8_t* __restrict__ plut,
                                                       const uint32_t* __restrict__ word_off,  // 2*n_rec+1 prefix
-                                                      int W, int w_scan, int which, RecMeta* __restrict__ meta,
+                                                      int W, int w_scan, int which, int true_strands,
+                                                      RecMeta* __restrict__ meta,
                                                       uint64_t* __restrict__ pwords, Item<2>* __restrict__ pairs,
                                                       uint32_t* __restrict__ stats) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,7 +205,9 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
         ext = which != 0 && extended_seed(BlobFwd{pr1}, n1, ho, w_scan, &kext);
         if (ho >= 0) m.tag = make_tag(BlobFwd{pr1}, n1, ho, which == 2 ? w_scan : W);
         encode_primer(BlobFwd{pr1}, n1, plut, pwords + m.p1_word);
-        encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p2_word);
+        // reference (engine.py:267): primer2 literally; me-PCR-true strands: its reverse complement
+        if (true_strands) encode_primer(BlobRc{pr2, n2}, n2, plut, pwords + m.p2_word);
+        else encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p2_word);
     } else {
         m.len1 = (uint16_t)n2; m.len2 = (uint16_t)n1;
         ho = first_clean_word(BlobFwd{pr2}, n2, W, &hbe);
@@ -869,6 +873,12 @@ int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
     free_table(c);
     return MPCR_OK;
 }
+int mpcr_ctx_set_true_strands(mpcr_ctx* c, int on) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    c->true_strands = on ? 1 : 0;
+    free_table(c);
+    return MPCR_OK;
+}
 int mpcr_ctx_sm_count(const mpcr_ctx* c) { return c ? c->sm_count : 0; }
 uint64_t mpcr_launch_count(const mpcr_ctx* c) { return c ? c->launches : 0; }
 uint64_t mpcr_fasta_workspace_bytes(uint64_t n, uint32_t max_records) {
@@ -1086,7 +1096,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         CUG(cudaMemcpyAsync(d_woff, word_off.data(), word_off.size() * 4, cudaMemcpyHostToDevice, st));
         CUG(cudaMemsetAsync(d_stats, 0, 16, st));
         encode_records<<<(n_rec + 127) / 128, 128, 0, st>>>(d_blob, d_off, d_pcr, n_lines, d_plut, d_woff, W,
-                                                             c->ext_which ? c->ext_w : W, c->ext_which, c->d_meta,
+                                                             c->ext_which ? c->ext_w : W, c->ext_which, c->true_strands,
+                                                             c->d_meta,
                                                              c->d_pwords, d_pairs, d_stats);
         c->launches++;
         CUG(cudaGetLastError());

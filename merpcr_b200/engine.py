@@ -145,6 +145,7 @@ class MerPCR:
         *,
         device: Optional[int] = None,
         shard: Optional[Sequence[int]] = None,
+        true_strands: bool = False,
     ):
         """Reference parameters (engine.py:47-57) plus two device knobs:
 
@@ -152,6 +153,9 @@ class MerPCR:
         shard  : (rank, world) -- scan only this rank's bp-balanced share of the genome (multi-GPU runs use
                  one process per GPU; hits are merged by the caller, no collective on the scan path).
         `threads` (-T) is accepted and stored for compatibility; the GPU path does not use host threads.
+        true_strands : NOT reference behaviour (off by default).  "+" records look for primer1 ... revcomp(primer2),
+                 a biologically normal forward amplicon as NCBI me-PCR reports it, instead of the reference's
+                 primer1 ... primer2 (engine.py:267).
         """
         self.wordsize = wordsize
         self.margin = margin
@@ -175,6 +179,7 @@ class MerPCR:
             device = int(os.environ.get("LOCAL_RANK", "0")) if self._be.device_kind == "cuda" else 0
         self.device = device
         self.shard = (int(shard[0]), int(shard[1])) if shard else (0, 1)
+        self.true_strands = bool(true_strands)
         if self._be.device_kind == "cuda":
             if not torch.cuda.is_available():
                 raise RuntimeError("merpcr_b200 needs a CUDA device (none visible); there is no CPU fallback")
@@ -200,6 +205,8 @@ class MerPCR:
                          1 if self.iupac_mode else 0)
         h = C.c_void_p()
         self._be.check(self._be.lib.mpcr_ctx_create(self.device, C.byref(p), C.byref(h)))
+        if self.true_strands:
+            self._be.check(self._be.lib.mpcr_ctx_set_true_strands(h, 1))
         return h
 
     def _create_ctx(self):
@@ -426,7 +433,9 @@ class MerPCR:
                 hol = ho.tolist()
                 for i in range(src.n):
                     if hol[2 * i] >= 0:
-                        recs.append(STSRecord(id=ids[i], primer1=p1s[i], primer2=p2s[i], pcr_size=sizes[i],
+                        recs.append(STSRecord(id=ids[i], primer1=p1s[i],
+                                              primer2=self._reverse_complement(p2s[i]) if self.true_strands else p2s[i],
+                                              pcr_size=sizes[i],
                                               alias=aliases[i], offset=line_nos[i], hash_offset=hol[2 * i], direct="+"))
                     if hol[2 * i + 1] >= 0:
                         recs.append(STSRecord(id=ids[i], primer1=p2s[i], primer2=self._reverse_complement(p1s[i]),

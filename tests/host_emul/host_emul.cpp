@@ -42,7 +42,7 @@ struct mpcr_ctx {
     uint64_t max_pcr = 0;
     bool table_ready = false;
     uint64_t launches = 0;
-    int ext_w = 0, ext_which = 0, scan_w = 0;
+    int ext_w = 0, ext_which = 0, scan_w = 0, true_strands = 0;
 };
 
 extern "C" {
@@ -63,6 +63,11 @@ int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
     return MPCR_OK;
 }
 void mpcr_ctx_destroy(mpcr_ctx* c) { delete c; }
+int mpcr_ctx_set_true_strands(mpcr_ctx* c, int on) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    c->true_strands = on ? 1 : 0; c->table_ready = false;
+    return MPCR_OK;
+}
 int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
     if (!c) return fail(MPCR_EINVAL, "null argument");
     if (which < 0 || which > 2) return fail(MPCR_EINVAL, "which must be 0, 1 or 2");
@@ -199,7 +204,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
                 ext = c->ext_which != 0 && extended_seed(Fwd{pr1}, n1, ho, c->ext_w, &kext);
                 if (ho >= 0) m.tag = make_tag(Fwd{pr1}, n1, ho, WS);
                 encode_primer(Fwd{pr1}, n1, plut, c->pwords.data() + m.p1_word);
-                encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p2_word);
+                if (c->true_strands) encode_primer(Rc{pr2, n2}, n2, plut, c->pwords.data() + m.p2_word);
+                else encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p2_word);
             } else {
                 ho = first_clean_word(Fwd{pr2}, n2, W, &hbe);
                 ext = c->ext_which != 0 && extended_seed(Fwd{pr2}, n2, ho, c->ext_w, &kext);

@@ -410,3 +410,10 @@ def test_survivor_list_overflow_verifies_in_place(tmp_path, monkeypatch, cap):
     got = parity.engine_hits(eng, _records(contigs))
     want = parity.oracle_hits(params, sts_text.decode(), [c.tobytes() for c in contigs])
     assert np.array_equal(got, want) and len(got) > 100
+
+
+def test_true_strands_option_on_device():
+    """mpcr_ctx_set_true_strands, pinned to the reference through per-strand identities."""
+    from merpcr_b200 import MerPCR
+    from test_host_logic import _true_strands_check
+    _true_strands_check(MerPCR, _records)

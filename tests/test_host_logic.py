@@ -323,3 +323,44 @@ def test_native_sts_parser_malformed_and_non_ascii(tmp_path):
     na.write_bytes("id\tACGTACGTACGTA\tACGTACGTACGTA\t100\tnaïve alias\n".encode("utf-8"))
     assert eng._parse_sts_native(np.fromfile(str(na), dtype=np.uint8)) is None
     assert eng.load_sts_file(str(na)) and eng.sts_records[0].alias == "naïve alias"
+
+
+def _true_strands_check(MerPCRcls, record_factory):
+    """true_strands=True is not reference behaviour, but it is pinned to the reference through two identities:
+    its (+) hits are the reference's (+) hits on the STS file with primer2 reverse-complemented, and its (-) hits are
+    the reference's (-) hits on the original file.  Planted, biologically normal amplicons must come out as (+)."""
+    import tempfile
+    rng = synth.Rng(8080)
+    contigs = [rng.dna(n) for n in (50000, 30000)]
+    sts = synth.make_sts_set(8081, 60, 18, 25, 100, 600)
+    # plant forward amplicons p1 ... rc(p2) by planting the reference's "+" form of the transformed table
+    sts_rc = dict(sts)
+    sts_rc["p2"] = sts["p2"].copy()
+    for i in range(len(sts["l2"])):
+        k = int(sts["l2"][i])
+        sts_rc["p2"][i, :k] = synth.revcomp_bytes(sts["p2"][i, :k])
+    planted = synth.plant_amplicons(8082, contigs, sts_rc, 50)
+    text, text_rc = synth.sts_lines(sts), synth.sts_lines(sts_rc)
+    params = dict(wordsize=11, margin=50, mismatches=1)
+    with tempfile.NamedTemporaryFile("wb", suffix=".sts", delete=False) as f:
+        f.write(text)
+    eng = MerPCRcls(**params, true_strands=True)
+    assert eng.load_sts_file(f.name)
+    os.unlink(f.name)
+    got = parity.engine_hits(eng, record_factory(contigs))
+    seqs = [c.tobytes() for c in contigs]
+    ref_plain = parity.oracle_hits(params, text.decode(), seqs)
+    ref_rc = parity.oracle_hits(params, text_rc.decode(), seqs)
+    as_set = lambda a, strand: {tuple(r) for r in a.tolist() if r[4] == strand}
+    assert as_set(got, 0) == as_set(ref_rc, 0) and as_set(got, 1) == as_set(ref_plain, 1)
+    plus = {(r[0], r[1], r[2]) for r in got.tolist() if r[4] == 0}
+    fwd = [(ci, a, b) for ci, a, b, _, strand in planted if strand == "+"]
+    assert len(fwd) > 10 and all(x in plus for x in fwd)
+    rec = next(r for r in eng.sts_records if r.direct == "+")
+    assert rec.primer2 == eng._reverse_complement(sts["p2"][0, : sts["l2"][0]].tobytes().decode())
+    eng.close()
+
+
+def test_true_strands_option():
+    from merpcr_b200 import FASTARecord, MerPCR
+    _true_strands_check(MerPCR, lambda cs: [FASTARecord(f">c{i}", c) for i, c in enumerate(cs)])
