@@ -650,76 +650,131 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
 }
 
 // Dense tables: when a large share of all 4^W words are seeds (W = 8 with 10^5..10^6 STS, or W = 11 with 10^6) a
-// Bloom filter cannot reject anything, so this scanner skips it.  A warp takes 32 consecutive hash positions:
-//   phase A, one position per lane: key + tag window straight from the planes (coalesced, L1-resident), one slot
-//            load (no shared-memory carve-out here, so plain loads run at full rate), inline tags for seeds with
-//            one or two records;
-//   phase B, one position at a time: seeds shared by three or more records are walked by the whole warp, 32 bucket
-//            entries per coalesced 256-byte load, each entry behind its own tag.
+// Bloom filter cannot reject anything, so this scanner skips it and probes the slot table at EVERY valid position.
+// No shared-memory carve-out is needed, so plain loads run at the full L1 rate (~1 random 16-byte load /clk/SM).
+// A warp takes units of 2048 hash positions of a tile; lane l owns positions [64l, 64l+64):
+//   phase A: the lane's bases arrive as 24 coalesced bytes of plane2 (+ 16 of the valid plane); rolling keys by
+//            funnel shift like the sparse scanner, eight slot loads in flight per lane, inline tags for seeds with one
+//            or two records, the tag window straight from the same registers;
+//   phase B: seeds shared by three or more records are walked by the whole warp, 32 bucket entries per coalesced
+//            256-byte load, four positions batched per round, each entry behind its own tag.
 // Same survivor list and verify_kernel as the sparse path.
-__global__ void __launch_bounds__(256, 3) dense_scan_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(256, 2) dense_scan_kernel(const ScanArgs a) {
+    constexpr int kUnit = 32 * kPosPerThread;
+    constexpr int kChunk = 4;                      // slot loads in flight per lane (divides 16)
     const int lane = threadIdx.x & 31;
     const int W = a.prm.W, N = a.prm.N;
     const uint32_t wmask = wmask_of(W);
-    const uint32_t need = (W + kTagBases) >= 32 ? 0xFFFFFFFFu : ((1u << (W + kTagBases)) - 1u);
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= a.n_tiles) return;
         const TileDesc td = a.tiles[tile];
-        for (uint32_t lp0 = 0; lp0 < td.nbases; lp0 += 32) {
-            const uint32_t lp = lp0 + lane;
-            const int64_t gpos = td.gbase + lp;
-            bool walk = false, clean = false;
-            uint32_t gcodes = 0, start = 0;
-            if (lp < td.nbases) {
-                const uint32_t vb = fetch_bits(a.valid, gpos, W + kTagBases);
-                if ((vb & wmask_bits(W)) == wmask_bits(W)) {          // all W bases of the window hashable (engine.py:483)
-                    clean = (vb & need) == need;                       // ... and the tag window as well
-                    const uint32_t key = extract_key(a.p2, gpos, wmask);
-                    gcodes = fetch_bits(a.p2, 2 * (gpos + W), 2 * kTagBases);
-                    Slot s;
-                    if (find_slot(a.slots, a.smap, key, &s)) {
-                        if (!(s.code & kWalkBucket) || ((s.tag_a | s.tag_b) >> 16)) {
-                            // one or two records: their tags are inline
-                            if (slot_survives(s, gcodes, clean ? 0xFFu : 0u, N)) push_survivor(a, tile, lp, s.code);
-                        } else {
-                            walk = true;                                // three or more (or untagged): phase B
-                            start = s.code & ~kWalkBucket;
+        for (uint32_t ubase = 0; ubase < td.nbases; ubase += kUnit) {
+            const uint32_t lp0 = ubase + (uint32_t)lane * kPosPerThread;   // tile-local
+            uint64_t walk = 0;    // positions whose seed is shared by >= 3 records (phase B)
+            uint64_t dirty = 0;   // ... of those, the ones whose tag window is not clean
+            uint32_t r[6] = {0, 0, 0, 0, 0, 0};
+            if (lp0 < td.nbases) {
+                const int64_t gpos = td.gbase + lp0;                    // multiple of 64
+                const uint64_t* vp = a.valid + (gpos >> 6);
+                const uint64_t v0 = __ldg(vp), v1 = __ldg(vp + 1);
+                uint64_t wv = window_valid(v0, v1, W);                 // seed window hashable (engine.py:483)
+                const uint64_t wt = window_valid(v0, v1, W + kTagBases); // ... and the tag window clean as well
+                const uint32_t left = td.nbases - lp0;
+                if (left < 64u) wv &= (1ull << left) - 1ull;
+                if (wv) {
+                    const uint32_t* pp = reinterpret_cast<const uint32_t*>(a.p2) + (gpos >> 4);
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(pp));
+                    const uint2 q2 = __ldg(reinterpret_cast<const uint2*>(pp + 4));
+                    r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; r[4] = q2.x; r[5] = q2.y;
+                    // four groups of 16 positions over a rotating three-word window (keeps the unrolled body small)
+                    uint32_t w0 = r[0], w1 = r[1], w2 = r[2];
+#pragma unroll 1
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t ww[4] = {w0, w1, w2, 0u};
+                        auto raw = [&](int j) -> uint32_t {   // 16 bases starting at position j of the group, j < 32
+                            return (j & 15) ? __funnelshift_r(ww[j >> 4], ww[(j >> 4) + 1], 2 * (j & 15)) : ww[j >> 4];
+                        };
+                        const uint32_t wv16 = (uint32_t)(wv >> (16 * g)) & 0xFFFFu, wt16 = (uint32_t)(wt >> (16 * g)) & 0xFFFFu;
+#pragma unroll
+                        for (int c0 = 0; c0 < 16; c0 += kChunk) {
+                            if (((wv16 >> c0) & ((1u << kChunk) - 1u)) == 0) continue;
+                            Slot sl[kChunk];
+#pragma unroll
+                            for (int u = 0; u < kChunk; ++u) {
+                                sl[u].code = kSlotEmpty;
+                                if ((wv16 >> (c0 + u)) & 1u) {
+                                    const uint32_t key = raw(c0 + u) & wmask;
+                                    if (a.smap.direct) sl[u] = load_slot(a.slots + key);
+                                    else if (!find_slot(a.slots, a.smap, key, &sl[u])) sl[u].code = kSlotEmpty;
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < kChunk; ++u) {
+                                const int j = c0 + u;
+                                if (sl[u].code == kSlotEmpty) continue;
+                                // the tag window: the 8 bases behind the seed (W == 16: the next register)
+                                const uint32_t gc = __funnelshift_rc(raw(j), raw(j + 16), 2 * W);
+                                const bool clean = (wt16 >> j) & 1u;
+                                if (!(sl[u].code & kWalkBucket) || ((sl[u].tag_a | sl[u].tag_b) >> 16)) {
+                                    if (!clean || !(tag_rejects(sl[u].tag_a, gc, N) && tag_rejects(sl[u].tag_b, gc, N)))
+                                        push_survivor(a, tile, lp0 + 16 * g + j, sl[u].code);
+                                } else {
+                                    walk |= 1ull << (16 * g + j);
+                                    if (!clean) dirty |= 1ull << (16 * g + j);
+                                }
+                            }
                         }
+                        w0 = w1; w1 = w2; w2 = g == 0 ? r[3] : (g == 1 ? r[4] : r[5]);
                     }
                 }
             }
-            uint32_t todo = __ballot_sync(0xffffffffu, walk);
-            while (todo) {
-                // four positions per round: their first 32 entries are loaded together (the walk is latency-bound)
-                constexpr int kBatch = 4;
-                int js[kBatch];
-                uint32_t es[kBatch];
-                BucketEntry bs[kBatch];
+            const uint32_t walk_lo = (uint32_t)walk, walk_hi = (uint32_t)(walk >> 32);
+            const uint32_t dirty_lo = (uint32_t)dirty, dirty_hi = (uint32_t)(dirty >> 32);
+            // ---- phase B: warp-cooperative bucket walks, lane by lane
+            uint32_t lanes_todo = __ballot_sync(0xffffffffu, walk != 0);
+            while (lanes_todo) {
+                const int src = __ffs(lanes_todo) - 1;
+                lanes_todo &= lanes_todo - 1;
+                uint64_t todo = ((uint64_t)__shfl_sync(0xffffffffu, walk_hi, src) << 32) | __shfl_sync(0xffffffffu, walk_lo, src);
+                const uint64_t dirt = ((uint64_t)__shfl_sync(0xffffffffu, dirty_hi, src) << 32) | __shfl_sync(0xffffffffu, dirty_lo, src);
+                const uint32_t lps = ubase + (uint32_t)src * kPosPerThread;
+                while (todo) {
+                    constexpr int kBatch = 4;   // four positions per round: their first 32 entries are loaded together
+                    int js[kBatch];
+                    uint32_t es[kBatch], gs[kBatch];
+                    BucketEntry bs[kBatch];
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    const bool on = todo != 0;
-                    js[u] = on ? __ffs(todo) - 1 : -1;
-                    todo &= todo - 1;                                   // 0 stays 0
-                    es[u] = __shfl_sync(0xffffffffu, start, js[u] & 31);
-                    bs[u] = on ? a.bucket[es[u] + lane] : BucketEntry{0x80000000u, 0u};   // the entry array is padded by 32
-                }
+                    for (int u = 0; u < kBatch; ++u) {
+                        const bool on = todo != 0;
+                        const int j = on ? __ffsll((long long)todo) - 1 : 0;
+                        js[u] = on ? j : -1;
+                        todo &= todo - 1;   // 0 stays 0
+                        // key and tag window once more, straight from the planes (uniform addresses, L1 hits)
+                        const int64_t gp = td.gbase + lps + j;
+                        gs[u] = fetch_bits(a.p2, 2 * (gp + W), 2 * kTagBases);
+                        Slot s;
+                        s.code = kSlotEmpty;
+                        if (on) find_slot(a.slots, a.smap, extract_key(a.p2, gp, wmask), &s);
+                        es[u] = s.code & ~kWalkBucket;
+                        bs[u] = on ? a.bucket[es[u] + lane] : BucketEntry{0x80000000u, 0u};   // the entry array is padded by 32
+                    }
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    const int j = js[u] & 31;
-                    const uint32_t gj = __shfl_sync(0xffffffffu, gcodes, j);
-                    const bool cj = __shfl_sync(0xffffffffu, (uint32_t)clean, j) != 0;
-                    BucketEntry b = bs[u];
-                    for (uint32_t e = es[u];;) {
-                        const uint32_t last = __ballot_sync(0xffffffffu, (b.rec_last >> 31) != 0);
-                        const int n_in = last ? __ffs(last) : 32;
-                        if (js[u] >= 0 && lane < n_in && (!cj || !tag_rejects(b.tag, gj, N)))
-                            push_survivor(a, tile, lp0 + j, b.rec_last & 0x7FFFFFFFu);
-                        if (last) break;
-                        e += 32;
-                        b = a.bucket[e + lane];
+                    for (int u = 0; u < kBatch; ++u) {
+                        const int j = js[u] & 63;
+                        const bool cj = !((dirt >> j) & 1ull);
+                        BucketEntry b = bs[u];
+                        for (uint32_t e = es[u];;) {
+                            const uint32_t last = __ballot_sync(0xffffffffu, (b.rec_last >> 31) != 0);
+                            const int n_in = last ? __ffs(last) : 32;
+                            if (js[u] >= 0 && lane < n_in && (!cj || !tag_rejects(b.tag, gs[u], N)))
+                                push_survivor(a, tile, lps + j, b.rec_last & 0x7FFFFFFFu);
+                            if (last) break;
+                            e += 32;
+                            b = a.bucket[e + lane];
+                        }
                     }
                 }
             }
