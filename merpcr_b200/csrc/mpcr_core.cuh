@@ -259,8 +259,41 @@ MPCR_HD uint64_t mismatch_lanes(uint64_t g, uint64_t q, uint64_t aux, uint64_t l
     }
     return (mis | aux) & lanes;
 }
+// 8 nibbles starting at plane-relative base b, from the 32-bit view of plane4
+MPCR_HD uint32_t fetch8(const uint64_t* p4, int64_t b) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p4);
+    const uint64_t i = (uint64_t)b >> 3;
+    const unsigned sh = ((unsigned)b & 7u) * 4u;
+    const uint32_t lo = w[i];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (w[i + 1] << (32u - sh));
+}
+MPCR_HD uint32_t mismatch_lanes32(uint32_t g, uint32_t q, uint32_t aux, uint32_t lanes, int iupac) {
+    uint32_t mis;
+    if (iupac) {
+        const uint32_t a = g & q;
+        const uint32_t nz = a | (a >> 1) | (a >> 2) | (a >> 3);
+        const uint32_t gz = ~(g | (g >> 1) | (g >> 2) | (g >> 3));
+        mis = ~(nz | (gz & (aux >> 1)));
+    } else {
+        const uint32_t x = g ^ q;
+        mis = x | (x >> 1) | (x >> 2) | (x >> 3);
+    }
+    return (mis | aux) & lanes;
+}
 MPCR_HD bool compare_view(const uint64_t* p4, int64_t gb, const PrimerView& v, const SearchParams& prm) {
-    // first 16 bases decide almost every position of the mate window: leave as early as the reference does
+    // the first 8 bases decide almost every position of the mate window (one 32-bit word): leave as early as the
+    // reference's per-character loop does
+    {
+        const uint32_t m8 = mismatch_lanes32(fetch8(p4, gb), (uint32_t)v.q[0], (uint32_t)v.aux[0], (uint32_t)v.lanes[0],
+                                             prm.iupac);
+#ifdef __CUDA_ARCH__
+        const int n8 = __popc(m8);
+#else
+        const int n8 = __builtin_popcount(m8);
+#endif
+        if ((m8 & (uint32_t)v.prot[0]) || n8 > prm.N) return false;   // :635-640
+    }
     const uint64_t m0 = mismatch_lanes(fetch16(p4, gb), v.q[0], v.aux[0], v.lanes[0], prm.iupac);
     const int n0 = popc64(m0);
     if ((m0 & v.prot[0]) || n0 > prm.N) return false;           // :635-640

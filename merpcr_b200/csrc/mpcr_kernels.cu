@@ -819,6 +819,7 @@ __device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& 
 
 __global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
     constexpr int kGroups = 32 / kVerifyLanes;
+    constexpr uint32_t kGrab = kGroups;       // survivors a warp takes per cursor atomic (one per lane group)
     const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
     const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     // every warp starts at its own sub-list and moves on when that one is drained, until it has seen them all;
@@ -835,11 +836,11 @@ __global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
         const uint32_t n = min(ctl[0], a.surv_cap);
         const Survivor* surv = a.surv + (size_t)list * a.surv_cap;
         for (;;) {
-            uint32_t idx = 0;
-            if (lane == 0) idx = atomicAdd(ctl + 1, (uint32_t)kGroups);
-            idx = __shfl_sync(0xffffffffu, idx, 0) + group;
-            if (idx - group >= n) break;
-            if (idx >= n) continue;   // the tail of the last batch (the whole warp leaves the list on the next round)
+            uint32_t first = 0;
+            if (lane == 0) first = __ldcg(ctl + 1) < n ? atomicAdd(ctl + 1, kGrab) : n;   // look before touching the line
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (first >= n) break;
+          for (uint32_t idx = first + group; idx < min(first + kGrab, n); idx += kGroups) {
             const Survivor sv = surv[idx];
             const TileDesc td = a.tiles[sv.tile];
             if (!(sv.code & kWalkBucket)) {
@@ -854,6 +855,7 @@ __global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
                     if (b.rec_last >> 31) break;
                 }
             }
+          }
         }
       }
     }
