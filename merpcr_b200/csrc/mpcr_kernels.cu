@@ -861,6 +861,54 @@ __global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
     }
 }
 
+// After the radix passes over (pos1, contig): hits that share contig and pos1 (a handful: duplicate STS lines,
+// several deltas of one primer-1 site) are put into the reference's discovery order (hash_off, rec, rank) by the
+// thread that finds the start of the run -- an insertion sort, runs are short.
+__global__ void __launch_bounds__(256) order_ties(mpcr_hit* __restrict__ hits, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = hits[i].contig, p = hits[i].pos1;
+    if (i > 0 && hits[i - 1].contig == c && hits[i - 1].pos1 == p) return;   // not the start of a run
+    uint64_t e = i + 1;
+    while (e < n && hits[e].contig == c && hits[e].pos1 == p) ++e;
+    auto less = [](const mpcr_hit& a, const mpcr_hit& b) {
+        if (a.hash_off != b.hash_off) return a.hash_off < b.hash_off;
+        if (a.rec != b.rec) return a.rec < b.rec;
+        return a.rank < b.rank;
+    };
+    const uint64_t m = e - i;
+    if (m <= 32) {
+        for (uint64_t k = i + 1; k < e; ++k) {
+            const mpcr_hit x = hits[k];
+            uint64_t j = k;
+            while (j > i && less(x, hits[j - 1])) { hits[j] = hits[j - 1]; --j; }
+            hits[j] = x;
+        }
+        return;
+    }
+    // a long run (thousands of identical STS lines on a repeat): heap sort keeps it O(m log m)
+    mpcr_hit* h = hits + i;
+    auto sift = [&](uint64_t root, uint64_t end) {
+        const mpcr_hit x = h[root];
+        for (;;) {
+            uint64_t child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && less(h[child], h[child + 1])) ++child;
+            if (!less(x, h[child])) break;
+            h[root] = h[child];
+            root = child;
+        }
+        h[root] = x;
+    };
+    for (uint64_t k = m / 2; k-- > 0;) sift(k, m);
+    for (uint64_t end = m - 1; end > 0; --end) {
+        const mpcr_hit t = h[0];
+        h[0] = h[end];
+        h[end] = t;
+        sift(0, end);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------------
@@ -1402,16 +1450,15 @@ int mpcr_sort_hits(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n, void* stream) {
     const uint64_t nblk = (n + kSortItemsPerBlock - 1) / kSortItemsPerBlock;
     rc = ensure((void**)&c->d_counts, &c->counts_cap, (size_t)256 * nblk * 4);
     if (rc) return rc;
-    // LSD order: rank, rec, hash_off, pos1, contig  (fields 4, 3, 5, 1, 0); digits bounded by what can occur
+    // LSD radix passes over pos1 then contig (fields 1, 0), digits bounded by the layout of the last scan; the rest of
+    // the key (hash_off, rec, rank) only matters inside runs of equal (contig, pos1), which order_ties settles
     PassDesc passes[24];
     int np = 0;
-    np = add_passes(passes, np, 4, 2ull * (uint64_t)c->prm.margin);
-    np = add_passes(passes, np, 3, c->n_rec ? c->n_rec - 1 : 0);
-    np = add_passes(passes, np, 5, c->max_hash_off);
-    // pos1 / contig digits are bounded by the layout of the last scan
     np = add_passes(passes, np, 1, c->lay_max_len ? c->lay_max_len : 0x7FFFFFFFull);
     np = add_passes(passes, np, 0, c->lay_contigs ? c->lay_contigs - 1 : 0xFFFFFFFFull);
     c->launches += radix_sort<6>((Item<6>*)d_hits, (Item<6>*)c->d_sort_tmp, n, passes, np, c->d_counts, st);
+    order_ties<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_hits, n);
+    c->launches++;
     CU(cudaGetLastError());
     return MPCR_OK;
 }
