@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: one genome copy per GPU (default); strong: ONE genome sharded over the GPUs "
+                         "(bp-balanced ranges with halos, the production multi-GPU mode)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; recorded in config)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -298,8 +301,11 @@ def run_b200(args):
     lengths, n_sts, sts = workload(args.scale)
     sts_text = synth.sts_lines(sts)
     ncont = len(lengths)
-    # world-sized layout: copy k of the 24 chromosomes is owned by rank k
-    all_lengths = lengths * world
+    # weak: world-sized layout, copy k of the 24 chromosomes is owned by rank k; strong: one copy, sharded by range
+    strong = args.scaling == "strong" and world > 1
+    copy = 0 if strong else rank
+    base_ci = 0 if strong else rank * ncont
+    all_lengths = lengths if strong else lengths * world
     with tempfile.NamedTemporaryFile("wb", suffix=".sts", delete=False) as f:
         f.write(sts_text)
         sts_path = f.name
@@ -311,23 +317,28 @@ def run_b200(args):
     layout = eng.make_layout(all_lengths)
 
     # ---- synthetic genome of this rank's copy, generated and planted directly in HBM
-    expected, writes = plan_writes(lengths, sts, rank)
+    expected, writes = plan_writes(lengths, sts, copy)
     dev_contigs = []
     by_contig = {}
     for ci, off, b in writes:
         by_contig.setdefault(ci, []).append((off, b))
     for ci, L in enumerate(lengths):
-        t = synth.dna_torch(contig_seed(rank, ci), 0, L, dev)
+        t = synth.dna_torch(contig_seed(copy, ci), 0, L, dev)
         w = by_contig.get(ci)
         if w:
             idx = np.concatenate([np.arange(off, off + len(b), dtype=np.int64) for off, b in w])
             val = np.concatenate([b for _, b in w])
             t[torch.from_numpy(idx).to(dev)] = torch.from_numpy(val).to(dev)
         dev_contigs.append(t)
-    seqs_dev = [None] * (ncont * world)
+    seqs_dev = [None] * len(all_lengths)
     for ci in range(ncont):
-        seqs_dev[rank * ncont + ci] = dev_contigs[ci]
-    my_bp = int(sum(lengths))
+        seqs_dev[base_ci + ci] = dev_contigs[ci]
+    if strong:   # bases of this rank's range of the padded coordinate
+        cg = layout["contigs"]
+        my_bp = int(sum(max(0, min(int(c["gstart"]) + int(c["length"]), layout["end"]) - max(int(c["gstart"]), layout["begin"]))
+                        for c in cg))
+    else:
+        my_bp = int(sum(lengths))
     shard = eng.upload(layout, seqs_dev)
     torch.cuda.synchronize()
 
@@ -372,8 +383,13 @@ def run_b200(args):
     # planted truth + ordering sanity on the resident result (not timed)
     hits_t, n = eng.scan_device(layout, shard)
     hits = hits_t[: n * _capi.HIT_DTYPE.itemsize].cpu().numpy().view(_capi.HIT_DTYPE)
-    found = set(zip((hits["contig"] - rank * ncont).tolist(), hits["pos1"].tolist(), hits["pos2"].tolist()))
-    planted_ok = all((c, a, b) in found for c, a, b, _, _ in expected)
+    all_hits = hits
+    if strong:   # the planted truth is checked on the merged hit lists of all shards
+        gathered = [None] * world
+        dist.all_gather_object(gathered, np.array(hits))
+        all_hits = np.concatenate(gathered)
+    found = set(zip((all_hits["contig"] - base_ci).tolist(), all_hits["pos1"].tolist(), all_hits["pos2"].tolist()))
+    planted_ok = all((c, a, b) in found for c, a, b, _, _ in expected) and (not strong or len(all_hits) == len(found))
     key = np.stack([hits["contig"], hits["pos1"]], axis=1).astype(np.int64)
     sorted_ok = bool(np.all((key[1:, 0] > key[:-1, 0]) | ((key[1:, 0] == key[:-1, 0]) & (key[1:, 1] >= key[:-1, 1]))))
 
@@ -385,9 +401,9 @@ def run_b200(args):
         for h, d in zip(host_contigs, dev_contigs):
             h.copy_(d)
         torch.cuda.synchronize()
-        seqs_host = [None] * (ncont * world)
+        seqs_host = [None] * len(all_lengths)
         for ci in range(ncont):
-            seqs_host[rank * ncont + ci] = host_contigs[ci]
+            seqs_host[base_ci + ci] = host_contigs[ci]
         del dev_contigs, seqs_dev
         e2e_steps = max(2, min(args.steps, 5))
         sh2 = None
@@ -401,7 +417,7 @@ def run_b200(args):
             d2h = out.nbytes + 8
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-        e2e = dict(value=total_bp / dt / 1e9, unit="Gbp/s", h2d_bytes_per_step=int(sum_over_ranks(float(my_bp))),
+        e2e = dict(value=total_bp / dt / 1e9, unit="Gbp/s", h2d_bytes_per_step=int(sum_over_ranks(float(eng.last_h2d_bytes))),
                    d2h_bytes_per_step=int(sum_over_ranks(float(d2h))), ms_per_step=dt * 1e3, steps=e2e_steps,
                    hits=int(sum_over_ranks(float(len(out)))))
         assert len(out) == n_hits, "e2e and resident hit counts differ"
@@ -445,10 +461,13 @@ def run_b200(args):
             pass
         line = dict(
             metric=METRIC, value=value, unit="Gbp/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-            ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8",
+            ms_per_step=ms_per_step, higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None,
+            dtype="u8",
             data="synthetic", impl="b200",
             config=dict(workload="cfg3: 24-chromosome synthetic genome (GRCh38 lengths) x 100k planted STS, "
-                                 "-W 11 -N 1 -X 1 -M 50; one genome copy per GPU",
+                                 "-W 11 -N 1 -X 1 -M 50; " +
+                                 ("ONE genome sharded over the GPUs (bp-balanced ranges + halos)" if strong
+                                  else "one genome copy per GPU"),
                         scale=args.scale, bp_per_gpu=my_bp, n_sts=n_sts, hits_per_gpu=int(n_hits),
                         l2="inputs (2.7 GB of planes per GPU) exceed the 126 MB L2; no flush needed",
                         numa_node=numa,
