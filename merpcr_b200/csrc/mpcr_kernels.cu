@@ -424,9 +424,10 @@ __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ s_
 // re-probe entry 0 and are masked out, so the R rounds interleave freely.  CLEAN: every base of the unit (and its
 // read-ahead) is A/C/G/T, so the tag verdict can be used without looking at the valid bits.
 template <bool CLEAN, int R>
-__device__ __forceinline__ void probe_rounds(const ScanArgs& a, ScanSmem::Warp& ws, const uint32_t* __restrict__ s_p2,
-                                             const uint32_t* __restrict__ s_v, uint32_t base, uint32_t cnt, int lane,
-                                             uint32_t tile, uint32_t ubase, unsigned long long& n_dbg) {
+__device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
+                                             const uint32_t* __restrict__ s_p2, const uint32_t* __restrict__ s_v,
+                                             uint32_t base, uint32_t cnt, int lane, uint32_t tile, uint32_t ubase,
+                                             unsigned long long& n_dbg) {
     const int W = a.prm.W, N = a.prm.N;
     const uint32_t wmask = wmask_of(W);
     const bool hashed = !a.smap.direct;
@@ -436,7 +437,7 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, ScanSmem::Warp& 
     for (int u = 0; u < R; ++u) {
         const uint32_t qi = base + 32 * u + lane;
         ok[u] = qi < cnt;
-        const uint32_t lp = ws.queue[ok[u] ? qi : 0u];
+        const uint32_t lp = queue[ok[u] ? qi : 0u];
         // key (2W bits) and the 8-base tag window (16 bits) out of three staged words
         const uint32_t wi = lp >> 4, sh = (lp & 15u) * 2u;
         const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1], w2 = s_p2[wi + 2];
@@ -449,7 +450,7 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, ScanSmem::Warp& 
             const uint32_t vb = lp + (uint32_t)W, vi = vb >> 5, vs = vb & 31u;
             dirty[u] = !tag_window_clean(__funnelshift_r(s_v[vi], s_v[vi + 1], vs));
         }
-        gather16_async(&ws.landing[u][lane], a.slots + slot_index(key[u], a.smap));
+        gather16_async(&landing[u][lane], a.slots + slot_index(key[u], a.smap));
         gather_commit();
     }
 #pragma unroll
@@ -458,7 +459,7 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, ScanSmem::Warp& 
         else if (u == 1) gather_wait<(R > 2 ? R - 2 : 0)>();
         else if (u == 2) gather_wait<(R > 3 ? R - 3 : 0)>();
         else gather_wait<0>();
-        const uint4 v = ws.landing[u][lane];
+        const uint4 v = landing[u][lane];
         const bool collide = hashed && v.x != key[u];
         const bool pass = dirty[u] || !(tag_rejects(v.z, gcodes[u], N) && tag_rejects(v.w, gcodes[u], N));
         if (ok[u] && v.y != kSlotEmpty && (collide || pass)) {  // about one queued position in a thousand
@@ -471,19 +472,56 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, ScanSmem::Warp& 
 }
 
 template <bool CLEAN>
-__device__ __forceinline__ void probe_queue(const ScanArgs& a, ScanSmem::Warp& ws, const uint32_t* __restrict__ s_p2,
-                                            const uint32_t* __restrict__ s_v, uint32_t cnt, int lane, uint32_t tile,
-                                            uint32_t ubase, unsigned long long& n_dbg) {
+__device__ __forceinline__ void probe_queue(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
+                                            const uint32_t* __restrict__ s_p2, const uint32_t* __restrict__ s_v,
+                                            uint32_t cnt, int lane, uint32_t tile, uint32_t ubase,
+                                            unsigned long long& n_dbg) {
     constexpr int kIlp = ScanSmem::kIlp;
     static_assert(kIlp >= 1 && kIlp <= 4, "kIlp");
     uint32_t base = 0;
     for (; base + 32 * kIlp <= cnt; base += 32 * kIlp)
-        probe_rounds<CLEAN, kIlp>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+        probe_rounds<CLEAN, kIlp>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
     const uint32_t rounds = (cnt - base + 31) >> 5;  // tail: only the rounds that hold something
-    if (rounds == 1) probe_rounds<CLEAN, 1>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 2) probe_rounds<CLEAN, (kIlp >= 2 ? 2 : 1)>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 3) probe_rounds<CLEAN, (kIlp >= 3 ? 3 : 1)>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 4) probe_rounds<CLEAN, (kIlp >= 4 ? 4 : 1)>(a, ws, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    if (rounds == 1) probe_rounds<CLEAN, 1>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 2) probe_rounds<CLEAN, (kIlp >= 2 ? 2 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 3) probe_rounds<CLEAN, (kIlp >= 3 ? 3 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 4) probe_rounds<CLEAN, (kIlp >= 4 ? 4 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+}
+
+// Stage 1 for one unit of 2048 positions: lane l owns positions [64l, 64l+64) -- rolling keys by funnel shift out of
+// five registers, one shared-memory Bloom probe (two bits of one word) per position.  c_lo / c_hi: pass masks.
+template <bool WIDE>
+__device__ __forceinline__ void stage1_unit(const uint32_t* __restrict__ s_filter, const uint32_t* __restrict__ s_p2,
+                                            const uint32_t* __restrict__ s_v, int lane, uint32_t unit_nbases, int W,
+                                            uint32_t cw, uint32_t fw, uint32_t& c_lo, uint32_t& c_hi, bool& my_clean) {
+    const uint32_t lp0 = (uint32_t)lane * kPosPerThread;  // unit-local
+    if (lp0 < unit_nbases) {
+        const uint2 v0 = *reinterpret_cast<const uint2*>(s_v + 2 * lane);
+        const uint2 v1 = *reinterpret_cast<const uint2*>(s_v + 2 * lane + 2);
+        my_clean = (v0.x & v0.y & v1.x) == 0xFFFFFFFFu;  // own 64 bases + the 32 behind them (W + tag <= 24)
+        // W-mer validity of the 64 positions: all ones on clean sequence, else log-doubling over the valid bits
+        uint64_t wv = ~0ull;
+        if (!my_clean) wv = window_valid(((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v1.y << 32) | v1.x, W);
+        const uint32_t left = unit_nbases - lp0;
+        if (left < 64u) wv &= (1ull << left) - 1ull;
+        if (wv) {
+            const uint4 q = *reinterpret_cast<const uint4*>(s_p2 + 4 * lane);
+            const uint32_t r[6] = {q.x, q.y, q.z, q.w, s_p2[4 * lane + 4], 0u};
+            // raw register of position j (its low 2W bits are the key); positions 64..66 only feed shift amounts
+            auto raw = [&](int j) -> uint32_t {
+                return (j & 15) ? __funnelshift_r(r[j >> 4], r[(j >> 4) + 1], 2 * (j & 15)) : r[j >> 4];
+            };
+            // collect the MSB of each probe result as bit j of the pass mask (descending j: one funnel shift each)
+#pragma unroll
+            for (int j = 31; j >= 0; --j)
+                c_lo = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_lo, 1);
+#pragma unroll
+            for (int j = 63; j >= 32; --j)
+                c_hi = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_hi, 1);
+            c_lo &= (uint32_t)wv;
+            c_hi &= (uint32_t)(wv >> 32);
+        }
+    }
 }
 
 // Persistent CTAs, one per SM, made of AUTONOMOUS warps: there is no CTA-wide barrier after the prologue, so
@@ -573,33 +611,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         const uint32_t lp0 = (uint32_t)lane * kPosPerThread;  // unit-local
         uint32_t c_lo = 0, c_hi = 0;
         bool my_clean = false;
-        if (lp0 < unit_nbases) {
-            const uint2 v0 = *reinterpret_cast<const uint2*>(s_v + 2 * lane);
-            const uint2 v1 = *reinterpret_cast<const uint2*>(s_v + 2 * lane + 2);
-            my_clean = (v0.x & v0.y & v1.x) == 0xFFFFFFFFu;  // own 64 bases + the 32 behind them (W + tag <= 24)
-            // W-mer validity of the 64 positions: all ones on clean sequence, else log-doubling over the valid bits
-            uint64_t wv = ~0ull;
-            if (!my_clean) wv = window_valid(((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v1.y << 32) | v1.x, W);
-            const uint32_t left = unit_nbases - lp0;
-            if (left < 64u) wv &= (1ull << left) - 1ull;
-            if (wv) {
-                const uint4 q = *reinterpret_cast<const uint4*>(s_p2 + 4 * lane);
-                const uint32_t r[6] = {q.x, q.y, q.z, q.w, s_p2[4 * lane + 4], 0u};
-                // raw register of position j (its low 2W bits are the key); positions 64..66 only feed shift amounts
-                auto raw = [&](int j) -> uint32_t {
-                    return (j & 15) ? __funnelshift_r(r[j >> 4], r[(j >> 4) + 1], 2 * (j & 15)) : r[j >> 4];
-                };
-                // collect the MSB of each probe result as bit j of the pass mask (descending j: one funnel shift each)
-#pragma unroll
-                for (int j = 31; j >= 0; --j)
-                    c_lo = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_lo, 1);
-#pragma unroll
-                for (int j = 63; j >= 32; --j)
-                    c_hi = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_hi, 1);
-                c_lo &= (uint32_t)wv;
-                c_hi &= (uint32_t)(wv >> 32);
-            }
-        }
+        stage1_unit<WIDE>(s_filter, s_p2, s_v, lane, unit_nbases, W, cw, fw, c_lo, c_hi, my_clean);
         if (a.debug & 1) {
             n_dbg += __popc(c_lo) + __popc(c_hi);
             __syncwarp();
@@ -636,8 +648,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
                                      ? total
                                      : __shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));  // lane 0 always fits
             __syncwarp();
-            if (all_clean) probe_queue<true>(a, ws, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
-            else probe_queue<false>(a, ws, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
+            if (all_clean) probe_queue<true>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
+            else probe_queue<false>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
             __syncwarp();
             if (fit_mask == 0xffffffffu) break;
         }
