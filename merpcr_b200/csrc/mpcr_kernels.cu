@@ -105,6 +105,15 @@ static int ensure(void** p, size_t* cap, size_t need) {
 // ---------------------------------------------------------------------------------------------------------
 // One thread packs 64 bases: 4 x 16-byte loads -> 1 valid word, 2 plane2 words, 4 plane4 words.
 // lut[c] = nibble | code2 << 4 | clean << 6.
+// The source may start at any byte (records of the device-side FASTA ingest lie back to back in one buffer): a strip
+// then reads the five ALIGNED 16-byte chunks that cover it and funnel-shifts them into place.  An aligned chunk that
+// holds at least one byte of the record lies inside the caller's allocation (allocations begin and end on 16-byte
+// boundaries), so nothing outside it is touched.
+template <int WS>
+__device__ __forceinline__ void pack_shift_words(const uint32_t (&a)[20], uint32_t byte_shift, uint32_t (&w)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = __funnelshift_r(a[i + WS], a[i + WS + 1], byte_shift);
+}
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ ascii, uint64_t n, uint64_t dst_rel,
                                                    uint64_t* __restrict__ plane2, uint64_t* __restrict__ plane4,
                                                    uint64_t* __restrict__ valid, const uint8_t* __restrict__ lut_g) {
@@ -115,37 +124,52 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ a
     const uint64_t b0 = strip * 64;
     if (b0 >= n) return;
     uint64_t v = 0, p2[2] = {0, 0}, p4[4] = {0, 0, 0, 0};
-    const bool full = (b0 + 64 <= n) && ((reinterpret_cast<uintptr_t>(ascii) & 15u) == 0);
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(ascii) & 15u);
+    uint32_t w[16];
+    if (b0 + 64 <= n && mis == 0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint32_t w[4];
-        if (full) {
-            uint4 t = *reinterpret_cast<const uint4*>(ascii + b0 + 16 * q);
-            w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t x = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    uint64_t i = b0 + 16 * q + 4 * k + b;
-                    // bytes past n encode as 0 ('\0' maps to an invalid zero nibble in every LUT)
-                    uint32_t c = i < n ? ascii[i] : 0u;
-                    x |= c << (8 * b);
-                }
-                w[k] = x;
-            }
+        for (int q = 0; q < 4; ++q) {
+            const uint4 t = *reinterpret_cast<const uint4*>(ascii + b0 + 16 * q);
+            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
         }
+    } else if (b0 + 64 <= n) {
+        uint32_t a[20];
+        const uint4* src = reinterpret_cast<const uint4*>(ascii - mis + b0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int q = 0; q < 5; ++q) {
+            const uint4 t = src[q];
+            a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w;
+        }
+        const uint32_t bs = 8u * (mis & 3u);
+        switch (mis >> 2) {   // the same for every thread of the launch
+            case 0: pack_shift_words<0>(a, bs, w); break;
+            case 1: pack_shift_words<1>(a, bs, w); break;
+            case 2: pack_shift_words<2>(a, bs, w); break;
+            default: pack_shift_words<3>(a, bs, w); break;
+        }
+    } else {   // the last strip of the call
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            uint32_t x = 0;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const int j = 16 * q + 4 * k + b;  // base index inside the strip
-                const uint32_t e = lut[(w[k] >> (8 * b)) & 0xFFu];
-                p4[j >> 4] |= (uint64_t)(e & 15u) << (4 * (j & 15));
-                p2[j >> 5] |= (uint64_t)((e >> 4) & 3u) << (2 * (j & 31));
-                v |= (uint64_t)((e >> 6) & 1u) << j;
+                const uint64_t i = b0 + 4 * k + b;
+                // bytes past n encode as 0 ('\0' maps to an invalid zero nibble in every LUT)
+                const uint32_t c = i < n ? ascii[i] : 0u;
+                x |= c << (8 * b);
             }
+            w[k] = x;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = 4 * k + b;  // base index inside the strip
+            const uint32_t e = lut[(w[k] >> (8 * b)) & 0xFFu];
+            p4[j >> 4] |= (uint64_t)(e & 15u) << (4 * (j & 15));
+            p2[j >> 5] |= (uint64_t)((e >> 4) & 3u) << (2 * (j & 31));
+            v |= (uint64_t)((e >> 6) & 1u) << j;
         }
     }
     const uint64_t s = dst_rel / 64 + strip;
@@ -306,6 +330,10 @@ struct ScanArgs {
     uint32_t surv_cap;
     uint32_t* surv_ctl;    // per sub-list, 128 bytes apart: [0] entries appended (may exceed surv_cap), [1] verify cursor
     int debug;  // MPCR_DEBUG bit0: stop after the filter stage; bit1: probe the table but drop the survivors
+    // Pipe balancing of stage 1 (MPCR_S1_FMA): multipliers the compiler cannot see through, so that shifts by a
+    // constant stay multiplies (IMAD / IMAD.HI on the fma pipe) instead of becoming SHF / LEA on the saturated alu pipe.
+    uint32_t k4;          // 4
+    uint32_t pow2[32];    // pow2[j] = 2^(j+1) for j < 31 (x * pow2[j] >> 32 == x >> (31 - j)), pow2[31] = 1
 };
 
 // shared-memory plan of the scanner CTA (dynamic shared memory): one private block per warp, then the filter
@@ -410,10 +438,23 @@ __device__ __noinline__ void probe_collision(const ScanArgs& a, uint32_t key, ui
 // One filter probe: returns a word whose MSB is set iff both Bloom bits of the key are set.
 // x holds the key in its low 2W bits (anything above cancels in the multiply by cw); x3 is the raw register of
 // the position three bases further on, i.e. x >> 6 in its low bits (WIDE: W >= 6, else the second bit == the first).
+#ifndef MPCR_S1_FMA
+#define MPCR_S1_FMA 1   // bit0: filter word address by IMAD; bit1: pass-bit collection by IMAD.HI; bit2: keys by IMAD.HI
+#endif
+struct FilterView {
+    const uint32_t* words;   // the filter in shared memory
+    uint32_t base32;         // its shared-window address
+    uint32_t cw, n_words;
+};
 template <bool WIDE>
-__device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ s_filter, uint32_t x, uint32_t x3,
-                                                 uint32_t cw, uint32_t n_words) {
-    const uint32_t word = s_filter[__umulhi(x * cw, n_words)];
+__device__ __forceinline__ uint32_t filter_probe(const FilterView& f, const ScanArgs& a, uint32_t x, uint32_t x3) {
+    uint32_t word;
+#if MPCR_S1_FMA & 1
+    const uint32_t addr = __umulhi(x * f.cw, f.n_words) * a.k4 + f.base32;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
+#else
+    word = f.words[__umulhi(x * f.cw, f.n_words)];
+#endif
     const uint32_t t1 = __funnelshift_l(0u, word, x);  // word << (x & 31)
     if (!WIDE) return t1;
     return t1 & __funnelshift_l(0u, word, x3);
@@ -491,9 +532,9 @@ __device__ __forceinline__ void probe_queue(const ScanArgs& a, const uint16_t* _
 // Stage 1 for one unit of 2048 positions: lane l owns positions [64l, 64l+64) -- rolling keys by funnel shift out of
 // five registers, one shared-memory Bloom probe (two bits of one word) per position.  c_lo / c_hi: pass masks.
 template <bool WIDE>
-__device__ __forceinline__ void stage1_unit(const uint32_t* __restrict__ s_filter, const uint32_t* __restrict__ s_p2,
+__device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs& a, const uint32_t* __restrict__ s_p2,
                                             const uint32_t* __restrict__ s_v, int lane, uint32_t unit_nbases, int W,
-                                            uint32_t cw, uint32_t fw, uint32_t& c_lo, uint32_t& c_hi, bool& my_clean) {
+                                            uint32_t& c_lo, uint32_t& c_hi, bool& my_clean) {
     const uint32_t lp0 = (uint32_t)lane * kPosPerThread;  // unit-local
     if (lp0 < unit_nbases) {
         const uint2 v0 = *reinterpret_cast<const uint2*>(s_v + 2 * lane);
@@ -509,15 +550,33 @@ __device__ __forceinline__ void stage1_unit(const uint32_t* __restrict__ s_filte
             const uint32_t r[6] = {q.x, q.y, q.z, q.w, s_p2[4 * lane + 4], 0u};
             // raw register of position j (its low 2W bits are the key); positions 64..66 only feed shift amounts
             auto raw = [&](int j) -> uint32_t {
+#if MPCR_S1_FMA & 4
+                // 2 (j & 15) + 2W <= 32: a plain right shift of one register holds the whole key -> IMAD.HI
+                if ((j & 15) && 2 * (j & 15) <= 10) return __umulhi(r[j >> 4], a.pow2[31 - 2 * (j & 15)]);
+#endif
                 return (j & 15) ? __funnelshift_r(r[j >> 4], r[(j >> 4) + 1], 2 * (j & 15)) : r[j >> 4];
             };
+#if MPCR_S1_FMA & 2
+            // pass bit j = MSB of the probe result: (m * 2^(j+1)) >> 32 puts it at bit j, as one IMAD.HI with addend
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t m = filter_probe<WIDE>(f, a, raw(j), raw(j + 3)) & 0x80000000u;
+                c_lo = (j < 31 ? __umulhi(m, a.pow2[j]) : m * a.pow2[31]) + c_lo;
+            }
+#pragma unroll
+            for (int j = 32; j < 64; ++j) {
+                const uint32_t m = filter_probe<WIDE>(f, a, raw(j), raw(j + 3)) & 0x80000000u;
+                c_hi = (j < 63 ? __umulhi(m, a.pow2[j - 32]) : m * a.pow2[31]) + c_hi;
+            }
+#else
             // collect the MSB of each probe result as bit j of the pass mask (descending j: one funnel shift each)
 #pragma unroll
             for (int j = 31; j >= 0; --j)
-                c_lo = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_lo, 1);
+                c_lo = __funnelshift_l(filter_probe<WIDE>(f, a, raw(j), raw(j + 3)), c_lo, 1);
 #pragma unroll
             for (int j = 63; j >= 32; --j)
-                c_hi = __funnelshift_l(filter_probe<WIDE>(s_filter, raw(j), raw(j + 3), cw, fw), c_hi, 1);
+                c_hi = __funnelshift_l(filter_probe<WIDE>(f, a, raw(j), raw(j + 3)), c_hi, 1);
+#endif
             c_lo &= (uint32_t)wv;
             c_hi &= (uint32_t)(wv >> 32);
         }
@@ -587,7 +646,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     __syncthreads();
 
     const int W = a.prm.W;
-    const uint32_t cw = a.cw, fw = a.filter_words;
+    const FilterView fv{s_filter, smem_u32(s_filter), a.cw, a.filter_words};
     unsigned long long n_dbg = 0;
 
     for (uint32_t it = 0; p_tile < a.n_tiles; ++it) {
@@ -611,7 +670,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         const uint32_t lp0 = (uint32_t)lane * kPosPerThread;  // unit-local
         uint32_t c_lo = 0, c_hi = 0;
         bool my_clean = false;
-        stage1_unit<WIDE>(s_filter, s_p2, s_v, lane, unit_nbases, W, cw, fw, c_lo, c_hi, my_clean);
+        stage1_unit<WIDE>(fv, a, s_p2, s_v, lane, unit_nbases, W, c_lo, c_hi, my_clean);
         if (a.debug & 1) {
             n_dbg += __popc(c_lo) + __popc(c_hi);
             __syncwarp();
@@ -1403,6 +1462,9 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.prm.W = c->scan_w; a.prm.M = c->prm.margin; a.prm.N = c->prm.mismatches; a.prm.X = c->prm.three_prime_match;
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
     a.debug = getenv("MPCR_DEBUG") ? atoi(getenv("MPCR_DEBUG")) : 0;
+    a.k4 = 4u;
+    for (int j = 0; j < 31; ++j) a.pow2[j] = 2u << j;
+    a.pow2[31] = 1u;
     a.hits = d_hits; a.capacity = capacity; a.count = (unsigned long long*)d_count; a.tile_counter = c->d_tile_counter;
     a.surv = c->d_surv; a.surv_cap = (uint32_t)(c->surv_bytes / sizeof(Survivor) / kSurvLists); a.surv_ctl = c->d_surv_ctl;
     if (const char* env = getenv("MPCR_SURVIVOR_CAP")) {   // test hook: force the list-full path (in-kernel verify)

@@ -108,6 +108,32 @@ def test_pack_planes_match_numpy():
         assert not sh.plane4.cpu().numpy().view(np.uint64)[len(p4):].any()     # padding stays zero / invalid
 
 
+def test_pack_from_unaligned_device_source():
+    """Sequences the device-side ingest leaves in HBM start at arbitrary byte offsets of one buffer: pack_kernel's
+    aligned-chunk path (five 16-byte loads + funnel shifts) must give the same planes as the aligned path, for every
+    misalignment and for lengths around the strip size."""
+    import torch
+    from merpcr_b200 import MerPCR
+    rng = synth.Rng(17)
+    big = rng.dna(70000)
+    letters = np.frombuffer(b"NRYKMSWBDHVXnacgt", dtype=np.uint8)
+    pos = rng.ints(0, len(big) - 1, 3000)
+    big[pos] = letters[rng.ints(0, len(letters) - 1, 3000)]
+    eng = MerPCR()
+    eng.load_sts_file(goldens.FIXTURE_STS)
+    dev = torch.from_numpy(big).to(eng._tdev)
+    for n in (1, 15, 63, 64, 65, 127, 128, 1000, 65536 + 21):
+        ref = None
+        for mis in range(0, 17):
+            src = dev[mis: mis + n]
+            lay = eng.make_layout([n])
+            sh = eng.upload(lay, [big[mis: mis + n]])            # host bytes -> aligned staging buffer
+            want = (sh.plane2.cpu().numpy().copy(), sh.plane4.cpu().numpy().copy(), sh.valid.cpu().numpy().copy())
+            sh2 = eng.upload(lay, [src])                          # device slice, misaligned by `mis` bytes
+            got = (sh2.plane2.cpu().numpy(), sh2.plane4.cpu().numpy(), sh2.valid.cpu().numpy())
+            assert all(np.array_equal(a, b) for a, b in zip(want, got)), (n, mis)
+
+
 def test_device_table_matches_oracle(tmp_path):
     """Device-built records (hash offsets, hash values, reverse complements) vs the oracle's load (engine.py:253-281)."""
     from merpcr_b200 import MerPCR
