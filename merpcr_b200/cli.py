@@ -86,6 +86,9 @@ def create_parser() -> argparse.ArgumentParser:
                         help=f"Max. line length for the STS file (default: {DEFAULT_MAX_STS_LINE_LENGTH})")
     parser.add_argument("-v", "--version", action="version", version="merPCR version 1.0.0")
     parser.add_argument("--debug", action="store_true", help="Enable debug logging")
+    parser.add_argument("--gpus", type=int, default=1,
+                        help="NOT a reference flag: scan on this many GPUs of the node (one process per GPU, the genome "
+                             "sharded by bp-balanced ranges with halos, final hit gather on rank 0); 0 = all visible")
     parser.add_argument("--true-strands", action="store_true",
                         help="NOT reference behaviour: report forward amplicons primer1 ... revcomp(primer2) as (+), "
                              "like NCBI me-PCR, instead of the reference's primer1 ... primer2")
@@ -97,11 +100,25 @@ def main() -> int:
     args = create_parser().parse_args(convert_mepcr_arguments(sys.argv[1:]))
     setup_logging(args.quiet, args.debug)
     logger = logging.getLogger("merpcr")
+    from . import multi
+    rank, world, local = multi.env_world()
+    if world == 1 and args.gpus != 1:        # parent of a multi-GPU run: re-launch this command line as N ranks
+        n = args.gpus
+        if n == 0:
+            import torch
+            n = torch.cuda.device_count()
+        if n > 1:
+            return multi.launch(n, sys.argv[1:])
     try:
+        if world > 1:                        # one rank of a multi-GPU run (launched above or by torchrun)
+            multi.init_from_env()
+            if rank != 0:
+                logger.setLevel(logging.WARNING)
         mer_pcr = MerPCR(wordsize=args.wordsize, margin=args.margin, mismatches=args.mismatches,
                          three_prime_match=args.three_prime_match, iupac_mode=args.iupac,
                          default_pcr_size=args.default_pcr_size, threads=args.threads,
-                         max_sts_line_length=args.max_sts_line_length, true_strands=args.true_strands)
+                         max_sts_line_length=args.max_sts_line_length, true_strands=args.true_strands,
+                         **(dict(shard=(rank, world), device=local) if world > 1 else {}))
         if not mer_pcr.load_sts_file(args.sts_file):
             logger.error(f"Failed to load STS file: {args.sts_file}")
             return 1
@@ -118,6 +135,11 @@ def main() -> int:
             import traceback
             traceback.print_exc()
         return 1
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -512,8 +512,13 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
     }
 }
 
+#ifdef MPCR_PROBE_NOINLINE
+#define MPCR_PROBE_INLINE __noinline__
+#else
+#define MPCR_PROBE_INLINE __forceinline__
+#endif
 template <bool CLEAN>
-__device__ __forceinline__ void probe_queue(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
+__device__ MPCR_PROBE_INLINE void probe_queue(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
                                             const uint32_t* __restrict__ s_p2, const uint32_t* __restrict__ s_v,
                                             uint32_t cnt, int lane, uint32_t tile, uint32_t ubase,
                                             unsigned long long& n_dbg) {
@@ -671,6 +676,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         uint32_t c_lo = 0, c_hi = 0;
         bool my_clean = false;
         stage1_unit<WIDE>(fv, a, s_p2, s_v, lane, unit_nbases, W, c_lo, c_hi, my_clean);
+#ifdef MPCR_STAGE1_ONLY   // tuning builds: the kernel without its stage 2 (what the register allocator does to stage 1 alone)
+        n_dbg += __popc(c_lo) + __popc(c_hi);
+        __syncwarp();
+        continue;
+#else
         if (a.debug & 1) {
             n_dbg += __popc(c_lo) + __popc(c_hi);
             __syncwarp();
@@ -713,6 +723,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
             if (fit_mask == 0xffffffffu) break;
         }
         __syncwarp();  // every lane is done with this buffer before lane 0 refills it two steps from now
+#endif
     }
     if (a.debug) {
         for (int d = 16; d; d >>= 1) n_dbg += __shfl_xor_sync(0xffffffffu, n_dbg, d);

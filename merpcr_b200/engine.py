@@ -25,7 +25,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from . import _capi
+from . import _capi, multi
 from .alphabet import genome_exotics, genome_lut, primer_exotics, primer_lut
 from .fasta import FASTALoader
 from .models import FASTARecord, STSHit, STSRecord, ThreadData  # noqa: F401  (re-exported like the reference)
@@ -531,15 +531,23 @@ class MerPCR:
     def search(self, fasta_records: List[FASTARecord], output_file: str = None) -> int:
         """Search for STS markers in the provided FASTA sequences; prints one line per hit (engine.py:442)."""
         total_hits = 0
-        if output_file and output_file.lower() != "stdout":
+        # one rank of a multi-GPU run (multi.py): every rank scans its shard, rank 0 gathers, merges and writes
+        gather = multi.active_world(self.shard)
+        writer = not gather or self.shard[0] == 0
+        if writer and output_file and output_file.lower() != "stdout":
             output = open(output_file, "w")
         else:
             output = sys.stdout
         try:
             hits = self.search_hits(fasta_records) if fasta_records else np.zeros(0, dtype=_capi.HIT_DTYPE)
-            for record in fasta_records:
-                logger.info(f"Processing sequence: {record.label} ({len(record)} bp)")
+            if writer:
+                for record in fasta_records:
+                    logger.info(f"Processing sequence: {record.label} ({len(record)} bp)")
             total_hits = int(hits.size)
+            if gather:
+                hits, total_hits = multi.gather_hits(hits)
+                if hits is None:
+                    hits = np.zeros(0, dtype=_capi.HIT_DTYPE)
             src = self._sts_lines
             labels = [r.label for r in fasta_records]
             if hits.size and src is not None and src.lines is not None and all(lb.isascii() for lb in labels):

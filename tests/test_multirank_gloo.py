@@ -77,3 +77,93 @@ def _rank_main_planted(rank, world, port, sts_path, out_path, contigs_path, leng
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the product's own multi-GPU path (merpcr_b200/multi.py): `search` and the CLI as ranks of a process group --
+# every rank scans its shard, rank 0 gathers, merges and writes exactly the single-process output text
+# ---------------------------------------------------------------------------------------------------------
+def _fasta_and_sts(tmp_path, seed):
+    import synth
+    rng = synth.Rng(seed)
+    contigs = [rng.dna(n) for n in (90000, 300, 51000, 12, 70001)]
+    sts = synth.make_sts_set(seed + 1, 120, 18, 25, 100, 700)
+    synth.plant_amplicons(seed + 2, contigs, sts, 50, sub_mode="cfg3")
+    sts_path, fa_path = str(tmp_path / "m.sts"), str(tmp_path / "m.fa")
+    with open(sts_path, "wb") as f:
+        f.write(synth.sts_lines(sts))
+    with open(fa_path, "wb") as f:
+        for i, c in enumerate(contigs):
+            f.write(b">ctg%d some text\n" % i)
+            for a in range(0, len(c), 70):
+                f.write(c[a:a + 70].tobytes() + b"\n")
+    return sts_path, fa_path
+
+
+def _single_process_text(sts_path, fa_path, out_path):
+    import emul
+    emul.inject()
+    from merpcr_b200 import MerPCR
+    eng = MerPCR(**PARAMS)
+    assert eng.load_sts_file(sts_path)
+    n = eng.search(eng.load_fasta_file(fa_path), out_path)
+    return n, open(out_path).read()
+
+
+def _rank_main_search(rank, world, port, sts_path, fa_path, out_path, totals_path):
+    for p in (os.path.dirname(HERE), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    import emul
+    emul.inject()
+    from merpcr_b200 import MerPCR
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        eng = MerPCR(**PARAMS, shard=(rank, world))
+        assert eng.load_sts_file(sts_path)
+        n = eng.search(eng.load_fasta_file(fa_path), out_path)
+        assert n == eng.total_hits
+        with open(f"{totals_path}.{rank}", "w") as f:
+            f.write(str(n))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_search_gathers_hits_on_rank0(tmp_path, world):
+    import torch.multiprocessing as mp
+    sts_path, fa_path = _fasta_and_sts(tmp_path, 611)
+    n1, want = _single_process_text(sts_path, fa_path, str(tmp_path / "one.txt"))
+    assert n1 > 50
+    out_path, totals = str(tmp_path / "multi.txt"), str(tmp_path / "total")
+    mp.spawn(_rank_main_search, args=(world, _free_port(), sts_path, fa_path, out_path, totals), nprocs=world, join=True)
+    assert open(out_path).read() == want                       # rank 0 wrote the merged list, byte for byte
+    assert [int(open(f"{totals}.{r}").read()) for r in range(world)] == [n1] * world   # every rank knows the total
+
+
+def _rank_main_cli(rank, world, port, argv, rc_path):
+    for p in (os.path.dirname(HERE), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import emul
+    emul.inject()
+    from merpcr_b200 import cli
+    sys.argv = ["merpcr"] + argv
+    rc = cli.main()
+    with open(f"{rc_path}.{rank}", "w") as f:
+        f.write(str(rc))
+
+
+def test_cli_as_ranks_of_a_launch(tmp_path):
+    """What `python -m merpcr_b200 --gpus 2 ...` runs in each of its worker processes (torchrun environment)."""
+    import torch.multiprocessing as mp
+    sts_path, fa_path = _fasta_and_sts(tmp_path, 733)
+    n1, want = _single_process_text(sts_path, fa_path, str(tmp_path / "one.txt"))
+    out_path, rc_path = str(tmp_path / "cli.txt"), str(tmp_path / "rc")
+    argv = ["-M", "50", "N=1", "-W", "11", "--gpus", "2", "-O", out_path, sts_path, fa_path]
+    mp.spawn(_rank_main_cli, args=(2, _free_port(), argv, rc_path), nprocs=2, join=True)
+    assert [open(f"{rc_path}.{r}").read() for r in range(2)] == ["0", "0"]
+    assert open(out_path).read() == want
