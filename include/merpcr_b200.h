@@ -93,6 +93,12 @@ void mpcr_ctx_destroy(mpcr_ctx *ctx);
  * Scanning both tables over the same planes and sorting the concatenated hits gives exactly the one-table result.
  * Call before mpcr_table_build; drops the current table. */
 int mpcr_ctx_set_seed_extension(mpcr_ctx *ctx, int w_ext, int which);
+/* Table partitioning: this context's next table holds only the STS lines with (line index % parts) == part
+ * (parts = 0 or 1: every line, the default).  The shared-memory filter of the scanner has room for about 6.5 bits per
+ * key at 2*10^5 keys; an exact search with 10^6 STS is therefore split into several extended tables (which = 2) of
+ * at most a few 10^5 records each, scanned one after the other over the same planes -- every record lives in exactly
+ * one table, so the concatenated, sorted hits are again the one-table result.  Call before mpcr_table_build. */
+int mpcr_ctx_set_table_part(mpcr_ctx *ctx, uint32_t part, uint32_t parts);
 /* NOT reference behaviour, off by default: with on != 0 the "+" record of an STS line looks for
  * primer1 ... revcomp(primer2) -- a biologically normal forward amplicon, as NCBI me-PCR does -- instead of the
  * reference's primer1 ... primer2 (core/engine.py:267).  "-" records are unchanged.  Call before mpcr_table_build. */

@@ -379,6 +379,11 @@ struct Slot {          // 16 bytes, one 128-bit gather
 static_assert(sizeof(Slot) == 16, "Slot layout");
 static constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu;   // cudaMemset(0xFF) == all slots empty
 static constexpr uint32_t kWalkBucket = 0x80000000u;  // survivor code flag: "walk the bucket starting at code & ~flag"
+// Open-addressed tables only: set on every slot that the probe sequence of some key stored FURTHER ON passes through
+// (mark_chains, after the table is complete).  A first probe that lands on another key's slot without this flag has
+// proved its key absent -- which is what keeps the scanner's false-positive candidates off the synchronous probe path.
+// Record indices stay below 2^30 (< 2^29 STS lines), so the bit is free; readers strip it from survivor codes.
+static constexpr uint32_t kSlotChain = 0x40000000u;
 
 struct BucketEntry {
     uint32_t rec_last;  // record index | last-of-bucket << 31
@@ -463,7 +468,7 @@ MPCR_HD bool find_slot(const Slot* slots, SlotMap sm, uint32_t key, Slot* out) {
     for (;;) {
         const Slot s = load_slot(slots + i);
         if (s.code == kSlotEmpty) return false;
-        if (sm.direct || s.key == key) { *out = s; return true; }
+        if (sm.direct || s.key == key) { *out = s; out->code &= ~kSlotChain; return true; }
         i = (i + 1) & sm.mask;
     }
 }

@@ -62,6 +62,7 @@ struct mpcr_ctx {
     uint32_t n_keys = 0;
     bool dense = false;
     int ext_w = 0, ext_which = 0;   // seed extension (mpcr_ctx_set_seed_extension)
+    uint32_t part = 0, parts = 1;   // table partition (mpcr_ctx_set_table_part)
     int true_strands = 0;           // mpcr_ctx_set_true_strands
     int scan_w = 0;                 // word width the scanner keys on: ext_w for an extended table, else wordsize
     uint32_t max_hash_off = 0, max_len = 0;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
                                                       const uint8_t* __restrict__ plut,
                                                       const uint32_t* __restrict__ word_off,  // 2*n_rec+1 prefix
                                                       int W, int w_scan, int which, int true_strands,
+                                                      uint32_t part, uint32_t parts,
                                                       RecMeta* __restrict__ meta,
                                                       uint64_t* __restrict__ pwords, Item<2>* __restrict__ pairs,
                                                       uint32_t* __restrict__ stats) {
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
         encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p1_word);
         encode_primer(BlobRc{pr1, n1}, n1, plut, pwords + m.p2_word);
     }
-    const bool here = ho >= 0 && (which == 0 || (which == 1 ? !ext : ext));
+    const bool here = ho >= 0 && (which == 0 || (which == 1 ? !ext : ext)) && (parts <= 1u || line % parts == part);
     m.hash_be = hbe;
     m.key = which == 2 ? kext : reverse_digits(hbe, W);
     m.hash_off = (uint16_t)(ho < 0 ? 0 : ho);
@@ -297,6 +299,16 @@ __global__ void __launch_bounds__(256) build_buckets(const Item<2>* __restrict__
         atomicOr(&filter[filter_word(key, cw, filter_words)], filter_bits_of(key, W));
         atomicAdd(n_keys, 1u);
     }
+}
+
+// Open-addressed tables, after build_buckets: flag every slot a stored key had to step over (kSlotChain).
+__global__ void __launch_bounds__(256) mark_chains(const Item<2>* __restrict__ pairs, uint32_t n_valid,
+                                                   Slot* __restrict__ slots, SlotMap sm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_valid) return;
+    const uint32_t key = pairs[i].f[0];
+    if (i != 0 && pairs[i - 1].f[0] == key) return;   // one walk per distinct key
+    for (uint32_t s = slot_index(key, sm); slots[s].key != key; s = (s + 1) & sm.mask) atomicOr(&slots[s].code, kSlotChain);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -501,13 +513,15 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
         else if (u == 2) gather_wait<(R > 3 ? R - 3 : 0)>();
         else gather_wait<0>();
         const uint4 v = landing[u][lane];
-        const bool collide = hashed && v.x != key[u];
-        const bool pass = dirty[u] || !(tag_rejects(v.z, gcodes[u], N) && tag_rejects(v.w, gcodes[u], N));
+        // hashed mode: another key's slot ends the search unless a stored key's probe sequence runs through it
+        const bool other = hashed && v.x != key[u];
+        const bool collide = other && (v.y & kSlotChain);
+        const bool pass = !other && (dirty[u] || !(tag_rejects(v.z, gcodes[u], N) && tag_rejects(v.w, gcodes[u], N)));
         if (ok[u] && v.y != kSlotEmpty && (collide || pass)) {  // about one queued position in a thousand
             const uint32_t lp = ubase + lpv[u];
             if (a.debug & 2) ++n_dbg;
             else if (collide) probe_collision(a, key[u], gcodes[u] & 0xFFFFu, dirty[u] ? 0u : 0xFFu, tile, lp);
-            else push_survivor(a, tile, lp, v.y);
+            else push_survivor(a, tile, lp, v.y & ~kSlotChain);
         }
     }
 }
@@ -1060,6 +1074,15 @@ int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
     free_table(c);
     return MPCR_OK;
 }
+int mpcr_ctx_set_table_part(mpcr_ctx* c, uint32_t part, uint32_t parts) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (parts == 0) parts = 1;
+    if (part >= parts) return fail(MPCR_EINVAL, "part must be < parts");
+    c->part = part;
+    c->parts = parts;
+    free_table(c);
+    return MPCR_OK;
+}
 int mpcr_ctx_set_true_strands(mpcr_ctx* c, int on) {
     if (!c) return fail(MPCR_EINVAL, "null argument");
     c->true_strands = on ? 1 : 0;
@@ -1284,7 +1307,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         CUG(cudaMemsetAsync(d_stats, 0, 16, st));
         encode_records<<<(n_rec + 127) / 128, 128, 0, st>>>(d_blob, d_off, d_pcr, n_lines, d_plut, d_woff, W,
                                                              c->ext_which ? c->ext_w : W, c->ext_which, c->true_strands,
-                                                             c->d_meta,
+                                                             c->part, c->parts, c->d_meta,
                                                              c->d_pwords, d_pairs, d_stats);
         c->launches++;
         CUG(cudaGetLastError());
@@ -1326,6 +1349,11 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
                                                                      c->filter_words, filter_mul(WS), WS, d_stats);
             c->launches++;
             CUG(cudaGetLastError());
+            if (!c->smap.direct) {
+                mark_chains<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_pairs, c->n_valid, c->d_slots, c->smap);
+                c->launches++;
+                CUG(cudaGetLastError());
+            }
             CUG(cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, st));
         }
         CUG(cudaStreamSynchronize(st));

@@ -46,7 +46,8 @@ MIN_MARGIN, MAX_MARGIN = 0, 10000
 MIN_THREE_PRIME_MATCH = 0
 MIN_PCR_SIZE, MAX_PCR_SIZE = 1, 10000
 
-EXTENDED_WORDSIZE = 11        # key width of the second table of exact, candidate-heavy searches
+EXTENDED_WORDSIZE = 16        # key width of the extended tables of exact, candidate-heavy searches
+EXT_LINES_PER_TABLE = 125_000  # STS lines per extended table: 2.5*10^5 keys is what the scanner's filter holds at ~5 % f.p.
 PCR_SIZE_CLAMP = 0x7FFFFFFF   # any expected size >= a contig length behaves identically (engine.py:531-533)
 PLANE_SLACK_BASES = 1024      # read-ahead of the last strip / last primer window
 
@@ -187,7 +188,7 @@ class MerPCR:
         else:
             self._tdev = torch.device("cpu")
         self._ctx = None
-        self._ctx_ext = None      # second table for exact, candidate-heavy searches (mpcr_ctx_set_seed_extension)
+        self._ctx_exts = []       # extended tables of exact, candidate-heavy searches (mpcr_ctx_set_seed_extension)
         self._create_ctx()
         # parsed STS lines kept so the table can be re-encoded if a sequence brings an unusual alphabet
         self._sts_lines = None
@@ -213,9 +214,9 @@ class MerPCR:
         self._ctx = self._new_ctx()
 
     def close(self):
-        for name in ("_ctx", "_ctx_ext"):
-            ctx = getattr(self, name, None)
-            setattr(self, name, None)
+        ctxs = [getattr(self, "_ctx", None)] + list(getattr(self, "_ctx_exts", []))
+        self._ctx, self._ctx_exts = None, []
+        for ctx in ctxs:
             if ctx:
                 self._be.lib.mpcr_ctx_destroy(ctx)
 
@@ -236,10 +237,10 @@ class MerPCR:
 
     @property
     def gpu_launches(self) -> int:
-        n = int(self._be.lib.mpcr_launch_count(self._ctx))
-        if self._ctx_ext:
-            n += int(self._be.lib.mpcr_launch_count(self._ctx_ext))
-        return n
+        return sum(int(self._be.lib.mpcr_launch_count(c)) for c in self._all_ctxs())
+
+    def _all_ctxs(self):
+        return [self._ctx] + list(self._ctx_exts)
 
     # ------------------------------------------------------------------ engine.py:80-97
     def _validate_parameters(self):
@@ -386,25 +387,30 @@ class MerPCR:
             np.minimum(np.asarray(src.sizes, dtype=np.int64), PCR_SIZE_CLAMP).astype(np.uint32)
         plut = primer_lut(self.iupac_mode, self._zero_char)
         # Exact searches whose seed words cover a quarter or more of all 4^W words (small -W, many STS) are keyed on
-        # 11-letter words instead: two tables -- the records whose seed extends to 11 plain letters, and the rest.
+        # 16-letter words instead: the records whose seed extends to 16 plain letters go to extended tables of at most
+        # EXT_LINES_PER_TABLE lines each (what the scanner's shared-memory filter can hold), the rest stay in the
+        # ordinary table; every table is scanned over the same planes and the hits are sorted once.
         w_ext = EXTENDED_WORDSIZE
-        extend = (self.mismatches == 0 and not self.iupac_mode and self.wordsize < w_ext and
-                  8 * n >= 4 ** self.wordsize)
+        can_extend = self.mismatches == 0 and not self.iupac_mode and self.wordsize < w_ext
+        extend = can_extend and 8 * n >= 4 ** self.wordsize
         env = os.environ.get("MPCR_SEED_EXTENSION")
-        if env is not None and self.mismatches == 0 and not self.iupac_mode and self.wordsize < w_ext:
+        if env is not None and can_extend:
             extend = env not in ("0", "")
+        parts = max(1, -(-n // EXT_LINES_PER_TABLE)) if extend else 0
+        if extend and os.environ.get("MPCR_SEED_PARTS"):
+            parts = max(1, int(os.environ["MPCR_SEED_PARTS"]))
         self._be.check(lib.mpcr_ctx_set_seed_extension(self._ctx, w_ext if extend else 0, 1 if extend else 0))
         self._be.check(lib.mpcr_table_build(self._ctx, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
                                             plut.ctypes.data, self._stream()))
-        if extend:
-            if not self._ctx_ext:
-                self._ctx_ext = self._new_ctx()
-            self._be.check(lib.mpcr_ctx_set_seed_extension(self._ctx_ext, w_ext, 2))
-            self._be.check(lib.mpcr_table_build(self._ctx_ext, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
+        while len(self._ctx_exts) > parts:
+            lib.mpcr_ctx_destroy(self._ctx_exts.pop())
+        while len(self._ctx_exts) < parts:
+            self._ctx_exts.append(self._new_ctx())
+        for k, ctx in enumerate(self._ctx_exts):
+            self._be.check(lib.mpcr_ctx_set_seed_extension(ctx, w_ext, 2))
+            self._be.check(lib.mpcr_ctx_set_table_part(ctx, k, parts))
+            self._be.check(lib.mpcr_table_build(ctx, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
                                                 plut.ctypes.data, self._stream()))
-        elif self._ctx_ext:
-            lib.mpcr_ctx_destroy(self._ctx_ext)
-            self._ctx_ext = None
         ho = np.full(2 * n, -1, dtype=np.int32)
         hv = np.zeros(2 * n, dtype=np.uint32)
         self._be.check(lib.mpcr_table_records(self._ctx, ho.ctypes.data, hv.ctypes.data))
@@ -725,7 +731,7 @@ class MerPCR:
             sh.count = torch.zeros(1, dtype=torch.int64, device=self._tdev)
         isz = _capi.HIT_DTYPE.itemsize
         cap = 1 << 16 if sh.hits is None else sh.hits.numel() // isz
-        ctxs = [self._ctx] + ([self._ctx_ext] if self._ctx_ext else [])
+        ctxs = self._all_ctxs()
         while True:
             if sh.hits is None or sh.hits.numel() < cap * isz:
                 sh.hits = torch.empty(cap * isz, dtype=torch.uint8, device=self._tdev)

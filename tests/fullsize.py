@@ -97,7 +97,7 @@ def run(name, lengths, n_sts, params, sub_mode, ranged, seed, decorate, dev, ora
         hits_t, n = eng.scan_device(layout, shard, sort="--timing-only" not in sys.argv)
         torch.cuda.synchronize(); times.append(time.time() - t0)
     scan_ms = float(eng.last_scan_ms)      # scan kernels of every table (exact dense searches use two)
-    ver_ms = sum(float(eng._be.lib.mpcr_last_verify_ms(c)) for c in (eng._ctx, eng._ctx_ext) if c)
+    ver_ms = sum(float(eng._be.lib.mpcr_last_verify_ms(c)) for c in eng._all_ctxs() if c)
     if "--timing-only" in sys.argv:   # used with MPCR_DEBUG phase switches, where the "hits" are only a counter
         print(json.dumps(dict(config=name, count=int(n), scan_kernel_ms=round(scan_ms, 3), verify_kernel_ms=round(ver_ms, 3),
                               debug=os.environ.get("MPCR_DEBUG", "0"))), flush=True)

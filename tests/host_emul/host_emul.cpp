@@ -43,6 +43,7 @@ struct mpcr_ctx {
     bool table_ready = false;
     uint64_t launches = 0;
     int ext_w = 0, ext_which = 0, scan_w = 0, true_strands = 0;
+    uint32_t part = 0, parts = 1;
 };
 
 extern "C" {
@@ -77,6 +78,13 @@ int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
         if (w_ext <= c->prm.wordsize || w_ext > 16) return fail(MPCR_EINVAL, "extended word must be in (wordsize, 16]");
     }
     c->ext_w = which ? w_ext : 0; c->ext_which = which; c->table_ready = false;
+    return MPCR_OK;
+}
+int mpcr_ctx_set_table_part(mpcr_ctx* c, uint32_t part, uint32_t parts) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (parts == 0) parts = 1;
+    if (part >= parts) return fail(MPCR_EINVAL, "part must be < parts");
+    c->part = part; c->parts = parts; c->table_ready = false;
     return MPCR_OK;
 }
 int mpcr_ctx_sm_count(const mpcr_ctx*) { return 1; }
@@ -213,7 +221,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
                 encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p1_word);
                 encode_primer(Rc{pr1, n1}, n1, plut, c->pwords.data() + m.p2_word);
             }
-            const bool here = ho >= 0 && (c->ext_which == 0 || (c->ext_which == 1 ? !ext : ext));
+            const bool here = ho >= 0 && (c->ext_which == 0 || (c->ext_which == 1 ? !ext : ext)) &&
+                              (c->parts <= 1u || (r >> 1) % c->parts == c->part);
             m.hash_be = hbe; m.key = c->ext_which == 2 ? kext : reverse_digits(hbe, W);
             m.hash_off = (uint16_t)(ho < 0 ? 0 : ho); m.flags = (ho >= 0 ? 1 : 0) | (here ? 2 : 0);
             if (ho >= 0) c->max_hash_off = std::max(c->max_hash_off, (uint32_t)ho);

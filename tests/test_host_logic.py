@@ -244,11 +244,12 @@ def test_seed_extension_two_tables_equal_one(tmp_path, monkeypatch):
     params = dict(wordsize=8, margin=30, mismatches=0)
     recs = [FASTARecord(f">c{i}", c) for i, c in enumerate(contigs)]
     want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
-    for flag in ("0", "1"):
+    for flag, parts in (("0", "1"), ("1", "1"), ("1", "3")):
         monkeypatch.setenv("MPCR_SEED_EXTENSION", flag)
+        monkeypatch.setenv("MPCR_SEED_PARTS", parts)      # several extended tables, every STS line in exactly one
         eng = MerPCR(**params)
         assert eng.load_sts_file(str(stsf))
-        assert (eng._ctx_ext is not None) == (flag == "1")
+        assert len(eng._ctx_exts) == (int(parts) if flag == "1" else 0)
         got = parity.engine_hits(eng, recs)
         assert np.array_equal(got, want), flag
         eng.close()
