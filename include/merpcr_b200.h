@@ -99,6 +99,11 @@ int mpcr_ctx_set_seed_extension(mpcr_ctx *ctx, int w_ext, int which);
  * at most a few 10^5 records each, scanned one after the other over the same planes -- every record lives in exactly
  * one table, so the concatenated, sorted hits are again the one-table result.  Call before mpcr_table_build. */
 int mpcr_ctx_set_table_part(mpcr_ctx *ctx, uint32_t part, uint32_t parts);
+/* Append mode (off by default): with on != 0, mpcr_scan no longer zeroes *d_count first -- the caller zeroes it once,
+ * passes the SAME d_hits / capacity to a series of calls (several tables, or the ranges of a genome that is still being
+ * uploaded) and reads the total once at the end, so the calls queue up on the stream without a host round trip in
+ * between.  *d_count keeps counting past capacity; nothing is written beyond it. */
+int mpcr_ctx_set_append(mpcr_ctx *ctx, int on);
 /* NOT reference behaviour, off by default: with on != 0 the "+" record of an STS line looks for
  * primer1 ... revcomp(primer2) -- a biologically normal forward amplicon, as NCBI me-PCR does -- instead of the
  * reference's primer1 ... primer2 (core/engine.py:267).  "-" records are unchanged.  Call before mpcr_table_build. */

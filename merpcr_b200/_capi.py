@@ -18,7 +18,7 @@ ABI_VERSION = 6
 
 # every symbol include/merpcr_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_set_seed_extension", "mpcr_ctx_set_table_part", "mpcr_ctx_set_true_strands", "mpcr_ctx_sm_count",
+    "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_set_seed_extension", "mpcr_ctx_set_table_part", "mpcr_ctx_set_append", "mpcr_ctx_set_true_strands", "mpcr_ctx_sm_count",
     "mpcr_pack_sequence", "mpcr_fasta_workspace_bytes", "mpcr_fasta_index", "mpcr_fasta_compact",
     "mpcr_sts_parse", "mpcr_sts_blob", "mpcr_format_hits", "mpcr_table_build", "mpcr_table_records", "mpcr_table_primer_words", "mpcr_scan",
     "mpcr_halo_left", "mpcr_halo_right", "mpcr_tile_bases", "mpcr_sort_hits", "mpcr_launch_count", "mpcr_last_scan_ms", "mpcr_last_verify_ms",
@@ -52,6 +52,8 @@ class Backend:
         lib.mpcr_ctx_destroy.argtypes = [vp]
         lib.mpcr_ctx_set_seed_extension.restype = i32
         lib.mpcr_ctx_set_seed_extension.argtypes = [vp, i32, i32]
+        lib.mpcr_ctx_set_append.restype = i32
+        lib.mpcr_ctx_set_append.argtypes = [vp, i32]
         lib.mpcr_ctx_set_table_part.restype = i32
         lib.mpcr_ctx_set_table_part.argtypes = [vp, C.c_uint32, C.c_uint32]
         lib.mpcr_ctx_set_true_strands.restype = i32

@@ -63,6 +63,7 @@ struct mpcr_ctx {
     bool dense = false;
     int ext_w = 0, ext_which = 0;   // seed extension (mpcr_ctx_set_seed_extension)
     uint32_t part = 0, parts = 1;   // table partition (mpcr_ctx_set_table_part)
+    int append = 0;                 // mpcr_ctx_set_append
     int true_strands = 0;           // mpcr_ctx_set_true_strands
     int scan_w = 0;                 // word width the scanner keys on: ext_w for an extended table, else wordsize
     uint32_t max_hash_off = 0, max_len = 0;
@@ -476,14 +477,13 @@ __device__ __forceinline__ uint32_t filter_probe(const FilterView& f, const Scan
 // gathers in flight, then the tag check on what came back).  Straight-line code: lanes past the end of the queue
 // re-probe entry 0 and are masked out, so the R rounds interleave freely.  CLEAN: every base of the unit (and its
 // read-ahead) is A/C/G/T, so the tag verdict can be used without looking at the valid bits.
-template <bool CLEAN, int R>
+template <bool CLEAN, bool HASHED, int R>
 __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
                                              const uint32_t* __restrict__ s_p2, const uint32_t* __restrict__ s_v,
                                              uint32_t base, uint32_t cnt, int lane, uint32_t tile, uint32_t ubase,
                                              unsigned long long& n_dbg) {
     const int W = a.prm.W, N = a.prm.N;
     const uint32_t wmask = wmask_of(W);
-    const bool hashed = !a.smap.direct;
     uint32_t lpv[R], key[R], gcodes[R];
     bool ok[R], dirty[R];
 #pragma unroll
@@ -513,15 +513,16 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
         else if (u == 2) gather_wait<(R > 3 ? R - 3 : 0)>();
         else gather_wait<0>();
         const uint4 v = landing[u][lane];
-        // hashed mode: another key's slot ends the search unless a stored key's probe sequence runs through it
-        const bool other = hashed && v.x != key[u];
+        // HASHED (open-addressed table, W >= 12): another key's slot ends the search unless a stored key's probe
+        // sequence runs through it (kSlotChain); direct tables never collide
+        const bool other = HASHED && v.x != key[u];
         const bool collide = other && (v.y & kSlotChain);
         const bool pass = !other && (dirty[u] || !(tag_rejects(v.z, gcodes[u], N) && tag_rejects(v.w, gcodes[u], N)));
         if (ok[u] && v.y != kSlotEmpty && (collide || pass)) {  // about one queued position in a thousand
             const uint32_t lp = ubase + lpv[u];
             if (a.debug & 2) ++n_dbg;
             else if (collide) probe_collision(a, key[u], gcodes[u] & 0xFFFFu, dirty[u] ? 0u : 0xFFu, tile, lp);
-            else push_survivor(a, tile, lp, v.y & ~kSlotChain);
+            else push_survivor(a, tile, lp, HASHED ? (v.y & ~kSlotChain) : v.y);
         }
     }
 }
@@ -531,7 +532,7 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
 #else
 #define MPCR_PROBE_INLINE __forceinline__
 #endif
-template <bool CLEAN>
+template <bool CLEAN, bool HASHED>
 __device__ MPCR_PROBE_INLINE void probe_queue(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
                                             const uint32_t* __restrict__ s_p2, const uint32_t* __restrict__ s_v,
                                             uint32_t cnt, int lane, uint32_t tile, uint32_t ubase,
@@ -540,12 +541,12 @@ __device__ MPCR_PROBE_INLINE void probe_queue(const ScanArgs& a, const uint16_t*
     static_assert(kIlp >= 1 && kIlp <= 4, "kIlp");
     uint32_t base = 0;
     for (; base + 32 * kIlp <= cnt; base += 32 * kIlp)
-        probe_rounds<CLEAN, kIlp>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+        probe_rounds<CLEAN, HASHED, kIlp>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
     const uint32_t rounds = (cnt - base + 31) >> 5;  // tail: only the rounds that hold something
-    if (rounds == 1) probe_rounds<CLEAN, 1>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 2) probe_rounds<CLEAN, (kIlp >= 2 ? 2 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 3) probe_rounds<CLEAN, (kIlp >= 3 ? 3 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 4) probe_rounds<CLEAN, (kIlp >= 4 ? 4 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    if (rounds == 1) probe_rounds<CLEAN, HASHED, 1>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 2) probe_rounds<CLEAN, HASHED, (kIlp >= 2 ? 2 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 3) probe_rounds<CLEAN, HASHED, (kIlp >= 3 ? 3 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 4) probe_rounds<CLEAN, HASHED, (kIlp >= 4 ? 4 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
 }
 
 // Stage 1 for one unit of 2048 positions: lane l owns positions [64l, 64l+64) -- rolling keys by funnel shift out of
@@ -613,7 +614,7 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
 //             16-byte L1-bypassing async gathers of the slot table in flight per lane; key + tag window come
 //             from the staged unit; inline tag check.
 //   What is left (about one position in 10^4) goes to the survivor list for verify_kernel.
-template <bool WIDE>
+template <bool WIDE, bool HASHED>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -731,8 +732,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
                                      ? total
                                      : __shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));  // lane 0 always fits
             __syncwarp();
-            if (all_clean) probe_queue<true>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
-            else probe_queue<false>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
+            if (all_clean) probe_queue<true, HASHED>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
+            else probe_queue<false, HASHED>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
             __syncwarp();
             if (fit_mask == 0xffffffffu) break;
         }
@@ -1081,6 +1082,11 @@ int mpcr_ctx_set_table_part(mpcr_ctx* c, uint32_t part, uint32_t parts) {
     c->part = part;
     c->parts = parts;
     free_table(c);
+    return MPCR_OK;
+}
+int mpcr_ctx_set_append(mpcr_ctx* c, int on) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    c->append = on ? 1 : 0;
     return MPCR_OK;
 }
 int mpcr_ctx_set_true_strands(mpcr_ctx* c, int on) {
@@ -1437,15 +1443,23 @@ static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_conti
         if (L <= (uint64_t)c->prm.wordsize) continue;  // engine.py:458 (Q3: len <= W is skipped)
         if (g0 & 127u) return fail(MPCR_EINVAL, "contig %u: gstart not a multiple of 128", i);
         if (L >= (1ull << 31)) return fail(MPCR_EINVAL, "contig %u longer than 2^31-1 bases", i);
-        for (uint64_t ls = 0; ls < L; ls += tb) {
-            const uint64_t g = g0 + ls;
-            if (g < sb || g >= se) continue;  // tile ownership by first base (tiles never straddle shards)
+        // Ownership is decided per 2048-position unit (unit starts are multiples of 2048 from the contig start): a
+        // unit belongs to the range that holds its first base.  That is independent of the tile size chosen above,
+        // so neighbouring ranges -- other ranks, or the ranges of a genome scanned while it uploads -- never overlap
+        // and never leave a gap, whatever tile size each of them picks.
+        if (se <= g0 || sb >= g0 + L) continue;
+        const uint64_t unit = 2048;
+        const uint64_t lo = sb > g0 ? round_up(sb - g0, unit) : 0;             // first owned unit
+        const uint64_t stop = se - g0 < L ? se - g0 : L;                       // owned unit starts are < stop
+        if (lo >= stop) continue;
+        const uint64_t hi = round_up(stop, unit) < L ? round_up(stop, unit) : L;   // positions the owned units cover
+        for (uint64_t ls = lo; ls < hi; ls += tb) {
             TileDesc t;
-            t.gbase = (int64_t)(g - origin);
+            t.gbase = (int64_t)(g0 + ls - origin);
             t.contig = i;
             t.lstart = (uint32_t)ls;
             t.length = (uint32_t)L;
-            t.nbases = (uint32_t)(L - ls < tb ? L - ls : tb);
+            t.nbases = (uint32_t)(hi - ls < tb ? hi - ls : tb);
             tiles.push_back(t);
         }
     }
@@ -1476,7 +1490,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     CU(cudaSetDevice(c->device));
     int rc = build_tiles(c, h_contigs, n_contigs, plane_origin, shard_begin, shard_end, st);
     if (rc) return rc;
-    CU(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    if (!c->append) CU(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     c->scan_timed = false;
     if (c->n_tiles == 0 || c->n_valid == 0) return MPCR_OK;
     CU(cudaMemsetAsync(c->d_tile_counter, 0, 16, st));
@@ -1516,12 +1530,15 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     CU(cudaEventRecord(c->ev0, st));
     if (c->dense) {
         dense_scan_kernel<<<c->sm_count * 8, 256, 0, st>>>(a);
+    } else if (!c->smap.direct) {   // open-addressed slot table (W >= 12)
+        CU(cudaFuncSetAttribute(scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        scan_kernel<true, true><<<grid, kScanThreads, smem, st>>>(a);
     } else if (a.prm.W >= 6) {
-        CU(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        scan_kernel<true><<<grid, kScanThreads, smem, st>>>(a);
+        CU(cudaFuncSetAttribute(scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        scan_kernel<true, false><<<grid, kScanThreads, smem, st>>>(a);
     } else {
-        CU(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        scan_kernel<false><<<grid, kScanThreads, smem, st>>>(a);
+        CU(cudaFuncSetAttribute(scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        scan_kernel<false, false><<<grid, kScanThreads, smem, st>>>(a);
     }
     CU(cudaEventRecord(c->ev1, st));
     c->launches++;

@@ -47,6 +47,7 @@ MIN_THREE_PRIME_MATCH = 0
 MIN_PCR_SIZE, MAX_PCR_SIZE = 1, 10000
 
 EXTENDED_WORDSIZE = 16        # key width of the extended tables of exact, candidate-heavy searches
+STREAM_SCAN_BASES = 1 << 25    # upload_and_scan: scan a finished contig (group) once this many bases are packed
 EXT_LINES_PER_TABLE = 125_000  # STS lines per extended table: 2.5*10^5 keys is what the scanner's filter holds at ~5 % f.p.
 PCR_SIZE_CLAMP = 0x7FFFFFFF   # any expected size >= a contig length behaves identically (engine.py:531-533)
 PLANE_SLACK_BASES = 1024      # read-ahead of the last strip / last primer window
@@ -127,7 +128,7 @@ class _Shard:
     """Device-resident packed genome of one shard (planes + the layout they were built for)."""
 
     __slots__ = ("device", "origin", "bases", "plane2", "plane4", "valid", "begin", "end", "hits", "count", "staging",
-                 "contig_sig")
+                 "stage2", "contig_sig")
 
 
 class MerPCR:
@@ -188,6 +189,7 @@ class MerPCR:
         else:
             self._tdev = torch.device("cpu")
         self._ctx = None
+        self._copy_stream = None  # upload_and_scan: the H2D copies run beside pack + scan
         self._ctx_exts = []       # extended tables of exact, candidate-heavy searches (mpcr_ctx_set_seed_extension)
         self._create_ctx()
         # parsed STS lines kept so the table can be re-encoded if a sequence brings an unusual alphabet
@@ -605,11 +607,9 @@ class MerPCR:
                 r.sequence_device.device == self._tdev else r.sequence_bytes for r in fasta_records]
         self._check_alphabet(fasta_records, seqs)
         layout = self.make_layout([len(r) for r in fasta_records])
-        shard = self.upload(layout, seqs)
-        t1 = time.perf_counter()
-        hits = self.scan(layout, shard)
-        t2 = time.perf_counter()
-        self.last_timing = dict(upload_s=t1 - t0, scan_s=t2 - t1)
+        _, hits_t, n = self.upload_and_scan(layout, seqs)
+        hits = self._hits_to_host(hits_t, n)
+        self.last_timing = dict(search_s=time.perf_counter() - t0)
         return hits
 
     # -- alphabet corner cases: sequences built through the API may hold letters FASTA files cannot
@@ -652,11 +652,8 @@ class MerPCR:
         end = (total * (rank + 1) // world) // 128 * 128 if rank + 1 < world else max(total, 128)
         return dict(contigs=contigs, total=total, begin=begin, end=end, lengths=list(lengths))
 
-    def upload(self, layout: dict, seqs: Sequence, shard: Optional[_Shard] = None) -> _Shard:
-        """FASTA ingest, device half: copy the bases this shard needs (its range + halos) to the GPU and pack them
-        into the planes.  seqs[i] is the i-th contig as a uint8 numpy array, a torch uint8 tensor (pinned host or
-        already on the device) or None for a contig this shard never touches.  Passing the previous `shard`
-        re-uses its buffers (steady-state re-upload)."""
+    def _prepare_shard(self, layout: dict, shard: Optional[_Shard]) -> _Shard:
+        """Plane buffers of this rank's range (+ halos), zeroed where that matters; re-uses `shard` when it fits."""
         lib = self._be.lib
         total, begin, end = layout["total"], layout["begin"], layout["end"]
         halo_l, halo_r = int(lib.mpcr_halo_left(self._ctx)), int(lib.mpcr_halo_right(self._ctx))
@@ -678,20 +675,20 @@ class MerPCR:
             sh.plane2 = torch.zeros(alloc // 4, dtype=torch.uint8, device=self._tdev)
             sh.plane4 = torch.zeros(alloc // 2, dtype=torch.uint8, device=self._tdev)
             sh.valid = torch.zeros(alloc // 8, dtype=torch.uint8, device=self._tdev)
-            sh.hits, sh.count, sh.staging = None, None, None
+            sh.hits, sh.count, sh.staging, sh.stage2 = None, None, None, None
         sh.contig_sig = contig_sig
-        lut = genome_lut(self.iupac_mode)
-        stream = self._stream()
-        chunk = 1 << 28
-        h2d = 0
+        return sh
+
+    @staticmethod
+    def _pieces(layout: dict, seqs: Sequence, sh: _Shard, chunk: int):
+        """(contig index, global begin, global end, source slice, last piece of its contig) for every stretch of bases
+        this shard holds, in genome order."""
         for ci, s in enumerate(seqs):
             if s is None:
                 continue
             g0 = int(layout["contigs"][ci]["gstart"])
             L = int(layout["contigs"][ci]["length"])
-            lo, hi = max(g0, origin), min(g0 + L, origin + bases)
-            if hi <= lo:
-                continue
+            lo, hi = max(g0, sh.origin), min(g0 + L, sh.origin + sh.bases)
             for a in range(lo, hi, chunk):
                 b = min(hi, a + chunk)
                 if isinstance(s, torch.Tensor):
@@ -699,24 +696,131 @@ class MerPCR:
                 else:
                     arr = s[a - g0: b - g0]
                     src = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
-                if src.device != self._tdev:
-                    # one device staging buffer, reused: copy and pack are ordered on the same stream
-                    h2d += b - a
-                    if sh.staging is None or sh.staging.numel() < b - a:
-                        sh.staging = torch.empty(min(chunk, max(b - a, 1 << 24)), dtype=torch.uint8, device=self._tdev)
-                    dst = sh.staging[: b - a]
-                    dst.copy_(src, non_blocking=True)
-                    src = dst
-                self._be.check(lib.mpcr_pack_sequence(self._ctx, src.data_ptr(), b - a, a, origin,
-                                                      sh.plane2.data_ptr(), sh.plane4.data_ptr(), sh.valid.data_ptr(),
-                                                      lut.ctypes.data, stream))
+                yield ci, a, b, src, b == hi
+
+    def upload(self, layout: dict, seqs: Sequence, shard: Optional[_Shard] = None) -> _Shard:
+        """FASTA ingest, device half: copy the bases this shard needs (its range + halos) to the GPU and pack them
+        into the planes.  seqs[i] is the i-th contig as a uint8 numpy array, a torch uint8 tensor (pinned host or
+        already on the device) or None for a contig this shard never touches.  Passing the previous `shard`
+        re-uses its buffers (steady-state re-upload)."""
+        lib = self._be.lib
+        sh = self._prepare_shard(layout, shard)
+        lut = genome_lut(self.iupac_mode)
+        stream = self._stream()
+        chunk = 1 << 28
+        h2d = 0
+        for ci, a, b, src, _ in self._pieces(layout, seqs, sh, chunk):
+            if src.device != self._tdev:
+                # one device staging buffer, reused: copy and pack are ordered on the same stream
+                h2d += b - a
+                if sh.staging is None or sh.staging.numel() < b - a:
+                    sh.staging = torch.empty(min(chunk, max(b - a, 1 << 24)), dtype=torch.uint8, device=self._tdev)
+                dst = sh.staging[: b - a]
+                dst.copy_(src, non_blocking=True)
+                src = dst
+            self._be.check(lib.mpcr_pack_sequence(self._ctx, src.data_ptr(), b - a, a, sh.origin,
+                                                  sh.plane2.data_ptr(), sh.plane4.data_ptr(), sh.valid.data_ptr(),
+                                                  lut.ctypes.data, stream))
         self._sync()
         self.last_h2d_bytes = h2d
         return sh
 
+    def upload_and_scan(self, layout: dict, seqs: Sequence, shard: Optional[_Shard] = None, sort: bool = True):
+        """`upload` + `scan_device` as one pipeline for sequences that still sit in host memory: a copy stream moves
+        64 MiB pieces into two staging buffers while the compute stream packs the previous piece, and every contig
+        (group of small contigs) is scanned as soon as its bases are packed -- the tables append to one hit buffer
+        (mpcr_ctx_set_append), the host reads the count once at the end, the hits are sorted once.  Host -> hits time
+        is then the PCIe copy plus the last contig's scan.  Returns (shard, hit tensor, n_hits)."""
+        if self._tdev.type != "cuda" or all(s is None or (isinstance(s, torch.Tensor) and s.device == self._tdev)
+                                            for s in seqs):
+            sh = self.upload(layout, seqs, shard)
+            hits, n = self.scan_device(layout, sh, sort=sort)
+            return sh, hits, n
+        lib = self._be.lib
+        sh = self._prepare_shard(layout, shard)
+        lut = genome_lut(self.iupac_mode)
+        compute = torch.cuda.current_stream(self._tdev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self._tdev)
+        copy = self._copy_stream
+        chunk = 1 << 26
+        if sh.stage2 is None:
+            sh.stage2 = [torch.empty(chunk, dtype=torch.uint8, device=self._tdev) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        packed = [torch.cuda.Event() for _ in range(2)]
+        isz = _capi.HIT_DTYPE.itemsize
+        if sh.count is None:
+            sh.count = torch.zeros(1, dtype=torch.int64, device=self._tdev)
+        if sh.hits is None:
+            sh.hits = torch.empty((1 << 16) * isz, dtype=torch.uint8, device=self._tdev)
+        cap = sh.hits.numel() // isz
+        sh.count.zero_()
+        copy.wait_stream(compute)              # the staging buffers and the zeroed planes exist before the first copy
+        contigs = layout["contigs"]
+        ctxs = self._all_ctxs()
+        nxt = [int(c["gstart"]) for c in contigs[1:]] + [max(layout["total"], sh.end)]
+
+        def scan_range(lo: int, hi: int):
+            for ctx in ctxs:
+                self._be.check(lib.mpcr_scan(ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
+                                             sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.bases, lo, hi,
+                                             sh.hits.data_ptr(), cap, sh.count.data_ptr(), compute.cuda_stream))
+
+        for ctx in ctxs:
+            self._be.check(lib.mpcr_ctx_set_append(ctx, 1))
+        try:
+            k, h2d, pending, done_to, deferred = 0, 0, 0, sh.begin, None
+            for ci, a, b, src, last in self._pieces(layout, seqs, sh, chunk):
+                slot = -1
+                if src.device != self._tdev:
+                    slot = k & 1
+                    k += 1
+                    buf = sh.stage2[slot][: b - a]
+                    copy.wait_event(packed[slot])              # the pack that last read this buffer is done
+                    with torch.cuda.stream(copy):
+                        buf.copy_(src, non_blocking=True)
+                    copied[slot].record(copy)
+                    h2d += b - a
+                    src = buf
+                if deferred:                                   # the finished contig is scanned while this copy runs
+                    scan_range(*deferred)
+                    deferred = None
+                if slot >= 0:
+                    compute.wait_event(copied[slot])
+                self._be.check(lib.mpcr_pack_sequence(self._ctx, src.data_ptr(), b - a, a, sh.origin,
+                                                      sh.plane2.data_ptr(), sh.plane4.data_ptr(), sh.valid.data_ptr(),
+                                                      lut.ctypes.data, compute.cuda_stream))
+                if slot >= 0:
+                    packed[slot].record(compute)
+                pending += b - a
+                # a finished contig (or run of small ones) whose right neighbourhood is complete can be scanned
+                if last and pending >= STREAM_SCAN_BASES and done_to < nxt[ci] < sh.end:
+                    deferred = (done_to, nxt[ci])
+                    done_to, pending = nxt[ci], 0
+            if deferred:
+                scan_range(*deferred)
+            if sh.end > done_to:
+                scan_range(done_to, sh.end)
+            need = int(sh.count.item())                        # the one host round trip
+            self.last_scan_ms = float(lib.mpcr_last_scan_ms(self._ctx))
+        finally:
+            for ctx in ctxs:
+                lib.mpcr_ctx_set_append(ctx, 0)
+        self.last_h2d_bytes = h2d
+        if need > cap:      # the hit list outgrew the buffer: the planes are resident now, scan them again with room
+            hits, n = self.scan_device(layout, sh, sort=sort)
+            return sh, hits, n
+        if sort and need > 1:
+            self._be.check(lib.mpcr_sort_hits(self._ctx, sh.hits.data_ptr(), need, self._stream()))
+        return sh, sh.hits, need
+
     def scan(self, layout: dict, sh: _Shard, sort: bool = True) -> np.ndarray:
         """scanner + verifier + hit emitter + ordering on the resident planes; returns the hits on the host."""
         hits, n = self.scan_device(layout, sh, sort=sort)
+        return self._hits_to_host(hits, n)
+
+    @staticmethod
+    def _hits_to_host(hits, n: int) -> np.ndarray:
         if n == 0:
             return np.zeros(0, dtype=_capi.HIT_DTYPE)
         raw = hits[: n * _capi.HIT_DTYPE.itemsize].cpu().numpy()

@@ -44,6 +44,7 @@ struct mpcr_ctx {
     uint64_t launches = 0;
     int ext_w = 0, ext_which = 0, scan_w = 0, true_strands = 0;
     uint32_t part = 0, parts = 1;
+    int append = 0;
 };
 
 extern "C" {
@@ -85,6 +86,11 @@ int mpcr_ctx_set_table_part(mpcr_ctx* c, uint32_t part, uint32_t parts) {
     if (parts == 0) parts = 1;
     if (part >= parts) return fail(MPCR_EINVAL, "part must be < parts");
     c->part = part; c->parts = parts; c->table_ready = false;
+    return MPCR_OK;
+}
+int mpcr_ctx_set_append(mpcr_ctx* c, int on) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    c->append = on ? 1 : 0;
     return MPCR_OK;
 }
 int mpcr_ctx_sm_count(const mpcr_ctx*) { return 1; }
@@ -304,17 +310,21 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
     SearchParams prm{c->scan_w, c->prm.margin, c->prm.mismatches, c->prm.three_prime_match, c->prm.iupac_mode ? 1 : 0};
     const int W_ref = c->prm.wordsize;   // the contig-length rule of engine.py:458 uses the reference's word size
     const uint32_t wmask = wmask_of(prm.W), cw = filter_mul(prm.W);
-    uint64_t n = 0;
+    uint64_t n = c->append ? *count : 0;   // append mode: keep counting behind the previous calls' hits
     c->launches++;
     for (uint32_t ci = 0; ci < n_contigs && c->n_valid; ++ci) {
         const uint64_t L = contigs[ci].length, g0 = contigs[ci].gstart;
         if (L <= (uint64_t)W_ref) continue;
         if (g0 & 127u) return fail(MPCR_EINVAL, "contig %u: gstart not a multiple of 128", ci);
-        for (uint64_t ls = 0; ls < L; ls += kTileBases) {
+        // ownership per 2048-position unit, by the unit's first base (same rule as the CUDA library's build_tiles)
+        if (se <= g0 || sb >= g0 + L) continue;
+        const uint64_t lo = sb > g0 ? round_up(sb - g0, 2048) : 0, stop = std::min<uint64_t>(se - g0, L);
+        if (lo >= stop) continue;
+        const uint64_t hi = std::min<uint64_t>(round_up(stop, 2048), L);
+        for (uint64_t ls = lo; ls < hi; ls += kTileBases) {
             const uint64_t g = g0 + ls;
-            if (g < sb || g >= se) continue;
             const int64_t gbase = (int64_t)(g - origin);
-            const uint32_t nb = (uint32_t)std::min<uint64_t>(L - ls, kTileBases);
+            const uint32_t nb = (uint32_t)std::min<uint64_t>(hi - ls, kTileBases);
             for (uint32_t lp0 = 0; lp0 < nb; lp0 += 64) {
                 const int64_t gb = gbase + lp0;
                 if ((uint64_t)gb + 128 > plane_bases + 128) return fail(MPCR_EINVAL, "planes too small for the shard");

@@ -278,6 +278,61 @@ def test_sharded_equals_whole_on_device(tmp_path):
         assert np.array_equal(merged[order], ref), world
 
 
+def test_append_mode_range_scans_equal_one_scan_on_device(tmp_path):
+    """mpcr_ctx_set_append + mpcr_scan over consecutive ranges (cuts on any multiple of 128, inside contigs too) == one
+    scan; then the pipelined `upload_and_scan` from pinned host memory == upload + scan."""
+    import torch
+    from merpcr_b200 import MerPCR, _capi
+    rng = synth.Rng(901)
+    contigs = [rng.dna(n) for n in (900_000, 12, 330_000, 2047, 2049, 70_000_000 // 64, 410_000)]
+    sts = synth.make_sts_set(902, 1500, 18, 25, 100, 600)
+    synth.plant_amplicons(903, [c for c in contigs if len(c) > 100_000], sts, 50, sub_mode="cfg3")
+    stsf = _write(tmp_path, "s.sts", synth.sts_lines(sts))
+    eng = MerPCR(wordsize=11, margin=50, mismatches=1)
+    assert eng.load_sts_file(stsf)
+    recs = _records(contigs)
+    layout = eng.make_layout([len(c) for c in contigs])
+    sh = eng.upload(layout, contigs)
+    want = eng.scan(layout, sh)
+    assert len(want) > 1000
+    lib, cg, dev = eng._be.lib, layout["contigs"], eng._tdev
+    isz = _capi.HIT_DTYPE.itemsize
+    for cuts in ([int(c["gstart"]) for c in cg[1:]],
+                 [128 * k for k in (7, 100, 101, 3950, 3960, 6400, 9000, 12000, 20000)],
+                 [2048 * 5 + 128, 2048 * 5 + 256]):
+        bounds = [layout["begin"]] + [c for c in sorted(cuts) if layout["begin"] < c < layout["end"]] + [layout["end"]]
+        hits = torch.zeros(4 * len(want) * isz, dtype=torch.uint8, device=dev)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        eng._be.check(lib.mpcr_ctx_set_append(eng._ctx, 1))
+        try:
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                eng._be.check(lib.mpcr_scan(eng._ctx, cg.ctypes.data, len(cg), sh.plane2.data_ptr(), sh.plane4.data_ptr(),
+                                            sh.valid.data_ptr(), sh.origin, sh.bases, lo, hi, hits.data_ptr(),
+                                            4 * len(want), count.data_ptr(), eng._stream()))
+        finally:
+            eng._be.check(lib.mpcr_ctx_set_append(eng._ctx, 0))
+        n = int(count.item())
+        assert n == len(want), cuts
+        eng._be.check(lib.mpcr_sort_hits(eng._ctx, hits.data_ptr(), n, eng._stream()))
+        got = hits[: n * isz].cpu().numpy().view(_capi.HIT_DTYPE)
+        assert np.array_equal(got, want), cuts
+    # the pipeline: pinned host contigs, small scan groups so that several ranges are scanned while the copy runs
+    import merpcr_b200.engine as E
+    pinned = [torch.from_numpy(c).pin_memory() for c in contigs]
+    old = E.STREAM_SCAN_BASES
+    E.STREAM_SCAN_BASES = 200_000
+    try:
+        sh2 = None
+        for _ in range(3):                                   # steady state re-uses the buffers
+            sh2, hits_t, n = eng.upload_and_scan(layout, pinned, shard=sh2)
+            assert np.array_equal(eng._hits_to_host(hits_t, n), want)
+        sh3, hits_t, n = eng.upload_and_scan(layout, contigs)   # pageable numpy sources
+        assert np.array_equal(eng._hits_to_host(hits_t, n), want)
+    finally:
+        E.STREAM_SCAN_BASES = old
+    assert np.array_equal(eng.search_hits(recs), want)
+
+
 def test_idempotent_rescan_on_resident_planes(tmp_path):
     """Scanning the same resident planes twice gives the same sorted list (no state leaks between launches)."""
     from merpcr_b200 import MerPCR

@@ -167,6 +167,49 @@ def test_sharded_scan_equals_whole(tmp_path):
         assert np.array_equal(merged[order], whole.search_hits(recs)), world
 
 
+def test_append_mode_range_scans_equal_one_scan(tmp_path):
+    """mpcr_ctx_set_append + mpcr_scan over consecutive ranges of the padded coordinate (what `upload_and_scan` does
+    while a genome is still uploading): ranges cut anywhere on a multiple of 128 -- inside contigs too -- own disjoint
+    2048-position units, so the appended hits are exactly the hits of one scan."""
+    import ctypes as C
+    import torch
+    from merpcr_b200 import FASTARecord, MerPCR, _capi
+    rng = synth.Rng(901)
+    contigs = [rng.dna(n) for n in (50000, 12, 33000, 2047, 2049, 41000)]
+    sts = synth.make_sts_set(902, 150, 18, 25, 100, 600)
+    synth.plant_amplicons(903, [contigs[0], contigs[2], contigs[5]], sts, 50, sub_mode="cfg3")
+    stsf = tmp_path / "s.sts"
+    stsf.write_bytes(synth.sts_lines(sts))
+    eng = MerPCR(wordsize=11, margin=50, mismatches=1)
+    assert eng.load_sts_file(str(stsf))
+    recs = [FASTARecord(f">c{i}", c) for i, c in enumerate(contigs)]
+    want = eng.search_hits(recs)
+    assert len(want) > 100
+    layout = eng.make_layout([len(c) for c in contigs])
+    sh = eng.upload(layout, [r.sequence_bytes for r in recs])
+    lib, cg = eng._be.lib, layout["contigs"]
+    isz = _capi.HIT_DTYPE.itemsize
+    for cuts in ([int(c["gstart"]) for c in cg[1:]],                       # contig boundaries
+                 [128 * k for k in (7, 100, 101, 395, 396, 640, 900, 1200)],  # anywhere, inside contigs
+                 [2048 * 5 + 128, 2048 * 5 + 256]):                        # two cuts inside one unit
+        bounds = [layout["begin"]] + [c for c in sorted(cuts) if layout["begin"] < c < layout["end"]] + [layout["end"]]
+        hits = torch.zeros(4 * len(want) * isz, dtype=torch.uint8)
+        count = torch.zeros(1, dtype=torch.int64)
+        eng._be.check(lib.mpcr_ctx_set_append(eng._ctx, 1))
+        try:
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                eng._be.check(lib.mpcr_scan(eng._ctx, cg.ctypes.data, len(cg), sh.plane2.data_ptr(), sh.plane4.data_ptr(),
+                                            sh.valid.data_ptr(), sh.origin, sh.bases, lo, hi, hits.data_ptr(),
+                                            4 * len(want), count.data_ptr(), 0))
+        finally:
+            eng._be.check(lib.mpcr_ctx_set_append(eng._ctx, 0))
+        n = int(count.item())
+        assert n == len(want), cuts
+        eng._be.check(lib.mpcr_sort_hits(eng._ctx, hits.data_ptr(), n, 0))
+        got = hits[: n * isz].numpy().view(_capi.HIT_DTYPE)
+        assert np.array_equal(got, want), cuts
+
+
 def test_cli_in_process(tmp_path, monkeypatch, capsys):
     # reference tests/test_cli.py, test_cli_enhanced.py:23-156 (flag set, K=V conversion, exit codes)
     from merpcr_b200 import cli
