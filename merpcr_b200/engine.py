@@ -47,7 +47,7 @@ MIN_THREE_PRIME_MATCH = 0
 MIN_PCR_SIZE, MAX_PCR_SIZE = 1, 10000
 
 EXTENDED_WORDSIZE = 16        # key width of the extended tables of exact, candidate-heavy searches
-STREAM_SCAN_BASES = 1 << 25    # upload_and_scan: scan a finished contig (group) once this many bases are packed
+STREAM_SCAN_BASES = 1 << 27    # upload_and_scan: scan a finished contig (group) once this many bases are packed
 EXT_LINES_PER_TABLE = 125_000  # STS lines per extended table: 2.5*10^5 keys is what the scanner's filter holds at ~5 % f.p.
 PCR_SIZE_CLAMP = 0x7FFFFFFF   # any expected size >= a contig length behaves identically (engine.py:531-533)
 PLANE_SLACK_BASES = 1024      # read-ahead of the last strip / last primer window

@@ -43,3 +43,16 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 sh.plane2.zero_(); sh.plane4.zero_(); sh.valid.zero_()
 torch.cuda.synchronize(); t1 = time.perf_counter()
 print(f"zeroing planes: {1e3*(t1-t0):.2f} ms")
+
+# the pipeline (upload_and_scan): copy stream | pack | per-contig range scans, at several scan-group sizes
+import merpcr_b200.engine as E
+for grp in (1 << 25, 1 << 27, 1 << 40):
+    E.STREAM_SCAN_BASES = grp
+    shp = None
+    for it in range(4):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        shp, hits_t, n = eng.upload_and_scan(lay, host, shard=shp)
+        out = eng._hits_to_host(hits_t, n)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        if it:
+            print(f"upload_and_scan, scan groups >= {grp} bases, iter {it}: {1e3*(t1-t0):.1f} ms ({sum(lengths)/(t1-t0)/1e9:.1f} Gbp/s), hits {len(out)}", flush=True)
