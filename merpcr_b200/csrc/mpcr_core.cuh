@@ -420,18 +420,19 @@ MPCR_HD bool tag_rejects(uint32_t tag, uint32_t gcodes, int N) {
 }
 MPCR_HD bool tag_window_clean(uint32_t gvalid) { return (gvalid & 0xFFu) == 0xFFu; }
 
-// the tag of a primer: up to kTagBases A/C/G/T letters following the seed [ho+W, ...)
+// the tag of a primer: the kTagBases letters following the seed [ho+W, ho+W+kTagBases), lane i = letter i; lanes that
+// hold a plain A/C/G/T letter are masked in, every other lane (degenerate or foreign letter, past the primer's end) is
+// left out -- it could match or not, so it must not count as a mismatch
 template <class CharAt>
 MPCR_HD uint32_t make_tag(CharAt at, int len, int ho, int W) {
-    uint32_t codes = 0, mask = 0, n = 0;
-    for (int i = ho + W; i < len && n < (uint32_t)kTagBases; ++i) {
+    uint32_t codes = 0, mask = 0;
+    for (int i = ho + W, n = 0; i < len && n < kTagBases; ++i, ++n) {
         const uint8_t c = at(i);
         uint32_t code;
         if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3;
-        else break;
+        else continue;
         codes |= code << (2 * n);
         mask |= 3u << (2 * n);
-        ++n;
     }
     return codes | (mask << 16);
 }

@@ -503,7 +503,7 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
             const uint32_t vb = lp + (uint32_t)W, vi = vb >> 5, vs = vb & 31u;
             dirty[u] = !tag_window_clean(__funnelshift_r(s_v[vi], s_v[vi + 1], vs));
         }
-        gather16_async(&landing[u][lane], a.slots + slot_index(key[u], a.smap));
+        gather16_async(&landing[u][lane], a.slots + (HASHED ? (slot_hash(key[u]) & a.smap.mask) : key[u]));
         gather_commit();
     }
 #pragma unroll
