@@ -477,12 +477,14 @@ __device__ __forceinline__ uint32_t filter_probe(const FilterView& f, const Scan
 // gathers in flight, then the tag check on what came back).  Straight-line code: lanes past the end of the queue
 // re-probe entry 0 and are masked out, so the R rounds interleave freely.  CLEAN: every base of the unit (and its
 // read-ahead) is A/C/G/T, so the tag verdict can be used without looking at the valid bits.
-template <bool CLEAN, bool HASHED, int R>
+template <bool CLEAN, bool HASHED, int R, int WC, int NC>
 __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
                                              const uint32_t* __restrict__ s_p2, const uint32_t* __restrict__ s_v,
                                              uint32_t base, uint32_t cnt, int lane, uint32_t tile, uint32_t ubase,
                                              unsigned long long& n_dbg) {
-    const int W = a.prm.W, N = a.prm.N;
+    // WC / NC: word size and mismatch budget known at compile time (the reference's default -W 11 with -N 0..2), 0 / -1
+    // = read them from the arguments
+    const int W = WC ? WC : a.prm.W, N = NC >= 0 ? NC : a.prm.N;
     const uint32_t wmask = wmask_of(W);
     uint32_t lpv[R], key[R], gcodes[R];
     bool ok[R], dirty[R];
@@ -532,7 +534,7 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
 #else
 #define MPCR_PROBE_INLINE __forceinline__
 #endif
-template <bool CLEAN, bool HASHED>
+template <bool CLEAN, bool HASHED, int WC, int NC>
 __device__ MPCR_PROBE_INLINE void probe_queue(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
                                             const uint32_t* __restrict__ s_p2, const uint32_t* __restrict__ s_v,
                                             uint32_t cnt, int lane, uint32_t tile, uint32_t ubase,
@@ -541,12 +543,12 @@ __device__ MPCR_PROBE_INLINE void probe_queue(const ScanArgs& a, const uint16_t*
     static_assert(kIlp >= 1 && kIlp <= 4, "kIlp");
     uint32_t base = 0;
     for (; base + 32 * kIlp <= cnt; base += 32 * kIlp)
-        probe_rounds<CLEAN, HASHED, kIlp>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+        probe_rounds<CLEAN, HASHED, kIlp, WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
     const uint32_t rounds = (cnt - base + 31) >> 5;  // tail: only the rounds that hold something
-    if (rounds == 1) probe_rounds<CLEAN, HASHED, 1>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 2) probe_rounds<CLEAN, HASHED, (kIlp >= 2 ? 2 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 3) probe_rounds<CLEAN, HASHED, (kIlp >= 3 ? 3 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 4) probe_rounds<CLEAN, HASHED, (kIlp >= 4 ? 4 : 1)>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    if (rounds == 1) probe_rounds<CLEAN, HASHED, 1, WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 2) probe_rounds<CLEAN, HASHED, (kIlp >= 2 ? 2 : 1), WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 3) probe_rounds<CLEAN, HASHED, (kIlp >= 3 ? 3 : 1), WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 4) probe_rounds<CLEAN, HASHED, (kIlp >= 4 ? 4 : 1), WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
 }
 
 // Stage 1 for one unit of 2048 positions: lane l owns positions [64l, 64l+64) -- rolling keys by funnel shift out of
@@ -614,7 +616,7 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
 //             16-byte L1-bypassing async gathers of the slot table in flight per lane; key + tag window come
 //             from the staged unit; inline tag check.
 //   What is left (about one position in 10^4) goes to the survivor list for verify_kernel.
-template <bool WIDE, bool HASHED>
+template <bool WIDE, bool HASHED, int WC, int NC>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     }
     __syncthreads();
 
-    const int W = a.prm.W;
+    const int W = WC ? WC : a.prm.W;
     const FilterView fv{s_filter, smem_u32(s_filter), a.cw, a.filter_words};
     unsigned long long n_dbg = 0;
 
@@ -732,8 +734,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
                                      ? total
                                      : __shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));  // lane 0 always fits
             __syncwarp();
-            if (all_clean) probe_queue<true, HASHED>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
-            else probe_queue<false, HASHED>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
+            if (all_clean) probe_queue<true, HASHED, WC, NC>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
+            else probe_queue<false, HASHED, WC, NC>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
             __syncwarp();
             if (fit_mask == 0xffffffffu) break;
         }
@@ -883,7 +885,10 @@ __global__ void __launch_bounds__(256, 2) dense_scan_kernel(const ScanArgs a) {
 // a chain of dependent loads, so narrow groups keep more of them in flight).  Primer 1 is compared by every lane of
 // the group (same addresses, broadcast loads); the mate search of engine.py:543-593 is spread over the lanes, one
 // delta per lane and round (rank 0: delta 0, 2i-1: -i, 2i: +i), neighbouring lanes touching neighbouring plane4 words.
-static constexpr int kVerifyLanes = 8;
+#ifndef MPCR_VERIFY_LANES
+#define MPCR_VERIFY_LANES 8
+#endif
+static constexpr int kVerifyLanes = MPCR_VERIFY_LANES;   // lanes per survivor (one mate-search offset each)
 
 __device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& td, uint32_t lp, uint32_t rec, int gl) {
     const RecMeta m = a.meta[rec];
@@ -1530,15 +1535,17 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     CU(cudaEventRecord(c->ev0, st));
     if (c->dense) {
         dense_scan_kernel<<<c->sm_count * 8, 256, 0, st>>>(a);
-    } else if (!c->smap.direct) {   // open-addressed slot table (W >= 12)
-        CU(cudaFuncSetAttribute(scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        scan_kernel<true, true><<<grid, kScanThreads, smem, st>>>(a);
-    } else if (a.prm.W >= 6) {
-        CU(cudaFuncSetAttribute(scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        scan_kernel<true, false><<<grid, kScanThreads, smem, st>>>(a);
     } else {
-        CU(cudaFuncSetAttribute(scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        scan_kernel<false, false><<<grid, kScanThreads, smem, st>>>(a);
+        // instantiations: the open-addressed table (W >= 12), the narrow filter (W < 6), the general direct table, and
+        // the reference's default word size with the usual mismatch budgets fixed at compile time
+        void (*kern)(const ScanArgs) = scan_kernel<true, false, 0, -1>;
+        if (!c->smap.direct) kern = scan_kernel<true, true, 0, -1>;
+        else if (a.prm.W < 6) kern = scan_kernel<false, false, 0, -1>;
+        else if (a.prm.W == 11 && a.prm.N == 0) kern = scan_kernel<true, false, 11, 0>;
+        else if (a.prm.W == 11 && a.prm.N == 1) kern = scan_kernel<true, false, 11, 1>;
+        else if (a.prm.W == 11 && a.prm.N == 2) kern = scan_kernel<true, false, 11, 2>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kScanThreads, smem, st>>>(a);
     }
     CU(cudaEventRecord(c->ev1, st));
     c->launches++;
