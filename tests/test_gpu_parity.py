@@ -328,6 +328,18 @@ def test_append_mode_range_scans_equal_one_scan_on_device(tmp_path):
             assert np.array_equal(eng._hits_to_host(hits_t, n), want)
         sh3, hits_t, n = eng.upload_and_scan(layout, contigs)   # pageable numpy sources
         assert np.array_equal(eng._hits_to_host(hits_t, n), want)
+        # ... and as ranks of a sharded run: every rank pipelines its own range (cuts inside contigs), merged == whole
+        from merpcr_b200 import multi
+        for world in (2, 3):
+            parts = []
+            for rank in range(world):
+                e = MerPCR(wordsize=11, margin=50, mismatches=1, shard=(rank, world))
+                assert e.load_sts_file(stsf)
+                lay = e.make_layout([len(c) for c in contigs])
+                _, hits_t, n = e.upload_and_scan(lay, pinned)
+                parts.append(e._hits_to_host(hits_t, n))
+                e.close()
+            assert np.array_equal(multi.merge_hits(parts), want), world
     finally:
         E.STREAM_SCAN_BASES = old
     assert np.array_equal(eng.search_hits(recs), want)
