@@ -413,7 +413,7 @@ def run_b200(args):
                 barrier()
                 t0 = time.perf_counter()
             sh2, hits_t, n_e2e = eng.upload_and_scan(layout, seqs_host, shard=sh2)   # copy | pack | scan pipelined
-            out = eng._hits_to_host(hits_t, n_e2e)                                    # sorted hits back on the host
+            out = eng._hits_to_host(hits_t, n_e2e, copy=False)                        # sorted hits back on the host (pinned)
             d2h = out.nbytes + 8
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps

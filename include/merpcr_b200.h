@@ -183,6 +183,13 @@ int mpcr_table_primer_words(mpcr_ctx *ctx, uint32_t rec, int which /*1|2*/, uint
                             uint32_t *n_words);
 
 /* ---- (3)+(4)+(5) scanner, verifier, hit emitter ------------------------------------------------- */
+/* Optional, before a series of mpcr_scan calls over sub-ranges of [shard_begin, shard_end): builds and uploads the
+ * scanner's work descriptors for the WHOLE range once (host pointers, synchronous on `stream`).  Later mpcr_scan calls
+ * with the same contig table and origin whose range is cut between contigs (or at these bounds) then reuse them
+ * without any upload or host round trip -- a genome can be scanned contig by contig, in append mode, while its
+ * later contigs are still being copied to the device (the copy engine is never needed by the scan calls). */
+int mpcr_scan_prepare(mpcr_ctx *ctx, const mpcr_contig *contigs, uint32_t n_contigs, uint64_t plane_origin,
+                      uint64_t shard_begin, uint64_t shard_end, void *stream);
 /* Replaces MerPCR._process_thread + _match_sts + _compare_seqs (core/engine.py:453-642) over the hash
  * positions whose global base coordinate lies in [shard_begin, shard_end) (multiples of 128; pass 0 and
  * UINT64_MAX for everything).  The planes must cover every base the shard can touch:

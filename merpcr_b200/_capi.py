@@ -18,7 +18,7 @@ ABI_VERSION = 6
 
 # every symbol include/merpcr_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_set_seed_extension", "mpcr_ctx_set_table_part", "mpcr_ctx_set_append", "mpcr_ctx_set_true_strands", "mpcr_ctx_sm_count",
+    "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_set_seed_extension", "mpcr_ctx_set_table_part", "mpcr_ctx_set_append", "mpcr_scan_prepare", "mpcr_ctx_set_true_strands", "mpcr_ctx_sm_count",
     "mpcr_pack_sequence", "mpcr_fasta_workspace_bytes", "mpcr_fasta_index", "mpcr_fasta_compact",
     "mpcr_sts_parse", "mpcr_sts_blob", "mpcr_format_hits", "mpcr_table_build", "mpcr_table_records", "mpcr_table_primer_words", "mpcr_scan",
     "mpcr_halo_left", "mpcr_halo_right", "mpcr_tile_bases", "mpcr_sort_hits", "mpcr_launch_count", "mpcr_last_scan_ms", "mpcr_last_verify_ms",
@@ -81,6 +81,8 @@ class Backend:
         lib.mpcr_table_records.argtypes = [vp, vp, vp]
         lib.mpcr_table_primer_words.restype = i32
         lib.mpcr_table_primer_words.argtypes = [vp, u32, i32, vp, u32, C.POINTER(u32)]
+        lib.mpcr_scan_prepare.restype = i32
+        lib.mpcr_scan_prepare.argtypes = [vp, vp, u32, u64, u64, u64, vp]
         lib.mpcr_scan.restype = i32
         lib.mpcr_scan.argtypes = [vp, vp, u32, vp, vp, vp, u64, u64, u64, u64, vp, u64, vp, vp]
         lib.mpcr_halo_left.restype = u64

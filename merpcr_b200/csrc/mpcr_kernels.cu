@@ -73,7 +73,10 @@ struct mpcr_ctx {
     TileDesc* d_tiles = nullptr;
     size_t tiles_cap = 0;
     uint32_t n_tiles = 0;
-    uint64_t tiles_sig = 0;
+    uint64_t tiles_sig = 0;         // layout (contigs, origin, word size) the descriptor array was built for
+    uint64_t tiles_sb = 0, tiles_se = 0;   // ... and the range it covers
+    std::vector<uint64_t> h_tile_g;        // global first base of every descriptor (ascending): sub-range views
+    uint32_t view_first = 0, view_count = 0;   // the descriptors the next scan walks
     uint32_t lay_contigs = 0, lay_max_len = 0;  // bounds of the last scanned layout (sort digit counts)
     uint32_t* d_tile_counter = nullptr;  // [0] tile counter, [1..2] survivor count / verify cursor
     Survivor* d_surv = nullptr;
@@ -1428,9 +1431,30 @@ static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_conti
     // signature of the layout: rebuild the descriptor array only when it changes
     uint64_t sig = 1469598103934665603ull;
     auto mix = [&](uint64_t v) { sig = (sig ^ v) * 1099511628211ull; };
-    mix(n_contigs); mix(origin); mix(sb); mix(se); mix((uint64_t)c->prm.wordsize);
+    mix(n_contigs); mix(origin); mix((uint64_t)c->prm.wordsize);
     for (uint32_t i = 0; i < n_contigs; ++i) { mix(contigs[i].gstart); mix(contigs[i].length); }
-    if (sig == c->tiles_sig && c->d_tiles) return MPCR_OK;
+    if (sig == c->tiles_sig && c->d_tiles) {
+        if (sb == c->tiles_sb && se == c->tiles_se) {
+            c->view_first = 0; c->view_count = c->n_tiles;
+            return MPCR_OK;
+        }
+        // A sub-range of the cached one that is cut between contigs (or at the cached bounds) is a contiguous run of
+        // the cached descriptors (tiles never span contigs): no rebuild, no upload, no host round trip -- this is what
+        // lets a genome be scanned contig by contig while it is still uploading (mpcr_scan_prepare + append mode).
+        auto clean = [&](uint64_t x) {
+            if (x == c->tiles_sb || x == c->tiles_se) return true;
+            uint32_t lo = 0, hi = n_contigs;   // last contig that starts before x
+            while (lo < hi) { const uint32_t mid = (lo + hi) / 2; if (contigs[mid].gstart < x) lo = mid + 1; else hi = mid; }
+            return lo == 0 || x >= contigs[lo - 1].gstart + contigs[lo - 1].length;
+        };
+        if (sb >= c->tiles_sb && se <= c->tiles_se && sb <= se && clean(sb) && clean(se)) {
+            const auto b0 = std::lower_bound(c->h_tile_g.begin(), c->h_tile_g.end(), sb);
+            const auto b1 = std::lower_bound(c->h_tile_g.begin(), c->h_tile_g.end(), se);
+            c->view_first = (uint32_t)(b0 - c->h_tile_g.begin());
+            c->view_count = (uint32_t)(b1 - b0);
+            return MPCR_OK;
+        }
+    }
     // tile size: kTileBases for big inputs; halved (down to one 2048-position unit) while the scanner's warps would
     // get fewer than ~8 tiles each, so small inputs still spread over the whole GPU
     uint64_t span = 0;
@@ -1469,6 +1493,10 @@ static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_conti
         }
     }
     c->n_tiles = (uint32_t)tiles.size();
+    c->view_first = 0; c->view_count = c->n_tiles;
+    c->tiles_sb = sb; c->tiles_se = se;
+    c->h_tile_g.resize(tiles.size());
+    for (size_t i = 0; i < tiles.size(); ++i) c->h_tile_g[i] = (uint64_t)(tiles[i].gbase + (int64_t)origin);
     c->lay_contigs = n_contigs;
     c->lay_max_len = 0;
     for (uint32_t i = 0; i < n_contigs; ++i)
@@ -1480,6 +1508,14 @@ static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_conti
     CU(cudaStreamSynchronize(st));  // `tiles` is pageable host memory going out of scope
     c->tiles_sig = sig;
     return MPCR_OK;
+}
+
+int mpcr_scan_prepare(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, uint64_t plane_origin,
+                      uint64_t shard_begin, uint64_t shard_end, void* stream) {
+    if (!c || (n_contigs && !h_contigs)) return fail(MPCR_EINVAL, "null argument");
+    if ((plane_origin & 127u) || (shard_begin & 127u)) return fail(MPCR_EINVAL, "origin / shard_begin must be multiples of 128");
+    CU(cudaSetDevice(c->device));
+    return build_tiles(c, h_contigs, n_contigs, plane_origin, shard_begin, shard_end, (cudaStream_t)stream);
 }
 
 int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, const void* d_plane2, const void* d_plane4,
@@ -1497,7 +1533,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     if (rc) return rc;
     if (!c->append) CU(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     c->scan_timed = false;
-    if (c->n_tiles == 0 || c->n_valid == 0) return MPCR_OK;
+    if (c->view_count == 0 || c->n_valid == 0) return MPCR_OK;
     CU(cudaMemsetAsync(c->d_tile_counter, 0, 16, st));
     CU(cudaMemsetAsync(c->d_surv_ctl, 0, (size_t)kSurvLists * kSurvCtlStride * 4, st));
     // survivor list: ~1 position in 10^4 survives on random sequence; overflow falls back to in-kernel serial verify
@@ -1514,7 +1550,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     }
     ScanArgs a;
     a.p2 = (const uint64_t*)d_plane2; a.p4 = (const uint64_t*)d_plane4; a.valid = (const uint64_t*)d_valid;
-    a.tiles = c->d_tiles; a.n_tiles = c->n_tiles;
+    a.tiles = c->d_tiles + c->view_first; a.n_tiles = c->view_count;
     a.slots = c->d_slots; a.smap = c->smap; a.bucket = c->d_bucket; a.meta = c->d_meta; a.pwords = c->d_pwords;
     a.filter = c->d_filter; a.filter_words = c->filter_words; a.cw = filter_mul(c->scan_w);
     a.prm.W = c->scan_w; a.prm.M = c->prm.margin; a.prm.N = c->prm.mismatches; a.prm.X = c->prm.three_prime_match;
@@ -1531,7 +1567,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     }
     const size_t smem = (size_t)ScanSmem::kFilterOff + (size_t)c->filter_words * 4;
     uint32_t grid = (uint32_t)c->sm_count;
-    if (grid > c->n_tiles) grid = c->n_tiles;
+    if (grid > c->view_count) grid = c->view_count;
     CU(cudaEventRecord(c->ev0, st));
     if (c->dense) {
         dense_scan_kernel<<<c->sm_count * 8, 256, 0, st>>>(a);

@@ -47,7 +47,7 @@ MIN_THREE_PRIME_MATCH = 0
 MIN_PCR_SIZE, MAX_PCR_SIZE = 1, 10000
 
 EXTENDED_WORDSIZE = 16        # key width of the extended tables of exact, candidate-heavy searches
-STREAM_SCAN_BASES = 1 << 27    # upload_and_scan: scan a finished contig (group) once this many bases are packed
+STREAM_SCAN_BASES = 1 << 26    # upload_and_scan: scan a finished contig (group) once this many bases are packed
 EXT_LINES_PER_TABLE = 125_000  # STS lines per extended table: 2.5*10^5 keys is what the scanner's filter holds at ~5 % f.p.
 PCR_SIZE_CLAMP = 0x7FFFFFFF   # any expected size >= a contig length behaves identically (engine.py:531-533)
 PLANE_SLACK_BASES = 1024      # read-ahead of the last strip / last primer window
@@ -189,6 +189,7 @@ class MerPCR:
         else:
             self._tdev = torch.device("cpu")
         self._ctx = None
+        self._pinned_hits = None  # D2H staging of the hit list
         self._copy_stream = None  # upload_and_scan: the H2D copies run beside pack + scan
         self._ctx_exts = []       # extended tables of exact, candidate-heavy searches (mpcr_ctx_set_seed_extension)
         self._create_ctx()
@@ -547,7 +548,7 @@ class MerPCR:
         else:
             output = sys.stdout
         try:
-            hits = self.search_hits(fasta_records) if fasta_records else np.zeros(0, dtype=_capi.HIT_DTYPE)
+            hits = self.search_hits(fasta_records, copy=False) if fasta_records else np.zeros(0, dtype=_capi.HIT_DTYPE)
             if writer:
                 for record in fasta_records:
                     logger.info(f"Processing sequence: {record.label} ({len(record)} bp)")
@@ -595,7 +596,7 @@ class MerPCR:
         self.total_hits = total_hits
         return total_hits
 
-    def search_hits(self, fasta_records: Sequence[FASTARecord]) -> np.ndarray:
+    def search_hits(self, fasta_records: Sequence[FASTARecord], copy: bool = True) -> np.ndarray:
         """The device path of `search`: returns this shard's hits (structured array, _capi.HIT_DTYPE) in the
         reference's output order; `contig` indexes `fasta_records`, positions are 0-based inclusive."""
         t0 = time.perf_counter()
@@ -608,7 +609,7 @@ class MerPCR:
         self._check_alphabet(fasta_records, seqs)
         layout = self.make_layout([len(r) for r in fasta_records])
         _, hits_t, n = self.upload_and_scan(layout, seqs)
-        hits = self._hits_to_host(hits_t, n)
+        hits = self._hits_to_host(hits_t, n, copy=copy)
         self.last_timing = dict(search_s=time.perf_counter() - t0)
         return hits
 
@@ -767,6 +768,10 @@ class MerPCR:
                                              sh.hits.data_ptr(), cap, sh.count.data_ptr(), compute.cuda_stream))
 
         for ctx in ctxs:
+            # work descriptors of the whole range go up now, while the copy engine is idle; the range scans below
+            # are views into them
+            self._be.check(lib.mpcr_scan_prepare(ctx, contigs.ctypes.data, len(contigs), sh.origin, sh.begin, sh.end,
+                                                 compute.cuda_stream))
             self._be.check(lib.mpcr_ctx_set_append(ctx, 1))
         try:
             k, h2d, pending, done_to, deferred = 0, 0, 0, sh.begin, None
@@ -819,12 +824,22 @@ class MerPCR:
         hits, n = self.scan_device(layout, sh, sort=sort)
         return self._hits_to_host(hits, n)
 
-    @staticmethod
-    def _hits_to_host(hits, n: int) -> np.ndarray:
+    def _hits_to_host(self, hits, n: int, copy: bool = True) -> np.ndarray:
+        """The first n hit records as a host array.  copy=False returns a view of the engine's pinned staging buffer,
+        valid until the next call (what `search` formats its output from)."""
         if n == 0:
             return np.zeros(0, dtype=_capi.HIT_DTYPE)
-        raw = hits[: n * _capi.HIT_DTYPE.itemsize].cpu().numpy()
-        return raw.view(_capi.HIT_DTYPE).copy()
+        nb = n * _capi.HIT_DTYPE.itemsize
+        if hits.device.type != "cuda":
+            return hits[:nb].numpy().view(_capi.HIT_DTYPE).copy()
+        # through a pinned staging buffer: a pageable D2H of a few MB costs more than the copy itself
+        if self._pinned_hits is None or self._pinned_hits.numel() < nb:
+            self._pinned_hits = torch.empty(max(nb, 1 << 22), dtype=torch.uint8).pin_memory()
+        stage = self._pinned_hits[:nb]
+        stage.copy_(hits[:nb], non_blocking=True)
+        self._sync()
+        out = stage.numpy().view(_capi.HIT_DTYPE)
+        return out.copy() if copy else out
 
     def scan_device(self, layout: dict, sh: _Shard, sort: bool = True):
         """Device-resident scan: returns (uint8 tensor holding mpcr_hit records, n_hits).  Re-runs with a larger

@@ -300,6 +300,13 @@ uint64_t mpcr_halo_right(const mpcr_ctx* c) {
     return c ? round_up(c->max_pcr + (uint64_t)c->prm.margin + c->max_len + 64 + 128, 128) + kTileBases : 0;
 }
 
+int mpcr_scan_prepare(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, uint64_t origin, uint64_t sb, uint64_t,
+                      void*) {
+    if (!c || (n_contigs && !contigs)) return fail(MPCR_EINVAL, "null argument");
+    if ((origin & 127u) || (sb & 127u)) return fail(MPCR_EINVAL, "origin / shard_begin must be multiples of 128");
+    return MPCR_OK;   // the emulation walks the contig table directly
+}
+
 int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const void* plane2, const void* plane4,
               const void* valid, uint64_t origin, uint64_t plane_bases, uint64_t sb, uint64_t se, mpcr_hit* hits,
               uint64_t capacity, uint64_t* count, void*) {
