@@ -744,8 +744,8 @@ class MerPCR:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self._tdev)
         copy = self._copy_stream
-        chunk = 1 << 26
-        if sh.stage2 is None:
+        chunk = min(1 << 26, max(1 << 20, (sh.bases + 127) // 128 * 128))   # small genomes: small staging buffers
+        if sh.stage2 is None or sh.stage2[0].numel() < chunk:
             sh.stage2 = [torch.empty(chunk, dtype=torch.uint8, device=self._tdev) for _ in range(2)]
         copied = [torch.cuda.Event() for _ in range(2)]
         packed = [torch.cuda.Event() for _ in range(2)]
