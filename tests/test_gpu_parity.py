@@ -240,6 +240,29 @@ def test_synthetic_configs_bit_exact_vs_oracle(tmp_path, case):
     assert len(got) > 100 and len(expected) > 100
 
 
+def test_long_primers_bit_exact_vs_oracle(tmp_path):
+    """Primers of 30..120 bases: several nibble words per primer, the multi-word compare of the verifier (primers past
+    32 bases have no hoisted view), tags and seeds at the front of long primers, amplicons barely longer than them."""
+    from merpcr_b200 import MerPCR
+    for seed, params in ((41, dict(wordsize=11, margin=50, mismatches=2, three_prime_match=1)),
+                         (43, dict(wordsize=14, margin=10, mismatches=0, three_prime_match=3)),
+                         (47, dict(wordsize=9, margin=30, mismatches=1, three_prime_match=0, iupac_mode=1))):
+        rng = synth.Rng(seed)
+        contigs = [rng.dna(n) for n in (700_000, 300_000, 150)]
+        sts = synth.make_sts_set(seed + 1, 600, 30, 120, 260, 1000)
+        expected = synth.plant_amplicons(seed + 2, contigs[:2], sts, params["margin"], sub_mode="cfg3", plant_count=300)
+        sts["p1"][::9, 40] = ord("N")            # a degenerate letter deep inside some long primers
+        sts["p2"][::7, 3] = ord("R")
+        text = synth.sts_lines(sts)
+        eng = MerPCR(**params)
+        assert eng.load_sts_file(_write(tmp_path, f"s{seed}.sts", text))
+        got = parity.engine_hits(eng, _records(contigs))
+        want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
+        assert got.shape == want.shape and np.array_equal(got, want), params
+        assert len(want) > 50, (len(want), len(expected))
+        eng.close()
+
+
 def test_hit_buffer_regrows_and_sort_is_total(tmp_path):
     """More hits than the initial 65 536-entry buffer: nothing is truncated, order key is exact
     (repeat-rich sequence, duplicate STS lines, multi-delta hits)."""

@@ -210,6 +210,27 @@ def test_append_mode_range_scans_equal_one_scan(tmp_path):
         assert np.array_equal(got, want), cuts
 
 
+def test_long_primers_equal_the_oracle(tmp_path):
+    """Primers of 30..120 bases (multi-word compare, no hoisted primer view past 32 bases) through the host stack."""
+    from merpcr_b200 import FASTARecord, MerPCR
+    for seed, params in ((41, dict(wordsize=11, margin=50, mismatches=2, three_prime_match=1)),
+                         (47, dict(wordsize=9, margin=30, mismatches=1, three_prime_match=0, iupac_mode=1))):
+        rng = synth.Rng(seed)
+        contigs = [rng.dna(n) for n in (120_000, 60_000, 150)]
+        sts = synth.make_sts_set(seed + 1, 120, 30, 120, 260, 1000)
+        synth.plant_amplicons(seed + 2, contigs[:2], sts, params["margin"], sub_mode="cfg3", plant_count=60)
+        sts["p1"][::9, 40] = ord("N")
+        sts["p2"][::7, 3] = ord("R")
+        text = synth.sts_lines(sts)
+        f = tmp_path / f"s{seed}.sts"
+        f.write_bytes(text)
+        eng = MerPCR(**params)
+        assert eng.load_sts_file(str(f))
+        got = parity.engine_hits(eng, [FASTARecord(f">c{i}", c) for i, c in enumerate(contigs)])
+        want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
+        assert got.shape == want.shape and np.array_equal(got, want) and len(want) > 20, params
+
+
 def test_cli_in_process(tmp_path, monkeypatch, capsys):
     # reference tests/test_cli.py, test_cli_enhanced.py:23-156 (flag set, K=V conversion, exit codes)
     from merpcr_b200 import cli
