@@ -279,6 +279,27 @@ def test_hit_buffer_regrows_and_sort_is_total(tmp_path):
     assert len(want) > 65536 and np.array_equal(got, want)
 
 
+def test_long_runs_of_equal_pos1_keep_discovery_order(tmp_path):
+    """Hundreds of identical STS lines (and a few with other sizes) meeting the same positions of a tandem repeat: runs
+    of equal (contig, pos1) far longer than 32 hits, which `order_ties` settles with its heap sort -- the order inside
+    a run is the reference's discovery order (file order of the lines, then the probing order of the offsets)."""
+    from merpcr_b200 import MerPCR
+    unit = "ACGGTCATTGCAGT" + "TTGACCGGTATCAG" + "CATGCATGAACC"      # 40-mer tandem repeat
+    seq = np.frombuffer(("G" * 500 + unit * 60 + "C" * 500).encode(), dtype=np.uint8).copy()
+    lines = [f"D{i}\tACGGTCATTGCAGT\tTTGACCGGTATCAG\t{68 + 40 * (i % 3)}\tdup {i}\n" for i in range(300)]
+    sts_text = "".join(lines).encode()
+    path = _write(tmp_path, "d.sts", sts_text)
+    for params in (dict(wordsize=8, margin=45, mismatches=0), dict(wordsize=11, margin=45, mismatches=1)):
+        eng = MerPCR(**params)
+        assert eng.load_sts_file(path)
+        got = parity.engine_hits(eng, _records([seq]))
+        want = parity.oracle_hits(params, sts_text.decode(), [seq.tobytes()])
+        assert np.array_equal(got, want) and len(want) > 20000
+        pos1, counts = np.unique(want[:, 1], return_counts=True)
+        assert counts.max() > 300                                    # runs well past the insertion-sort limit
+        eng.close()
+
+
 def test_sharded_equals_whole_on_device(tmp_path):
     from merpcr_b200 import MerPCR
     contigs, sts_text, _ = _make_workload(901, [700_000, 300_000, 64, 500_001], 1200,
