@@ -346,10 +346,9 @@ struct ScanArgs {
     uint32_t surv_cap;
     uint32_t* surv_ctl;    // per sub-list, 128 bytes apart: [0] entries appended (may exceed surv_cap), [1] verify cursor
     int debug;  // MPCR_DEBUG bit0: stop after the filter stage; bit1: probe the table but drop the survivors
-    // Pipe balancing of stage 1 (MPCR_S1_FMA): multipliers the compiler cannot see through, so that shifts by a
-    // constant stay multiplies (IMAD / IMAD.HI on the fma pipe) instead of becoming SHF / LEA on the saturated alu pipe.
+    // Pipe balancing of stage 1: a multiplier the compiler cannot see through, so that the filter word's address stays a
+    // multiply-add (IMAD, fma pipe) instead of becoming a LEA on the busier alu pipe (2.97 -> 2.89 ms).
     uint32_t k4;          // 4
-    uint32_t pow2[32];    // pow2[j] = 2^(j+1) for j < 31 (x * pow2[j] >> 32 == x >> (31 - j)), pow2[31] = 1
 };
 
 // shared-memory plan of the scanner CTA (dynamic shared memory): one private block per warp, then the filter
@@ -454,9 +453,6 @@ __device__ __noinline__ void probe_collision(const ScanArgs& a, uint32_t key, ui
 // One filter probe: returns a word whose MSB is set iff both Bloom bits of the key are set.
 // x holds the key in its low 2W bits (anything above cancels in the multiply by cw); x3 is the raw register of
 // the position three bases further on, i.e. x >> 6 in its low bits (WIDE: W >= 6, else the second bit == the first).
-#ifndef MPCR_S1_FMA
-#define MPCR_S1_FMA 1   // bit0: filter word address by IMAD; bit1: pass-bit collection by IMAD.HI; bit2: keys by IMAD.HI
-#endif
 struct FilterView {
     const uint32_t* words;   // the filter in shared memory
     uint32_t base32;         // its shared-window address
@@ -465,12 +461,8 @@ struct FilterView {
 template <bool WIDE>
 __device__ __forceinline__ uint32_t filter_probe(const FilterView& f, const ScanArgs& a, uint32_t x, uint32_t x3) {
     uint32_t word;
-#if MPCR_S1_FMA & 1
     const uint32_t addr = __umulhi(x * f.cw, f.n_words) * a.k4 + f.base32;
     asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
-#else
-    word = f.words[__umulhi(x * f.cw, f.n_words)];
-#endif
     const uint32_t t1 = __funnelshift_l(0u, word, x);  // word << (x & 31)
     if (!WIDE) return t1;
     return t1 & __funnelshift_l(0u, word, x3);
@@ -575,25 +567,8 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
             const uint32_t r[6] = {q.x, q.y, q.z, q.w, s_p2[4 * lane + 4], 0u};
             // raw register of position j (its low 2W bits are the key); positions 64..66 only feed shift amounts
             auto raw = [&](int j) -> uint32_t {
-#if MPCR_S1_FMA & 4
-                // 2 (j & 15) + 2W <= 32: a plain right shift of one register holds the whole key -> IMAD.HI
-                if ((j & 15) && 2 * (j & 15) <= 10) return __umulhi(r[j >> 4], a.pow2[31 - 2 * (j & 15)]);
-#endif
                 return (j & 15) ? __funnelshift_r(r[j >> 4], r[(j >> 4) + 1], 2 * (j & 15)) : r[j >> 4];
             };
-#if MPCR_S1_FMA & 2
-            // pass bit j = MSB of the probe result: (m * 2^(j+1)) >> 32 puts it at bit j, as one IMAD.HI with addend
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const uint32_t m = filter_probe<WIDE>(f, a, raw(j), raw(j + 3)) & 0x80000000u;
-                c_lo = (j < 31 ? __umulhi(m, a.pow2[j]) : m * a.pow2[31]) + c_lo;
-            }
-#pragma unroll
-            for (int j = 32; j < 64; ++j) {
-                const uint32_t m = filter_probe<WIDE>(f, a, raw(j), raw(j + 3)) & 0x80000000u;
-                c_hi = (j < 63 ? __umulhi(m, a.pow2[j - 32]) : m * a.pow2[31]) + c_hi;
-            }
-#else
             // collect the MSB of each probe result as bit j of the pass mask (descending j: one funnel shift each)
 #pragma unroll
             for (int j = 31; j >= 0; --j)
@@ -601,7 +576,6 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
 #pragma unroll
             for (int j = 63; j >= 32; --j)
                 c_hi = __funnelshift_l(filter_probe<WIDE>(f, a, raw(j), raw(j + 3)), c_hi, 1);
-#endif
             c_lo &= (uint32_t)wv;
             c_hi &= (uint32_t)(wv >> 32);
         }
@@ -1557,8 +1531,6 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
     a.debug = getenv("MPCR_DEBUG") ? atoi(getenv("MPCR_DEBUG")) : 0;
     a.k4 = 4u;
-    for (int j = 0; j < 31; ++j) a.pow2[j] = 2u << j;
-    a.pow2[31] = 1u;
     a.hits = d_hits; a.capacity = capacity; a.count = (unsigned long long*)d_count; a.tile_counter = c->d_tile_counter;
     a.surv = c->d_surv; a.surv_cap = (uint32_t)(c->surv_bytes / sizeof(Survivor) / kSurvLists); a.surv_ctl = c->d_surv_ctl;
     if (const char* env = getenv("MPCR_SURVIVOR_CAP")) {   // test hook: force the list-full path (in-kernel verify)
