@@ -112,11 +112,11 @@ __global__ void __launch_bounds__(kSortThreads) rs_scatter(const Item<NF>* __res
     }
 }
 
-// All passes in ONE cooperative launch for small inputs (n_blk <= kFusedMaxBlocks chunks of 2048 records, one CTA
+// All passes in ONE cooperative launch while the grid is co-resident (n_blk <= kFusedMaxBlocks chunks of 2048 records, one CTA
 // each): per pass a block histogram, a grid barrier, every CTA derives its own 256 scatter offsets from the
 // histograms of all CTAs, the same stable match_any scatter as rs_scatter, a grid barrier.  This is what orders
 // the ~10^5 hits of a human-sized scan: 9 passes in one launch instead of 27 launches.
-static constexpr int kFusedMaxBlocks = 128;
+static constexpr int kFusedMaxBlocks = 1024;   // tried cooperatively; a grid that is not co-resident falls back below
 static constexpr int kMaxPasses = 24;
 struct PassList {
     PassDesc p[kMaxPasses];
