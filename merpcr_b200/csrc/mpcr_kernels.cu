@@ -44,6 +44,7 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 struct Survivor;
+struct LongRun;
 struct mpcr_ctx {
     int device = 0;
     mpcr_params prm{};
@@ -84,6 +85,7 @@ struct mpcr_ctx {
     uint32_t* d_surv_ctl = nullptr;
     // sort scratch
     void* d_sort_tmp = nullptr;
+    LongRun* d_long_runs = nullptr;   // order_ties -> order_long_runs queue + its two counters behind it
     size_t sort_tmp_cap = 0;
     uint32_t* d_counts = nullptr;
     size_t counts_cap = 0;
@@ -940,40 +942,31 @@ __global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
     }
 }
 
-// After the radix passes over (pos1, contig): hits that share contig and pos1 (a handful: duplicate STS lines,
-// several deltas of one primer-1 site) are put into the reference's discovery order (hash_off, rec, rank) by the
-// thread that finds the start of the run -- an insertion sort, runs are short.
-__global__ void __launch_bounds__(256) order_ties(mpcr_hit* __restrict__ hits, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t c = hits[i].contig, p = hits[i].pos1;
-    if (i > 0 && hits[i - 1].contig == c && hits[i - 1].pos1 == p) return;   // not the start of a run
-    uint64_t e = i + 1;
-    while (e < n && hits[e].contig == c && hits[e].pos1 == p) ++e;
-    auto less = [](const mpcr_hit& a, const mpcr_hit& b) {
-        if (a.hash_off != b.hash_off) return a.hash_off < b.hash_off;
-        if (a.rec != b.rec) return a.rec < b.rec;
-        return a.rank < b.rank;
-    };
-    const uint64_t m = e - i;
-    if (m <= 32) {
-        for (uint64_t k = i + 1; k < e; ++k) {
-            const mpcr_hit x = hits[k];
-            uint64_t j = k;
-            while (j > i && less(x, hits[j - 1])) { hits[j] = hits[j - 1]; --j; }
-            hits[j] = x;
-        }
-        return;
-    }
-    // a long run (thousands of identical STS lines on a repeat): heap sort keeps it O(m log m)
-    mpcr_hit* h = hits + i;
+// After the radix passes over (pos1, contig): hits that share contig and pos1 (duplicate STS lines, several deltas of
+// one primer-1 site) are put into the reference's discovery order (hash_off, rec, rank).  Runs of up to 32 hits are
+// insertion-sorted by the thread that finds their start; longer ones (identical STS lines on a repeat, or a mate
+// window inside an N-run in IUPAC mode: every offset matches) go to a queue for order_long_runs, because a lone thread
+// sorting a hundred 24-byte records in global memory is a chain of thousands of dependent L2 round trips.
+struct LongRun {
+    uint32_t first, len;
+};
+static constexpr uint32_t kLongRunQueue = 1u << 16;   // queue entries (a full queue sorts in place, below)
+static constexpr uint32_t kLongRunMax = 1024;         // hits one CTA sorts in shared memory
+
+__device__ __forceinline__ bool tie_less(const mpcr_hit& a, const mpcr_hit& b) {
+    if (a.hash_off != b.hash_off) return a.hash_off < b.hash_off;
+    if (a.rec != b.rec) return a.rec < b.rec;
+    return a.rank < b.rank;
+}
+// heap sort of one run by one thread, O(m log m): the fallback for runs no CTA can hold
+__device__ __noinline__ void tie_heap_sort(mpcr_hit* h, uint64_t m) {
     auto sift = [&](uint64_t root, uint64_t end) {
         const mpcr_hit x = h[root];
         for (;;) {
             uint64_t child = 2 * root + 1;
             if (child >= end) break;
-            if (child + 1 < end && less(h[child], h[child + 1])) ++child;
-            if (!less(x, h[child])) break;
+            if (child + 1 < end && tie_less(h[child], h[child + 1])) ++child;
+            if (!tie_less(x, h[child])) break;
             h[root] = h[child];
             root = child;
         }
@@ -985,6 +978,78 @@ __global__ void __launch_bounds__(256) order_ties(mpcr_hit* __restrict__ hits, u
         h[0] = h[end];
         h[end] = t;
         sift(0, end);
+    }
+}
+
+__global__ void __launch_bounds__(256) order_ties(mpcr_hit* __restrict__ hits, uint64_t n, LongRun* __restrict__ queue,
+                                                  uint32_t* __restrict__ queue_ctl /* [0] entries, [1] cursor */) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = hits[i].contig, p = hits[i].pos1;
+    if (i > 0 && hits[i - 1].contig == c && hits[i - 1].pos1 == p) return;   // not the start of a run
+    uint64_t e = i + 1;
+    while (e < n && hits[e].contig == c && hits[e].pos1 == p) ++e;
+    const uint64_t m = e - i;
+    if (m <= 32) {
+        for (uint64_t k = i + 1; k < e; ++k) {
+            const mpcr_hit x = hits[k];
+            uint64_t j = k;
+            while (j > i && tie_less(x, hits[j - 1])) { hits[j] = hits[j - 1]; --j; }
+            hits[j] = x;
+        }
+        return;
+    }
+    if (m <= kLongRunMax && i < 0xFFFFFFFFull) {
+        const uint32_t q = atomicAdd(queue_ctl, 1u);
+        if (q < kLongRunQueue) { queue[q] = LongRun{(uint32_t)i, (uint32_t)m}; return; }
+    }
+    tie_heap_sort(hits + i, m);
+}
+
+// One CTA per queued run: the records and their 61-bit tie keys (hash_off, rec, rank) go to shared memory, a bitonic
+// network orders (key, index) pairs, the records are written back in that order.
+__global__ void __launch_bounds__(256) order_long_runs(mpcr_hit* __restrict__ hits, const LongRun* __restrict__ queue,
+                                                       uint32_t* __restrict__ queue_ctl) {
+    __shared__ mpcr_hit rec[kLongRunMax];
+    __shared__ unsigned long long key[kLongRunMax];
+    __shared__ uint16_t idx[kLongRunMax];
+    __shared__ uint32_t s_q;
+    const uint32_t n_q = min(queue_ctl[0], kLongRunQueue);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_q = atomicAdd(queue_ctl + 1, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= n_q) return;
+        const LongRun r = queue[q];
+        uint32_t np = 64;
+        while (np < r.len) np <<= 1;
+        for (uint32_t k = threadIdx.x; k < np; k += blockDim.x) {
+            unsigned long long kk = ~0ull;   // padding sorts to the end
+            if (k < r.len) {
+                const mpcr_hit h = hits[r.first + k];
+                rec[k] = h;
+                kk = ((unsigned long long)h.hash_off << 45) | ((unsigned long long)h.rec << 15) | (unsigned long long)h.rank;
+            }
+            key[k] = kk;
+            idx[k] = (uint16_t)k;
+        }
+        __syncthreads();
+        for (uint32_t size = 2; size <= np; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = threadIdx.x; t < np / 2; t += blockDim.x) {
+                    const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const unsigned long long a = key[lo], b = key[hi];
+                    if ((a > b) == up) {
+                        key[lo] = b; key[hi] = a;
+                        const uint16_t ia = idx[lo]; idx[lo] = idx[hi]; idx[hi] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t k = threadIdx.x; k < r.len; k += blockDim.x) hits[r.first + k] = rec[idx[k]];
     }
 }
 
@@ -1035,7 +1100,7 @@ void mpcr_ctx_destroy(mpcr_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     free_table(c);
-    cudaFree(c->d_tiles); cudaFree(c->d_tile_counter); cudaFree(c->d_sort_tmp); cudaFree(c->d_counts); cudaFree(c->d_lut);
+    cudaFree(c->d_tiles); cudaFree(c->d_tile_counter); cudaFree(c->d_sort_tmp); cudaFree(c->d_long_runs); cudaFree(c->d_counts); cudaFree(c->d_lut);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -1602,8 +1667,12 @@ int mpcr_sort_hits(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n, void* stream) {
     np = add_passes(passes, np, 1, c->lay_max_len ? c->lay_max_len : 0x7FFFFFFFull);
     np = add_passes(passes, np, 0, c->lay_contigs ? c->lay_contigs - 1 : 0xFFFFFFFFull);
     c->launches += radix_sort<6>((Item<6>*)d_hits, (Item<6>*)c->d_sort_tmp, n, passes, np, c->d_counts, st);
-    order_ties<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_hits, n);
-    c->launches++;
+    if (!c->d_long_runs) CU(cudaMalloc(&c->d_long_runs, (size_t)kLongRunQueue * sizeof(LongRun) + 16));
+    uint32_t* queue_ctl = reinterpret_cast<uint32_t*>(c->d_long_runs + kLongRunQueue);
+    CU(cudaMemsetAsync(queue_ctl, 0, 16, st));
+    order_ties<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_hits, n, c->d_long_runs, queue_ctl);
+    order_long_runs<<<(uint32_t)c->sm_count * 2u, 256, 0, st>>>(d_hits, c->d_long_runs, queue_ctl);
+    c->launches += 2;
     CU(cudaGetLastError());
     return MPCR_OK;
 }
