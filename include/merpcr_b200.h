@@ -192,7 +192,10 @@ int mpcr_scan_prepare(mpcr_ctx *ctx, const mpcr_contig *contigs, uint32_t n_cont
                       uint64_t shard_begin, uint64_t shard_end, void *stream);
 /* Replaces MerPCR._process_thread + _match_sts + _compare_seqs (core/engine.py:453-642) over the hash
  * positions whose global base coordinate lies in [shard_begin, shard_end) (multiples of 128; pass 0 and
- * UINT64_MAX for everything).  The planes must cover every base the shard can touch:
+ * UINT64_MAX for everything).  Ownership is decided per unit of 2048 hash positions (units start at multiples of
+ * 2048 from their contig's first base): a unit belongs to the range that holds its first base, so consecutive
+ * ranges -- other ranks, or the ranges of one genome scanned one after the other -- neither overlap nor leave a gap,
+ * wherever they are cut.  The planes must cover every base the shard can touch:
  * [shard_begin - mpcr_halo_left(), shard_end + mpcr_halo_right()) clipped to the genome.
  * Hits are appended (unordered) to d_hits; *d_count receives the TRUE number of hits even when it
  * exceeds capacity (the caller re-runs with a larger buffer; nothing is silently truncated). */
