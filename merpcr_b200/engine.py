@@ -732,23 +732,29 @@ class MerPCR:
         (group of small contigs) is scanned as soon as its bases are packed -- the tables append to one hit buffer
         (mpcr_ctx_set_append), the host reads the count once at the end, the hits are sorted once.  Host -> hits time
         is then the PCIe copy plus the last contig's scan.  Returns (shard, hit tensor, n_hits)."""
-        if self._tdev.type != "cuda" or all(s is None or (isinstance(s, torch.Tensor) and s.device == self._tdev)
-                                            for s in seqs):
+        if all(s is None or (isinstance(s, torch.Tensor) and s.device == self._tdev) for s in seqs):
             sh = self.upload(layout, seqs, shard)
             hits, n = self.scan_device(layout, sh, sort=sort)
             return sh, hits, n
         lib = self._be.lib
         sh = self._prepare_shard(layout, shard)
         lut = genome_lut(self.iupac_mode)
-        compute = torch.cuda.current_stream(self._tdev)
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(self._tdev)
-        copy = self._copy_stream
+        # (with the CPU test tier's emulated library everything below runs in program order: host memory IS device
+        # memory there, so no piece is ever staged, and the range / append logic is exercised as is)
+        gpu = self._tdev.type == "cuda"
         chunk = min(1 << 26, max(1 << 20, (sh.bases + 127) // 128 * 128))   # small genomes: small staging buffers
-        if sh.stage2 is None or sh.stage2[0].numel() < chunk:
-            sh.stage2 = [torch.empty(chunk, dtype=torch.uint8, device=self._tdev) for _ in range(2)]
-        copied = [torch.cuda.Event() for _ in range(2)]
-        packed = [torch.cuda.Event() for _ in range(2)]
+        compute = copy = None
+        copied = packed = ()
+        if gpu:
+            compute = torch.cuda.current_stream(self._tdev)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(self._tdev)
+            copy = self._copy_stream
+            if sh.stage2 is None or sh.stage2[0].numel() < chunk:
+                sh.stage2 = [torch.empty(chunk, dtype=torch.uint8, device=self._tdev) for _ in range(2)]
+            copied = [torch.cuda.Event() for _ in range(2)]
+            packed = [torch.cuda.Event() for _ in range(2)]
+        stream = compute.cuda_stream if gpu else 0
         isz = _capi.HIT_DTYPE.itemsize
         if sh.count is None:
             sh.count = torch.zeros(1, dtype=torch.int64, device=self._tdev)
@@ -756,7 +762,8 @@ class MerPCR:
             sh.hits = torch.empty((1 << 16) * isz, dtype=torch.uint8, device=self._tdev)
         cap = sh.hits.numel() // isz
         sh.count.zero_()
-        copy.wait_stream(compute)              # the staging buffers and the zeroed planes exist before the first copy
+        if gpu:
+            copy.wait_stream(compute)          # the staging buffers and the zeroed planes exist before the first copy
         contigs = layout["contigs"]
         ctxs = self._all_ctxs()
         nxt = [int(c["gstart"]) for c in contigs[1:]] + [max(layout["total"], sh.end)]
@@ -765,13 +772,13 @@ class MerPCR:
             for ctx in ctxs:
                 self._be.check(lib.mpcr_scan(ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
                                              sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.bases, lo, hi,
-                                             sh.hits.data_ptr(), cap, sh.count.data_ptr(), compute.cuda_stream))
+                                             sh.hits.data_ptr(), cap, sh.count.data_ptr(), stream))
 
         for ctx in ctxs:
             # work descriptors of the whole range go up now, while the copy engine is idle; the range scans below
             # are views into them
             self._be.check(lib.mpcr_scan_prepare(ctx, contigs.ctypes.data, len(contigs), sh.origin, sh.begin, sh.end,
-                                                 compute.cuda_stream))
+                                                 stream))
             self._be.check(lib.mpcr_ctx_set_append(ctx, 1))
         try:
             k, h2d, pending, done_to, deferred = 0, 0, 0, sh.begin, None
@@ -794,7 +801,7 @@ class MerPCR:
                     compute.wait_event(copied[slot])
                 self._be.check(lib.mpcr_pack_sequence(self._ctx, src.data_ptr(), b - a, a, sh.origin,
                                                       sh.plane2.data_ptr(), sh.plane4.data_ptr(), sh.valid.data_ptr(),
-                                                      lut.ctypes.data, compute.cuda_stream))
+                                                      lut.ctypes.data, stream))
                 if slot >= 0:
                     packed[slot].record(compute)
                 pending += b - a

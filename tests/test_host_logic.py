@@ -210,6 +210,46 @@ def test_append_mode_range_scans_equal_one_scan(tmp_path):
         assert np.array_equal(got, want), cuts
 
 
+def test_pipelined_search_scans_contig_groups_as_they_complete(tmp_path, monkeypatch):
+    """`upload_and_scan` (what `search` runs for host-resident sequences): contig groups are scanned in append mode as
+    soon as they are packed -- several mpcr_scan calls, one hit buffer, one sort -- and give exactly the hits of
+    upload + one scan; also as ranks of a sharded run (ranges cut inside contigs at the shard bounds)."""
+    import merpcr_b200.engine as E
+    from merpcr_b200 import FASTARecord, MerPCR, multi
+    monkeypatch.setattr(E, "STREAM_SCAN_BASES", 30000)
+    rng = synth.Rng(1201)
+    contigs = [rng.dna(n) for n in (50000, 12, 33000, 2047, 2049, 41000, 10, 29000)]
+    sts = synth.make_sts_set(1202, 200, 18, 25, 100, 600)
+    synth.plant_amplicons(1203, [c for c in contigs if len(c) > 20000], sts, 50, sub_mode="cfg3")
+    f = tmp_path / "p.sts"
+    f.write_bytes(synth.sts_lines(sts))
+    params = dict(wordsize=11, margin=50, mismatches=1)
+    eng = MerPCR(**params)
+    assert eng.load_sts_file(str(f))
+    layout = eng.make_layout([len(c) for c in contigs])
+    want = eng.scan(layout, eng.upload(layout, contigs))
+    assert len(want) > 100
+    before = eng.gpu_launches
+    _, hits_t, n = eng.upload_and_scan(layout, contigs)
+    assert eng.gpu_launches - before >= 4                      # several range scans (the emulation counts one each)
+    assert np.array_equal(eng._hits_to_host(hits_t, n), want)
+    for world in (2, 3):
+        parts = []
+        for rank in range(world):
+            e = MerPCR(**params, shard=(rank, world))
+            assert e.load_sts_file(str(f))
+            lay = e.make_layout([len(c) for c in contigs])
+            _, hits_t, n = e.upload_and_scan(lay, contigs)
+            parts.append(e._hits_to_host(hits_t, n))
+        assert np.array_equal(multi.merge_hits(parts), want), world
+    # a hit buffer that is too small: the pipeline notices at the end and rescans the resident planes with room
+    import torch
+    sh = eng._prepare_shard(layout, None)
+    sh.hits = torch.empty(8 * want.dtype.itemsize, dtype=torch.uint8)
+    _, hits_t, n = eng.upload_and_scan(layout, contigs, shard=sh)
+    assert np.array_equal(eng._hits_to_host(hits_t, n), want)
+
+
 def test_long_primers_equal_the_oracle(tmp_path):
     """Primers of 30..120 bases (multi-word compare, no hoisted primer view past 32 bases) through the host stack."""
     from merpcr_b200 import FASTARecord, MerPCR
