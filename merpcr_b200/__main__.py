@@ -1,5 +1,4 @@
-"""Entry point: python -m merpcr_b200 (mirror of the reference's merpcr/__main__.py)."""
-from .cli import main
+"""`python -m merpcr_b200 ...` == the `merpcr` console script of the reference (src/merpcr/__main__.py)."""
+from merpcr_b200.cli import main as _cli_main
 
-if __name__ == "__main__":
-    raise SystemExit(main())
+raise SystemExit(_cli_main())

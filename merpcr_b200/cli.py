@@ -59,40 +59,47 @@ pcr_size_type = _bounded("pcr_size_type", 1, 10000, "PCR size must be between 1-
 sts_line_length_type = _bounded("sts_line_length_type", 1, None, "STS line length must be > 0, got {}")
 
 
+# The reference's command line as data (cli.py:127-214): flag, long name, value parser, default, help text.  The help
+# texts show the default the way the reference words them.
+_OPTIONS = (
+    ("-M", "--margin", margin_type, DEFAULT_MARGIN, "Margin (default: {d})"),
+    ("-N", "--mismatches", mismatch_type, DEFAULT_MISMATCHES, "Number of mismatches allowed (default: {d})"),
+    ("-W", "--wordsize", wordsize_type, DEFAULT_WORDSIZE, "Word size (default: {d})"),
+    ("-T", "--threads", threads_type, DEFAULT_THREADS, "Number of threads (default: {d})"),
+    ("-X", "--three-prime-match", int, DEFAULT_THREE_PRIME_MATCH,
+     "Number of 3'-ward bases in which to disallow mismatches (default: {d})"),
+    ("-O", "--output", str, None, "Output file name (default: stdout)"),
+    ("-Q", "--quiet", (0, 1), 1, "Quiet flag (0=verbose, 1=quiet)"),
+    ("-Z", "--default-pcr-size", pcr_size_type, DEFAULT_PCR_SIZE, "Default PCR size (default: {d})"),
+    ("-I", "--iupac", (0, 1), DEFAULT_IUPAC_MODE,
+     "IUPAC flag (0=don't honor IUPAC ambiguity symbols, 1=honor IUPAC symbols)"),
+    ("-S", "--max-sts-line-length", sts_line_length_type, DEFAULT_MAX_STS_LINE_LENGTH,
+     "Max. line length for the STS file (default: {d})"),
+)
+
+
 def create_parser() -> argparse.ArgumentParser:
-    """cli.py:127-214."""
-    parser = argparse.ArgumentParser(description="merPCR - Modern Electronic Rapid PCR",
-                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    parser.add_argument("sts_file", type=str, help="STS file (tab-delimited)")
-    parser.add_argument("fasta_file", type=str, help="FASTA sequence file")
-    parser.add_argument("-M", "--margin", type=margin_type, default=DEFAULT_MARGIN,
-                        help=f"Margin (default: {DEFAULT_MARGIN})")
-    parser.add_argument("-N", "--mismatches", type=mismatch_type, default=DEFAULT_MISMATCHES,
-                        help=f"Number of mismatches allowed (default: {DEFAULT_MISMATCHES})")
-    parser.add_argument("-W", "--wordsize", type=wordsize_type, default=DEFAULT_WORDSIZE,
-                        help=f"Word size (default: {DEFAULT_WORDSIZE})")
-    parser.add_argument("-T", "--threads", type=threads_type, default=DEFAULT_THREADS,
-                        help=f"Number of threads (default: {DEFAULT_THREADS})")
-    parser.add_argument("-X", "--three-prime-match", type=int, default=DEFAULT_THREE_PRIME_MATCH,
-                        help="Number of 3'-ward bases in which to disallow mismatches "
-                             f"(default: {DEFAULT_THREE_PRIME_MATCH})")
-    parser.add_argument("-O", "--output", type=str, default=None, help="Output file name (default: stdout)")
-    parser.add_argument("-Q", "--quiet", type=int, choices=[0, 1], default=1, help="Quiet flag (0=verbose, 1=quiet)")
-    parser.add_argument("-Z", "--default-pcr-size", type=pcr_size_type, default=DEFAULT_PCR_SIZE,
-                        help=f"Default PCR size (default: {DEFAULT_PCR_SIZE})")
-    parser.add_argument("-I", "--iupac", type=int, choices=[0, 1], default=DEFAULT_IUPAC_MODE,
-                        help="IUPAC flag (0=don't honor IUPAC ambiguity symbols, 1=honor IUPAC symbols)")
-    parser.add_argument("-S", "--max-sts-line-length", type=sts_line_length_type, default=DEFAULT_MAX_STS_LINE_LENGTH,
-                        help=f"Max. line length for the STS file (default: {DEFAULT_MAX_STS_LINE_LENGTH})")
-    parser.add_argument("-v", "--version", action="version", version="merPCR version 1.0.0")
-    parser.add_argument("--debug", action="store_true", help="Enable debug logging")
-    parser.add_argument("--gpus", type=int, default=1,
-                        help="NOT a reference flag: scan on this many GPUs of the node (one process per GPU, the genome "
-                             "sharded by bp-balanced ranges with halos, final hit gather on rank 0); 0 = all visible")
-    parser.add_argument("--true-strands", action="store_true",
-                        help="NOT reference behaviour: report forward amplicons primer1 ... revcomp(primer2) as (+), "
-                             "like NCBI me-PCR, instead of the reference's primer1 ... primer2")
-    return parser
+    """The reference's parser (cli.py:127-214) plus the two switches of this implementation."""
+    ap = argparse.ArgumentParser(description="merPCR - Modern Electronic Rapid PCR",
+                                 formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    for name, text in (("sts_file", "STS file (tab-delimited)"), ("fasta_file", "FASTA sequence file")):
+        ap.add_argument(name, type=str, help=text)
+    for short, long_name, kind, default, text in _OPTIONS:
+        kw = dict(default=default, help=text.format(d=default))
+        if isinstance(kind, tuple):          # a closed set of integer values
+            kw.update(type=int, choices=list(kind))
+        else:
+            kw["type"] = kind
+        ap.add_argument(short, long_name, **kw)
+    ap.add_argument("-v", "--version", action="version", version="merPCR version 1.0.0")
+    ap.add_argument("--debug", action="store_true", help="Enable debug logging")
+    ap.add_argument("--gpus", type=int, default=1,
+                    help="NOT a reference flag: scan on this many GPUs of the node (one process per GPU, the genome "
+                         "sharded by bp-balanced ranges with halos, final hit gather on rank 0); 0 = all visible")
+    ap.add_argument("--true-strands", action="store_true",
+                    help="NOT reference behaviour: report forward amplicons primer1 ... revcomp(primer2) as (+), "
+                         "like NCBI me-PCR, instead of the reference's primer1 ... primer2")
+    return ap
 
 
 def main() -> int:
