@@ -93,13 +93,15 @@ void mpcr_ctx_destroy(mpcr_ctx *ctx);
  * Scanning both tables over the same planes and sorting the concatenated hits gives exactly the one-table result.
  * Call before mpcr_table_build; drops the current table. */
 int mpcr_ctx_set_seed_extension(mpcr_ctx *ctx, int w_ext, int which);
-/* Table partitioning: this context's next table holds only the STS lines with (line index % parts) == part
+/* Table partitioning (no reference counterpart; the reference keeps one dict, core/engine.py:324-329): this context's
+ * next table holds only the STS lines with (line index % parts) == part
  * (parts = 0 or 1: every line, the default).  The shared-memory filter of the scanner has room for about 6.5 bits per
  * key at 2*10^5 keys; an exact search with 10^6 STS is therefore split into several extended tables (which = 2) of
  * at most a few 10^5 records each, scanned one after the other over the same planes -- every record lives in exactly
  * one table, so the concatenated, sorted hits are again the one-table result.  Call before mpcr_table_build. */
 int mpcr_ctx_set_table_part(mpcr_ctx *ctx, uint32_t part, uint32_t parts);
-/* Append mode (off by default): with on != 0, mpcr_scan no longer zeroes *d_count first -- the caller zeroes it once,
+/* Append mode (off by default; the counterpart of the reference collecting the hits of all chunks into one list,
+ * core/engine.py:415-423): with on != 0, mpcr_scan no longer zeroes *d_count first -- the caller zeroes it once,
  * passes the SAME d_hits / capacity to a series of calls (several tables, or the ranges of a genome that is still being
  * uploaded) and reads the total once at the end, so the calls queue up on the stream without a host round trip in
  * between.  *d_count keeps counting past capacity; nothing is written beyond it. */
@@ -183,7 +185,8 @@ int mpcr_table_primer_words(mpcr_ctx *ctx, uint32_t rec, int which /*1|2*/, uint
                             uint32_t *n_words);
 
 /* ---- (3)+(4)+(5) scanner, verifier, hit emitter ------------------------------------------------- */
-/* Optional, before a series of mpcr_scan calls over sub-ranges of [shard_begin, shard_end): builds and uploads the
+/* Optional (the counterpart of the chunk table `search` draws up before it starts its workers,
+ * core/engine.py:386-411), before a series of mpcr_scan calls over sub-ranges of [shard_begin, shard_end): builds and uploads the
  * scanner's work descriptors for the WHOLE range once (host pointers, synchronous on `stream`).  Later mpcr_scan calls
  * with the same contig table and origin whose range is cut between contigs (or at these bounds) then reuse them
  * without any upload or host round trip -- a genome can be scanned contig by contig, in append mode, while its
