@@ -167,3 +167,23 @@ def test_cli_as_ranks_of_a_launch(tmp_path):
     mp.spawn(_rank_main_cli, args=(2, _free_port(), argv, rc_path), nprocs=2, join=True)
     assert [open(f"{rc_path}.{r}").read() for r in range(2)] == ["0", "0"]
     assert open(out_path).read() == want
+
+
+def test_merge_hits_order_key_and_empty_ranks():
+    """merge_hits: ranks without hits, a single rank, and boundaries that interleave (pos1 = seed - hash_offset)."""
+    from merpcr_b200 import _capi, multi
+    dt = _capi.HIT_DTYPE
+
+    def mk(rows):
+        a = np.zeros(len(rows), dtype=dt)
+        for i, (c, p1, ho, rec, rank) in enumerate(rows):
+            a[i]["contig"], a[i]["pos1"], a[i]["pos2"], a[i]["rec"], a[i]["rank"], a[i]["hash_off"] = c, p1, p1 + 100, rec, rank, ho
+        return a
+    r0 = mk([(0, 10, 0, 4, 0), (0, 995, 7, 9, 0), (0, 1000, 0, 2, 1)])
+    r1 = mk([(0, 990, 12, 5, 0), (0, 1000, 0, 2, 0), (1, 3, 0, 1, 0)])     # starts before rank 0's last hits end
+    empty = np.zeros(0, dtype=dt)
+    m = multi.merge_hits([r0, empty, r1, None])
+    key = list(zip(m["contig"].tolist(), m["pos1"].tolist(), m["hash_off"].tolist(), m["rec"].tolist(), m["rank"].tolist()))
+    assert key == sorted(key) and len(m) == 6
+    assert np.array_equal(multi.merge_hits([r0]), r0)
+    assert len(multi.merge_hits([empty, empty])) == 0 and len(multi.merge_hits([])) == 0
