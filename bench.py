@@ -8,8 +8,9 @@
 One "step" = one pass of the hot path (scan + verify + emit + sort) over the rank's resident genome shard.
 `value` is whole-job throughput with the packed genome and the table resident in HBM; `e2e` repeats the step
 from pinned HOST bytes (H2D + pack + scan + sort + D2H of the hits inside the timed region).
-N > 1: weak scaling -- every rank owns one 3.1 Gbp genome copy ("individual") of a world-sized multi-genome
-layout, selected through the engine's (rank, world) sharding; there is no collective on the scan path.
+N > 1: strong scaling by default -- ONE 3.1 Gbp genome cut into bp-balanced ranges (+ halos), one per rank, through
+the engine's (rank, world) sharding (BASELINE.json config 3); there is no collective on the scan path, NCCL only
+carries the timing barrier / max-over-ranks.  `--scaling weak` gives every rank its own genome copy instead.
 
 The CPU baseline is oracle/merpcr_oracle.c (a C restatement of the reference's algorithm; the Python reference
 itself cannot travel to the GPU box), timed on a bounded sample with all host threads.
@@ -47,9 +48,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
-                    help="weak: one genome copy per GPU (default); strong: ONE genome sharded over the GPUs "
-                         "(bp-balanced ranges with halos, the production multi-GPU mode)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="strong",
+                    help="strong (default): ONE 3.1 Gbp genome sharded over the GPUs -- bp-balanced ranges with halos, "
+                         "BASELINE.json config 3 and the production multi-GPU mode; weak: one genome copy per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; recorded in config)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -187,13 +188,46 @@ def cpu_sample_search(sts_text: bytes, sample: np.ndarray, threads: int, repeats
     return best, hits, o
 
 
-def host_sample(lengths, sts, nbases: int) -> np.ndarray:
-    """First `nbases` of chr1 of copy 0 (same bytes the GPU arm scans), built on the host."""
-    nbases = min(nbases, lengths[0])
-    arr = synth.dna_chunked(contig_seed(0, 0), nbases)
+def cpu_genome_pass(orc, samples, threads: int):
+    """One pass of the reference's search loop (engine.py:373-423) over a list of sequences: record after record,
+    each cut into `threads` overlapping chunks searched concurrently (the C restatement of -T).  Returns (s, hits)."""
+    t0 = time.perf_counter()
+    hits = 0
+    for a in samples:
+        hits += orc.search_count_buffer(a.ctypes.data, int(a.size), threads)
+    return time.perf_counter() - t0, hits
+
+
+def sample_fraction(rate_bp_s: float, seconds: float, total_bp: int) -> float:
+    """Share of every contig (its first f * L bases) one CPU step covers within `seconds`."""
+    return float(min(1.0, max(1e-3, rate_bp_s * seconds / total_bp)))
+
+
+def host_genome(lengths, sts, frac: float):
+    """The first frac * L bases of every contig of copy 0 -- the same bytes the GPU arm scans -- built on the host
+    (numpy, contigs generated concurrently)."""
+    from concurrent.futures import ThreadPoolExecutor
     _, writes = plan_writes(lengths, sts, 0)
-    apply_writes_numpy(arr, 0, writes)
-    return arr
+    by = {}
+    for ci, off, b in writes:
+        by.setdefault(ci, []).append((ci, off, b))
+
+    def one(ci):
+        n = max(2000, int(lengths[ci] * frac)) if frac < 1.0 else lengths[ci]
+        n = min(n, lengths[ci])
+        arr = synth.dna_chunked(contig_seed(0, ci), n)
+        apply_writes_numpy(arr, ci, by.get(ci, ()))
+        return arr
+
+    with ThreadPoolExecutor(max_workers=min(len(lengths), os.cpu_count() or 1)) as ex:
+        return list(ex.map(one, range(len(lengths))))
+
+
+def sample_text(frac: float, samples, cores: int) -> str:
+    bp = int(sum(a.size for a in samples))
+    what = "the whole genome" if frac >= 1.0 else f"the first {frac:.4f} of every contig"
+    return (f"{what} ({len(samples)} contigs, {bp} bp) x all STS per step, record after record, each cut into "
+            f"{cores} overlapping chunks on {cores} threads (oracle/merpcr_oracle.c restating engine.py:381-423)")
 
 
 def run_reference(args):
@@ -203,32 +237,31 @@ def run_reference(args):
     lengths, n_sts, sts = workload(args.scale)
     sts_text = synth.sts_lines(sts)
     cores = os.cpu_count() or 1
-    calib = host_sample(lengths, sts, min(lengths[0], 4_000_000))
-    dt, _, _ = cpu_sample_search(sts_text, calib, cores)
+    total = int(sum(lengths))
+    calib = synth.dna_chunked(contig_seed(0, 0), min(lengths[0], 4_000_000))   # rate calibration only
+    dt, _, orc = cpu_sample_search(sts_text, calib, cores)
     rate = calib.size / dt
     budget = 150.0 / max(1, args.steps + args.warmup)
-    nb = int(min(lengths[0], max(calib.size, rate * min(budget, args.cpu_seconds))))
-    sample = host_sample(lengths, sts, nb) if nb != calib.size else calib
-    from oracle.oracle import Oracle
-    o = Oracle(**PARAMS)
-    assert o.load_sts_text(sts_text)
+    frac = sample_fraction(rate, min(budget, args.cpu_seconds), total)
+    samples = host_genome(lengths, sts, frac)
     for _ in range(args.warmup):
-        o.search_count_buffer(sample.ctypes.data, int(sample.size), cores)
-    t0 = time.perf_counter()
-    hits = 0
+        cpu_genome_pass(orc, samples, cores)
+    total_s, hits = 0.0, 0
     for _ in range(args.steps):
-        hits = o.search_count_buffer(sample.ctypes.data, int(sample.size), cores)
-    total = time.perf_counter() - t0
-    ms = 1e3 * total / args.steps
-    value = sample.size / (ms * 1e-3) / 1e9
+        dt, hits = cpu_genome_pass(orc, samples, cores)
+        total_s += dt
+    ms = 1e3 * total_s / args.steps
+    bp = int(sum(a.size for a in samples))
+    value = bp / (ms * 1e-3) / 1e9
     line = dict(metric=METRIC, value=value, unit="Gbp/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
-                impl="reference",
-                config=dict(workload="cfg3: 24-chromosome synthetic genome x 100k planted STS, -W 11 -N 1 -X 1 -M 50",
-                            scale=args.scale, n_sts=n_sts, sample_bp=int(sample.size), hits_in_sample=int(hits)),
-                cpu_baseline=dict(value=value, unit="Gbp/s", cores=cores, kind="port",
-                                  sample=f"first {sample.size} bp of chr1 x all {n_sts} STS per step "
-                                         "(oracle/merpcr_oracle.c, pthreads chunking as engine.py:381-419)"),
+                ms_per_step=ms, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="u8",
+                data="synthetic", impl="reference",
+                config=dict(workload="cfg3: 24-chromosome synthetic genome (GRCh38 lengths) x 100k planted STS, "
+                                     "-W 11 -N 1 -X 1 -M 50",
+                            scale=args.scale, n_sts=n_sts, sample_bp=bp, sample_fraction=frac, hits_in_sample=int(hits),
+                            note="the Python reference cannot travel to the GPU box (and runs ~0.0013 Gbp/s, "
+                                 "profiles/r2_python_reference_rate.json); this is its algorithm restated in C"),
+                cpu_baseline=dict(value=value, unit="Gbp/s", cores=cores, kind="port", sample=sample_text(frac, samples, cores)),
                 e2e=dict(value=value, unit="Gbp/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
@@ -302,7 +335,7 @@ def run_b200(args):
     sts_text = synth.sts_lines(sts)
     ncont = len(lengths)
     # weak: world-sized layout, copy k of the 24 chromosomes is owned by rank k; strong: one copy, sharded by range
-    strong = args.scaling == "strong" and world > 1
+    strong = args.scaling == "strong"
     copy = 0 if strong else rank
     base_ci = 0 if strong else rank * ncont
     all_lengths = lengths if strong else lengths * world
@@ -384,7 +417,7 @@ def run_b200(args):
     hits_t, n = eng.scan_device(layout, shard)
     hits = hits_t[: n * _capi.HIT_DTYPE.itemsize].cpu().numpy().view(_capi.HIT_DTYPE)
     all_hits = hits
-    if strong:   # the planted truth is checked on the merged hit lists of all shards
+    if strong and world > 1:   # the planted truth is checked on the merged hit lists of all shards
         gathered = [None] * world
         dist.all_gather_object(gathered, np.array(hits))
         all_hits = np.concatenate(gathered)
@@ -422,25 +455,32 @@ def run_b200(args):
                    hits=int(sum_over_ranks(float(len(out)))))
         assert len(out) == n_hits, "e2e and resident hit counts differ"
 
-    # ---- CPU baseline on the host cores (rank 0, N = 1 only)
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only) + bit-exact parity against the GPU result
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import fullsize
         cores = os.cpu_count() or 1
-        chr1 = host_contigs[0].numpy() if host_contigs is not None else dev_contigs[0].cpu().numpy()
-        calib_n = min(len(chr1), 4_000_000)
-        dt, _, _ = cpu_sample_search(sts_text, chr1[:calib_n], cores)
-        nb = int(min(len(chr1), max(calib_n, calib_n / dt * args.cpu_seconds)))
-        dt, cpu_hits, orc = cpu_sample_search(sts_text, chr1[:nb], cores)
-        # bit-exact check of a sub-sample against the GPU result (single-thread oracle == reference -T 1)
-        sub = min(nb, 8_000_000)
-        oh = orc.search_hits(chr1[:sub].tobytes(), threads=1)
-        safe = sub - (int(sts["size"].max()) + PARAMS["margin"] + 64)
-        oh = oh[oh[:, 1] < safe]
-        g = hits[(hits["contig"] == 0) & (hits["pos2"] < safe)]
-        parity_ok = len(oh) == len(g) and bool(np.array_equal(oh[:, 0], g["pos1"]) and np.array_equal(oh[:, 1], g["pos2"]))
-        cpu = dict(value=nb / dt / 1e9, unit="Gbp/s", cores=cores, kind="port",
-                   sample=f"first {nb} bp of chr1 x all {n_sts} STS, one pass, {cores} threads "
-                          "(oracle/merpcr_oracle.c)", seconds=dt, hits=int(cpu_hits), parity_vs_gpu_first_8Mbp=parity_ok)
+        total = int(sum(lengths))
+        get = (lambda ci: host_contigs[ci].numpy()) if host_contigs is not None else (lambda ci: dev_contigs[ci].cpu().numpy())
+        calib = get(0)[: min(lengths[0], 4_000_000)]
+        dt, _, orc = cpu_sample_search(sts_text, calib, cores)
+        frac = sample_fraction(calib.size / dt, args.cpu_seconds, total)
+        samples = [get(ci)[: (lengths[ci] if frac >= 1.0 else max(2000, int(lengths[ci] * frac)))] for ci in range(ncont)]
+        dt, cpu_hits = cpu_genome_pass(orc, samples, cores)
+        nb = int(sum(a.size for a in samples))
+        # parity: the COMPLETE ordered hit lists of whole chromosomes (every contig of at most 65 Mbp at full scale: chr19
+        # .. chr22 and chrY, 278 Mbp) from the single-threaded oracle (== reference -T 1), one chromosome per host thread
+        whole = [ci for ci in range(ncont) if lengths[ci] <= 65_000_000 * max(args.scale, 1e-9)] or [ncont - 1]
+        jobs = [(ci, 0, lengths[ci], lengths[ci]) for ci in whole]
+        t0 = time.perf_counter()
+        want = np.concatenate(fullsize.oracle_rows(PARAMS, sts_text, jobs, lambda ci, a, b: get(ci)[a:b]))
+        rows = fullsize.gpu_rows(eng, hits[np.isin(hits["contig"], whole)])
+        parity_ok = want.shape == rows.shape and bool(np.array_equal(want, rows))
+        cpu = dict(value=nb / dt / 1e9, unit="Gbp/s", cores=cores, kind="port", sample=sample_text(frac, samples, cores),
+                   seconds=dt, hits=int(cpu_hits), sample_fraction=frac,
+                   parity=dict(bit_exact=parity_ok, contigs=[int(c) for c in whole], bp=int(sum(lengths[c] for c in whole)),
+                               hits=int(len(want)), seconds=round(time.perf_counter() - t0, 2),
+                               what="complete ordered hit list of whole chromosomes, GPU vs single-threaded oracle"))
 
     if rank == 0:
         peaks = {}

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 6
+#define MPCR_ABI_VERSION 7
 
 enum {
     MPCR_OK = 0,
@@ -200,6 +200,11 @@ int mpcr_scan_prepare(mpcr_ctx *ctx, const mpcr_contig *contigs, uint32_t n_cont
  * ranges -- other ranks, or the ranges of one genome scanned one after the other -- neither overlap nor leave a gap,
  * wherever they are cut.  The planes must cover every base the shard can touch:
  * [shard_begin - mpcr_halo_left(), shard_end + mpcr_halo_right()) clipped to the genome.
+ * plane_bases = the number of bases the three plane ALLOCATIONS hold, counted from plane_origin (zero-filled where no
+ * contig lies).  The call checks it against what the kernels read -- whole units of 2048 positions plus 256 bases of
+ * read-ahead behind the last scanned position, the mate window of the last position (never past its contig's end)
+ * plus 64 bases of word over-read, nothing in front of plane_origin -- and fails with MPCR_EINVAL instead of reading
+ * out of bounds.  Allocating (last base touched - plane_origin) + mpcr_tile_bases() + 1024 bases always suffices.
  * Hits are appended (unordered) to d_hits; *d_count receives the TRUE number of hits even when it
  * exceeds capacity (the caller re-runs with a larger buffer; nothing is silently truncated). */
 int mpcr_scan(mpcr_ctx *ctx, const mpcr_contig *h_contigs, uint32_t n_contigs, const void *d_plane2,
@@ -215,6 +220,13 @@ uint64_t mpcr_halo_right(const mpcr_ctx *ctx);
 /* Replaces the sort of MerPCR.search (core/engine.py:434) including its tie order: orders n hits by
  * (contig, pos1, hash_off, rec, rank) == "stable sort of discovery order by pos1" (SURVEY.md A.7). */
 int mpcr_sort_hits(mpcr_ctx *ctx, mpcr_hit *d_hits, uint64_t n, void *stream);
+/* The same sort queued right behind mpcr_scan with no host round trip in between (the reference sorts as soon as its
+ * workers return, core/engine.py:424-434): the record count is read ON THE DEVICE as min(*d_count, capacity), with
+ * d_count / capacity the arguments mpcr_scan was given.  n_hint = the count the caller expects (e.g. the previous
+ * scan's), 0 = unknown; it only selects which kernels are launched (lists of up to ~12k hits are ordered by one
+ * rank-sort launch instead of the radix passes), never the result. */
+int mpcr_sort_hits_dev(mpcr_ctx *ctx, mpcr_hit *d_hits, const uint64_t *d_count, uint64_t capacity, uint64_t n_hint,
+                       void *stream);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mpcr_launch_count(const mpcr_ctx *ctx);

@@ -43,6 +43,26 @@ static int fail(int code, const char* fmt, ...) {
                                            __FILE__, __LINE__);                                           \
     } while (0)
 
+// Entry points run on the context's device and leave the caller's current device as they found it (the Python
+// host shares the process with PyTorch, whose notion of the current device must not change under it).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+        else prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define GUARD(c)                                                                                          \
+    DeviceGuard guard_((c)->device);                                                                      \
+    if (!guard_.ok) return fail(MPCR_ECUDA, "cudaSetDevice(%d) failed", (c)->device)
+
 struct Survivor;
 struct LongRun;
 struct mpcr_ctx {
@@ -77,6 +97,7 @@ struct mpcr_ctx {
     uint64_t tiles_sig = 0;         // layout (contigs, origin, word size) the descriptor array was built for
     uint64_t tiles_sb = 0, tiles_se = 0;   // ... and the range it covers
     std::vector<uint64_t> h_tile_g;        // global first base of every descriptor (ascending): sub-range views
+    std::vector<TileDesc> h_tiles;         // host copy of the descriptors (extent checks of a view)
     uint32_t view_first = 0, view_count = 0;   // the descriptors the next scan walks
     uint32_t lay_contigs = 0, lay_max_len = 0;  // bounds of the last scanned layout (sort digit counts)
     uint32_t* d_tile_counter = nullptr;  // [0] tile counter, [1..2] survivor count / verify cursor
@@ -93,6 +114,13 @@ struct mpcr_ctx {
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     bool scan_timed = false;
+    int env_debug = 0;          // $MPCR_DEBUG, read once at context creation
+    long env_surv_cap = -1;     // $MPCR_SURVIVOR_CAP (test hook), ditto
+    bool ctl_dirty = false;     // the scanner's control words were left non-zero (debug runs skip the verifier)
+    uint8_t lut_host[256] = {}; // what d_lut holds (re-uploaded only when the caller's LUT changes)
+    bool lut_valid = false;
+    uint64_t tiles_need = 0;    // plane extent (bases from the origin) the cached descriptors read up to
+    int64_t tiles_min = 0;      // ... and down to
 };
 
 static int ensure(void** p, size_t* cap, size_t need) {
@@ -898,7 +926,7 @@ __device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& 
     }
 }
 
-__global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
+__device__ __forceinline__ void verify_body(const ScanArgs& a) {
     constexpr int kGroups = 32 / kVerifyLanes;
     constexpr uint32_t kGrab = kGroups;       // survivors a warp takes per cursor atomic (one per lane group)
     const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
@@ -942,6 +970,28 @@ __global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
+    verify_body(a);
+    // The last CTA to finish zeroes the scanner's control words (survivor counters and cursors, tile counter), so the
+    // next scan needs no memset launches in front of it.  tile_counter[4] counts finished CTAs.
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(a.tile_counter + 4, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    for (uint32_t i = threadIdx.x; i < kSurvLists; i += blockDim.x) {
+        a.surv_ctl[i * kSurvCtlStride] = 0u;
+        a.surv_ctl[i * kSurvCtlStride + 1] = 0u;
+    }
+    if (threadIdx.x == 0) {
+        a.tile_counter[0] = 0u;
+        a.tile_counter[4] = 0u;
+    }
+}
+
 // After the radix passes over (pos1, contig): hits that share contig and pos1 (duplicate STS lines, several deltas of
 // one primer-1 site) are put into the reference's discovery order (hash_off, rec, rank).  Runs of up to 32 hits are
 // insertion-sorted by the thread that finds their start; longer ones (identical STS lines on a repeat, or a mate
@@ -981,15 +1031,27 @@ __device__ __noinline__ void tie_heap_sort(mpcr_hit* h, uint64_t m) {
     }
 }
 
-__global__ void __launch_bounds__(256) order_ties(mpcr_hit* __restrict__ hits, uint64_t n, LongRun* __restrict__ queue,
+__global__ void __launch_bounds__(256) order_ties(const mpcr_hit* __restrict__ in, mpcr_hit* __restrict__ hits,
+                                                  uint64_t n_host, const unsigned long long* d_n, uint32_t skip_upto,
+                                                  LongRun* __restrict__ queue,
                                                   uint32_t* __restrict__ queue_ctl /* [0] entries, [1] cursor */) {
+    // `in` is where the radix passes left the records (the hit buffer itself, or the sort's scratch buffer after an
+    // odd number of passes): the thread that owns a run moves it home first, so no separate copy pass is needed
+    const uint64_t n = sort_count(d_n, n_host);
+    if (n <= skip_upto) return;   // rank_sort_small ordered this list completely
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t c = hits[i].contig, p = hits[i].pos1;
-    if (i > 0 && hits[i - 1].contig == c && hits[i - 1].pos1 == p) return;   // not the start of a run
+    const mpcr_hit h0 = in[i];
+    const uint32_t c = h0.contig, p = h0.pos1;
+    if (i > 0 && in[i - 1].contig == c && in[i - 1].pos1 == p) return;   // not the start of a run
     uint64_t e = i + 1;
-    while (e < n && hits[e].contig == c && hits[e].pos1 == p) ++e;
+    while (e < n && in[e].contig == c && in[e].pos1 == p) ++e;
     const uint64_t m = e - i;
+    if (in != hits) {
+        hits[i] = h0;
+        for (uint64_t k = i + 1; k < e; ++k) hits[k] = in[k];
+    }
+    if (m == 1) return;
     if (m <= 32) {
         for (uint64_t k = i + 1; k < e; ++k) {
             const mpcr_hit x = hits[k];
@@ -1009,7 +1071,7 @@ __global__ void __launch_bounds__(256) order_ties(mpcr_hit* __restrict__ hits, u
 // One CTA per queued run: the records and their 61-bit tie keys (hash_off, rec, rank) go to shared memory, a bitonic
 // network orders (key, index) pairs, the records are written back in that order.
 __global__ void __launch_bounds__(256) order_long_runs(mpcr_hit* __restrict__ hits, const LongRun* __restrict__ queue,
-                                                       uint32_t* __restrict__ queue_ctl) {
+                                                       uint32_t* __restrict__ queue_ctl /* [0] entries [1] cursor [2] CTAs done */) {
     __shared__ mpcr_hit rec[kLongRunMax];
     __shared__ unsigned long long key[kLongRunMax];
     __shared__ uint16_t idx[kLongRunMax];
@@ -1017,10 +1079,10 @@ __global__ void __launch_bounds__(256) order_long_runs(mpcr_hit* __restrict__ hi
     const uint32_t n_q = min(queue_ctl[0], kLongRunQueue);
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_q = atomicAdd(queue_ctl + 1, 1u);
+        if (threadIdx.x == 0) s_q = n_q ? atomicAdd(queue_ctl + 1, 1u) : 0u;
         __syncthreads();
         const uint32_t q = s_q;
-        if (q >= n_q) return;
+        if (q >= n_q) break;
         const LongRun r = queue[q];
         uint32_t np = 64;
         while (np < r.len) np <<= 1;
@@ -1051,6 +1113,15 @@ __global__ void __launch_bounds__(256) order_long_runs(mpcr_hit* __restrict__ hi
         }
         for (uint32_t k = threadIdx.x; k < r.len; k += blockDim.x) hits[r.first + k] = rec[idx[k]];
     }
+    // the last CTA to leave zeroes the control words for the next sort (every CTA has read n_q by then)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(queue_ctl + 2, 1u) == gridDim.x - 1) {
+            queue_ctl[0] = 0; queue_ctl[1] = 0;
+            __threadfence();
+            queue_ctl[2] = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1061,6 +1132,7 @@ extern "C" {
 int mpcr_abi_version(void) { return MPCR_ABI_VERSION; }
 const char* mpcr_last_error(void) { return g_err; }
 
+void mpcr_ctx_destroy(mpcr_ctx* c);
 int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
     if (!p || !out) return fail(MPCR_EINVAL, "null argument");
     // core/engine.py:80-97
@@ -1074,18 +1146,30 @@ int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
         return fail(MPCR_ECUDA, "no CUDA device available (%s); merpcr_b200 has no CPU fallback",
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(MPCR_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
-    CU(cudaSetDevice(device));
+    DeviceGuard guard_(device);
+    if (!guard_.ok) return fail(MPCR_ECUDA, "cudaSetDevice(%d) failed", device);
     mpcr_ctx* c = new mpcr_ctx();
     c->device = device;
     c->prm = *p;
-    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    CU(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    CU(cudaMalloc(&c->d_tile_counter, 256));
-    CU(cudaMalloc(&c->d_surv_ctl, 256 * 128));   // kSurvLists control lines
-    CU(cudaMalloc(&c->d_lut, 256));
-    CU(cudaEventCreate(&c->ev0));
-    CU(cudaEventCreate(&c->ev1));
-    CU(cudaEventCreate(&c->ev2));
+    // tuning / test switches are read once here, never on the scan path
+    c->env_debug = getenv("MPCR_DEBUG") ? atoi(getenv("MPCR_DEBUG")) : 0;
+    c->env_surv_cap = getenv("MPCR_SURVIVOR_CAP") ? atol(getenv("MPCR_SURVIVOR_CAP")) : -1;
+    cudaError_t err = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    step(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    step(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    step(cudaMalloc(&c->d_tile_counter, 256));
+    step(cudaMalloc(&c->d_surv_ctl, (size_t)kSurvLists * kSurvCtlStride * 4));   // kSurvLists control lines
+    step(cudaMalloc(&c->d_lut, 256));
+    if (err == cudaSuccess) step(cudaMemset(c->d_tile_counter, 0, 256));
+    if (err == cudaSuccess) step(cudaMemset(c->d_surv_ctl, 0, (size_t)kSurvLists * kSurvCtlStride * 4));
+    step(cudaEventCreate(&c->ev0));
+    step(cudaEventCreate(&c->ev1));
+    step(cudaEventCreate(&c->ev2));
+    if (err != cudaSuccess) {
+        mpcr_ctx_destroy(c);   // frees whatever was allocated
+        return fail(MPCR_ECUDA, "context setup failed: %s", cudaGetErrorString(err));
+    }
     *out = c;
     return MPCR_OK;
 }
@@ -1098,7 +1182,7 @@ static void free_table(mpcr_ctx* c) {
 
 void mpcr_ctx_destroy(mpcr_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard_(c->device);
     free_table(c);
     cudaFree(c->d_tiles); cudaFree(c->d_tile_counter); cudaFree(c->d_sort_tmp); cudaFree(c->d_long_runs); cudaFree(c->d_counts); cudaFree(c->d_lut);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1157,8 +1241,14 @@ int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* d_ascii, uint64_t n, uint64_t
     if (n == 0) return MPCR_OK;
     if (!d_ascii) return fail(MPCR_EINVAL, "null sequence pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(c->d_lut, h_lut, 256, cudaMemcpyHostToDevice, st));
+    GUARD(c);
+    // the 256-byte LUT goes up only when it changes: a pageable upload per call queues on the H2D copy engine behind
+    // the 64 MiB pieces of a streaming ingest and stalls the pack behind them
+    if (!c->lut_valid || memcmp(c->lut_host, h_lut, 256) != 0) {
+        memcpy(c->lut_host, h_lut, 256);
+        CU(cudaMemcpyAsync(c->d_lut, c->lut_host, 256, cudaMemcpyHostToDevice, st));
+        c->lut_valid = true;
+    }
     const uint64_t strips = (n + 63) / 64;
     const uint32_t blocks = (uint32_t)((strips + 255) / 256);
     pack_kernel<<<blocks, 256, 0, st>>>(d_ascii, n, dst_base - plane_origin, (uint64_t*)d_plane2, (uint64_t*)d_plane4,
@@ -1199,7 +1289,7 @@ int mpcr_fasta_index(mpcr_ctx* c, uint8_t* d_text, uint64_t n, mpcr_fasta_record
     if (mpcr_fasta_workspace_bytes(n, max_records) > ws_bytes || !d_ws)
         return fail(MPCR_EINVAL, "workspace too small (need %llu bytes)", (unsigned long long)mpcr_fasta_workspace_bytes(n, max_records));
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(c->device));
+    GUARD(c);
     // workspace: [block offsets u64 (n_blk+1)] [block counts u32 n_blk] [headers max_records] [positions/offsets 4*max] [ctr]
     const uint64_t n_blk = (n + kFastaBlock - 1) / kFastaBlock;
     uint8_t* w = (uint8_t*)d_ws;
@@ -1259,7 +1349,7 @@ int mpcr_fasta_compact(mpcr_ctx* c, const uint8_t* d_text, uint64_t n, const voi
     if (n == 0) return MPCR_OK;
     if (!d_text || !d_ws || !d_seq) return fail(MPCR_EINVAL, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(c->device));
+    GUARD(c);
     const uint64_t n_blk = (n + kFastaBlock - 1) / kFastaBlock;
     fasta_compact<<<(uint32_t)n_blk, kFastaThreads, 0, st>>>(d_text, n, (const uint64_t*)d_ws, d_seq);
     c->launches++;
@@ -1273,7 +1363,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
     if (n_lines && (!h_blob || !h_off || !h_pcr)) return fail(MPCR_EINVAL, "null argument");
     if (n_lines >= (1u << 29)) return fail(MPCR_EINVAL, "too many STS lines");
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(c->device));
+    GUARD(c);
     free_table(c);
     const int W = c->prm.wordsize;
     const int WS = c->ext_which == 2 ? c->ext_w : W;   // key width of THIS table
@@ -1317,21 +1407,11 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         c->filter_words = (uint32_t)words & ~3u;
     }
     c->n_keys = 0;
-    CU(cudaMalloc(&c->d_filter, (size_t)c->filter_words * 4));
-    CU(cudaMemsetAsync(c->d_filter, 0, (size_t)c->filter_words * 4, st));
-    if (n_lines == 0) {
-        c->smap = SlotMap{1023u, 0u};
-        CU(cudaMalloc(&c->d_slots, 1024 * sizeof(Slot)));
-        CU(cudaMemsetAsync(c->d_slots, 0xFF, 1024 * sizeof(Slot), st));
-        CU(cudaStreamSynchronize(st));
-        c->table_ready = true;
-        return MPCR_OK;
-    }
-    const size_t blob_bytes = (size_t)h_off[2 * (size_t)n_lines];
+    const size_t blob_bytes = n_lines ? (size_t)h_off[2 * (size_t)n_lines] : 0;
     uint8_t *d_blob = nullptr, *d_plut = nullptr;
     uint64_t* d_off = nullptr;
     uint32_t *d_pcr = nullptr, *d_woff = nullptr, *d_stats = nullptr;
-    Item<2>*d_pairs = nullptr, *d_pairs2 = nullptr;
+    Item<2>*d_pairs = nullptr, *d_pairs2 = nullptr, *d_sorted = nullptr;
     int rc = MPCR_OK;
 #define CUG(call)                                                                                        \
     do {                                                                                                 \
@@ -1341,6 +1421,16 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
             goto done;                                                                                   \
         }                                                                                                \
     } while (0)
+    CUG(cudaMalloc(&c->d_filter, (size_t)c->filter_words * 4));
+    CUG(cudaMemsetAsync(c->d_filter, 0, (size_t)c->filter_words * 4, st));
+    if (n_lines == 0) {
+        c->smap = SlotMap{1023u, 0u};
+        CUG(cudaMalloc(&c->d_slots, 1024 * sizeof(Slot)));
+        CUG(cudaMemsetAsync(c->d_slots, 0xFF, 1024 * sizeof(Slot), st));
+        CUG(cudaStreamSynchronize(st));
+        c->table_ready = true;
+        goto done;
+    }
     {
         CUG(cudaMalloc(&d_blob, blob_bytes + 16));
         CUG(cudaMalloc(&d_plut, 256));
@@ -1376,7 +1466,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         const uint32_t nblk = (n_rec + kSortItemsPerBlock - 1) / kSortItemsPerBlock;
         rc = ensure((void**)&c->d_counts, &c->counts_cap, (size_t)256 * nblk * 4);
         if (rc) goto done;
-        c->launches += radix_sort<2>(d_pairs, d_pairs2, n_rec, passes, np, c->d_counts, st);
+        c->launches += radix_sort<2>(d_pairs, d_pairs2, n_rec, nullptr, 0, passes, np, c->d_counts, st, &d_sorted);
         CUG(cudaGetLastError());
         // slot table: direct-indexed by the key while 4^W slots stay L2-sized (W <= 11 -> 64 MiB), else open
         // addressing at load <= 1/8 (distinct seeds <= min(records, 4^W))
@@ -1397,13 +1487,13 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         CUG(cudaMemsetAsync(c->d_bucket, 0, ((size_t)c->n_valid + 33) * sizeof(BucketEntry), st));
         if (c->n_valid) {
             CUG(cudaMemsetAsync(d_stats, 0, 16, st));
-            build_buckets<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_pairs, c->n_valid, c->d_meta, c->d_bucket,
+            build_buckets<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_sorted, c->n_valid, c->d_meta, c->d_bucket,
                                                                      c->d_slots, c->smap, c->d_filter,
                                                                      c->filter_words, filter_mul(WS), WS, d_stats);
             c->launches++;
             CUG(cudaGetLastError());
             if (!c->smap.direct) {
-                mark_chains<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_pairs, c->n_valid, c->d_slots, c->smap);
+                mark_chains<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_sorted, c->n_valid, c->d_slots, c->smap);
                 c->launches++;
                 CUG(cudaGetLastError());
             }
@@ -1429,7 +1519,7 @@ done:
 int mpcr_table_records(mpcr_ctx* c, int32_t* h_hash_offset, uint32_t* h_hash) {
     if (!c || !c->table_ready) return fail(MPCR_ESTATE, "table not built");
     if (c->n_rec == 0) return MPCR_OK;
-    CU(cudaSetDevice(c->device));
+    GUARD(c);
     std::vector<RecMeta> m(c->n_rec);
     CU(cudaMemcpy(m.data(), c->d_meta, (size_t)c->n_rec * sizeof(RecMeta), cudaMemcpyDeviceToHost));
     for (uint32_t r = 0; r < c->n_rec; ++r) {
@@ -1443,7 +1533,7 @@ int mpcr_table_primer_words(mpcr_ctx* c, uint32_t rec, int which, uint64_t* h_wo
                             uint32_t* n_words) {
     if (!c || !c->table_ready) return fail(MPCR_ESTATE, "table not built");
     if (rec >= c->n_rec || (which != 1 && which != 2)) return fail(MPCR_EINVAL, "bad record / primer index");
-    CU(cudaSetDevice(c->device));
+    GUARD(c);
     RecMeta m;
     CU(cudaMemcpy(&m, c->d_meta + rec, sizeof m, cudaMemcpyDeviceToHost));
     const uint32_t len = which == 1 ? m.len1 : m.len2, nw = 2 * ((len + 15) / 16);
@@ -1465,8 +1555,37 @@ uint64_t mpcr_halo_right(const mpcr_ctx* c) {
     return round_up(c->max_pcr + (uint64_t)c->prm.margin + c->max_len + 64 + 128, 128) + kTileBases;
 }
 
+// Plane extent the current view touches.  Descriptors ascend in the padded coordinate, so the first one bounds the
+// reads on the left (a primer-1 site starts at most max_hash_off bases in front of its seed, never in front of its
+// contig) and the last one on the right (scanner: whole units + read-ahead; verifier: the end of the mate window,
+// never past the contig's end; both plus the word over-read of the plane accessors).
+static void view_extent(mpcr_ctx* c) {
+    c->tiles_min = 0;
+    c->tiles_need = 0;
+    if (c->view_count == 0 || c->h_tiles.size() < (size_t)c->view_first + c->view_count) return;
+    const TileDesc& f = c->h_tiles[c->view_first];
+    const TileDesc& l = c->h_tiles[c->view_first + c->view_count - 1];
+    const int64_t f_contig = f.gbase - (int64_t)f.lstart;
+    const int64_t reach = f.gbase - (int64_t)c->max_hash_off;
+    c->tiles_min = reach > f_contig ? reach : f_contig;
+    const uint64_t scan_end = (uint64_t)l.gbase + round_up(l.nbases, 2048) + 256;
+    const uint64_t contig_end = (uint64_t)(l.gbase - (int64_t)l.lstart) + l.length;
+    uint64_t mate_end = (uint64_t)l.gbase + l.nbases + c->max_pcr + (uint64_t)c->prm.margin + c->max_len;
+    if (mate_end > contig_end) mate_end = contig_end;
+    mate_end += 64;
+    c->tiles_need = scan_end > mate_end ? scan_end : mate_end;
+}
+
+static int build_tiles_impl(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, uint64_t origin, uint64_t sb,
+                            uint64_t se, cudaStream_t st);
 static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, uint64_t origin, uint64_t sb,
                        uint64_t se, cudaStream_t st) {
+    const int rc = build_tiles_impl(c, contigs, n_contigs, origin, sb, se, st);
+    if (rc == MPCR_OK) view_extent(c);
+    return rc;
+}
+static int build_tiles_impl(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, uint64_t origin, uint64_t sb,
+                            uint64_t se, cudaStream_t st) {
     // signature of the layout: rebuild the descriptor array only when it changes
     uint64_t sig = 1469598103934665603ull;
     auto mix = [&](uint64_t v) { sig = (sig ^ v) * 1099511628211ull; };
@@ -1523,6 +1642,9 @@ static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_conti
         const uint64_t hi = round_up(stop, unit) < L ? round_up(stop, unit) : L;   // positions the owned units cover
         for (uint64_t ls = lo; ls < hi; ls += tb) {
             TileDesc t;
+            if (g0 + ls < origin)
+                return fail(MPCR_EINVAL, "shard_begin lies in front of plane_origin (contig %u, base %llu)", i,
+                            (unsigned long long)ls);
             t.gbase = (int64_t)(g0 + ls - origin);
             t.contig = i;
             t.lstart = (uint32_t)ls;
@@ -1536,6 +1658,7 @@ static int build_tiles(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_conti
     c->tiles_sb = sb; c->tiles_se = se;
     c->h_tile_g.resize(tiles.size());
     for (size_t i = 0; i < tiles.size(); ++i) c->h_tile_g[i] = (uint64_t)(tiles[i].gbase + (int64_t)origin);
+    c->h_tiles = tiles;
     c->lay_contigs = n_contigs;
     c->lay_max_len = 0;
     for (uint32_t i = 0; i < n_contigs; ++i)
@@ -1553,7 +1676,7 @@ int mpcr_scan_prepare(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_cont
                       uint64_t shard_begin, uint64_t shard_end, void* stream) {
     if (!c || (n_contigs && !h_contigs)) return fail(MPCR_EINVAL, "null argument");
     if ((plane_origin & 127u) || (shard_begin & 127u)) return fail(MPCR_EINVAL, "origin / shard_begin must be multiples of 128");
-    CU(cudaSetDevice(c->device));
+    GUARD(c);
     return build_tiles(c, h_contigs, n_contigs, plane_origin, shard_begin, shard_end, (cudaStream_t)stream);
 }
 
@@ -1565,16 +1688,28 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     if (n_contigs && (!h_contigs || !d_plane2 || !d_plane4 || !d_valid)) return fail(MPCR_EINVAL, "null argument");
     if ((plane_origin & 127u) || (shard_begin & 127u)) return fail(MPCR_EINVAL, "origin / shard_begin must be multiples of 128");
     if (capacity && !d_hits) return fail(MPCR_EINVAL, "null hit buffer");
-    (void)plane_bases;
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(c->device));
+    GUARD(c);
     int rc = build_tiles(c, h_contigs, n_contigs, plane_origin, shard_begin, shard_end, st);
     if (rc) return rc;
     if (!c->append) CU(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     c->scan_timed = false;
     if (c->view_count == 0 || c->n_valid == 0) return MPCR_OK;
-    CU(cudaMemsetAsync(c->d_tile_counter, 0, 16, st));
-    CU(cudaMemsetAsync(c->d_surv_ctl, 0, (size_t)kSurvLists * kSurvCtlStride * 4, st));
+    // The planes must hold every base the kernels touch: units are staged whole (2048 positions + 128 bases of
+    // read-ahead), the verifier reads up to the mate window's end (+ 64 bases of word over-read), and nothing lies in
+    // front of the origin.  plane_bases = bases the three plane allocations hold, counted from plane_origin.
+    if (c->tiles_min < 0)
+        return fail(MPCR_EINVAL, "shard_begin - halo lies in front of plane_origin (planes start %lld bases too late)",
+                    (long long)-c->tiles_min);
+    if (c->tiles_need > plane_bases)
+        return fail(MPCR_EINVAL, "planes too small for the shard: %llu bases given, %llu needed (last unit + read-ahead, "
+                    "mate window, word over-read)", (unsigned long long)plane_bases,
+                    (unsigned long long)c->tiles_need);
+    if (c->ctl_dirty) {   // only after a debug run (the verifier, which re-zeroes the control words, did not run)
+        CU(cudaMemsetAsync(c->d_tile_counter, 0, 32, st));
+        CU(cudaMemsetAsync(c->d_surv_ctl, 0, (size_t)kSurvLists * kSurvCtlStride * 4, st));
+        c->ctl_dirty = false;
+    }
     // survivor list: ~1 position in 10^4 survives on random sequence; overflow falls back to in-kernel serial verify
     {
         uint64_t scanned = 0;
@@ -1594,14 +1729,12 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.filter = c->d_filter; a.filter_words = c->filter_words; a.cw = filter_mul(c->scan_w);
     a.prm.W = c->scan_w; a.prm.M = c->prm.margin; a.prm.N = c->prm.mismatches; a.prm.X = c->prm.three_prime_match;
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
-    a.debug = getenv("MPCR_DEBUG") ? atoi(getenv("MPCR_DEBUG")) : 0;
+    a.debug = c->env_debug;
     a.k4 = 4u;
     a.hits = d_hits; a.capacity = capacity; a.count = (unsigned long long*)d_count; a.tile_counter = c->d_tile_counter;
     a.surv = c->d_surv; a.surv_cap = (uint32_t)(c->surv_bytes / sizeof(Survivor) / kSurvLists); a.surv_ctl = c->d_surv_ctl;
-    if (const char* env = getenv("MPCR_SURVIVOR_CAP")) {   // test hook: force the list-full path (in-kernel verify)
-        const long v = atol(env);
-        if (v >= 0 && (uint32_t)v < a.surv_cap) a.surv_cap = (uint32_t)v;
-    }
+    if (c->env_surv_cap >= 0 && (uint32_t)c->env_surv_cap < a.surv_cap)   // test hook: force the list-full path
+        a.surv_cap = (uint32_t)c->env_surv_cap;
     const size_t smem = (size_t)ScanSmem::kFilterOff + (size_t)c->filter_words * 4;
     uint32_t grid = (uint32_t)c->sm_count;
     if (grid > c->view_count) grid = c->view_count;
@@ -1627,6 +1760,8 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
         verify_kernel<<<c->sm_count * 8, 256, 0, st>>>(a);
         c->launches++;
         CU(cudaGetLastError());
+    } else {
+        c->ctl_dirty = true;
     }
     CU(cudaEventRecord(c->ev2, st));
     c->scan_timed = true;
@@ -1648,33 +1783,70 @@ float mpcr_last_verify_ms(mpcr_ctx* c) {
     return ms;
 }
 
-int mpcr_sort_hits(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n, void* stream) {
-    if (!c) return fail(MPCR_EINVAL, "null argument");
-    if (n < 2) return MPCR_OK;
-    if (!d_hits) return fail(MPCR_EINVAL, "null hit buffer");
-    cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(c->device));
+// Shared by both sort entry points: n_host records, or -- with d_n -- as many as *d_n says (at most n_host, the
+// buffer's capacity), read on the device so that the sort queues up behind the scan without a host round trip.
+static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const unsigned long long* d_n,
+                          uint64_t n_hint, cudaStream_t st) {
     static_assert(sizeof(mpcr_hit) == sizeof(Item<6>), "hit layout");
-    int rc = ensure(&c->d_sort_tmp, &c->sort_tmp_cap, n * sizeof(mpcr_hit));
+    int rc = ensure(&c->d_sort_tmp, &c->sort_tmp_cap, n_host * sizeof(mpcr_hit));
     if (rc) return rc;
-    const uint64_t nblk = (n + kSortItemsPerBlock - 1) / kSortItemsPerBlock;
+    const uint64_t nblk = (n_host + kSortItemsPerBlock - 1) / kSortItemsPerBlock;
     rc = ensure((void**)&c->d_counts, &c->counts_cap, (size_t)256 * nblk * 4);
     if (rc) return rc;
+    if (!c->d_long_runs) {
+        CU(cudaMalloc(&c->d_long_runs, (size_t)kLongRunQueue * sizeof(LongRun) + 16));
+        CU(cudaMemsetAsync(c->d_long_runs + kLongRunQueue, 0, 16, st));   // order_long_runs re-zeroes them itself
+    }
+    Item<6>*hits = (Item<6>*)d_hits, *tmp = (Item<6>*)c->d_sort_tmp;
+    // short lists: one rank-sort launch (+ the move home) instead of the cooperative radix passes.  Launched when the
+    // count is known to be short, or unknown (hint 0) and the buffer itself is not huge.
+    uint32_t skip = 0;
+    const uint64_t n_known = d_n ? n_hint : n_host;
+    if (n_known ? n_known <= kRankSortMax : true) {
+        const uint64_t grid_n = n_host < kRankSortMax ? n_host : kRankSortMax;
+        rank_sort_small<<<(uint32_t)((grid_n + kRankThreads / kRankSplit - 1) / (kRankThreads / kRankSplit)), kRankThreads, 0, st>>>(
+            hits, tmp, d_n, n_host);
+        rank_sort_copy_back<<<(uint32_t)((grid_n + 255) / 256), 256, 0, st>>>(tmp, hits, d_n, n_host);
+        c->launches += 2;
+        skip = kRankSortMax;
+        if (!d_n) return cudaGetLastError() == cudaSuccess ? MPCR_OK : fail(MPCR_ECUDA, "rank sort launch failed");
+        if (n_host <= kRankSortMax) {   // the buffer cannot hold a longer list: nothing else to launch
+            CU(cudaGetLastError());
+            return MPCR_OK;
+        }
+    }
     // LSD radix passes over pos1 then contig (fields 1, 0), digits bounded by the layout of the last scan; the rest of
     // the key (hash_off, rec, rank) only matters inside runs of equal (contig, pos1), which order_ties settles
     PassDesc passes[24];
     int np = 0;
     np = add_passes(passes, np, 1, c->lay_max_len ? c->lay_max_len : 0x7FFFFFFFull);
     np = add_passes(passes, np, 0, c->lay_contigs ? c->lay_contigs - 1 : 0xFFFFFFFFull);
-    c->launches += radix_sort<6>((Item<6>*)d_hits, (Item<6>*)c->d_sort_tmp, n, passes, np, c->d_counts, st);
-    if (!c->d_long_runs) CU(cudaMalloc(&c->d_long_runs, (size_t)kLongRunQueue * sizeof(LongRun) + 16));
+    Item<6>* sorted = hits;
+    c->launches += radix_sort<6>(hits, tmp, n_host, d_n, skip, passes, np, c->d_counts, st, &sorted, &skip);
     uint32_t* queue_ctl = reinterpret_cast<uint32_t*>(c->d_long_runs + kLongRunQueue);
-    CU(cudaMemsetAsync(queue_ctl, 0, 16, st));
-    order_ties<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_hits, n, c->d_long_runs, queue_ctl);
-    order_long_runs<<<(uint32_t)c->sm_count * 2u, 256, 0, st>>>(d_hits, c->d_long_runs, queue_ctl);
+    order_ties<<<(uint32_t)((n_host + 255) / 256), 256, 0, st>>>((const mpcr_hit*)sorted, d_hits, n_host, d_n, skip,
+                                                                 c->d_long_runs, queue_ctl);
+    order_long_runs<<<(uint32_t)c->sm_count, 256, 0, st>>>(d_hits, c->d_long_runs, queue_ctl);
     c->launches += 2;
     CU(cudaGetLastError());
     return MPCR_OK;
+}
+
+int mpcr_sort_hits(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n, void* stream) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (n < 2) return MPCR_OK;
+    if (!d_hits) return fail(MPCR_EINVAL, "null hit buffer");
+    GUARD(c);
+    return sort_hits_impl(c, d_hits, n, nullptr, 0, (cudaStream_t)stream);
+}
+
+int mpcr_sort_hits_dev(mpcr_ctx* c, mpcr_hit* d_hits, const uint64_t* d_count, uint64_t capacity, uint64_t n_hint,
+                       void* stream) {
+    if (!c || !d_count) return fail(MPCR_EINVAL, "null argument");
+    if (capacity < 2) return MPCR_OK;
+    if (!d_hits) return fail(MPCR_EINVAL, "null hit buffer");
+    GUARD(c);
+    return sort_hits_impl(c, d_hits, capacity, (const unsigned long long*)d_count, n_hint, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -26,10 +26,21 @@ struct Item {
 static constexpr int kSortThreads = 256;
 static constexpr int kSortItemsPerBlock = 2048;
 
+// Record counts may live on the device: the scan leaves the number of hits in *d_n, and the sort is queued right
+// behind it without a host round trip.  d_n == nullptr: the count is n_host; otherwise min(*d_n, n_host), with
+// n_host the capacity of the buffer (the grids are sized for it, CTAs past the count find nothing to do).
+__device__ __forceinline__ uint64_t sort_count(const unsigned long long* d_n, uint64_t n_host) {
+    if (!d_n) return n_host;
+    const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(d_n);
+    return v < n_host ? v : n_host;
+}
+
 template <int NF>
-__global__ void __launch_bounds__(kSortThreads) rs_hist(const Item<NF>* __restrict__ in, uint64_t n, PassDesc pd,
+__global__ void __launch_bounds__(kSortThreads) rs_hist(const Item<NF>* __restrict__ in, uint64_t n_host,
+                                                        const unsigned long long* d_n, PassDesc pd,
                                                         uint32_t* __restrict__ counts, uint32_t nblk) {
     __shared__ uint32_t h[256];
+    const uint64_t n = sort_count(d_n, n_host);
     h[threadIdx.x] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * kSortItemsPerBlock;
@@ -78,8 +89,9 @@ __global__ void __launch_bounds__(1024) rs_scan(uint32_t* __restrict__ a, uint32
 
 template <int NF>
 __global__ void __launch_bounds__(kSortThreads) rs_scatter(const Item<NF>* __restrict__ in, Item<NF>* __restrict__ out,
-                                                           uint64_t n, PassDesc pd, const uint32_t* __restrict__ offsets,
-                                                           uint32_t nblk) {
+                                                           uint64_t n_host, const unsigned long long* d_n, PassDesc pd,
+                                                           const uint32_t* __restrict__ offsets, uint32_t nblk) {
+    const uint64_t n = sort_count(d_n, n_host);
     __shared__ uint32_t running[256];
     __shared__ uint32_t wc[kSortThreads / 32][256];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -124,10 +136,14 @@ struct PassList {
 };
 
 template <int NF>
-__global__ void __launch_bounds__(kSortThreads) rs_sort_fused(Item<NF>* a, Item<NF>* b, uint32_t n, PassList pl,
+__global__ void __launch_bounds__(kSortThreads) rs_sort_fused(Item<NF>* a, Item<NF>* b, uint32_t n_host,
+                                                              const unsigned long long* d_n, uint32_t skip_upto,
+                                                              PassList pl,
                                                               uint32_t* __restrict__ counts /* 256 * gridDim.x */) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
+    const uint32_t n = (uint32_t)sort_count(d_n, n_host);
+    if (n <= skip_upto) return;   // the whole grid takes this branch together (lists that short were rank-sorted)
     __shared__ uint32_t hist[256];
     __shared__ uint32_t running[256];
     __shared__ uint32_t wc[kSortThreads / 32][256];
@@ -196,37 +212,100 @@ __global__ void __launch_bounds__(kSortThreads) rs_sort_fused(Item<NF>* a, Item<
     }
 }
 
-// Host driver: sorts `n` records in d_a using d_b as the ping-pong buffer; the result ends in d_a.
-// d_counts must hold 256 * ceil(n / kSortItemsPerBlock) uint32.  Returns the number of kernels launched.
+// Host driver: sorts the records of d_a using d_b as the ping-pong buffer.  n_host is the record count, or -- with
+// d_n != nullptr -- the capacity the grids are sized for while the true count min(*d_n, n_host) is read on the device.
+// The result is left in *result (d_a after an even number of passes, d_b after an odd one: no copy back; the caller's
+// next kernel reads from there).  Lists of up to skip_upto records are left untouched (see rank_sort_small).
+// d_counts must hold 256 * ceil(n_host / kSortItemsPerBlock) uint32.  Returns the number of kernels launched.
 template <int NF>
-inline int radix_sort(Item<NF>* d_a, Item<NF>* d_b, uint64_t n, const PassDesc* passes, int npass, uint32_t* d_counts,
-                      cudaStream_t st) {
-    if (n < 2 || npass == 0) return 0;
-    const uint32_t nblk = (uint32_t)((n + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
+inline int radix_sort(Item<NF>* d_a, Item<NF>* d_b, uint64_t n_host, const unsigned long long* d_n, uint32_t skip_upto,
+                      const PassDesc* passes, int npass, uint32_t* d_counts, cudaStream_t st, Item<NF>** result,
+                      uint32_t* skipped_upto = nullptr) {
+    *result = d_a;
+    if (skipped_upto) *skipped_upto = skip_upto;
+    if (n_host < 2 || npass == 0) return 0;
+    *result = (npass & 1) ? d_b : d_a;
+    const uint32_t nblk = (uint32_t)((n_host + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
     if (nblk <= (uint32_t)kFusedMaxBlocks && npass <= kMaxPasses) {
         PassList pl;
         pl.n = npass;
         for (int p = 0; p < npass; ++p) pl.p[p] = passes[p];
-        uint32_t n32 = (uint32_t)n;
-        void* args[] = {&d_a, &d_b, &n32, &pl, &d_counts};
+        uint32_t n32 = (uint32_t)n_host;
+        void* args[] = {&d_a, &d_b, &n32, &d_n, &skip_upto, &pl, &d_counts};
         if (cudaLaunchCooperativeKernel((const void*)rs_sort_fused<NF>, dim3(nblk), dim3(kSortThreads), args, 0, st) ==
-            cudaSuccess) {
-            if (npass & 1) cudaMemcpyAsync(d_a, d_b, n * sizeof(Item<NF>), cudaMemcpyDeviceToDevice, st);
+            cudaSuccess)
             return 1;
-        }
         (void)cudaGetLastError();  // not launchable cooperatively here: fall through to the three-kernel passes
     }
+    // the three-kernel passes sort short lists as well (a stable re-sort of what rank_sort_small ordered): tell the
+    // caller that nothing was skipped, so that its next kernel picks the records up from *result
+    if (skipped_upto) *skipped_upto = 0;
     Item<NF>*src = d_a, *dst = d_b;
     int launches = 0;
     for (int p = 0; p < npass; ++p) {
-        rs_hist<NF><<<nblk, kSortThreads, 0, st>>>(src, n, passes[p], d_counts, nblk);
+        rs_hist<NF><<<nblk, kSortThreads, 0, st>>>(src, n_host, d_n, passes[p], d_counts, nblk);
         rs_scan<<<1, 1024, 0, st>>>(d_counts, 256u * nblk);
-        rs_scatter<NF><<<nblk, kSortThreads, 0, st>>>(src, dst, n, passes[p], d_counts, nblk);
+        rs_scatter<NF><<<nblk, kSortThreads, 0, st>>>(src, dst, n_host, d_n, passes[p], d_counts, nblk);
         launches += 3;
         Item<NF>* t = src; src = dst; dst = t;
     }
-    if (src != d_a) cudaMemcpyAsync(d_a, src, n * sizeof(Item<NF>), cudaMemcpyDeviceToDevice, st);
     return launches;
+}
+
+// Short hit lists (a rank of a multi-GPU run holds ~10^4 hits): ONE launch instead of five cooperative passes.
+// Every record's final position is the number of records with a smaller order key -- kRankSplit threads share the
+// count for one record, the keys of all records stream through shared memory in tiles.  The key is the complete
+// order (contig, pos1 | hash_off, rec, rank), which no two hits share, so ranks are a permutation and no tie pass
+// is needed afterwards.  Records go to `out` (the sort's scratch buffer); rank_sort_copy_back moves them home.
+static constexpr uint32_t kRankSortMax = 12288;     // n^2 key compares: 24 us at this size on 148 SMs
+static constexpr int kRankSplit = 8;                // threads per record
+static constexpr int kRankThreads = 256;
+static constexpr int kRankTile = 1024;              // keys per shared-memory tile (16 KB)
+
+__device__ __forceinline__ void hit_order_key(const Item<6>& h, unsigned long long& a, unsigned long long& b) {
+    a = ((unsigned long long)h.f[0] << 32) | h.f[1];                                               // contig, pos1
+    b = ((unsigned long long)h.f[5] << 45) | ((unsigned long long)h.f[3] << 15) | h.f[4];          // hash_off, rec, rank
+}
+
+__global__ void __launch_bounds__(kRankThreads) rank_sort_small(const Item<6>* __restrict__ in, Item<6>* __restrict__ out,
+                                                                const unsigned long long* d_n, uint64_t n_host) {
+    __shared__ ulonglong2 keys[kRankTile];
+    const uint32_t n = (uint32_t)sort_count(d_n, n_host);
+    if (n > kRankSortMax || n < 2) return;
+    constexpr int kPerBlock = kRankThreads / kRankSplit;
+    const uint32_t first = blockIdx.x * kPerBlock;
+    if (first >= n) return;
+    const uint32_t i = first + threadIdx.x / kRankSplit, part = threadIdx.x % kRankSplit;
+    const bool act = i < n;
+    Item<6> mine{};
+    unsigned long long ka = 0, kb = 0;
+    if (act) { mine = in[i]; hit_order_key(mine, ka, kb); }
+    uint32_t rank = 0;
+    for (uint32_t t0 = 0; t0 < n; t0 += kRankTile) {
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < kRankTile; k += kRankThreads) {
+            ulonglong2 v = make_ulonglong2(~0ull, ~0ull);   // padding never counts as smaller
+            if (t0 + k < n) { const Item<6> h = in[t0 + k]; hit_order_key(h, v.x, v.y); }
+            keys[k] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = part; k < kRankTile; k += kRankSplit) {
+            const ulonglong2 v = keys[k];
+            rank += (v.x < ka || (v.x == ka && v.y < kb)) ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int d = 1; d < kRankSplit; d <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
+    if (act && part == 0) out[rank] = mine;
+}
+
+__global__ void __launch_bounds__(256) rank_sort_copy_back(const Item<6>* __restrict__ in, Item<6>* __restrict__ out,
+                                                           const unsigned long long* d_n, uint64_t n_host) {
+    const uint32_t n = (uint32_t)sort_count(d_n, n_host);
+    if (n > kRankSortMax || n < 2) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
 }
 
 // append the 8-bit digit passes needed to cover values in [0, max_value] of `field`

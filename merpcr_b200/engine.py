@@ -127,8 +127,8 @@ class _STSLines:
 class _Shard:
     """Device-resident packed genome of one shard (planes + the layout they were built for)."""
 
-    __slots__ = ("device", "origin", "bases", "plane2", "plane4", "valid", "begin", "end", "hits", "count", "staging",
-                 "stage2", "contig_sig")
+    __slots__ = ("device", "origin", "bases", "alloc", "plane2", "plane4", "valid", "begin", "end", "hits", "count",
+                 "staging", "stage2", "contig_sig", "last_n")
 
 
 class MerPCR:
@@ -175,6 +175,13 @@ class MerPCR:
         self.total_hits = 0
 
         self._validate_parameters()
+        if threads > 1:
+            # with -T > 1 the reference cuts sequences of >= 100 kbp into overlapping chunks and, because
+            # its de-duplication compares an absolute position with the overlap length (engine.py:424-431), prints the
+            # hits of every overlap twice.  One GPU pass owns every position exactly once.
+            logger.warning("-T/threads=%d is accepted for compatibility only: the GPU path does not chunk, so the "
+                           "duplicate overlap hits the reference prints with -T > 1 are not reproduced "
+                           "(output equals the reference's -T 1)", threads)
 
         self._be = _capi.backend()
         if device is None:
@@ -673,6 +680,7 @@ class MerPCR:
         else:
             sh = _Shard()
             sh.device, sh.origin, sh.bases, sh.begin, sh.end = self._tdev, origin, bases, begin, end
+            sh.alloc, sh.last_n = alloc, 0     # alloc = bases the plane allocations hold (mpcr_scan checks it)
             sh.plane2 = torch.zeros(alloc // 4, dtype=torch.uint8, device=self._tdev)
             sh.plane4 = torch.zeros(alloc // 2, dtype=torch.uint8, device=self._tdev)
             sh.valid = torch.zeros(alloc // 8, dtype=torch.uint8, device=self._tdev)
@@ -771,7 +779,7 @@ class MerPCR:
         def scan_range(lo: int, hi: int):
             for ctx in ctxs:
                 self._be.check(lib.mpcr_scan(ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
-                                             sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.bases, lo, hi,
+                                             sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.alloc, lo, hi,
                                              sh.hits.data_ptr(), cap, sh.count.data_ptr(), stream))
 
         for ctx in ctxs:
@@ -813,6 +821,9 @@ class MerPCR:
                 scan_range(*deferred)
             if sh.end > done_to:
                 scan_range(done_to, sh.end)
+            if sort:    # queued behind the last scan: the count is read on the device
+                self._be.check(lib.mpcr_sort_hits_dev(self._ctx, sh.hits.data_ptr(), sh.count.data_ptr(), cap,
+                                                      sh.last_n, stream))
             need = int(sh.count.item())                        # the one host round trip
             self.last_scan_ms = float(lib.mpcr_last_scan_ms(self._ctx))
         finally:
@@ -822,8 +833,7 @@ class MerPCR:
         if need > cap:      # the hit list outgrew the buffer: the planes are resident now, scan them again with room
             hits, n = self.scan_device(layout, sh, sort=sort)
             return sh, hits, n
-        if sort and need > 1:
-            self._be.check(lib.mpcr_sort_hits(self._ctx, sh.hits.data_ptr(), need, self._stream()))
+        sh.last_n = need
         return sh, sh.hits, need
 
     def scan(self, layout: dict, sh: _Shard, sort: bool = True) -> np.ndarray:
@@ -858,24 +868,28 @@ class MerPCR:
         isz = _capi.HIT_DTYPE.itemsize
         cap = 1 << 16 if sh.hits is None else sh.hits.numel() // isz
         ctxs = self._all_ctxs()
-        while True:
-            if sh.hits is None or sh.hits.numel() < cap * isz:
-                sh.hits = torch.empty(cap * isz, dtype=torch.uint8, device=self._tdev)
-            n, need = 0, 0
-            self.last_scan_ms = 0.0
-            for ctx in ctxs:   # every table appends behind the previous one's hits
-                room = max(cap - n, 0)
-                self._be.check(lib.mpcr_scan(ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
-                                             sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.bases, sh.begin,
-                                             sh.end, sh.hits.data_ptr() + n * isz if room else 0, room,
-                                             sh.count.data_ptr(), self._stream()))
-                k = int(sh.count.item())  # synchronises the stream
-                self.last_scan_ms += float(lib.mpcr_last_scan_ms(ctx))
-                need += k
-                n += min(k, room)
-            if need <= cap:
-                break
-            cap = max(need, 2 * cap)
-        if sort and n > 1:
-            self._be.check(lib.mpcr_sort_hits(self._ctx, sh.hits.data_ptr(), n, self._stream()))
-        return sh.hits, n
+        stream = self._stream()
+        try:
+            for ctx in ctxs:    # every table appends behind the previous one's hits; one count, read once
+                self._be.check(lib.mpcr_ctx_set_append(ctx, 1))
+            while True:
+                if sh.hits is None or sh.hits.numel() < cap * isz:
+                    sh.hits = torch.empty(cap * isz, dtype=torch.uint8, device=self._tdev)
+                sh.count.zero_()
+                for ctx in ctxs:
+                    self._be.check(lib.mpcr_scan(ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
+                                                 sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.alloc, sh.begin,
+                                                 sh.end, sh.hits.data_ptr(), cap, sh.count.data_ptr(), stream))
+                if sort:        # queued right behind the scan: the count is read on the device
+                    self._be.check(lib.mpcr_sort_hits_dev(self._ctx, sh.hits.data_ptr(), sh.count.data_ptr(), cap,
+                                                          sh.last_n, stream))
+                need = int(sh.count.item())     # the one host round trip of a step (synchronises the stream)
+                if need <= cap:
+                    break
+                cap = max(need, 2 * cap)        # nothing is ever truncated: scan again with room
+        finally:
+            for ctx in ctxs:
+                lib.mpcr_ctx_set_append(ctx, 0)
+        self.last_scan_ms = sum(float(lib.mpcr_last_scan_ms(ctx)) for ctx in ctxs)
+        sh.last_n = need
+        return sh.hits, need

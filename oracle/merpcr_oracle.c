@@ -375,6 +375,11 @@ int orc_rec_hash_offset(const orc_engine *e, int i) { return e->recs[i].hash_off
 uint32_t orc_rec_hash(const orc_engine *e, int i) { return e->recs[i].hash; }
 int orc_rec_line(const orc_engine *e, int i) { return e->recs[i].offset; }
 char orc_rec_direct(const orc_engine *e, int i) { return e->recs[i].direct; }
+/* Bulk read-back for large tables (tests map record indices to STS lines): source line number and '+' / '-' of
+ * every record, in insertion order (engine.py:265-281). */
+void orc_rec_lines(const orc_engine *e, int *lines, char *directs) {
+    for (int i = 0; i < e->nrec; i++) { lines[i] = e->recs[i].offset; directs[i] = e->recs[i].direct; }
+}
 const char *orc_last_error(const orc_engine *e) { return e->err; }
 
 /* ------------------------------------------------------------------ FASTA (io/fasta.py:19-71) */

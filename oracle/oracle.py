@@ -54,6 +54,7 @@ def lib() -> C.CDLL:
         L.orc_rec_line.argtypes = [vp, i32]
         L.orc_rec_direct.restype = C.c_char
         L.orc_rec_direct.argtypes = [vp, i32]
+        L.orc_rec_lines.argtypes = [vp, vp, vp]
         L.orc_last_error.restype = cp
         L.orc_last_error.argtypes = [vp]
         L.orc_hash_value.restype = i32
@@ -143,6 +144,15 @@ class Oracle:
     def records(self) -> List[dict]:
         return [self.record(i) for i in range(self.num_records)]
 
+    def record_lines(self):
+        """(source line number, is-minus-strand) of every record as two int64 arrays (insertion order)."""
+        import numpy as np
+        n = self.num_records
+        lines = np.zeros(max(n, 1), dtype=np.int32)
+        directs = np.zeros(max(n, 1), dtype=np.uint8)
+        lib().orc_rec_lines(self._h, lines.ctypes.data, directs.ctypes.data)
+        return lines[:n].astype(np.int64), (directs[:n] == ord("-")).astype(np.int64)
+
     # -- helpers mirrored from the reference's private API ------------------
     def hash_value(self, primer: str) -> Tuple[int, int]:
         h = C.c_uint32(0)
@@ -183,6 +193,20 @@ class Oracle:
         finally:
             lib().orc_free_text(ptr)
         return arr
+
+    def search_hits_array(self, arr, threads: int = 1):
+        """`search_hits` over a contiguous uint8 numpy array, without copying it (the C call releases the GIL, so
+        several contigs can be searched from Python threads at once; the engine is read-only while searching)."""
+        import numpy as np
+        assert arr.dtype == np.uint8 and arr.flags.c_contiguous
+        ptr = C.POINTER(C.c_int64)()
+        n = lib().orc_search_seq_hits(self._h, C.cast(C.c_void_p(arr.ctypes.data), C.c_char_p), int(arr.size), threads,
+                                      C.byref(ptr))
+        try:
+            out = np.ctypeslib.as_array(ptr, shape=(max(n, 1) * 3,))[: n * 3].copy().reshape(-1, 3)
+        finally:
+            lib().orc_free_text(ptr)
+        return out
 
     def search_count_buffer(self, addr: int, length: int, threads: int) -> int:
         """Count-only search over a raw ASCII buffer (timing legs; nothing formatted)."""

@@ -22,7 +22,7 @@ def main():
     dev = torch.device("cuda", 0)
     cfgs = fullsize.configs(scale)
     for k in which:
-        fullsize.run(*cfgs[k], dev, oracle_bp=300_000 if k == "cfg5" else 1_000_000)
+        fullsize.run(*cfgs[k], dev, oracle=("slices", 16, 2_000_000) if k == "cfg5" else "whole")
 
 
 if __name__ == "__main__":

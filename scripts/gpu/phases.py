@@ -58,7 +58,7 @@ def main():
         ms = []
         for _ in range(args.reps):
             eng._be.check(lib.mpcr_scan(ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(), sh.plane4.data_ptr(),
-                                        sh.valid.data_ptr(), sh.origin, sh.bases, sh.begin, sh.end, 0, 0, count.data_ptr(),
+                                        sh.valid.data_ptr(), sh.origin, sh.alloc, sh.begin, sh.end, 0, 0, count.data_ptr(),
                                         eng._stream()))
             k = int(count.item())
             ms.append(float(lib.mpcr_last_scan_ms(ctx)))

@@ -1,7 +1,8 @@
 """BASELINE.json configs at (or near) full size on one B200 (test / probe infrastructure): build the synthetic workload
-in HBM, scan it through the public engine, and check the size-independent properties -- every planted amplicon found,
-output sorted, rescan idempotent, the head of contig 0 bit-exact against the oracle.  Used by
-tests/test_gpu_fullsize.py and scripts/gpu/configs_probe.py."""
+in HBM, scan it through the public engine, and check it against the oracle -- the COMPLETE ordered hit list of every
+contig (oracle single-threaded per contig == reference -T 1, contigs spread over the host cores), or slices spread over
+the contigs for the candidate-heavy config -- plus the size-independent properties: every planted amplicon found, output
+sorted, rescan idempotent.  Used by tests/test_gpu_fullsize.py and scripts/gpu/configs_probe.py."""
 import json
 import os
 import sys
@@ -71,7 +72,98 @@ def degenerate_primers(sts, seed, frac=0.2):
                 sts[which][i, j] = DEGEN[base][rng.randint(0, 3)]
 
 
-def run(name, lengths, n_sts, params, sub_mode, ranged, seed, decorate, dev, oracle_bp=1_000_000, verbose=True):
+def gpu_rows(eng, hits):
+    """(contig, pos1, pos2, source line of the STS, strand) rows of a hit array, in its order."""
+    line_nos = np.asarray(eng._sts_lines.line_nos, dtype=np.int64)
+    return np.stack([hits["contig"].astype(np.int64), hits["pos1"].astype(np.int64), hits["pos2"].astype(np.int64),
+                     line_nos[hits["rec"] >> 1], (hits["rec"] & 1).astype(np.int64)], axis=1)
+
+
+def oracle_rows(params, sts_text, jobs, fetch, workers=None):
+    """Oracle hit rows for slices of contigs.  jobs = [(contig, start, stop, cut)]: the bases [start, stop) of the
+    contig are searched as one sequence by ONE thread (== the reference with -T 1; never its threaded path)
+    and the hits with slice-local pos2 < cut are kept (cut = stop - start when the slice ends where the contig ends,
+    otherwise far enough from the slice's end that its artificial end clamp cannot matter).  fetch(contig, start, stop)
+    returns the bases as a contiguous uint8 array.  Jobs run concurrently on `workers` host threads (the C oracle
+    releases the GIL; the engine is read-only while searching).  Returns a list of row arrays, one per job."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import Oracle
+    o = Oracle(**params)
+    assert o.load_sts_text(sts_text)
+    line, minus = o.record_lines()
+
+    def one(job):
+        ci, a, b, cut = job
+        h = o.search_hits_array(fetch(ci, a, b), threads=1)
+        h = h[h[:, 1] < cut]
+        return np.stack([np.full(len(h), ci, dtype=np.int64), h[:, 0] + a, h[:, 1] + a, line[h[:, 2]], minus[h[:, 2]]], axis=1)
+
+    workers = workers or max(1, min(len(jobs), os.cpu_count() or 1))
+    order = sorted(range(len(jobs)), key=lambda i: jobs[i][1] - jobs[i][2])     # longest first
+    out = [None] * len(jobs)
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        for i, rows in zip(order, ex.map(one, [jobs[i] for i in order])):
+            out[i] = rows
+    return out
+
+
+def slice_jobs(lengths, n_slices, size, safe):
+    """n_slices slices of `size` bases spread over the contigs, the first at the very start of contig 0 and the last
+    ending exactly where the last contig ends (a genuine end clamp); the others are cut `safe` bases short."""
+    jobs = []
+    nc = len(lengths)
+    for k in range(n_slices):
+        ci = (k * nc) // n_slices if k + 1 < n_slices else nc - 1
+        L = lengths[ci]
+        sz = min(size, L)
+        if k == 0:
+            a = 0
+        elif k + 1 == n_slices:
+            a = L - sz
+        else:
+            a = ((k * 2654435761) % max(1, L - sz)) // 64 * 64
+        b = a + sz
+        jobs.append((ci, a, b, sz if b == L else sz - safe))
+    return jobs
+
+
+def compare_with_oracle(eng, hits, params, sts_text, contigs, lengths, safe, mode):
+    """mode = "whole" (every contig, the complete ordered list) or ("slices", n, size).  Returns a dict of facts."""
+    def fetch(ci, a, b):
+        return contigs[ci][a:b].cpu().numpy()
+
+    rows = gpu_rows(eng, hits)
+    t0 = time.time()
+    if mode == "whole":
+        jobs = [(ci, 0, L, L) for ci, L in enumerate(lengths)]
+        want = oracle_rows(params, sts_text, jobs, fetch)
+        want = np.concatenate(want) if want else np.zeros((0, 5), dtype=np.int64)
+        ok = want.shape == rows.shape and bool(np.array_equal(want, rows))
+        first_diff = None
+        if not ok:
+            m = min(len(want), len(rows))
+            d = np.flatnonzero((want[:m] != rows[:m]).any(axis=1))
+            first_diff = dict(index=int(d[0]) if d.size else m, want=want[d[0]].tolist() if d.size else None,
+                              got=rows[d[0]].tolist() if d.size else None, n_want=len(want), n_got=len(rows))
+        return dict(oracle_mode="whole genome, every contig, complete ordered hit list", oracle_bp=int(sum(lengths)),
+                    oracle_hits=int(len(want)), oracle_bit_exact=ok, oracle_first_diff=first_diff,
+                    oracle_seconds=round(time.time() - t0, 2))
+    _, n_slices, size = mode
+    jobs = slice_jobs(lengths, n_slices, size, safe)
+    want = oracle_rows(params, sts_text, jobs, fetch)
+    ok, total, bad = True, 0, None
+    for (ci, a, b, cut), w in zip(jobs, want):
+        g = rows[(rows[:, 0] == ci) & (rows[:, 1] >= a) & (rows[:, 2] < a + cut)]
+        total += len(w)
+        if w.shape != g.shape or not np.array_equal(w, g):
+            ok = False
+            bad = bad or dict(job=[ci, a, b, cut], n_want=len(w), n_got=len(g))
+    return dict(oracle_mode=f"{n_slices} slices of {size} bp spread over the contigs (both genome ends included)",
+                oracle_bp=int(sum(b - a for _, a, b, _ in jobs)), oracle_hits=int(total), oracle_bit_exact=ok,
+                oracle_first_diff=bad, oracle_seconds=round(time.time() - t0, 2))
+
+
+def run(name, lengths, n_sts, params, sub_mode, ranged, seed, decorate, dev, oracle="whole", verbose=True):
     t0 = time.time()
     sts = synth.make_sts_set(seed + 1, n_sts, 18, 25, 100, 1000)
     contigs = build_genome(seed, lengths, dev, 0.05 if decorate else 0.0, 1e-4 if decorate else 0.0)
@@ -111,28 +203,12 @@ def run(name, lengths, n_sts, params, sub_mode, ranged, seed, decorate, dev, ora
     planted_ok = all((c, a, b) in found for c, a, b, _, _ in expected)
     key = np.stack([hits["contig"], hits["pos1"]], axis=1).astype(np.int64)
     sorted_ok = bool(np.all((key[1:, 0] > key[:-1, 0]) | ((key[1:, 0] == key[:-1, 0]) & (key[1:, 1] >= key[:-1, 1]))))
-    # oracle on the head of contig 0 (single thread == reference -T 1)
-    from oracle.oracle import Oracle
-    sub = min(oracle_bp, lengths[0])
-    head = contigs[0][:sub].cpu().numpy()
-    o = Oracle(**params)
-    assert o.load_sts_text(sts_text)
-    t0 = time.time()
-    oh = o.search_hits(head.tobytes(), threads=1)
-    t_or = time.time() - t0
-    safe = sub - (int(sts["size"].max()) + 40 + params["margin"] + 64)
-    oh = oh[oh[:, 1] < safe]
-    g = hits[(hits["contig"] == 0) & (hits["pos2"] < safe)]
-    recs = o.records()
-    line = np.array([r["offset"] for r in recs], dtype=np.int64)
-    minus = np.array([r["direct"] == "-" for r in recs], dtype=np.int64)
-    gl = np.array([eng.sts_records[i].offset for i in eng._rec_to_idx[g["rec"]].tolist()], dtype=np.int64)
-    parity = (len(oh) == len(g) and bool(np.array_equal(oh[:, 0], g["pos1"]) and np.array_equal(oh[:, 1], g["pos2"]) and
-                                         np.array_equal(line[oh[:, 2]], gl) and np.array_equal(minus[oh[:, 2]], g["rec"] & 1)))
+    # the oracle (single thread per contig == reference -T 1) against the complete result
+    safe = int(sts["size"].max()) + 40 + params["margin"] + 64
+    facts = compare_with_oracle(eng, hits, params, sts_text, contigs, lengths, safe, oracle)
     bp = int(sum(lengths))
     out = dict(config=name, bp=bp, n_sts=n_sts, params=params, hits=int(n), planted=len(expected), planted_found=planted_ok,
-               sorted=sorted_ok, idempotent=idem, oracle_head_bp=sub, oracle_head_hits=int(len(oh)), oracle_head_bit_exact=parity,
-               oracle_head_seconds=round(t_or, 2), scan_kernel_ms=round(scan_ms, 3), verify_kernel_ms=round(ver_ms, 3),
+               sorted=sorted_ok, idempotent=idem, **facts, scan_kernel_ms=round(scan_ms, 3), verify_kernel_ms=round(ver_ms, 3),
                step_ms=round(1e3 * min(times), 3), gbp_per_s=round(bp / min(times) / 1e9, 2), load_sts_s=round(t_sts, 2),
                gen_s=round(t_gen, 1))
     if verbose:

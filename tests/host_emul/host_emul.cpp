@@ -370,4 +370,9 @@ int mpcr_sort_hits(mpcr_ctx* c, mpcr_hit* hits, uint64_t n, void*) {
     return MPCR_OK;
 }
 
+int mpcr_sort_hits_dev(mpcr_ctx* c, mpcr_hit* hits, const uint64_t* count, uint64_t capacity, uint64_t, void* st) {
+    if (!c || !count) return fail(MPCR_EINVAL, "null argument");
+    return mpcr_sort_hits(c, hits, *count < capacity ? *count : capacity, st);
+}
+
 }  // extern "C"

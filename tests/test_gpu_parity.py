@@ -351,7 +351,7 @@ def test_append_mode_range_scans_equal_one_scan_on_device(tmp_path):
         try:
             for lo, hi in zip(bounds[:-1], bounds[1:]):
                 eng._be.check(lib.mpcr_scan(eng._ctx, cg.ctypes.data, len(cg), sh.plane2.data_ptr(), sh.plane4.data_ptr(),
-                                            sh.valid.data_ptr(), sh.origin, sh.bases, lo, hi, hits.data_ptr(),
+                                            sh.valid.data_ptr(), sh.origin, sh.alloc, lo, hi, hits.data_ptr(),
                                             4 * len(want), count.data_ptr(), eng._stream()))
         finally:
             eng._be.check(lib.mpcr_ctx_set_append(eng._ctx, 0))

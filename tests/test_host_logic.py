@@ -199,7 +199,7 @@ def test_append_mode_range_scans_equal_one_scan(tmp_path):
         try:
             for lo, hi in zip(bounds[:-1], bounds[1:]):
                 eng._be.check(lib.mpcr_scan(eng._ctx, cg.ctypes.data, len(cg), sh.plane2.data_ptr(), sh.plane4.data_ptr(),
-                                            sh.valid.data_ptr(), sh.origin, sh.bases, lo, hi, hits.data_ptr(),
+                                            sh.valid.data_ptr(), sh.origin, sh.alloc, lo, hi, hits.data_ptr(),
                                             4 * len(want), count.data_ptr(), 0))
         finally:
             eng._be.check(lib.mpcr_ctx_set_append(eng._ctx, 0))
@@ -469,3 +469,43 @@ def _true_strands_check(MerPCRcls, record_factory):
 def test_true_strands_option():
     from merpcr_b200 import FASTARecord, MerPCR
     _true_strands_check(MerPCR, lambda cs: [FASTARecord(f">c{i}", c) for i, c in enumerate(cs)])
+
+
+def test_fullsize_oracle_comparison_helpers(tmp_path):
+    """tests/fullsize.py's whole-genome and slice comparisons (what the GPU tier runs at BASELINE sizes), here on a
+    small genome through the emulated backend -- including that they DO notice a missing or reordered hit."""
+    import torch
+    import fullsize
+    from merpcr_b200 import FASTARecord, MerPCR
+    rng = synth.Rng(515)
+    lengths = [180_000, 40_000, 90_001]
+    contigs = [rng.dna(n) for n in lengths]
+    sts = synth.make_sts_set(516, 400, 18, 25, 100, 600)
+    planted = synth.plant_amplicons(517, contigs, sts, 50, sub_mode="cfg3")
+    text = synth.sts_lines(sts)
+    sp = tmp_path / "f.sts"
+    sp.write_bytes(text)
+    params = dict(wordsize=11, margin=50, mismatches=1, three_prime_match=1)
+    eng = MerPCR(**params)
+    assert eng.load_sts_file(str(sp))
+    hits = eng.search_hits([FASTARecord(f">c{i}", c) for i, c in enumerate(contigs)])
+    assert len(hits) >= len(planted) > 100
+    tens = [torch.from_numpy(c) for c in contigs]
+    safe = int(sts["size"].max()) + 40 + 50 + 64
+    whole = fullsize.compare_with_oracle(eng, hits, params, text, tens, lengths, safe, "whole")
+    assert whole["oracle_bit_exact"] and whole["oracle_hits"] == len(hits) and whole["oracle_bp"] == sum(lengths)
+    jobs = fullsize.slice_jobs(lengths, 6, 30_000, safe)
+    assert jobs[0][:2] == (0, 0) and jobs[-1][0] == 2 and jobs[-1][2] == lengths[2] and jobs[-1][3] == 30_000
+    assert all(cut == 30_000 - safe for _, _, b, cut in jobs[1:-1])
+    sl = fullsize.compare_with_oracle(eng, hits, params, text, tens, lengths, safe, ("slices", 6, 30_000))
+    assert sl["oracle_bit_exact"] and sl["oracle_hits"] > 10
+    # a dropped hit and two swapped neighbours are both caught
+    assert not fullsize.compare_with_oracle(eng, np.delete(hits, len(hits) // 2), params, text, tens, lengths, safe,
+                                            "whole")["oracle_bit_exact"]
+    swapped = hits.copy()
+    swapped[[3, 4]] = swapped[[4, 3]]
+    assert not fullsize.compare_with_oracle(eng, swapped, params, text, tens, lengths, safe, "whole")["oracle_bit_exact"]
+    k = int(np.flatnonzero((hits["contig"] == 0) & (hits["pos2"] < 30_000 - safe))[0])
+    assert not fullsize.compare_with_oracle(eng, np.delete(hits, k), params, text, tens, lengths, safe,
+                                            ("slices", 6, 30_000))["oracle_bit_exact"]
+    eng.close()
