@@ -370,11 +370,11 @@ MPCR_HD bool filter_pass(uint32_t word, uint32_t key, int W) {
     return (word & m) == m;
 }
 
-struct Slot {          // 16 bytes, one 128-bit gather
-    uint32_t key;      // exact seed key (little-endian digits); checked only in hashed mode
+struct Slot {          // 16 bytes, one 128-bit gather; the scanner usually needs only the first 8 of them
     uint32_t code;     // survivor code: record index (one record) or kWalkBucket | first bucket entry; kSlotEmpty = free
     uint32_t tag_a;    // tag of the first record  (one record: tag_b == tag_a; three or more: both tags have mask 0,
     uint32_t tag_b;    // tag of the second record  i.e. they never reject)
+    uint32_t key;      // exact seed key (little-endian digits); checked only in hashed mode
 };
 static_assert(sizeof(Slot) == 16, "Slot layout");
 static constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu;   // cudaMemset(0xFF) == all slots empty

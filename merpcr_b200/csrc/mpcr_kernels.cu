@@ -317,11 +317,11 @@ __global__ void __launch_bounds__(256) build_buckets(const Item<2>* __restrict__
         // one record: both tags are its tag; two: one tag each; three or more: mask 0 = never reject
         const uint32_t code = n == 1 ? rec : (kWalkBucket | i);
         const uint32_t ta = n >= 3 ? 0u : tag, tb = n == 1 ? tag : (n == 2 ? tag_b : 0u);
-        const unsigned long long lo = (unsigned long long)key | ((unsigned long long)code << 32);
-        const unsigned long long hi = (unsigned long long)ta | ((unsigned long long)tb << 32);
+        const unsigned long long lo = (unsigned long long)code | ((unsigned long long)ta << 32);
+        const unsigned long long hi = (unsigned long long)tb | ((unsigned long long)key << 32);
         uint32_t s = slot_index(key, sm);
         if (!sm.direct) {
-            for (;;) {  // claim on the (key, code) half -- code == kSlotEmpty marks a free slot
+            for (;;) {  // claim on the (code, tag_a) half -- code == kSlotEmpty marks a free slot
                 unsigned long long* h = reinterpret_cast<unsigned long long*>(slots + s);
                 if (atomicCAS(h, ~0ull, lo) == ~0ull) break;
                 s = (s + 1) & sm.mask;
@@ -539,17 +539,26 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
         else if (u == 1) gather_wait<(R > 2 ? R - 2 : 0)>();
         else if (u == 2) gather_wait<(R > 3 ? R - 3 : 0)>();
         else gather_wait<0>();
-        const uint4 v = landing[u][lane];
+        // the first 8 bytes of the slot (code, tag of the first record) settle almost every candidate: half the
+        // shared-memory wavefronts of a 16-byte read.  The other half is needed for seeds shared by two or more records
+        // (second tag) and, in hashed mode, for the key.
+        const uint2 v = *reinterpret_cast<const uint2*>(&landing[u][lane]);
+        uint32_t tag_b = v.y, skey = key[u];
+        if (HASHED || ((v.x & kWalkBucket) && v.x != kSlotEmpty)) {
+            const uint2 w = reinterpret_cast<const uint2*>(&landing[u][lane])[1];
+            tag_b = w.x;
+            skey = w.y;
+        }
         // HASHED (open-addressed table, W >= 12): another key's slot ends the search unless a stored key's probe
         // sequence runs through it (kSlotChain); direct tables never collide
-        const bool other = HASHED && v.x != key[u];
-        const bool collide = other && (v.y & kSlotChain);
-        const bool pass = !other && (dirty[u] || !(tag_rejects(v.z, gcodes[u], N) && tag_rejects(v.w, gcodes[u], N)));
-        if (ok[u] && v.y != kSlotEmpty && (collide || pass)) {  // about one queued position in a thousand
+        const bool other = HASHED && skey != key[u];
+        const bool collide = other && (v.x & kSlotChain);
+        const bool pass = !other && (dirty[u] || !(tag_rejects(v.y, gcodes[u], N) && tag_rejects(tag_b, gcodes[u], N)));
+        if (ok[u] && v.x != kSlotEmpty && (collide || pass)) {  // about one queued position in a thousand
             const uint32_t lp = ubase + lpv[u];
             if (a.debug & 2) ++n_dbg;
             else if (collide) probe_collision(a, key[u], gcodes[u] & 0xFFFFu, dirty[u] ? 0u : 0xFFu, tile, lp);
-            else push_survivor(a, tile, lp, HASHED ? (v.y & ~kSlotChain) : v.y);
+            else push_survivor(a, tile, lp, HASHED ? (v.x & ~kSlotChain) : v.x);
         }
     }
 }
@@ -726,6 +735,25 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
             if (total == 0) break;
             const bool fits = incl <= (uint32_t)ScanSmem::kQCap;
             if (fits && n) {
+#ifdef MPCR_QUEUE_PAIRS
+                // two entries per 32-bit store (an odd start or a last single entry go out as 16-bit stores): half the
+                // store instructions -- and shared-memory wavefronts -- of the lane-by-lane compaction
+                uint64_t m = ((uint64_t)c_hi << 32) | c_lo;
+                uint32_t at = incl - n;
+                auto next = [&]() -> uint32_t {
+                    const uint32_t j = (uint32_t)__ffsll((long long)m) - 1u;
+                    m &= m - 1;
+                    return lp0 + j;
+                };
+                if (at & 1u) ws.queue[at++] = (uint16_t)next();
+                uint32_t* q2 = reinterpret_cast<uint32_t*>(ws.queue + at);
+                while (m & (m - 1)) {   // at least two left
+                    const uint32_t x0 = next(), x1 = next();
+                    *q2++ = x0 | (x1 << 16);
+                }
+                if (m) *reinterpret_cast<uint16_t*>(q2) = (uint16_t)next();
+                c_lo = 0; c_hi = 0;
+#else
                 uint16_t* q = ws.queue + (incl - n);
                 while (c_lo) {
                     *q++ = (uint16_t)(lp0 + __ffs(c_lo) - 1);
@@ -735,6 +763,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
                     *q++ = (uint16_t)(lp0 + 31 + __ffs(c_hi));
                     c_hi &= c_hi - 1;
                 }
+#endif
             }
             const uint32_t fit_mask = __ballot_sync(0xffffffffu, fits);
             const uint32_t cnt = total <= (uint32_t)ScanSmem::kQCap

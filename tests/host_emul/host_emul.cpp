@@ -263,8 +263,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
             uint32_t s = slot_index(key, c->smap);
             if (!direct) while (c->slots[s].code != kSlotEmpty) s = (s + 1) & c->smap.mask;
             const uint32_t tag_a = c->meta[rec].tag;
-            c->slots[s] = n == 1 ? Slot{key, rec, tag_a, tag_a}
-                          : n == 2 ? Slot{key, kWalkBucket | i, tag_a, tag_b} : Slot{key, kWalkBucket | i, 0u, 0u};
+            c->slots[s] = n == 1 ? Slot{rec, tag_a, tag_a, key}
+                          : n == 2 ? Slot{kWalkBucket | i, tag_a, tag_b, key} : Slot{kWalkBucket | i, 0u, 0u, key};
             c->filter[filter_word(key, cw, words)] |= filter_bits_of(key, WS);
         }
     }

@@ -555,3 +555,88 @@ def test_true_strands_option_on_device():
     from merpcr_b200 import MerPCR
     from test_host_logic import _true_strands_check
     _true_strands_check(MerPCR, _records)
+
+
+@pytest.mark.parametrize("n", [2, 37, 1000, 12288, 12289, 70000, 300000])
+def test_sort_with_the_count_on_the_device(n):
+    """mpcr_sort_hits_dev (count read on the device, rank sort for short lists, radix passes + tie kernels for long
+    ones, any hint) and mpcr_sort_hits order random hit lists -- many ties on (contig, pos1), one run of several
+    hundred equal positions -- exactly like a lexicographic sort on the reference's order key."""
+    import torch
+    from merpcr_b200 import MerPCR, _capi
+    eng = MerPCR()
+    lib = eng._be.lib
+    rng = np.random.default_rng(n)
+    h = np.zeros(n, dtype=_capi.HIT_DTYPE)
+    h["contig"] = rng.integers(0, 24, n)
+    h["pos1"] = rng.integers(0, max(4, n // 3), n)             # plenty of equal (contig, pos1)
+    if n >= 1000:
+        h["contig"][:700] = 5
+        h["pos1"][:700] = 77                                    # a long run for order_long_runs
+    h["pos2"] = h["pos1"] + rng.integers(50, 900, n)
+    h["rec"] = rng.permutation(n).astype(np.uint32)            # unique: the order key is total
+    h["rank"] = rng.integers(0, 100, n)
+    h["hash_off"] = rng.integers(0, 3, n)
+    order = np.lexsort((h["rank"], h["rec"], h["hash_off"], h["pos1"], h["contig"]))
+    want = h[order]
+    # the digit counts of the radix passes come from the layout of the last scan: give the context one
+    layout = eng.make_layout([max(4, n // 3) + 1000] * 24)
+    cg = layout["contigs"]
+    eng._be.check(lib.mpcr_scan_prepare(eng._ctx, cg.ctypes.data, len(cg), 0, 0, layout["total"], eng._stream()))
+    dev = torch.device("cuda", eng.device)
+    cap = n + 1000
+    for hint in (None, 0, 5, n, 10 * n + 50000):
+        buf = torch.zeros(cap * h.itemsize, dtype=torch.uint8, device=dev)
+        buf[: n * h.itemsize] = torch.from_numpy(h.view(np.uint8).copy()).to(dev)
+        if hint is None:
+            eng._be.check(lib.mpcr_sort_hits(eng._ctx, buf.data_ptr(), n, eng._stream()))
+        else:
+            count = torch.tensor([n], dtype=torch.int64, device=dev)
+            eng._be.check(lib.mpcr_sort_hits_dev(eng._ctx, buf.data_ptr(), count.data_ptr(), cap, hint, eng._stream()))
+        torch.cuda.synchronize()
+        got = buf[: n * h.itemsize].cpu().numpy().view(_capi.HIT_DTYPE)
+        assert np.array_equal(got, want), (n, hint)
+    # a count beyond the capacity sorts the records that were stored
+    buf = torch.from_numpy(h.view(np.uint8).copy()).to(dev)
+    count = torch.tensor([n + 12345], dtype=torch.int64, device=dev)
+    eng._be.check(lib.mpcr_sort_hits_dev(eng._ctx, buf.data_ptr(), count.data_ptr(), n, 0, eng._stream()))
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy().view(_capi.HIT_DTYPE), want)
+    eng.close()
+
+
+def test_scan_rejects_planes_that_are_too_small(tmp_path):
+    """mpcr_scan checks the plane extent it is told about against what the kernels read (whole units + read-ahead,
+    the last mate window, nothing in front of the origin) and fails with MPCR_EINVAL instead of reading out of bounds."""
+    import torch
+    from merpcr_b200 import MerPCR
+    rng = synth.Rng(31)
+    contigs = [rng.dna(50_000), rng.dna(20_000)]
+    sts = synth.make_sts_set(32, 50, 18, 25, 100, 600)
+    synth.plant_amplicons(33, contigs, sts, 50, sub_mode="none")
+    path = _write(tmp_path, "b.sts", synth.sts_lines(sts))
+    eng = MerPCR()
+    assert eng.load_sts_file(path)
+    lib = eng._be.lib
+    layout = eng.make_layout([len(c) for c in contigs])
+    sh = eng.upload(layout, contigs)
+    cg = layout["contigs"]
+    dev = torch.device("cuda", eng.device)
+    hits = torch.empty(4096 * 24, dtype=torch.uint8, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def scan(origin, plane_bases, lo, hi):
+        return lib.mpcr_scan(eng._ctx, cg.ctypes.data, len(cg), sh.plane2.data_ptr(), sh.plane4.data_ptr(),
+                             sh.valid.data_ptr(), origin, plane_bases, lo, hi, hits.data_ptr(), 4096, count.data_ptr(),
+                             eng._stream())
+    assert scan(sh.origin, sh.alloc, sh.begin, sh.end) == 0
+    n_ok = int(count.item())
+    assert n_ok >= 50
+    last = int(cg[1]["gstart"]) + int(cg[1]["length"])
+    for too_small in (0, 128, last - 1, last + 64):            # even the true genome length lacks the staging read-ahead
+        with pytest.raises(ValueError):
+            eng._be.check(scan(sh.origin, too_small, sh.begin, sh.end))
+    with pytest.raises(ValueError):                            # a range that starts in front of the planes' origin
+        eng._be.check(scan(1 << 20, sh.alloc, 0, sh.end))
+    assert scan(sh.origin, sh.alloc, sh.begin, sh.end) == 0 and int(count.item()) == n_ok
+    eng.close()
