@@ -52,6 +52,9 @@ def parse_args():
                     help="strong (default): ONE 3.1 Gbp genome sharded over the GPUs -- bp-balanced ranges with halos, "
                          "BASELINE.json config 3 and the production multi-GPU mode; weak: one genome copy per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; recorded in config)")
+    ap.add_argument("--as-shard", default="", metavar="R/W",
+                    help="tuning only (recorded in config): on ONE GPU, run rank R's share of a W-way sharded genome -- "
+                         "the per-GPU step of an N = W run without W GPUs")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -342,7 +345,12 @@ def run_b200(args):
     with tempfile.NamedTemporaryFile("wb", suffix=".sts", delete=False) as f:
         f.write(sts_text)
         sts_path = f.name
-    eng = MerPCR(**PARAMS, device=local, shard=(rank, world))
+    shard_rw = (rank, world)
+    if args.as_shard:
+        if world != 1:
+            raise SystemExit("--as-shard is a single-GPU tuning mode")
+        shard_rw = tuple(int(x) for x in args.as_shard.split("/"))
+    eng = MerPCR(**PARAMS, device=local, shard=shard_rw)
     try:
         assert eng.load_sts_file(sts_path)
     finally:
@@ -452,6 +460,9 @@ def run_b200(args):
         dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps
         e2e = dict(value=total_bp / dt / 1e9, unit="Gbp/s", h2d_bytes_per_step=int(sum_over_ranks(float(eng.last_h2d_bytes))),
                    d2h_bytes_per_step=int(sum_over_ranks(float(d2h))), ms_per_step=dt * 1e3, steps=e2e_steps,
+                   host_pack_ms=round(1e3 * float(eng.last_timing.get("host_pack_s", 0.0)), 3),
+                   host_pack_threads=int(eng.last_timing.get("host_pack_threads", 0)),
+                   wire="4-bit packed on the host cores (0.5 B/bp)" if eng.host_pack else "ASCII (1 B/bp)",
                    hits=int(sum_over_ranks(float(len(out)))))
         assert len(out) == n_hits, "e2e and resident hit counts differ"
 
@@ -509,6 +520,8 @@ def run_b200(args):
                                  ("ONE genome sharded over the GPUs (bp-balanced ranges + halos)" if strong
                                   else "one genome copy per GPU"),
                         scale=args.scale, bp_per_gpu=my_bp, n_sts=n_sts, hits_per_gpu=int(n_hits),
+                        **({"emulated_shard": args.as_shard, "note": "tuning run: one rank's share only, not a bench line"}
+                           if args.as_shard else {}),
                         l2="inputs (2.7 GB of planes per GPU) exceed the 126 MB L2; no flush needed",
                         numa_node=numa,
                         planted_found=planted_ok, sorted=sorted_ok),

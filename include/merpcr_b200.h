@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 7
+#define MPCR_ABI_VERSION 8
 
 enum {
     MPCR_OK = 0,
@@ -122,6 +122,20 @@ int mpcr_ctx_sm_count(const mpcr_ctx *ctx);
 int mpcr_pack_sequence(mpcr_ctx *ctx, const uint8_t *d_ascii, uint64_t n, uint64_t dst_base,
                        uint64_t plane_origin, void *d_plane2, void *d_plane4, void *d_valid,
                        const uint8_t *h_lut, void *stream);
+
+/* The same ingest for sequence that starts in HOST memory, shipping half the bytes over PCIe:
+ * mpcr_host_pack_nibbles (host cores, multi-threaded; AVX-512 / AVX2 / scalar) turns n ASCII bases into (n + 1) / 2
+ * bytes in plane4's own layout -- base 2k in the low nibble of byte k, base 2k+1 in the high one, nibble = h_lut[c] & 15
+ * -- so the caller's H2D copy lands them directly in d_plane4 at byte (dst_base - plane_origin) / 2 (dst_base even; a
+ * pinned staging buffer keeps the copy asynchronous), and mpcr_derive_planes then rebuilds the 2-bit and the valid
+ * plane from plane4 on the device for the bases [dst_base, dst_base + n) (dst_base a multiple of 64; whole 64-base
+ * strips are written, so what follows the sequence inside its last strip must be zero in plane4).
+ * threads <= 0: all hardware threads.  Returns 0; 1 when the input holds a byte whose 2-bit code / clean flag do not
+ * follow from its nibble (the one case: 'U' outside IUPAC mode, which hashes like T but equals nothing) -- the caller
+ * then takes the ASCII path (mpcr_pack_sequence) for that piece; -1 for a null argument. */
+int mpcr_host_pack_nibbles(const uint8_t *h_ascii, uint64_t n, const uint8_t *h_lut, uint8_t *h_dst, int threads);
+int mpcr_derive_planes(mpcr_ctx *ctx, uint64_t n, uint64_t dst_base, uint64_t plane_origin, const void *d_plane4,
+                       void *d_plane2, void *d_valid, void *stream);
 
 /* Device-side FASTA text ingest: replaces the whole of FASTALoader.load_file (io/fasta.py:43-66) for ASCII files.
  * d_text holds the raw file bytes (device memory, n bytes).  mpcr_fasta_index finds the header lines ('>' as the

@@ -10,7 +10,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "mpcr_kernels.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("mpcr_core.cuh", "mpcr_sort.cuh", "mpcr_fasta.cuh", "mpcr_hostio.h")] + \
+HOST_SRC = os.path.join(HERE, "csrc", "mpcr_hostpack.cpp")    # host-side packer: g++ (AVX2 / AVX-512 paths), linked in
+DEPS = SRC + [HOST_SRC] + [os.path.join(HERE, "csrc", f) for f in ("mpcr_core.cuh", "mpcr_sort.cuh", "mpcr_fasta.cuh", "mpcr_hostio.h")] + \
     [os.path.join(os.path.dirname(HERE), "include", "merpcr_b200.h")]
 OUT = os.path.join(HERE, "lib", "libmerpcr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -31,9 +32,13 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", defines
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
+    host_obj = out.replace(".so", "_hostpack.o")
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-Wno-psabi", "-c", HOST_SRC,
+                           "-o", host_obj])
     cmd = [find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", out] + SRC
+        ["-o", out] + SRC + [host_obj]
     subprocess.check_call(cmd)
+    os.unlink(host_obj)
     return out
 
 

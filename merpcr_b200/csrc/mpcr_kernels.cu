@@ -217,6 +217,47 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ a
     plane4[4 * s + 3] = p4[3];
 }
 
+// plane4 -> plane2 + valid for sequence that reached the device as packed nibbles (host packer, mpcr_hostpack.cpp):
+// a nibble with exactly one bit set is A/C/G/T (clean, 2-bit code = the bit's index), everything else is not clean
+// and has code 0 -- the same three planes pack_kernel writes from ASCII.  One thread = 64 bases: 32 bytes in, 24 out.
+__device__ __forceinline__ uint32_t gather_lsb4(uint64_t x) {   // bit 0 of each of the 16 nibbles -> 16 bits
+    x &= kLane1;
+    x = (x | (x >> 3)) & 0x0303030303030303ull;
+    x = (x | (x >> 6)) & 0x000F000F000F000Full;
+    x = (x | (x >> 12)) & 0x000000FF000000FFull;
+    return (uint32_t)((x | (x >> 24)) & 0xFFFFull);
+}
+__device__ __forceinline__ uint32_t gather_low2(uint64_t x) {   // bits 0..1 of each nibble -> 32 bits
+    x &= 0x3333333333333333ull;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+    return (uint32_t)((x | (x >> 16)) & 0xFFFFFFFFull);
+}
+__global__ void __launch_bounds__(256) derive_planes_kernel(const uint64_t* __restrict__ plane4, uint64_t n, uint64_t dst_rel,
+                                                            uint64_t* __restrict__ plane2, uint64_t* __restrict__ valid) {
+    const uint64_t strip = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (strip * 64 >= n) return;
+    const uint64_t s = dst_rel / 64 + strip;
+    const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(plane4 + 4 * s);
+    const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(plane4 + 4 * s + 2);
+    const uint64_t w[4] = {q0.x, q0.y, q1.x, q1.y};
+    uint64_t v = 0, p2[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t x = w[k];
+        const uint64_t b0 = x & kLane1, b1 = (x >> 1) & kLane1, b2 = (x >> 2) & kLane1, b3 = (x >> 3) & kLane1;
+        const uint64_t t = (b0 + b1 + b2 + b3) ^ kLane1;                        // 0 in the nibbles that hold one bit
+        const uint64_t one = ~(t | (t >> 1) | (t >> 2) | (t >> 3)) & kLane1;     // ... as a nibble-LSB mask
+        const uint64_t code = (((b1 | b3) & one)) | (((b2 | b3) & one) << 1);     // C1 G2 T3 in bits 0..1 of the nibble
+        v |= (uint64_t)gather_lsb4(one) << (16 * k);
+        p2[k >> 1] |= (uint64_t)gather_low2(code) << (32 * (k & 1));
+    }
+    valid[s] = v;
+    plane2[2 * s] = p2[0];
+    plane2[2 * s + 1] = p2[1];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // (2) table build
 // ---------------------------------------------------------------------------------------------------------
@@ -539,16 +580,11 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
         else if (u == 1) gather_wait<(R > 2 ? R - 2 : 0)>();
         else if (u == 2) gather_wait<(R > 3 ? R - 3 : 0)>();
         else gather_wait<0>();
-        // the first 8 bytes of the slot (code, tag of the first record) settle almost every candidate: half the
-        // shared-memory wavefronts of a 16-byte read.  The other half is needed for seeds shared by two or more records
-        // (second tag) and, in hashed mode, for the key.
-        const uint2 v = *reinterpret_cast<const uint2*>(&landing[u][lane]);
-        uint32_t tag_b = v.y, skey = key[u];
-        if (HASHED || ((v.x & kWalkBucket) && v.x != kSlotEmpty)) {
-            const uint2 w = reinterpret_cast<const uint2*>(&landing[u][lane])[1];
-            tag_b = w.x;
-            skey = w.y;
-        }
+        // (reading only the first 8 bytes -- code and first tag settle almost every candidate -- was measured and buys
+        // nothing: 8-byte reads at a 16-byte stride cost the same shared-memory wavefronts as the 16-byte read)
+        const uint4 sl = landing[u][lane];
+        const uint2 v = make_uint2(sl.x, sl.y);
+        const uint32_t tag_b = sl.z, skey = sl.w;
         // HASHED (open-addressed table, W >= 12): another key's slot ends the search unless a stored key's probe
         // sequence runs through it (kSlotChain); direct tables never collide
         const bool other = HASHED && skey != key[u];
@@ -735,25 +771,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
             if (total == 0) break;
             const bool fits = incl <= (uint32_t)ScanSmem::kQCap;
             if (fits && n) {
-#ifdef MPCR_QUEUE_PAIRS
-                // two entries per 32-bit store (an odd start or a last single entry go out as 16-bit stores): half the
-                // store instructions -- and shared-memory wavefronts -- of the lane-by-lane compaction
-                uint64_t m = ((uint64_t)c_hi << 32) | c_lo;
-                uint32_t at = incl - n;
-                auto next = [&]() -> uint32_t {
-                    const uint32_t j = (uint32_t)__ffsll((long long)m) - 1u;
-                    m &= m - 1;
-                    return lp0 + j;
-                };
-                if (at & 1u) ws.queue[at++] = (uint16_t)next();
-                uint32_t* q2 = reinterpret_cast<uint32_t*>(ws.queue + at);
-                while (m & (m - 1)) {   // at least two left
-                    const uint32_t x0 = next(), x1 = next();
-                    *q2++ = x0 | (x1 << 16);
-                }
-                if (m) *reinterpret_cast<uint16_t*>(q2) = (uint16_t)next();
-                c_lo = 0; c_hi = 0;
-#else
                 uint16_t* q = ws.queue + (incl - n);
                 while (c_lo) {
                     *q++ = (uint16_t)(lp0 + __ffs(c_lo) - 1);
@@ -763,7 +780,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
                     *q++ = (uint16_t)(lp0 + 31 + __ffs(c_hi));
                     c_hi &= c_hi - 1;
                 }
-#endif
             }
             const uint32_t fit_mask = __ballot_sync(0xffffffffu, fits);
             const uint32_t cnt = total <= (uint32_t)ScanSmem::kQCap
@@ -1282,6 +1298,21 @@ int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* d_ascii, uint64_t n, uint64_t
     const uint32_t blocks = (uint32_t)((strips + 255) / 256);
     pack_kernel<<<blocks, 256, 0, st>>>(d_ascii, n, dst_base - plane_origin, (uint64_t*)d_plane2, (uint64_t*)d_plane4,
                                         (uint64_t*)d_valid, c->d_lut);
+    c->launches++;
+    CU(cudaGetLastError());
+    return MPCR_OK;
+}
+
+int mpcr_derive_planes(mpcr_ctx* c, uint64_t n, uint64_t dst_base, uint64_t plane_origin, const void* d_plane4,
+                       void* d_plane2, void* d_valid, void* stream) {
+    if (!c || !d_plane2 || !d_plane4 || !d_valid) return fail(MPCR_EINVAL, "null argument");
+    if ((dst_base & 63u) || (plane_origin & 127u) || dst_base < plane_origin)
+        return fail(MPCR_EINVAL, "dst_base must be a multiple of 64 and >= plane_origin (multiple of 128)");
+    if (n == 0) return MPCR_OK;
+    GUARD(c);
+    const uint64_t strips = (n + 63) / 64;
+    derive_planes_kernel<<<(uint32_t)((strips + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint64_t*)d_plane4, n, dst_base - plane_origin, (uint64_t*)d_plane2, (uint64_t*)d_valid);
     c->launches++;
     CU(cudaGetLastError());
     return MPCR_OK;

@@ -198,6 +198,14 @@ class MerPCR:
         self._ctx = None
         self._pinned_hits = None  # D2H staging of the hit list
         self._copy_stream = None  # upload_and_scan: the H2D copies run beside pack + scan
+        self._host_stage = None   # pinned staging buffers of the host-side nibble packer
+        # host-resident sequence goes over PCIe as packed nibbles (0.5 byte/base) unless switched off
+        self.host_pack = os.environ.get("MPCR_HOST_PACK", "1") not in ("0", "")
+        try:
+            cpus = len(os.sched_getaffinity(0))
+        except AttributeError:  # pragma: no cover
+            cpus = os.cpu_count() or 1
+        self._pack_threads = max(1, cpus // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
         self._ctx_exts = []       # extended tables of exact, candidate-heavy searches (mpcr_ctx_set_seed_extension)
         self._create_ctx()
         # parsed STS lines kept so the table can be re-encoded if a sequence brings an unusual alphabet
@@ -788,30 +796,79 @@ class MerPCR:
             self._be.check(lib.mpcr_scan_prepare(ctx, contigs.ctypes.data, len(contigs), sh.origin, sh.begin, sh.end,
                                                  stream))
             self._be.check(lib.mpcr_ctx_set_append(ctx, 1))
+        # Host-resident pieces go over PCIe as packed nibbles (0.5 byte per base): the host cores pack them into pinned
+        # staging buffers in plane4's own layout (mpcr_host_pack_nibbles), the copy lands directly in plane4, and the
+        # device derives the other two planes (mpcr_derive_planes).  A piece the nibble path cannot carry (a 'U' outside
+        # IUPAC mode) goes up as ASCII through the device staging buffers like before.
+        use_nibbles = self.host_pack
+        n_stage = 3
+        hstage, hfree = None, ()
+        if use_nibbles:
+            if gpu:
+                if self._host_stage is None or self._host_stage[0].numel() < chunk // 2:
+                    self._host_stage = [torch.empty(chunk // 2, dtype=torch.uint8).pin_memory() for _ in range(n_stage)]
+                hfree = [torch.cuda.Event() for _ in range(n_stage)]
+            elif self._host_stage is None or self._host_stage[0].numel() < chunk // 2:
+                self._host_stage = [torch.empty(chunk // 2, dtype=torch.uint8) for _ in range(n_stage)]
+            hstage = self._host_stage
         try:
-            k, h2d, pending, done_to, deferred = 0, 0, 0, sh.begin, None
+            k, kn, h2d, pending, done_to, deferred, pack_s = 0, 0, 0, 0, sh.begin, None, 0.0
             for ci, a, b, src, last in self._pieces(layout, seqs, sh, chunk):
-                slot = -1
-                if src.device != self._tdev:
-                    slot = k & 1
-                    k += 1
-                    buf = sh.stage2[slot][: b - a]
-                    copy.wait_event(packed[slot])              # the pack that last read this buffer is done
-                    with torch.cuda.stream(copy):
-                        buf.copy_(src, non_blocking=True)
-                    copied[slot].record(copy)
-                    h2d += b - a
-                    src = buf
-                if deferred:                                   # the finished contig is scanned while this copy runs
-                    scan_range(*deferred)
-                    deferred = None
-                if slot >= 0:
-                    compute.wait_event(copied[slot])
-                self._be.check(lib.mpcr_pack_sequence(self._ctx, src.data_ptr(), b - a, a, sh.origin,
-                                                      sh.plane2.data_ptr(), sh.plane4.data_ptr(), sh.valid.data_ptr(),
-                                                      lut.ctypes.data, stream))
-                if slot >= 0:
-                    packed[slot].record(compute)
+                on_host = src.device.type == "cpu"
+                done = False
+                if on_host and use_nibbles:
+                    slot = kn % n_stage
+                    if gpu and kn >= n_stage:
+                        hfree[slot].synchronize()              # the copy that last read this staging buffer is done
+                    nb = (b - a + 1) // 2
+                    t_pack = time.perf_counter()
+                    rc = int(lib.mpcr_host_pack_nibbles(src.data_ptr(), b - a, lut.ctypes.data, hstage[slot].data_ptr(),
+                                                        self._pack_threads))
+                    pack_s += time.perf_counter() - t_pack
+                    if rc < 0:
+                        raise ValueError("mpcr_host_pack_nibbles: bad argument")
+                    if rc == 0:
+                        off = (a - sh.origin) // 2
+                        if gpu:
+                            with torch.cuda.stream(copy):
+                                sh.plane4[off: off + nb].copy_(hstage[slot][:nb], non_blocking=True)
+                            hfree[slot].record(copy)
+                        else:
+                            sh.plane4[off: off + nb].copy_(hstage[slot][:nb])
+                        kn += 1
+                        h2d += nb
+                        if deferred:                           # the finished contig is scanned while this copy runs
+                            scan_range(*deferred)
+                            deferred = None
+                        if gpu:
+                            compute.wait_event(hfree[slot])
+                        self._be.check(lib.mpcr_derive_planes(self._ctx, b - a, a, sh.origin, sh.plane4.data_ptr(),
+                                                              sh.plane2.data_ptr(), sh.valid.data_ptr(), stream))
+                        done = True
+                if not done:
+                    slot = -1
+                    if src.device != self._tdev:
+                        slot = k & 1
+                        k += 1
+                        buf = sh.stage2[slot][: b - a]
+                        copy.wait_event(packed[slot])              # the pack that last read this buffer is done
+                        if not src.is_pinned():
+                            src = src.pin_memory()                 # keeps the copy asynchronous
+                        with torch.cuda.stream(copy):
+                            buf.copy_(src, non_blocking=True)
+                        copied[slot].record(copy)
+                        h2d += b - a
+                        src = buf
+                    if deferred:                                   # the finished contig is scanned while this copy runs
+                        scan_range(*deferred)
+                        deferred = None
+                    if slot >= 0:
+                        compute.wait_event(copied[slot])
+                    self._be.check(lib.mpcr_pack_sequence(self._ctx, src.data_ptr(), b - a, a, sh.origin,
+                                                          sh.plane2.data_ptr(), sh.plane4.data_ptr(), sh.valid.data_ptr(),
+                                                          lut.ctypes.data, stream))
+                    if slot >= 0:
+                        packed[slot].record(compute)
                 pending += b - a
                 # a finished contig (or run of small ones) whose right neighbourhood is complete can be scanned
                 if last and pending >= STREAM_SCAN_BASES and done_to < nxt[ci] < sh.end:
@@ -830,6 +887,7 @@ class MerPCR:
             for ctx in ctxs:
                 lib.mpcr_ctx_set_append(ctx, 0)
         self.last_h2d_bytes = h2d
+        self.last_timing = dict(host_pack_s=pack_s, host_pack_threads=self._pack_threads)
         if need > cap:      # the hit list outgrew the buffer: the planes are resident now, scan them again with room
             hits, n = self.scan_device(layout, sh, sort=sort)
             return sh, hits, n

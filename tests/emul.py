@@ -7,13 +7,14 @@ SRC = os.path.join(HERE, "host_emul", "host_emul.cpp")
 OUT = os.path.join(HERE, "host_emul", "_build", "libmerpcr_emul.so")
 DEPS = [SRC, os.path.join(HERE, "..", "merpcr_b200", "csrc", "mpcr_core.cuh"),
         os.path.join(HERE, "..", "merpcr_b200", "csrc", "mpcr_hostio.h"),
+        os.path.join(HERE, "..", "merpcr_b200", "csrc", "mpcr_hostpack.cpp"),
         os.path.join(HERE, "..", "include", "merpcr_b200.h")]
 
 
 def build() -> str:
     if not os.path.exists(OUT) or any(os.path.getmtime(OUT) < os.path.getmtime(d) for d in DEPS):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", OUT, SRC])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-Wno-psabi", "-shared", "-o", OUT, SRC, "-lpthread"])
     return OUT
 
 

@@ -17,6 +17,7 @@
 #include "../../include/merpcr_b200.h"
 #include "../../merpcr_b200/csrc/mpcr_core.cuh"
 #include "../../merpcr_b200/csrc/mpcr_hostio.h"
+#include "../../merpcr_b200/csrc/mpcr_hostpack.cpp"   // the product's own host packer (host code): mpcr_host_pack_nibbles
 
 using namespace mpcr;
 
@@ -116,6 +117,28 @@ int mpcr_pack_sequence(mpcr_ctx* c, const uint8_t* ascii, uint64_t n, uint64_t d
         const uint64_t w = rel / 64 + s;
         V[w] = v; P2[2 * w] = p2[0]; P2[2 * w + 1] = p2[1];
         for (int k = 0; k < 4; ++k) P4[4 * w + k] = p4[k];
+    }
+    c->launches++;
+    return MPCR_OK;
+}
+
+int mpcr_derive_planes(mpcr_ctx* c, uint64_t n, uint64_t dst_base, uint64_t origin, const void* plane4, void* plane2,
+                       void* valid, void*) {
+    if (!c || !plane2 || !plane4 || !valid) return fail(MPCR_EINVAL, "null argument");
+    if ((dst_base & 63u) || (origin & 127u) || dst_base < origin) return fail(MPCR_EINVAL, "bad alignment");
+    const uint64_t* P4 = (const uint64_t*)plane4;
+    uint64_t *P2 = (uint64_t*)plane2, *V = (uint64_t*)valid;
+    const uint64_t rel = dst_base - origin;
+    for (uint64_t s = 0; s * 64 < n; ++s) {
+        const uint64_t w = rel / 64 + s;
+        uint64_t v = 0, p2[2] = {0, 0};
+        for (int j = 0; j < 64; ++j) {
+            const uint32_t nib = (uint32_t)(P4[4 * w + (j >> 4)] >> (4 * (j & 15))) & 15u;
+            const uint32_t code = nib == 2 ? 1u : nib == 4 ? 2u : nib == 8 ? 3u : 0u;
+            if (nib == 1 || nib == 2 || nib == 4 || nib == 8) v |= 1ull << j;
+            p2[j >> 5] |= (uint64_t)code << (2 * (j & 31));
+        }
+        V[w] = v; P2[2 * w] = p2[0]; P2[2 * w + 1] = p2[1];
     }
     c->launches++;
     return MPCR_OK;

@@ -509,3 +509,30 @@ def test_fullsize_oracle_comparison_helpers(tmp_path):
     assert not fullsize.compare_with_oracle(eng, np.delete(hits, k), params, text, tens, lengths, safe,
                                             ("slices", 6, 30_000))["oracle_bit_exact"]
     eng.close()
+
+
+@pytest.mark.parametrize("host_pack", ["1", "0"])
+def test_nibble_ingest_and_ascii_ingest_agree_with_the_oracle(tmp_path, monkeypatch, host_pack):
+    """Host-resident sequence reaches the planes either as host-packed nibbles (+ mpcr_derive_planes) or as ASCII
+    (mpcr_pack_sequence); a piece holding 'U' outside IUPAC mode (it hashes like T but equals nothing, so its planes do
+    not follow from its nibbles) must fall back to ASCII by itself.  Both give the oracle's hits."""
+    from merpcr_b200 import FASTARecord, MerPCR
+    monkeypatch.setenv("MPCR_HOST_PACK", host_pack)
+    rng = synth.Rng(808)
+    contigs = [rng.dna(70_001), rng.dna(33_333), rng.dna(64 * 700)]
+    sts = synth.make_sts_set(809, 150, 18, 25, 100, 500)
+    synth.plant_amplicons(810, contigs, sts, 50, sub_mode="cfg3")
+    contigs[0][1000:1040] = np.frombuffer(b"NNNNNRYKMSWBDHVXnacgtryNNNNNNNNNNNNNNNNN"[:40], dtype=np.uint8)
+    contigs[1][5:9] = np.frombuffer(b"UuUT", dtype=np.uint8)          # irregular under -I 0
+    contigs[1][20_000] = ord("U")
+    text = synth.sts_lines(sts)
+    sp = tmp_path / "n.sts"
+    sp.write_bytes(text)
+    for params in (dict(wordsize=11, margin=50, mismatches=1), dict(wordsize=11, margin=50, mismatches=2, iupac_mode=1)):
+        eng = MerPCR(**params)
+        assert eng.host_pack == (host_pack == "1")
+        assert eng.load_sts_file(str(sp))
+        got = parity.engine_hits(eng, [FASTARecord(f">c{i}", c) for i, c in enumerate(contigs)])
+        want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
+        assert np.array_equal(got, want) and len(want) > 50
+        eng.close()
