@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 8
+#define MPCR_ABI_VERSION 10
 
 enum {
     MPCR_OK = 0,
@@ -136,6 +136,12 @@ int mpcr_pack_sequence(mpcr_ctx *ctx, const uint8_t *d_ascii, uint64_t n, uint64
 int mpcr_host_pack_nibbles(const uint8_t *h_ascii, uint64_t n, const uint8_t *h_lut, uint8_t *h_dst, int threads);
 int mpcr_derive_planes(mpcr_ctx *ctx, uint64_t n, uint64_t dst_base, uint64_t plane_origin, const void *d_plane4,
                        void *d_plane2, void *d_valid, void *stream);
+
+/* Host helper for the file half of FASTALoader.load_file (io/fasta.py:36-41 `open` + line iteration): n bytes of the
+ * file at `offset` into h_dst (pinned staging memory in the Python host), read by `threads` concurrent pread streams
+ * (<= 0: all hardware threads) -- one thread copies out of the page cache at a few GB/s, the PCIe link behind it
+ * takes 55.  Returns the bytes read (short only at end of file) or -errno. */
+long long mpcr_file_read(const char *path, uint64_t offset, uint64_t n, uint8_t *h_dst, int threads);
 
 /* Device-side FASTA text ingest: replaces the whole of FASTALoader.load_file (io/fasta.py:43-66) for ASCII files.
  * d_text holds the raw file bytes (device memory, n bytes).  mpcr_fasta_index finds the header lines ('>' as the
@@ -241,6 +247,17 @@ int mpcr_sort_hits(mpcr_ctx *ctx, mpcr_hit *d_hits, uint64_t n, void *stream);
  * rank-sort launch instead of the radix passes), never the result. */
 int mpcr_sort_hits_dev(mpcr_ctx *ctx, mpcr_hit *d_hits, const uint64_t *d_count, uint64_t capacity, uint64_t n_hint,
                        void *stream);
+
+/* One step of the hot path in ONE call (what MerPCR.search does per sequence between reading it and printing,
+ * core/engine.py:373-434): mpcr_scan with every table of `ctxs` (the first zeroes *d_count, the others append behind
+ * it -- one context unless the search was split into several tables), then, if sort != 0, mpcr_sort_hits_dev with
+ * ctxs[0], all queued on `stream` without a host round trip.  h_count != NULL (pinned host memory): the true hit count
+ * is copied there and the call returns after the stream has drained, i.e. *h_count is valid on return (the caller
+ * re-runs with a larger buffer when it exceeds capacity); h_count == NULL: fully asynchronous. */
+int mpcr_scan_sorted(mpcr_ctx *const *ctxs, uint32_t n_ctx, const mpcr_contig *h_contigs, uint32_t n_contigs,
+                     const void *d_plane2, const void *d_plane4, const void *d_valid, uint64_t plane_origin,
+                     uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit *d_hits, uint64_t capacity,
+                     uint64_t *d_count, uint64_t *h_count, uint64_t n_hint, int sort, void *stream);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mpcr_launch_count(const mpcr_ctx *ctx);

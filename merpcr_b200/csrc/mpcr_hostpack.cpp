@@ -5,8 +5,11 @@
 // MerPCR._process_thread (core/engine.py:455,472,497 of the reference) exactly like mpcr_pack_sequence does.
 //
 // Compiled by g++ (AVX2 path behind a run-time CPU check, scalar path otherwise) and linked into libmerpcr_b200.so.
+#include <errno.h>
+#include <fcntl.h>
 #include <stdint.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -240,6 +243,45 @@ int mpcr_host_pack_nibbles(const uint8_t* h_ascii, uint64_t n, const uint8_t* h_
         if (kernel(t, h_ascii + a, b - a, h_dst + (a >> 1))) bad.store(1);
     });
     return bad.load();
+}
+
+// See include/merpcr_b200.h: n bytes of the file at `offset` into h_dst, the range cut into one pread stream per thread
+// (a single thread copies out of the page cache at a few GB/s; the PCIe link behind it takes 55).  Returns the number
+// of bytes read (short only at end of file) or -errno.
+long long mpcr_file_read(const char* path, uint64_t offset, uint64_t n, uint8_t* h_dst, int threads) {
+    if (!path || (n && !h_dst)) return -EINVAL;
+    if (n == 0) return 0;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return -(long long)errno;
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    if (threads <= 0 || threads > hw) threads = hw;
+    const uint64_t per = ((n + threads - 1) / threads + 4095) / 4096 * 4096;
+    const int parts = (int)((n + per - 1) / per);
+    std::atomic<long long> total(0), err(0);
+    auto part = [&](int p) {
+        uint64_t a = (uint64_t)p * per;
+        const uint64_t b = a + per < n ? a + per : n;
+        while (a < b) {
+            const ssize_t k = pread(fd, h_dst + a, b - a, (off_t)(offset + a));
+            if (k < 0) { if (errno == EINTR) continue; err.store(-(long long)errno); return; }
+            if (k == 0) break;   // end of file
+            a += (uint64_t)k;
+            total.fetch_add(k);
+        }
+    };
+    if (parts <= 1) {
+        part(0);
+    } else {
+        std::lock_guard<std::mutex> g(g_pool_mutex);
+        if (!g_pool || g_pool->size() < parts) {
+            delete g_pool;
+            g_pool = new Pool(parts > hw ? parts : hw);
+        }
+        g_pool->run(parts, part);
+    }
+    close(fd);
+    return err.load() ? err.load() : total.load();
 }
 
 }  // extern "C"

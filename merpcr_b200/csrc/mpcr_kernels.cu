@@ -976,18 +976,22 @@ __device__ __forceinline__ void verify_body(const ScanArgs& a) {
     constexpr uint32_t kGrab = kGroups;       // survivors a warp takes per cursor atomic (one per lane group)
     const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
     const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    // every warp starts at its own sub-list and moves on when that one is drained, until it has seen them all;
-    // 32 sub-lists are looked at per round (one per lane) so that drained ones cost nothing
+    // Every warp looks at 32 sub-lists at a time (one per lane: count and cursor, two loads per lane, all in flight
+    // together), takes the first one that still has work -- starting from a lane that differs between the warps that share
+    // the window -- drains it, and looks again.  A fresh look per list costs one round trip; walking a stale mask cost
+    // one round trip per ALREADY DRAINED list, 32 in a row, which was most of this kernel's time on short survivor lists.
+    const uint32_t rot = (warp_id / kSurvLists) & 31u;
     for (uint32_t round = 0; round < kSurvLists / 32; ++round) {
       const uint32_t my_list = (warp_id + 32 * round + lane) & (kSurvLists - 1u);
       const uint32_t* my_ctl = a.surv_ctl + my_list * kSurvCtlStride;
-      uint32_t open = __ballot_sync(0xffffffffu, __ldcg(my_ctl + 1) < min(__ldcg(my_ctl), a.surv_cap));
-      while (open) {
-        const int l = __ffs(open) - 1;
-        open &= open - 1;
+      const uint32_t my_n = min(__ldcg(my_ctl), a.surv_cap);      // final: the scanner has finished
+      for (;;) {
+        const uint32_t open = __ballot_sync(0xffffffffu, __ldcg(my_ctl + 1) < my_n);
+        if (!open) break;
+        const int l = (int)((__ffs(__funnelshift_r(open, open, rot)) - 1 + rot) & 31u);
         const uint32_t list = (warp_id + 32 * round + l) & (kSurvLists - 1u);
         uint32_t* ctl = a.surv_ctl + list * kSurvCtlStride;
-        const uint32_t n = min(ctl[0], a.surv_cap);
+        const uint32_t n = __shfl_sync(0xffffffffu, my_n, l);
         const Survivor* surv = a.surv + (size_t)list * a.surv_cap;
         for (;;) {
             uint32_t first = 0;
@@ -1682,7 +1686,9 @@ static int build_tiles_impl(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_
         if (a1 > a0) span += a1 - a0;
     }
     uint64_t tb = kTileBases;
-    const uint64_t want_tiles = 8ull * (uint64_t)c->sm_count * (kScanThreads / 32);
+    // (32 tiles per warp: the warps walk their tiles in lock step, so the launch ends with up to one tile-time of
+    // partly idle SMs -- 3 % of the launch at 32 tiles per warp, 10 % at 10)
+    const uint64_t want_tiles = 32ull * (uint64_t)c->sm_count * (kScanThreads / 32);
     while (tb > 2048 && span / tb < want_tiles) tb >>= 1;
     std::vector<TileDesc> tiles;
     for (uint32_t i = 0; i < n_contigs; ++i) {
@@ -1825,6 +1831,35 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     }
     CU(cudaEventRecord(c->ev2, st));
     c->scan_timed = true;
+    return MPCR_OK;
+}
+
+int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* h_contigs, uint32_t n_contigs,
+                     const void* d_plane2, const void* d_plane4, const void* d_valid, uint64_t plane_origin,
+                     uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit* d_hits, uint64_t capacity,
+                     uint64_t* d_count, uint64_t* h_count, uint64_t n_hint, int sort, void* stream) {
+    if (!ctxs || n_ctx == 0 || !d_count) return fail(MPCR_EINVAL, "null argument");
+    for (uint32_t i = 0; i < n_ctx; ++i)
+        if (!ctxs[i]) return fail(MPCR_EINVAL, "null context");
+    int rc = MPCR_OK;
+    std::vector<int> saved(n_ctx);
+    for (uint32_t i = 0; i < n_ctx; ++i) saved[i] = ctxs[i]->append;
+    for (uint32_t i = 0; i < n_ctx && rc == MPCR_OK; ++i) {
+        ctxs[i]->append = i == 0 ? 0 : 1;    // the first table zeroes the count, the others append behind it
+        rc = mpcr_scan(ctxs[i], h_contigs, n_contigs, d_plane2, d_plane4, d_valid, plane_origin, plane_bases, shard_begin,
+                       shard_end, d_hits, capacity, d_count, stream);
+    }
+    for (uint32_t i = 0; i < n_ctx; ++i) ctxs[i]->append = saved[i];
+    if (rc) return rc;
+    if (sort && capacity >= 2) {
+        rc = mpcr_sort_hits_dev(ctxs[0], d_hits, d_count, capacity, n_hint, stream);
+        if (rc) return rc;
+    }
+    if (h_count) {
+        GUARD(ctxs[0]);
+        CU(cudaMemcpyAsync(h_count, d_count, sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+    }
     return MPCR_OK;
 }
 

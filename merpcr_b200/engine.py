@@ -199,6 +199,7 @@ class MerPCR:
         self._pinned_hits = None  # D2H staging of the hit list
         self._copy_stream = None  # upload_and_scan: the H2D copies run beside pack + scan
         self._host_stage = None   # pinned staging buffers of the host-side nibble packer
+        self._count_host = None   # pinned landing place of a step's hit count
         # host-resident sequence goes over PCIe as packed nibbles (0.5 byte/base) unless switched off
         self.host_pack = os.environ.get("MPCR_HOST_PACK", "1") not in ("0", "")
         try:
@@ -206,6 +207,9 @@ class MerPCR:
         except AttributeError:  # pragma: no cover
             cpus = os.cpu_count() or 1
         self._pack_threads = max(1, cpus // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+        self.hybrid_wire = os.environ.get("MPCR_HYBRID_WIRE", "1") not in ("0", "")
+        self._pack_rate = 50e9    # bases / s the host packer sustains (refined while it runs)
+        self._h2d_rate = 50e9     # bytes / s of the host -> device link (PCIe Gen5 x16 moves ~55 GB/s)
         self._ctx_exts = []       # extended tables of exact, candidate-heavy searches (mpcr_ctx_set_seed_extension)
         self._create_ctx()
         # parsed STS lines kept so the table can be re-encoded if a sequence brings an unusual alphabet
@@ -813,10 +817,19 @@ class MerPCR:
             hstage = self._host_stage
         try:
             k, kn, h2d, pending, done_to, deferred, pack_s = 0, 0, 0, 0, sh.begin, None, 0.0
+            # Hybrid wire format (pinned sources only): the host cores pack at about the rate the link carries ASCII, so
+            # neither route alone beats ~56 ms for a human genome.  Both together do: a piece is packed only while the copy
+            # engine still has at least most of a pack's duration of work queued (packing then costs no wall clock and
+            # halves the piece's bytes); when the engine is about to run dry the next piece goes up as ASCII at once.
+            h2d_rate, busy_until = self._h2d_rate, time.perf_counter()
             for ci, a, b, src, last in self._pieces(layout, seqs, sh, chunk):
                 on_host = src.device.type == "cpu"
                 done = False
-                if on_host and use_nibbles:
+                pack_it = on_host and use_nibbles
+                if pack_it and gpu and self.hybrid_wire and src.is_pinned():
+                    backlog = busy_until - time.perf_counter()
+                    pack_it = backlog >= 0.7 * (b - a) / self._pack_rate
+                if pack_it:
                     slot = kn % n_stage
                     if gpu and kn >= n_stage:
                         hfree[slot].synchronize()              # the copy that last read this staging buffer is done
@@ -824,7 +837,10 @@ class MerPCR:
                     t_pack = time.perf_counter()
                     rc = int(lib.mpcr_host_pack_nibbles(src.data_ptr(), b - a, lut.ctypes.data, hstage[slot].data_ptr(),
                                                         self._pack_threads))
-                    pack_s += time.perf_counter() - t_pack
+                    dt_pack = time.perf_counter() - t_pack
+                    pack_s += dt_pack
+                    if b - a >= (1 << 22):     # running estimate of the packer's rate (bases / s) on this host
+                        self._pack_rate = 0.7 * self._pack_rate + 0.3 * (b - a) / max(dt_pack, 1e-6)
                     if rc < 0:
                         raise ValueError("mpcr_host_pack_nibbles: bad argument")
                     if rc == 0:
@@ -833,6 +849,7 @@ class MerPCR:
                             with torch.cuda.stream(copy):
                                 sh.plane4[off: off + nb].copy_(hstage[slot][:nb], non_blocking=True)
                             hfree[slot].record(copy)
+                            busy_until = max(busy_until, time.perf_counter()) + nb / h2d_rate
                         else:
                             sh.plane4[off: off + nb].copy_(hstage[slot][:nb])
                         kn += 1
@@ -857,6 +874,7 @@ class MerPCR:
                         with torch.cuda.stream(copy):
                             buf.copy_(src, non_blocking=True)
                         copied[slot].record(copy)
+                        busy_until = max(busy_until, time.perf_counter()) + (b - a) / h2d_rate
                         h2d += b - a
                         src = buf
                     if deferred:                                   # the finished contig is scanned while this copy runs
@@ -925,29 +943,27 @@ class MerPCR:
             sh.count = torch.zeros(1, dtype=torch.int64, device=self._tdev)
         isz = _capi.HIT_DTYPE.itemsize
         cap = 1 << 16 if sh.hits is None else sh.hits.numel() // isz
+        import ctypes as C
         ctxs = self._all_ctxs()
         stream = self._stream()
-        try:
-            for ctx in ctxs:    # every table appends behind the previous one's hits; one count, read once
-                self._be.check(lib.mpcr_ctx_set_append(ctx, 1))
-            while True:
-                if sh.hits is None or sh.hits.numel() < cap * isz:
-                    sh.hits = torch.empty(cap * isz, dtype=torch.uint8, device=self._tdev)
-                sh.count.zero_()
-                for ctx in ctxs:
-                    self._be.check(lib.mpcr_scan(ctx, contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
-                                                 sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.alloc, sh.begin,
-                                                 sh.end, sh.hits.data_ptr(), cap, sh.count.data_ptr(), stream))
-                if sort:        # queued right behind the scan: the count is read on the device
-                    self._be.check(lib.mpcr_sort_hits_dev(self._ctx, sh.hits.data_ptr(), sh.count.data_ptr(), cap,
-                                                          sh.last_n, stream))
-                need = int(sh.count.item())     # the one host round trip of a step (synchronises the stream)
-                if need <= cap:
-                    break
-                cap = max(need, 2 * cap)        # nothing is ever truncated: scan again with room
-        finally:
-            for ctx in ctxs:
-                lib.mpcr_ctx_set_append(ctx, 0)
+        arr = (C.c_void_p * len(ctxs))(*[c.value if hasattr(c, "value") else c for c in ctxs])
+        if self._count_host is None:    # where the one 8-byte read-back of a step lands
+            self._count_host = torch.zeros(1, dtype=torch.int64)
+            if self._tdev.type == "cuda":
+                self._count_host = self._count_host.pin_memory()
+        while True:
+            if sh.hits is None or sh.hits.numel() < cap * isz:
+                sh.hits = torch.empty(cap * isz, dtype=torch.uint8, device=self._tdev)
+            # one call per step: every table's scan + verify, the sort (count read on the device) and the read-back of
+            # the count, queued back to back; returns when the stream has drained
+            self._be.check(lib.mpcr_scan_sorted(arr, len(ctxs), contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
+                                                sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.alloc, sh.begin,
+                                                sh.end, sh.hits.data_ptr(), cap, sh.count.data_ptr(),
+                                                self._count_host.data_ptr(), sh.last_n, 1 if sort else 0, stream))
+            need = int(self._count_host[0])
+            if need <= cap:
+                break
+            cap = max(need, 2 * cap)        # nothing is ever truncated: scan again with room
         self.last_scan_ms = sum(float(lib.mpcr_last_scan_ms(ctx)) for ctx in ctxs)
         sh.last_n = need
         return sh.hits, need

@@ -398,4 +398,20 @@ int mpcr_sort_hits_dev(mpcr_ctx* c, mpcr_hit* hits, const uint64_t* count, uint6
     return mpcr_sort_hits(c, hits, *count < capacity ? *count : capacity, st);
 }
 
+int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* contigs, uint32_t n_contigs, const void* p2,
+                     const void* p4, const void* valid, uint64_t origin, uint64_t plane_bases, uint64_t sb, uint64_t se,
+                     mpcr_hit* hits, uint64_t capacity, uint64_t* count, uint64_t* h_count, uint64_t, int sort, void* st) {
+    if (!ctxs || n_ctx == 0 || !count) return fail(MPCR_EINVAL, "null argument");
+    for (uint32_t i = 0; i < n_ctx; ++i) {
+        const int saved = ctxs[i]->append;
+        ctxs[i]->append = i == 0 ? 0 : 1;
+        const int rc = mpcr_scan(ctxs[i], contigs, n_contigs, p2, p4, valid, origin, plane_bases, sb, se, hits, capacity, count, st);
+        ctxs[i]->append = saved;
+        if (rc) return rc;
+    }
+    if (sort) mpcr_sort_hits(ctxs[0], hits, *count < capacity ? *count : capacity, st);
+    if (h_count) *h_count = *count;
+    return MPCR_OK;
+}
+
 }  // extern "C"
