@@ -980,8 +980,13 @@ __device__ __forceinline__ void verify_body(const ScanArgs& a) {
     // together), takes the first one that still has work -- starting from a lane that differs between the warps that share
     // the window -- drains it, and looks again.  A fresh look per list costs one round trip; walking a stale mask cost
     // one round trip per ALREADY DRAINED list, 32 in a row, which was most of this kernel's time on short survivor lists.
+    // A warp drains its own window of 32 sub-lists (every sub-list lies in the window of 1/8 of the warps) and helps with
+    // the other windows only when its own turned out to be heavy: on light runs every window is equally light, and
+    // 9472 warps polling all 256 control lines cost more L2 round trips on those few hot lines than the work itself.
     const uint32_t rot = (warp_id / kSurvLists) & 31u;
+    uint32_t grabs = 0;
     for (uint32_t round = 0; round < kSurvLists / 32; ++round) {
+      if (round > 0 && grabs < 2) break;
       const uint32_t my_list = (warp_id + 32 * round + lane) & (kSurvLists - 1u);
       const uint32_t* my_ctl = a.surv_ctl + my_list * kSurvCtlStride;
       const uint32_t my_n = min(__ldcg(my_ctl), a.surv_cap);      // final: the scanner has finished
@@ -998,6 +1003,7 @@ __device__ __forceinline__ void verify_body(const ScanArgs& a) {
             if (lane == 0) first = __ldcg(ctl + 1) < n ? atomicAdd(ctl + 1, kGrab) : n;   // look before touching the line
             first = __shfl_sync(0xffffffffu, first, 0);
             if (first >= n) break;
+            ++grabs;
           for (uint32_t idx = first + group; idx < min(first + kGrab, n); idx += kGroups) {
             const Survivor sv = surv[idx];
             const TileDesc td = a.tiles[sv.tile];
@@ -1080,14 +1086,16 @@ __device__ __noinline__ void tie_heap_sort(mpcr_hit* h, uint64_t m) {
     }
 }
 
-__global__ void __launch_bounds__(256) order_ties(const mpcr_hit* __restrict__ in, mpcr_hit* __restrict__ hits,
-                                                  uint64_t n_host, const unsigned long long* d_n, uint32_t skip_upto,
+__global__ void __launch_bounds__(256) order_ties(const mpcr_hit* __restrict__ in_big, const mpcr_hit* __restrict__ in_small,
+                                                  mpcr_hit* __restrict__ hits, uint64_t n_host,
+                                                  const unsigned long long* d_n, uint32_t small_upto,
                                                   LongRun* __restrict__ queue,
                                                   uint32_t* __restrict__ queue_ctl /* [0] entries, [1] cursor */) {
-    // `in` is where the radix passes left the records (the hit buffer itself, or the sort's scratch buffer after an
-    // odd number of passes): the thread that owns a run moves it home first, so no separate copy pass is needed
+    // `in` is where the passes over (pos1, contig) left the records -- the scratch buffer for a list short enough for
+    // sort_small_cta, else the hit buffer itself or the scratch buffer after an odd number of radix passes: the thread
+    // that owns a run moves it home first, so no separate copy pass is needed
     const uint64_t n = sort_count(d_n, n_host);
-    if (n <= skip_upto) return;   // rank_sort_small ordered this list completely
+    const mpcr_hit* __restrict__ in = n <= small_upto ? in_small : in_big;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const mpcr_hit h0 = in[i];
@@ -1893,34 +1901,31 @@ static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const 
         CU(cudaMemsetAsync(c->d_long_runs + kLongRunQueue, 0, 16, st));   // order_long_runs re-zeroes them itself
     }
     Item<6>*hits = (Item<6>*)d_hits, *tmp = (Item<6>*)c->d_sort_tmp;
-    // short lists: one rank-sort launch (+ the move home) instead of the cooperative radix passes.  Launched when the
-    // count is known to be short, or unknown (hint 0) and the buffer itself is not huge.
-    uint32_t skip = 0;
-    const uint64_t n_known = d_n ? n_hint : n_host;
-    if (n_known ? n_known <= kRankSortMax : true) {
-        const uint64_t grid_n = n_host < kRankSortMax ? n_host : kRankSortMax;
-        rank_sort_small<<<(uint32_t)((grid_n + kRankThreads / kRankSplit - 1) / (kRankThreads / kRankSplit)), kRankThreads, 0, st>>>(
-            hits, tmp, d_n, n_host);
-        rank_sort_copy_back<<<(uint32_t)((grid_n + 255) / 256), 256, 0, st>>>(tmp, hits, d_n, n_host);
-        c->launches += 2;
-        skip = kRankSortMax;
-        if (!d_n) return cudaGetLastError() == cudaSuccess ? MPCR_OK : fail(MPCR_ECUDA, "rank sort launch failed");
-        if (n_host <= kRankSortMax) {   // the buffer cannot hold a longer list: nothing else to launch
-            CU(cudaGetLastError());
-            return MPCR_OK;
-        }
-    }
     // LSD radix passes over pos1 then contig (fields 1, 0), digits bounded by the layout of the last scan; the rest of
     // the key (hash_off, rec, rank) only matters inside runs of equal (contig, pos1), which order_ties settles
     PassDesc passes[24];
     int np = 0;
     np = add_passes(passes, np, 1, c->lay_max_len ? c->lay_max_len : 0x7FFFFFFFull);
     np = add_passes(passes, np, 0, c->lay_contigs ? c->lay_contigs - 1 : 0xFFFFFFFFull);
+    // short lists: ONE CTA sorts them in shared memory (records land in the scratch buffer, in key order).  Launched
+    // when the count is known to be short, or unknown (hint 0).
+    uint32_t small = 0;
+    const uint64_t n_known = d_n ? n_hint : n_host;
+    if (n_known <= kSmallSortMax) {   // 0 = unknown
+        PassList pl;
+        pl.n = np;
+        for (int p = 0; p < np; ++p) pl.p[p] = passes[p];
+        CU(cudaFuncSetAttribute(sort_small_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSortSmem));
+        sort_small_cta<<<1, kSmallSortThreads, kSmallSortSmem, st>>>(hits, tmp, d_n, n_host, pl);
+        c->launches++;
+        small = kSmallSortMax;
+    }
     Item<6>* sorted = hits;
-    c->launches += radix_sort<6>(hits, tmp, n_host, d_n, skip, passes, np, c->d_counts, st, &sorted, &skip);
+    if (!(small && n_host <= kSmallSortMax))   // (a buffer that short cannot hold a longer list)
+        c->launches += radix_sort<6>(hits, tmp, n_host, d_n, small, passes, np, c->d_counts, st, &sorted, &small);
     uint32_t* queue_ctl = reinterpret_cast<uint32_t*>(c->d_long_runs + kLongRunQueue);
-    order_ties<<<(uint32_t)((n_host + 255) / 256), 256, 0, st>>>((const mpcr_hit*)sorted, d_hits, n_host, d_n, skip,
-                                                                 c->d_long_runs, queue_ctl);
+    order_ties<<<(uint32_t)((n_host + 255) / 256), 256, 0, st>>>((const mpcr_hit*)sorted, (const mpcr_hit*)tmp, d_hits, n_host,
+                                                                 d_n, small, c->d_long_runs, queue_ctl);
     order_long_runs<<<(uint32_t)c->sm_count, 256, 0, st>>>(d_hits, c->d_long_runs, queue_ctl);
     c->launches += 2;
     CU(cudaGetLastError());

@@ -252,60 +252,83 @@ inline int radix_sort(Item<NF>* d_a, Item<NF>* d_b, uint64_t n_host, const unsig
     return launches;
 }
 
-// Short hit lists (a rank of a multi-GPU run holds ~10^4 hits): ONE launch instead of five cooperative passes.
-// Every record's final position is the number of records with a smaller order key -- kRankSplit threads share the
-// count for one record, the keys of all records stream through shared memory in tiles.  The key is the complete
-// order (contig, pos1 | hash_off, rec, rank), which no two hits share, so ranks are a permutation and no tie pass
-// is needed afterwards.  Records go to `out` (the sort's scratch buffer); rank_sort_copy_back moves them home.
-static constexpr uint32_t kRankSortMax = 12288;     // n^2 key compares: 24 us at this size on 148 SMs
-static constexpr int kRankSplit = 8;                // threads per record
-static constexpr int kRankThreads = 256;
-static constexpr int kRankTile = 1024;              // keys per shared-memory tile (16 KB)
+// Short hit lists (a rank of a multi-GPU run holds ~10^4 hits): ONE CTA sorts them in shared memory instead of five
+// cooperative passes over the grid.  The 64-bit keys (contig << 32 | pos1) stay where they are; what moves through
+// the stable LSD passes are 16-bit record indices (the same match_any ranking as rs_scatter, 1024 records per round).
+// The records are then gathered into `out` (the sort's scratch buffer) in key order; order_ties settles runs of equal
+// (contig, pos1) and moves the records home.  (A rank sort -- every record counts the records with a smaller key --
+// was measured first: 88 us for 10^4 hits, n^2 compares; this is ~10 us.)
+static constexpr uint32_t kSmallSortMax = 16384;
+static constexpr int kSmallSortThreads = 1024;
+static constexpr size_t kSmallSortSmem = (size_t)kSmallSortMax * (8 + 2 + 2);
 
-__device__ __forceinline__ void hit_order_key(const Item<6>& h, unsigned long long& a, unsigned long long& b) {
-    a = ((unsigned long long)h.f[0] << 32) | h.f[1];                                               // contig, pos1
-    b = ((unsigned long long)h.f[5] << 45) | ((unsigned long long)h.f[3] << 15) | h.f[4];          // hash_off, rec, rank
-}
-
-__global__ void __launch_bounds__(kRankThreads) rank_sort_small(const Item<6>* __restrict__ in, Item<6>* __restrict__ out,
-                                                                const unsigned long long* d_n, uint64_t n_host) {
-    __shared__ ulonglong2 keys[kRankTile];
+__global__ void __launch_bounds__(kSmallSortThreads, 1) sort_small_cta(const Item<6>* __restrict__ in, Item<6>* __restrict__ out,
+                                                                       const unsigned long long* d_n, uint64_t n_host,
+                                                                       PassList pl) {
+    extern __shared__ __align__(16) uint8_t small_smem[];
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(small_smem);
+    uint16_t* ia = reinterpret_cast<uint16_t*>(key + kSmallSortMax);
+    uint16_t* ib = ia + kSmallSortMax;
+    __shared__ uint32_t base[256];
+    __shared__ uint32_t tot[256];
+    __shared__ uint16_t wc[kSmallSortThreads / 32][256];
     const uint32_t n = (uint32_t)sort_count(d_n, n_host);
-    if (n > kRankSortMax || n < 2) return;
-    constexpr int kPerBlock = kRankThreads / kRankSplit;
-    const uint32_t first = blockIdx.x * kPerBlock;
-    if (first >= n) return;
-    const uint32_t i = first + threadIdx.x / kRankSplit, part = threadIdx.x % kRankSplit;
-    const bool act = i < n;
-    Item<6> mine{};
-    unsigned long long ka = 0, kb = 0;
-    if (act) { mine = in[i]; hit_order_key(mine, ka, kb); }
-    uint32_t rank = 0;
-    for (uint32_t t0 = 0; t0 < n; t0 += kRankTile) {
-        __syncthreads();
-        for (uint32_t k = threadIdx.x; k < kRankTile; k += kRankThreads) {
-            ulonglong2 v = make_ulonglong2(~0ull, ~0ull);   // padding never counts as smaller
-            if (t0 + k < n) { const Item<6> h = in[t0 + k]; hit_order_key(h, v.x, v.y); }
-            keys[k] = v;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int k = part; k < kRankTile; k += kRankSplit) {
-            const ulonglong2 v = keys[k];
-            rank += (v.x < ka || (v.x == ka && v.y < kb)) ? 1u : 0u;
-        }
+    if (n > kSmallSortMax || n == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (uint32_t i = tid; i < n; i += kSmallSortThreads) {
+        key[i] = ((unsigned long long)in[i].f[0] << 32) | in[i].f[1];
+        ia[i] = (uint16_t)i;
     }
+    __syncthreads();
+    uint16_t *src = ia, *dst = ib;
+    for (int p = 0; p < pl.n; ++p) {
+        const int shift = pl.p[p].shift + (pl.p[p].field == 0 ? 32 : 0);   // field 1 = pos1 (low half), 0 = contig
+        const uint32_t mask = pl.p[p].mask;
+        if (tid < 256) base[tid] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += kSmallSortThreads) atomicAdd(&base[(uint32_t)(key[src[i]] >> shift) & mask], 1u);
+        __syncthreads();
+        if (wid == 0) {   // exclusive scan of the 256 digit counts by one warp, 8 per lane
+            uint32_t v[8], sum = 0;
 #pragma unroll
-    for (int d = 1; d < kRankSplit; d <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
-    if (act && part == 0) out[rank] = mine;
-}
-
-__global__ void __launch_bounds__(256) rank_sort_copy_back(const Item<6>* __restrict__ in, Item<6>* __restrict__ out,
-                                                           const unsigned long long* d_n, uint64_t n_host) {
-    const uint32_t n = (uint32_t)sort_count(d_n, n_host);
-    if (n > kRankSortMax || n < 2) return;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i];
+            for (int k = 0; k < 8; ++k) { v[k] = base[8 * lane + k]; sum += v[k]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { base[8 * lane + k] = run; run += v[k]; }
+        }
+        __syncthreads();
+        for (uint32_t c0 = 0; c0 < n; c0 += kSmallSortThreads) {
+            for (int k = tid; k < (kSmallSortThreads / 32) * 256; k += kSmallSortThreads) (&wc[0][0])[k] = 0;
+            const uint32_t i = c0 + tid;
+            const bool act = i < n;
+            uint32_t d = 0x100u + (uint32_t)lane, me = 0;   // inactive lanes never match an active digit
+            if (act) { me = src[i]; d = (uint32_t)(key[me] >> shift) & mask; }
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            __syncthreads();
+            if (act && rank == 0) wc[wid][d] = (uint16_t)__popc(peers);
+            __syncthreads();
+            if (tid < 256) {   // records of digit tid in the warps before each warp
+                uint32_t run = 0;
+#pragma unroll 8
+                for (int w = 0; w < kSmallSortThreads / 32; ++w) { const uint32_t v = wc[w][tid]; wc[w][tid] = (uint16_t)run; run += v; }
+                tot[tid] = run;
+            }
+            __syncthreads();
+            if (act) dst[base[d] + wc[wid][d] + rank] = (uint16_t)me;
+            __syncthreads();
+            if (tid < 256) base[tid] += tot[tid];
+        }
+        __syncthreads();
+        uint16_t* t = src; src = dst; dst = t;
+    }
+    for (uint32_t j = tid; j < n; j += kSmallSortThreads) out[j] = in[src[j]];
 }
 
 // append the 8-bit digit passes needed to cover values in [0, max_value] of `field`

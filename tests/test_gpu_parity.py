@@ -557,7 +557,7 @@ def test_true_strands_option_on_device():
     _true_strands_check(MerPCR, _records)
 
 
-@pytest.mark.parametrize("n", [2, 37, 1000, 12288, 12289, 70000, 300000])
+@pytest.mark.parametrize("n", [2, 37, 1000, 1024, 1025, 16384, 16385, 70000, 300000])
 def test_sort_with_the_count_on_the_device(n):
     """mpcr_sort_hits_dev (count read on the device, rank sort for short lists, radix passes + tie kernels for long
     ones, any hint) and mpcr_sort_hits order random hit lists -- many ties on (contig, pos1), one run of several
