@@ -564,14 +564,25 @@ def run_b200(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         algo_bytes = ALGO_BYTES_PER_BP * my_bp + ALGO_BYTES_PER_HIT * n_hits
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same workload)
-        traffic = None
+        # DRAM bytes per launch of the dominant kernel: from the committed `ncu --set full` capture of the same workload
+        # (a number taken under a profiler cannot be measured inside this run).  It is only quoted while that capture
+        # still describes the kernel being timed: same scale, whole genome on one GPU, and a kernel duration within 5 %
+        # of the one measured here; otherwise null, with the reason.
+        traffic, traffic_source = None, None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "scan_kernel_ncu.json")))
-            if abs(args.scale - float(prof.get("scale", 1.0))) < 1e-9:
+            dur = float(prof.get("duration_ms", 0.0))
+            if abs(args.scale - float(prof.get("scale", 1.0))) > 1e-9 or world != 1 or args.as_shard:
+                traffic_source = "none: the committed capture is of the whole genome on one GPU at scale 1"
+            elif kern_ms <= 0 or abs(dur - kern_ms) > 0.05 * kern_ms:
+                traffic_source = (f"none: committed capture ran {dur:.3f} ms per launch, this run {kern_ms:.3f} ms "
+                                  "(the kernel changed; re-capture with scripts/gpu/profile.sh)")
+            else:
                 traffic = float(prof["dram_bytes_read"]) + float(prof["dram_bytes_write"])
-        except Exception:  # noqa: BLE001
-            pass
+                traffic_source = ("profiles/scan_kernel_ncu.json (ncu --set full capture of this kernel, "
+                                  f"{dur:.3f} ms per launch there vs {kern_ms:.3f} ms here)")
+        except Exception as e:  # noqa: BLE001
+            traffic_source = f"none: {e}"
         line = dict(
             metric=METRIC, value=value, unit="Gbp/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_per_step, higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None,
@@ -588,7 +599,7 @@ def run_b200(args):
                         numa_node=numa,
                         planted_found=planted_ok, sorted=sorted_ok),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,
-                          traffic=traffic, kernel="scan_kernel", kernel_ms=kern_ms,
+                          traffic=traffic, traffic_source=traffic_source, kernel="scan_kernel", kernel_ms=kern_ms,
                           verify_kernel_ms=float(np.mean(verify_ms)),
                           algorithmic_bytes_per_launch=algo_bytes,
                           peak_source="MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650"),

@@ -119,6 +119,12 @@ struct mpcr_ctx {
     bool ctl_dirty = false;     // the scanner's control words were left non-zero (debug runs skip the verifier)
     uint8_t lut_host[256] = {}; // what d_lut holds (re-uploaded only when the caller's LUT changes)
     bool lut_valid = false;
+    // bucket sort of short hit lists (mpcr_sort.cuh): contig table of the last layout on the device + scratch
+    unsigned long long* d_contig_g = nullptr;
+    size_t contig_g_cap = 0;
+    uint32_t n_contig_g = 0;
+    uint64_t genome_end = 0;    // padded coordinate behind the last contig of the last layout
+    uint32_t* d_bsort = nullptr;   // [cnt kSortBuckets][off kSortBuckets + 1][pad][slot kBucketSortMax][flag]
     uint64_t tiles_need = 0;    // plane extent (bases from the origin) the cached descriptors read up to
     int64_t tiles_min = 0;      // ... and down to
 };
@@ -1086,16 +1092,14 @@ __device__ __noinline__ void tie_heap_sort(mpcr_hit* h, uint64_t m) {
     }
 }
 
-__global__ void __launch_bounds__(256) order_ties(const mpcr_hit* __restrict__ in_big, const mpcr_hit* __restrict__ in_small,
-                                                  mpcr_hit* __restrict__ hits, uint64_t n_host,
-                                                  const unsigned long long* d_n, uint32_t small_upto,
-                                                  LongRun* __restrict__ queue,
+__global__ void __launch_bounds__(256) order_ties(const mpcr_hit* __restrict__ in, mpcr_hit* __restrict__ hits,
+                                                  uint64_t n_host, const unsigned long long* d_n, uint32_t skip_upto,
+                                                  const uint32_t* __restrict__ skip_off, LongRun* __restrict__ queue,
                                                   uint32_t* __restrict__ queue_ctl /* [0] entries, [1] cursor */) {
-    // `in` is where the passes over (pos1, contig) left the records -- the scratch buffer for a list short enough for
-    // sort_small_cta, else the hit buffer itself or the scratch buffer after an odd number of radix passes: the thread
-    // that owns a run moves it home first, so no separate copy pass is needed
+    // `in` is where the radix passes left the records (the hit buffer itself, or the sort's scratch buffer after an
+    // odd number of passes): the thread that owns a run moves it home first, so no separate copy pass is needed
     const uint64_t n = sort_count(d_n, n_host);
-    const mpcr_hit* __restrict__ in = n <= small_upto ? in_small : in_big;
+    if (n <= skip_upto && !(skip_off && *skip_off)) return;   // the bucket sort ordered this list completely
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const mpcr_hit h0 = in[i];
@@ -1247,6 +1251,8 @@ void mpcr_ctx_destroy(mpcr_ctx* c) {
     if (c->ev2) cudaEventDestroy(c->ev2);
     cudaFree(c->d_surv);
     cudaFree(c->d_surv_ctl);
+    cudaFree(c->d_contig_g);
+    cudaFree(c->d_bsort);
     delete c;
 }
 
@@ -1538,7 +1544,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         const uint32_t nblk = (n_rec + kSortItemsPerBlock - 1) / kSortItemsPerBlock;
         rc = ensure((void**)&c->d_counts, &c->counts_cap, (size_t)256 * nblk * 4);
         if (rc) goto done;
-        c->launches += radix_sort<2>(d_pairs, d_pairs2, n_rec, nullptr, 0, passes, np, c->d_counts, st, &d_sorted);
+        c->launches += radix_sort<2>(d_pairs, d_pairs2, n_rec, nullptr, 0, nullptr, passes, np, c->d_counts, st, &d_sorted);
         CUG(cudaGetLastError());
         // slot table: direct-indexed by the key while 4^W slots stay L2-sized (W <= 11 -> 64 MiB), else open
         // addressing at load <= 1/8 (distinct seeds <= min(records, 4^W))
@@ -1741,6 +1747,17 @@ static int build_tiles_impl(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_
     if (rc) return rc;
     if (!tiles.empty())
         CU(cudaMemcpyAsync(c->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+    // the contig table of this layout (global start coordinates): what the bucket sort of the hits slices on
+    std::vector<unsigned long long> cg(n_contigs ? n_contigs : 1, 0ull);
+    c->genome_end = 0;
+    for (uint32_t i = 0; i < n_contigs; ++i) {
+        cg[i] = contigs[i].gstart;
+        if (contigs[i].gstart + contigs[i].length > c->genome_end) c->genome_end = contigs[i].gstart + contigs[i].length;
+    }
+    rc = ensure((void**)&c->d_contig_g, &c->contig_g_cap, cg.size() * sizeof(unsigned long long));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_contig_g, cg.data(), cg.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    c->n_contig_g = n_contigs;
     CU(cudaStreamSynchronize(st));  // `tiles` is pageable host memory going out of scope
     c->tiles_sig = sig;
     return MPCR_OK;
@@ -1907,25 +1924,43 @@ static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const 
     int np = 0;
     np = add_passes(passes, np, 1, c->lay_max_len ? c->lay_max_len : 0x7FFFFFFFull);
     np = add_passes(passes, np, 0, c->lay_contigs ? c->lay_contigs - 1 : 0xFFFFFFFFull);
-    // short lists: ONE CTA sorts them in shared memory (records land in the scratch buffer, in key order).  Launched
-    // when the count is known to be short, or unknown (hint 0).
-    uint32_t small = 0;
+    // Lists of up to 2^17 hits: bucket sort on the global coordinate (four small launches, complete order).  Launched when
+    // the count is known to be that short, or unknown (hint 0), and a layout is known; a list that piles up in one
+    // slice raises the fall-back flag on the device and the radix passes below take over.
+    uint32_t skip = 0;
+    const uint32_t* skip_off = nullptr;
     const uint64_t n_known = d_n ? n_hint : n_host;
-    if (n_known <= kSmallSortMax) {   // 0 = unknown
-        PassList pl;
-        pl.n = np;
-        for (int p = 0; p < np; ++p) pl.p[p] = passes[p];
-        CU(cudaFuncSetAttribute(sort_small_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSortSmem));
-        sort_small_cta<<<1, kSmallSortThreads, kSmallSortSmem, st>>>(hits, tmp, d_n, n_host, pl);
-        c->launches++;
-        small = kSmallSortMax;
+    if (n_known <= kBucketSortMax && c->d_contig_g && c->genome_end) {   // n_known 0 = unknown
+        const size_t words = (size_t)kSortBuckets * 2 + 2 + kBucketSortMax + 2;
+        if (!c->d_bsort) {
+            CU(cudaMalloc(&c->d_bsort, words * 4));
+            CU(cudaMemsetAsync(c->d_bsort, 0, words * 4, st));   // the counters are re-zeroed by bsort_finish itself
+        }
+        BucketSortArgs b;
+        b.contig_g = c->d_contig_g;
+        b.n_contigs = c->n_contig_g;
+        b.g_lo = c->tiles_sb < c->genome_end ? c->tiles_sb : 0;
+        const uint64_t hi = c->tiles_se < c->genome_end ? c->tiles_se : c->genome_end;
+        b.span = hi > b.g_lo ? hi - b.g_lo : 1;
+        b.cnt = c->d_bsort;
+        b.off = b.cnt + kSortBuckets;
+        b.slot = b.off + kSortBuckets + 2;
+        b.fallback = b.slot + kBucketSortMax;
+        const uint64_t grid_n = n_host < kBucketSortMax ? n_host : kBucketSortMax;
+        const uint32_t gb = (uint32_t)((grid_n + 255) / 256);
+        bsort_count<<<gb, 256, 0, st>>>(hits, d_n, n_host, b);
+        bsort_scan<<<1, 1024, 0, st>>>(d_n, n_host, b);
+        bsort_scatter<<<gb, 256, 0, st>>>(hits, tmp, d_n, n_host, b);
+        bsort_finish<<<kSortBuckets / 256, 256, 0, st>>>(tmp, hits, b);
+        c->launches += 4;
+        skip = kBucketSortMax;
+        skip_off = b.fallback;
     }
     Item<6>* sorted = hits;
-    if (!(small && n_host <= kSmallSortMax))   // (a buffer that short cannot hold a longer list)
-        c->launches += radix_sort<6>(hits, tmp, n_host, d_n, small, passes, np, c->d_counts, st, &sorted, &small);
+    c->launches += radix_sort<6>(hits, tmp, n_host, d_n, skip, skip_off, passes, np, c->d_counts, st, &sorted, &skip);
     uint32_t* queue_ctl = reinterpret_cast<uint32_t*>(c->d_long_runs + kLongRunQueue);
-    order_ties<<<(uint32_t)((n_host + 255) / 256), 256, 0, st>>>((const mpcr_hit*)sorted, (const mpcr_hit*)tmp, d_hits, n_host,
-                                                                 d_n, small, c->d_long_runs, queue_ctl);
+    order_ties<<<(uint32_t)((n_host + 255) / 256), 256, 0, st>>>((const mpcr_hit*)sorted, d_hits, n_host, d_n, skip, skip_off,
+                                                                 c->d_long_runs, queue_ctl);
     order_long_runs<<<(uint32_t)c->sm_count, 256, 0, st>>>(d_hits, c->d_long_runs, queue_ctl);
     c->launches += 2;
     CU(cudaGetLastError());

@@ -138,12 +138,13 @@ struct PassList {
 template <int NF>
 __global__ void __launch_bounds__(kSortThreads) rs_sort_fused(Item<NF>* a, Item<NF>* b, uint32_t n_host,
                                                               const unsigned long long* d_n, uint32_t skip_upto,
-                                                              PassList pl,
+                                                              const uint32_t* __restrict__ skip_off, PassList pl,
                                                               uint32_t* __restrict__ counts /* 256 * gridDim.x */) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const uint32_t n = (uint32_t)sort_count(d_n, n_host);
-    if (n <= skip_upto) return;   // the whole grid takes this branch together (lists that short were rank-sorted)
+    // lists that short were bucket-sorted, unless that sort raised its fall-back flag (the whole grid branches together)
+    if (n <= skip_upto && !(skip_off && *reinterpret_cast<const volatile uint32_t*>(skip_off))) return;
     __shared__ uint32_t hist[256];
     __shared__ uint32_t running[256];
     __shared__ uint32_t wc[kSortThreads / 32][256];
@@ -215,12 +216,13 @@ __global__ void __launch_bounds__(kSortThreads) rs_sort_fused(Item<NF>* a, Item<
 // Host driver: sorts the records of d_a using d_b as the ping-pong buffer.  n_host is the record count, or -- with
 // d_n != nullptr -- the capacity the grids are sized for while the true count min(*d_n, n_host) is read on the device.
 // The result is left in *result (d_a after an even number of passes, d_b after an odd one: no copy back; the caller's
-// next kernel reads from there).  Lists of up to skip_upto records are left untouched (see rank_sort_small).
+// next kernel reads from there).  Lists of up to skip_upto records are left untouched unless *skip_off is set (see the
+// bucket sort below).
 // d_counts must hold 256 * ceil(n_host / kSortItemsPerBlock) uint32.  Returns the number of kernels launched.
 template <int NF>
 inline int radix_sort(Item<NF>* d_a, Item<NF>* d_b, uint64_t n_host, const unsigned long long* d_n, uint32_t skip_upto,
-                      const PassDesc* passes, int npass, uint32_t* d_counts, cudaStream_t st, Item<NF>** result,
-                      uint32_t* skipped_upto = nullptr) {
+                      const uint32_t* skip_off, const PassDesc* passes, int npass, uint32_t* d_counts, cudaStream_t st,
+                      Item<NF>** result, uint32_t* skipped_upto = nullptr) {
     *result = d_a;
     if (skipped_upto) *skipped_upto = skip_upto;
     if (n_host < 2 || npass == 0) return 0;
@@ -231,7 +233,7 @@ inline int radix_sort(Item<NF>* d_a, Item<NF>* d_b, uint64_t n_host, const unsig
         pl.n = npass;
         for (int p = 0; p < npass; ++p) pl.p[p] = passes[p];
         uint32_t n32 = (uint32_t)n_host;
-        void* args[] = {&d_a, &d_b, &n32, &d_n, &skip_upto, &pl, &d_counts};
+        void* args[] = {&d_a, &d_b, &n32, &d_n, &skip_upto, &skip_off, &pl, &d_counts};
         if (cudaLaunchCooperativeKernel((const void*)rs_sort_fused<NF>, dim3(nblk), dim3(kSortThreads), args, 0, st) ==
             cudaSuccess)
             return 1;
@@ -252,83 +254,115 @@ inline int radix_sort(Item<NF>* d_a, Item<NF>* d_b, uint64_t n_host, const unsig
     return launches;
 }
 
-// Short hit lists (a rank of a multi-GPU run holds ~10^4 hits): ONE CTA sorts them in shared memory instead of five
-// cooperative passes over the grid.  The 64-bit keys (contig << 32 | pos1) stay where they are; what moves through
-// the stable LSD passes are 16-bit record indices (the same match_any ranking as rs_scatter, 1024 records per round).
-// The records are then gathered into `out` (the sort's scratch buffer) in key order; order_ties settles runs of equal
-// (contig, pos1) and moves the records home.  (A rank sort -- every record counts the records with a smaller key --
-// was measured first: 88 us for 10^4 hits, n^2 compares; this is ~10 us.)
-static constexpr uint32_t kSmallSortMax = 16384;
-static constexpr int kSmallSortThreads = 1024;
-static constexpr size_t kSmallSortSmem = (size_t)kSmallSortMax * (8 + 2 + 2);
+// Hit lists of up to 2^17 records (a human-sized scan yields ~10^5 hits, a rank of an 8-GPU run ~10^4): a bucket sort
+// on the hits' GLOBAL coordinate instead of radix passes.  Hits spread over the scanned range, so 2^14 equal slices of
+// that range hold a handful of records each: count per slice (one atomic per record), one-CTA scan of the counts,
+// scatter, and one thread per slice puts its few records into the complete order (contig, pos1, hash_off, rec, rank)
+// -- no tie pass needed afterwards.  Four small launches, ~15 us, against ~110 us for five cooperative radix passes
+// (a rank sort and a one-CTA shared-memory radix were measured first: 88 us and 161 us for 10^4 hits).  A list that
+// piles up in one slice (> kBucketMaxFill records: repeats, an N-run in IUPAC mode) raises *fallback and is left to
+// the radix passes, which check the flag on the device.
+static constexpr uint32_t kBucketSortMax = 1u << 17;
+static constexpr uint32_t kSortBuckets = 1u << 14;
+static constexpr uint32_t kBucketMaxFill = 64;
 
-__global__ void __launch_bounds__(kSmallSortThreads, 1) sort_small_cta(const Item<6>* __restrict__ in, Item<6>* __restrict__ out,
-                                                                       const unsigned long long* d_n, uint64_t n_host,
-                                                                       PassList pl) {
-    extern __shared__ __align__(16) uint8_t small_smem[];
-    unsigned long long* key = reinterpret_cast<unsigned long long*>(small_smem);
-    uint16_t* ia = reinterpret_cast<uint16_t*>(key + kSmallSortMax);
-    uint16_t* ib = ia + kSmallSortMax;
-    __shared__ uint32_t base[256];
-    __shared__ uint32_t tot[256];
-    __shared__ uint16_t wc[kSmallSortThreads / 32][256];
-    const uint32_t n = (uint32_t)sort_count(d_n, n_host);
-    if (n > kSmallSortMax || n == 0) return;
+struct BucketSortArgs {
+    const unsigned long long* contig_g;   // global start coordinate of every contig
+    uint32_t n_contigs;
+    unsigned long long g_lo, span;        // scanned range [g_lo, g_lo + span)
+    uint32_t* cnt;                        // kSortBuckets counters (zero on entry, zeroed again by bsort_finish)
+    uint32_t* off;                        // kSortBuckets + 1 offsets
+    uint32_t* slot;                       // per record: position inside its slice << 14 | slice
+    uint32_t* fallback;                   // [0] 1: some slice is too full, the radix passes take over
+};
+
+__device__ __forceinline__ bool hit_less(const Item<6>& a, const Item<6>& b) {   // (contig, pos1, hash_off, rec, rank)
+    if (a.f[0] != b.f[0]) return a.f[0] < b.f[0];
+    if (a.f[1] != b.f[1]) return a.f[1] < b.f[1];
+    if (a.f[5] != b.f[5]) return a.f[5] < b.f[5];
+    if (a.f[3] != b.f[3]) return a.f[3] < b.f[3];
+    return a.f[4] < b.f[4];
+}
+
+__global__ void __launch_bounds__(256) bsort_count(const Item<6>* __restrict__ in, const unsigned long long* d_n, uint64_t n_host,
+                                                   BucketSortArgs b) {
+    const uint64_t n = sort_count(d_n, n_host);
+    if (n > kBucketSortMax) return;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t contig = in[i].f[0], pos1 = in[i].f[1];
+    unsigned long long g = (contig < b.n_contigs ? b.contig_g[contig] : 0ull) + pos1;
+    g = g > b.g_lo ? g - b.g_lo : 0ull;
+    unsigned long long s = b.span ? (g * kSortBuckets) / b.span : 0ull;   // monotone in (contig, pos1)
+    if (s >= kSortBuckets) s = kSortBuckets - 1;
+    const uint32_t at = atomicAdd(&b.cnt[(uint32_t)s], 1u);
+    b.slot[i] = (at << 14) | (uint32_t)s;
+}
+
+// exclusive scan of the kSortBuckets counters by one CTA of 1024 threads (16 each) + the too-full check
+__global__ void __launch_bounds__(1024) bsort_scan(const unsigned long long* d_n, uint64_t n_host, BucketSortArgs b) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t s_max;
+    const uint64_t n = sort_count(d_n, n_host);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (uint32_t i = tid; i < n; i += kSmallSortThreads) {
-        key[i] = ((unsigned long long)in[i].f[0] << 32) | in[i].f[1];
-        ia[i] = (uint16_t)i;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    constexpr int kPer = kSortBuckets / 1024;
+    uint32_t v[kPer], sum = 0, mx = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { v[k] = b.cnt[tid * kPer + k]; sum += v[k]; mx = max(mx, v[k]); }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    atomicMax(&s_max, mx);
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        warp_sums[lane] = wi - w;
     }
     __syncthreads();
-    uint16_t *src = ia, *dst = ib;
-    for (int p = 0; p < pl.n; ++p) {
-        const int shift = pl.p[p].shift + (pl.p[p].field == 0 ? 32 : 0);   // field 1 = pos1 (low half), 0 = contig
-        const uint32_t mask = pl.p[p].mask;
-        if (tid < 256) base[tid] = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < n; i += kSmallSortThreads) atomicAdd(&base[(uint32_t)(key[src[i]] >> shift) & mask], 1u);
-        __syncthreads();
-        if (wid == 0) {   // exclusive scan of the 256 digit counts by one warp, 8 per lane
-            uint32_t v[8], sum = 0;
+    uint32_t run = warp_sums[wid] + incl - sum;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { v[k] = base[8 * lane + k]; sum += v[k]; }
-            uint32_t incl = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            uint32_t run = incl - sum;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { base[8 * lane + k] = run; run += v[k]; }
-        }
-        __syncthreads();
-        for (uint32_t c0 = 0; c0 < n; c0 += kSmallSortThreads) {
-            for (int k = tid; k < (kSmallSortThreads / 32) * 256; k += kSmallSortThreads) (&wc[0][0])[k] = 0;
-            const uint32_t i = c0 + tid;
-            const bool act = i < n;
-            uint32_t d = 0x100u + (uint32_t)lane, me = 0;   // inactive lanes never match an active digit
-            if (act) { me = src[i]; d = (uint32_t)(key[me] >> shift) & mask; }
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            __syncthreads();
-            if (act && rank == 0) wc[wid][d] = (uint16_t)__popc(peers);
-            __syncthreads();
-            if (tid < 256) {   // records of digit tid in the warps before each warp
-                uint32_t run = 0;
-#pragma unroll 8
-                for (int w = 0; w < kSmallSortThreads / 32; ++w) { const uint32_t v = wc[w][tid]; wc[w][tid] = (uint16_t)run; run += v; }
-                tot[tid] = run;
-            }
-            __syncthreads();
-            if (act) dst[base[d] + wc[wid][d] + rank] = (uint16_t)me;
-            __syncthreads();
-            if (tid < 256) base[tid] += tot[tid];
-        }
-        __syncthreads();
-        uint16_t* t = src; src = dst; dst = t;
+    for (int k = 0; k < kPer; ++k) { b.off[tid * kPer + k] = run; run += v[k]; }
+    if (tid == 1023) b.off[kSortBuckets] = run;
+    if (tid == 0) b.fallback[0] = (n > kBucketSortMax || s_max > kBucketMaxFill) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) bsort_scatter(const Item<6>* __restrict__ in, Item<6>* __restrict__ out,
+                                                     const unsigned long long* d_n, uint64_t n_host, BucketSortArgs b) {
+    const uint64_t n = sort_count(d_n, n_host);
+    if (n > kBucketSortMax || b.fallback[0]) return;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t sl = b.slot[i];
+    out[b.off[sl & (kSortBuckets - 1u)] + (sl >> 14)] = in[i];
+}
+
+// one thread per slice: its records (in `tmp`) go home in the complete order; the counters are zeroed for the next sort
+__global__ void __launch_bounds__(256) bsort_finish(Item<6>* __restrict__ tmp, Item<6>* __restrict__ hits, BucketSortArgs b) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= kSortBuckets) return;
+    const uint32_t m = b.cnt[s];
+    b.cnt[s] = 0;
+    if (m == 0 || b.fallback[0]) return;
+    const uint32_t o = b.off[s];
+    for (uint32_t k = 1; k < m; ++k) {   // insertion sort in the scratch buffer (a handful of records)
+        const Item<6> x = tmp[o + k];
+        uint32_t j = k;
+        while (j > 0 && hit_less(x, tmp[o + j - 1])) { tmp[o + j] = tmp[o + j - 1]; --j; }
+        tmp[o + j] = x;
     }
-    for (uint32_t j = tid; j < n; j += kSmallSortThreads) out[j] = in[src[j]];
+    for (uint32_t k = 0; k < m; ++k) hits[o + k] = tmp[o + k];
 }
 
 // append the 8-bit digit passes needed to cover values in [0, max_value] of `field`

@@ -557,11 +557,13 @@ def test_true_strands_option_on_device():
     _true_strands_check(MerPCR, _records)
 
 
-@pytest.mark.parametrize("n", [2, 37, 1000, 1024, 1025, 16384, 16385, 70000, 300000])
-def test_sort_with_the_count_on_the_device(n):
-    """mpcr_sort_hits_dev (count read on the device, rank sort for short lists, radix passes + tie kernels for long
-    ones, any hint) and mpcr_sort_hits order random hit lists -- many ties on (contig, pos1), one run of several
-    hundred equal positions -- exactly like a lexicographic sort on the reference's order key."""
+@pytest.mark.parametrize("n,long_run", [(2, False), (37, False), (1000, True), (9000, False), (70000, False), (70000, True),
+                                        (131072, False), (131073, False), (300000, True)])
+def test_sort_with_the_count_on_the_device(n, long_run):
+    """mpcr_sort_hits_dev (count read on the device; bucket sort on the global coordinate for lists of up to 2^17 hits,
+    radix passes + tie kernels for longer ones and for lists that pile up in one place; any hint) and mpcr_sort_hits
+    order random hit lists -- many ties on (contig, pos1), optionally one run of several hundred equal positions --
+    exactly like a lexicographic sort on the reference's order key."""
     import torch
     from merpcr_b200 import MerPCR, _capi
     eng = MerPCR()
@@ -570,9 +572,9 @@ def test_sort_with_the_count_on_the_device(n):
     h = np.zeros(n, dtype=_capi.HIT_DTYPE)
     h["contig"] = rng.integers(0, 24, n)
     h["pos1"] = rng.integers(0, max(4, n // 3), n)             # plenty of equal (contig, pos1)
-    if n >= 1000:
+    if long_run:
         h["contig"][:700] = 5
-        h["pos1"][:700] = 77                                    # a long run for order_long_runs
+        h["pos1"][:700] = 77                                    # a long run: bucket overflow -> radix + order_long_runs
     h["pos2"] = h["pos1"] + rng.integers(50, 900, n)
     h["rec"] = rng.permutation(n).astype(np.uint32)            # unique: the order key is total
     h["rank"] = rng.integers(0, 100, n)
