@@ -125,6 +125,9 @@ struct mpcr_ctx {
     uint32_t n_contig_g = 0;
     uint64_t genome_end = 0;    // padded coordinate behind the last contig of the last layout
     uint32_t* d_bsort = nullptr;   // [cnt kSortBuckets][off kSortBuckets + 1][pad][slot kBucketSortMax][flag]
+    uint32_t* h_flag = nullptr;    // pinned landing place of the bucket sort's fall-back flag
+    const void* attr_kern = nullptr;   // scanner instantiation whose shared-memory attribute is set (and its size)
+    size_t attr_smem = 0;
     uint64_t tiles_need = 0;    // plane extent (bases from the origin) the cached descriptors read up to
     int64_t tiles_min = 0;      // ... and down to
 };
@@ -996,19 +999,30 @@ __device__ __forceinline__ void verify_body(const ScanArgs& a) {
       const uint32_t my_list = (warp_id + 32 * round + lane) & (kSurvLists - 1u);
       const uint32_t* my_ctl = a.surv_ctl + my_list * kSurvCtlStride;
       const uint32_t my_n = min(__ldcg(my_ctl), a.surv_cap);      // final: the scanner has finished
-      for (;;) {
-        const uint32_t open = __ballot_sync(0xffffffffu, __ldcg(my_ctl + 1) < my_n);
-        if (!open) break;
+      // walk the sub-lists that had work when the window was polled; two visits in a row that find a list already
+      // drained by other warps mean the picture is stale (short lists empty at once): poll again instead of paying one
+      // round trip per drained list
+      uint32_t open = __ballot_sync(0xffffffffu, __ldcg(my_ctl + 1) < my_n);
+      int stale = 0;
+      while (open) {
         const int l = (int)((__ffs(__funnelshift_r(open, open, rot)) - 1 + rot) & 31u);
+        open &= ~(1u << l);
         const uint32_t list = (warp_id + 32 * round + l) & (kSurvLists - 1u);
         uint32_t* ctl = a.surv_ctl + list * kSurvCtlStride;
         const uint32_t n = __shfl_sync(0xffffffffu, my_n, l);
         const Survivor* surv = a.surv + (size_t)list * a.surv_cap;
-        for (;;) {
+        for (bool first_try = true;; first_try = false) {
             uint32_t first = 0;
             if (lane == 0) first = __ldcg(ctl + 1) < n ? atomicAdd(ctl + 1, kGrab) : n;   // look before touching the line
             first = __shfl_sync(0xffffffffu, first, 0);
-            if (first >= n) break;
+            if (first >= n) {
+                if (first_try && ++stale >= 2) {
+                    open = __ballot_sync(0xffffffffu, __ldcg(my_ctl + 1) < my_n);
+                    stale = 0;
+                }
+                break;
+            }
+            stale = 0;
             ++grabs;
           for (uint32_t idx = first + group; idx < min(first + kGrab, n); idx += kGroups) {
             const Survivor sv = surv[idx];
@@ -1253,6 +1267,7 @@ void mpcr_ctx_destroy(mpcr_ctx* c) {
     cudaFree(c->d_surv_ctl);
     cudaFree(c->d_contig_g);
     cudaFree(c->d_bsort);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
     delete c;
 }
 
@@ -1841,7 +1856,11 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
         else if (a.prm.W == 11 && a.prm.N == 0) kern = scan_kernel<true, false, 11, 0>;
         else if (a.prm.W == 11 && a.prm.N == 1) kern = scan_kernel<true, false, 11, 1>;
         else if (a.prm.W == 11 && a.prm.N == 2) kern = scan_kernel<true, false, 11, 2>;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (c->attr_kern != (const void*)kern || c->attr_smem != smem) {   // once per (kernel, size), not per launch
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            c->attr_kern = (const void*)kern;
+            c->attr_smem = smem;
+        }
         kern<<<grid, kScanThreads, smem, st>>>(a);
     }
     CU(cudaEventRecord(c->ev1, st));
@@ -1859,6 +1878,8 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     return MPCR_OK;
 }
 
+static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const unsigned long long* d_n,
+                          uint64_t n_hint, cudaStream_t st, bool optimistic, bool* only_bucket);
 int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* h_contigs, uint32_t n_contigs,
                      const void* d_plane2, const void* d_plane4, const void* d_valid, uint64_t plane_origin,
                      uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit* d_hits, uint64_t capacity,
@@ -1876,14 +1897,34 @@ int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* h
     }
     for (uint32_t i = 0; i < n_ctx; ++i) ctxs[i]->append = saved[i];
     if (rc) return rc;
+    mpcr_ctx* c0 = ctxs[0];
+    bool only_bucket = false;
     if (sort && capacity >= 2) {
-        rc = mpcr_sort_hits_dev(ctxs[0], d_hits, d_count, capacity, n_hint, stream);
+        if (!d_hits) return fail(MPCR_EINVAL, "null hit buffer");
+        GUARD(c0);
+        rc = sort_hits_impl(c0, d_hits, capacity, (const unsigned long long*)d_count, n_hint, (cudaStream_t)stream,
+                            h_count != nullptr, &only_bucket);
         if (rc) return rc;
     }
     if (h_count) {
-        GUARD(ctxs[0]);
-        CU(cudaMemcpyAsync(h_count, d_count, sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-        CU(cudaStreamSynchronize((cudaStream_t)stream));
+        GUARD(c0);
+        cudaStream_t st = (cudaStream_t)stream;
+        CU(cudaMemcpyAsync(h_count, d_count, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        uint32_t* h_flag = nullptr;
+        if (only_bucket) {   // the bucket sort's fall-back flag comes back with the count
+            if (!c0->h_flag) CU(cudaMallocHost(&c0->h_flag, 16));
+            h_flag = c0->h_flag;
+            CU(cudaMemcpyAsync(h_flag, c0->d_bsort + (size_t)kSortBuckets * 2 + 4 + kBucketSortMax, 4, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaStreamSynchronize(st));
+        if (h_flag && *h_flag) {   // the list piled up in one slice (or outgrew the hint): radix passes, count known now
+            const uint64_t n = *h_count < capacity ? *h_count : capacity;
+            if (n >= 2) {
+                rc = sort_hits_impl(c0, d_hits, n, nullptr, 0, st, false, nullptr);
+                if (rc) return rc;
+                CU(cudaStreamSynchronize(st));
+            }
+        }
     }
     return MPCR_OK;
 }
@@ -1905,8 +1946,11 @@ float mpcr_last_verify_ms(mpcr_ctx* c) {
 
 // Shared by both sort entry points: n_host records, or -- with d_n -- as many as *d_n says (at most n_host, the
 // buffer's capacity), read on the device so that the sort queues up behind the scan without a host round trip.
+// optimistic: the caller synchronises right behind the sort and looks at the bucket sort's fall-back flag itself
+// (mpcr_scan_sorted) -- then a list hinted short gets the four bucket-sort launches and nothing else.
 static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const unsigned long long* d_n,
-                          uint64_t n_hint, cudaStream_t st) {
+                          uint64_t n_hint, cudaStream_t st, bool optimistic, bool* only_bucket) {
+    if (only_bucket) *only_bucket = false;
     static_assert(sizeof(mpcr_hit) == sizeof(Item<6>), "hit layout");
     int rc = ensure(&c->d_sort_tmp, &c->sort_tmp_cap, n_host * sizeof(mpcr_hit));
     if (rc) return rc;
@@ -1931,7 +1975,7 @@ static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const 
     const uint32_t* skip_off = nullptr;
     const uint64_t n_known = d_n ? n_hint : n_host;
     if (n_known <= kBucketSortMax && c->d_contig_g && c->genome_end) {   // n_known 0 = unknown
-        const size_t words = (size_t)kSortBuckets * 2 + 2 + kBucketSortMax + 2;
+        const size_t words = (size_t)kSortBuckets * 2 + 4 + kBucketSortMax + 4;
         if (!c->d_bsort) {
             CU(cudaMalloc(&c->d_bsort, words * 4));
             CU(cudaMemsetAsync(c->d_bsort, 0, words * 4, st));   // the counters are re-zeroed by bsort_finish itself
@@ -1943,8 +1987,8 @@ static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const 
         const uint64_t hi = c->tiles_se < c->genome_end ? c->tiles_se : c->genome_end;
         b.span = hi > b.g_lo ? hi - b.g_lo : 1;
         b.cnt = c->d_bsort;
-        b.off = b.cnt + kSortBuckets;
-        b.slot = b.off + kSortBuckets + 2;
+        b.off = b.cnt + kSortBuckets;               // 16-byte aligned (vector stores in bsort_scan)
+        b.slot = b.off + kSortBuckets + 4;
         b.fallback = b.slot + kBucketSortMax;
         const uint64_t grid_n = n_host < kBucketSortMax ? n_host : kBucketSortMax;
         const uint32_t gb = (uint32_t)((grid_n + 255) / 256);
@@ -1955,6 +1999,11 @@ static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const 
         c->launches += 4;
         skip = kBucketSortMax;
         skip_off = b.fallback;
+        if (optimistic && n_known != 0) {   // hinted short: the caller checks the flag after its synchronisation
+            if (only_bucket) *only_bucket = true;
+            CU(cudaGetLastError());
+            return MPCR_OK;
+        }
     }
     Item<6>* sorted = hits;
     c->launches += radix_sort<6>(hits, tmp, n_host, d_n, skip, skip_off, passes, np, c->d_counts, st, &sorted, &skip);
@@ -1972,7 +2021,7 @@ int mpcr_sort_hits(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n, void* stream) {
     if (n < 2) return MPCR_OK;
     if (!d_hits) return fail(MPCR_EINVAL, "null hit buffer");
     GUARD(c);
-    return sort_hits_impl(c, d_hits, n, nullptr, 0, (cudaStream_t)stream);
+    return sort_hits_impl(c, d_hits, n, nullptr, 0, (cudaStream_t)stream, false, nullptr);
 }
 
 int mpcr_sort_hits_dev(mpcr_ctx* c, mpcr_hit* d_hits, const uint64_t* d_count, uint64_t capacity, uint64_t n_hint,
@@ -1981,7 +2030,7 @@ int mpcr_sort_hits_dev(mpcr_ctx* c, mpcr_hit* d_hits, const uint64_t* d_count, u
     if (capacity < 2) return MPCR_OK;
     if (!d_hits) return fail(MPCR_EINVAL, "null hit buffer");
     GUARD(c);
-    return sort_hits_impl(c, d_hits, capacity, (const unsigned long long*)d_count, n_hint, (cudaStream_t)stream);
+    return sort_hits_impl(c, d_hits, capacity, (const unsigned long long*)d_count, n_hint, (cudaStream_t)stream, false, nullptr);
 }
 
 }  // extern "C"

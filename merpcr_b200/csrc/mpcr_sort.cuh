@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(256) bsort_count(const Item<6>* __restrict__ i
     b.slot[i] = (at << 14) | (uint32_t)s;
 }
 
-// exclusive scan of the kSortBuckets counters by one CTA of 1024 threads (16 each) + the too-full check
+// exclusive scan of the kSortBuckets counters by one CTA of 1024 threads (16 consecutive counters each, read and written
+// as four 16-byte vectors) + the too-full check
 __global__ void __launch_bounds__(1024) bsort_scan(const unsigned long long* d_n, uint64_t n_host, BucketSortArgs b) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t s_max;
@@ -308,9 +309,16 @@ __global__ void __launch_bounds__(1024) bsort_scan(const unsigned long long* d_n
     if (tid == 0) s_max = 0;
     __syncthreads();
     constexpr int kPer = kSortBuckets / 1024;
+    static_assert(kPer == 16, "16 counters per thread");
     uint32_t v[kPer], sum = 0, mx = 0;
+    const uint4* src = reinterpret_cast<const uint4*>(b.cnt) + tid * 4;
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) { v[k] = b.cnt[tid * kPer + k]; sum += v[k]; mx = max(mx, v[k]); }
+    for (int q = 0; q < 4; ++q) {
+        const uint4 t = src[q];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { sum += v[k]; mx = max(mx, v[k]); }
     uint32_t incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -318,7 +326,10 @@ __global__ void __launch_bounds__(1024) bsort_scan(const unsigned long long* d_n
         if (lane >= d) incl += t;
     }
     if (lane == 31) warp_sums[wid] = incl;
-    atomicMax(&s_max, mx);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 16)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 4)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    if (lane == 0) atomicMax(&s_max, mx);
     __syncthreads();
     if (wid == 0) {
         const uint32_t w = warp_sums[lane];
@@ -332,8 +343,16 @@ __global__ void __launch_bounds__(1024) bsort_scan(const unsigned long long* d_n
     }
     __syncthreads();
     uint32_t run = warp_sums[wid] + incl - sum;
+    uint4* dst = reinterpret_cast<uint4*>(b.off) + tid * 4;
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) { b.off[tid * kPer + k] = run; run += v[k]; }
+    for (int q = 0; q < 4; ++q) {
+        uint4 t;
+        t.x = run; run += v[4 * q];
+        t.y = run; run += v[4 * q + 1];
+        t.z = run; run += v[4 * q + 2];
+        t.w = run; run += v[4 * q + 3];
+        dst[q] = t;
+    }
     if (tid == 1023) b.off[kSortBuckets] = run;
     if (tid == 0) b.fallback[0] = (n > kBucketSortMax || s_max > kBucketMaxFill) ? 1u : 0u;
 }
