@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 10
+#define MPCR_ABI_VERSION 11
 
 enum {
     MPCR_OK = 0,
@@ -93,6 +93,21 @@ void mpcr_ctx_destroy(mpcr_ctx *ctx);
  * Scanning both tables over the same planes and sorting the concatenated hits gives exactly the one-table result.
  * Call before mpcr_table_build; drops the current table. */
 int mpcr_ctx_set_seed_extension(mpcr_ctx *ctx, int w_ext, int which);
+/* Position sampling for EXACT searches (mismatches 0, no IUPAC mode; MPCR_EINVAL otherwise; no reference counterpart --
+ * the reference probes its dict at every base, core/engine.py:467-489).  With no mismatch allowed every window of a
+ * record's first primer matches wherever the primer does, so a table may hold, per record, the w_samp-letter windows at
+ * offsets hash_offset .. hash_offset + stride - 1 (all plain A/C/G/T, inside the primer) and the scanner may probe
+ * only the positions that are multiples of `stride` in contig coordinates: exactly one of them sees each site.  The
+ * first-level filter of such a table lives in global memory (the keys of 10^6 STS do not fit a shared-memory filter).
+ *   role = 1 : this context's next table holds the records that can be sampled, `stride` windows each;
+ *   role = 2 : it holds only the records that can NOT (combine with mpcr_ctx_set_seed_extension / _table_part);
+ *   role = 0 : off (default).
+ * Scanning the role-1 and role-2 tables over the same planes and sorting the concatenated hits gives exactly the
+ * one-table result.  Ownership of a site (shards, ranges) goes by the probed position.  Call before
+ * mpcr_table_build; drops the current table. */
+int mpcr_ctx_set_sampling(mpcr_ctx *ctx, int w_samp, int stride, int role);
+/* Items in the context's current table (records, or records x stride for a sampled table); 0 before a build. */
+uint32_t mpcr_table_items(const mpcr_ctx *ctx);
 /* Table partitioning (no reference counterpart; the reference keeps one dict, core/engine.py:324-329): this context's
  * next table holds only the STS lines with (line index % parts) == part
  * (parts = 0 or 1: every line, the default).  The shared-memory filter of the scanner has room for about 6.5 bits per

@@ -135,6 +135,19 @@ MPCR_HD bool extended_seed(CharAt at, int len, int ho, int w_ext, uint32_t* key_
     return true;
 }
 
+// Position sampling (exact searches only, see mpcr_ctx_set_sampling): with no mismatch allowed EVERY window of the
+// primer matches where the primer does, so a table may hold the w-letter windows at offsets ho .. ho+S-1 and the
+// scanner may look at every S-th position only.  True iff those S windows exist and hold plain A/C/G/T letters only.
+template <class CharAt>
+MPCR_HD bool sampleable_seed(CharAt at, int len, int ho, int w, int S) {
+    if (ho < 0 || S < 1 || ho + S - 1 + w > len) return false;
+    for (int i = ho; i < ho + S - 1 + w; ++i) {
+        const uint8_t c = at(i);
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return false;
+    }
+    return true;
+}
+
 // Encode a primer into nibble words + aux words.  lut[c] = nibble | never_match<<4 | zero_code_char<<5.
 // dst[0..nw) nibbles, dst[nw..2nw) aux (bit0 of nibble i = never match, bit1 = "is the zero-code character").
 template <class CharAt>
@@ -402,6 +415,15 @@ MPCR_HD uint32_t slot_hash(uint32_t key) {
     return h ^ (h >> 15);
 }
 MPCR_HD uint32_t slot_index(uint32_t key, SlotMap sm) { return sm.direct ? key : (slot_hash(key) & sm.mask); }
+
+// Sampled tables (mpcr_ctx_set_sampling) are probed once per S positions of the whole genome through a Bloom filter that
+// lives in global memory (L2): one 32-bit word per probe, two bits per key.
+MPCR_HD uint32_t bloom_word(uint32_t key, uint32_t shift) { return slot_hash(key) >> shift; }
+MPCR_HD uint32_t bloom_bits(uint32_t key) {
+    const uint32_t h = (key ^ (key >> 13)) * 0x85EBCA77u;
+    return (1u << (h >> 27)) | (1u << ((h >> 22) & 31u));
+}
+
 
 // engine.py:614-640 restricted to the tag: true iff the full primer-1 compare is CERTAIN to fail because the
 // bases right after the seed already carry more than N mismatches.  tag = 2-bit codes of up to kTagBases

@@ -83,6 +83,9 @@ struct mpcr_ctx {
     uint32_t n_keys = 0;
     bool dense = false;
     int ext_w = 0, ext_which = 0;   // seed extension (mpcr_ctx_set_seed_extension)
+    int samp_w = 0, samp_s = 0, samp_role = 0;   // position sampling (mpcr_ctx_set_sampling)
+    uint32_t* d_bloom = nullptr;    // sampled tables: the first-level filter in global memory
+    uint32_t bloom_shift = 0;
     uint32_t part = 0, parts = 1;   // table partition (mpcr_ctx_set_table_part)
     int append = 0;                 // mpcr_ctx_set_append
     int true_strands = 0;           // mpcr_ctx_set_true_strands
@@ -280,62 +283,77 @@ struct BlobRc {  // engine.py:357-359 reverse complement, on the fly
     __device__ uint8_t operator()(int i) const { return complement_of(p[len - 1 - i]); }
 };
 
-// One thread per record slot r = 2*line + strand.  "+" : (P1,P2) = (primer1, primer2)   (engine.py:265-268)
-//                                                  "-" : (P1,P2) = (primer2, revcomp(primer1)) (engine.py:273-279)
+// One thread per table item.  Ordinary tables: item = record slot r = 2*line + strand.  Sampled tables (samp_role 1): item =
+// r * samp_s + d, the window of the record's first primer at offset hash_off + d.
+//   "+" : (P1,P2) = (primer1, primer2)   (engine.py:265-268)      "-" : (P1,P2) = (primer2, revcomp(primer1)) (engine.py:273-279)
 __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ off,
                                                       const uint32_t* __restrict__ pcr, uint32_t n_lines,
                                                       const uint8_t* __restrict__ plut,
                                                       const uint32_t* __restrict__ word_off,  // 2*n_rec+1 prefix
                                                       int W, int w_scan, int which, int true_strands,
-                                                      uint32_t part, uint32_t parts,
+                                                      uint32_t part, uint32_t parts, int samp_w, int samp_s, int samp_role,
                                                       RecMeta* __restrict__ meta,
                                                       uint64_t* __restrict__ pwords, Item<2>* __restrict__ pairs,
-                                                      uint32_t* __restrict__ stats) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= 2 * n_lines) return;
+                                                      uint32_t* __restrict__ tags, uint32_t* __restrict__ stats) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t per = samp_role == 1 ? (uint32_t)samp_s : 1u;
+    if (t >= 2 * n_lines * per) return;
+    const uint32_t r = t / per;
+    const int d = (int)(t - r * per);
+    const bool lead = d == 0;          // the item that writes the record's meta data and primer words
     const uint32_t line = r >> 1;
     const bool minus = r & 1u;
     const uint64_t a0 = off[2 * line], a1 = off[2 * line + 1], a2 = off[2 * line + 2];
     const uint8_t* pr1 = blob + a0;
     const uint8_t* pr2 = blob + a1;
     const int n1 = (int)(a1 - a0), n2 = (int)(a2 - a1);
+    // P1 is literal on both strands: primer1 for "+", primer2 for "-"
+    const BlobFwd q1{minus ? pr2 : pr1};
+    const int l1 = minus ? n2 : n1, l2 = minus ? n1 : n2;
     RecMeta m;
     m.pcr_size = pcr[line];
     m.p1_word = word_off[2 * r];
     m.p2_word = word_off[2 * r + 1];
-    m.tag = 0;
+    m.len1 = (uint16_t)l1; m.len2 = (uint16_t)l2;
     uint32_t hbe = 0, kext = 0;
-    int ho;
-    bool ext;
+    const int ho = first_clean_word(q1, l1, W, &hbe);
     // which: 0 = every record keyed by its W-mer; 1 = only records whose seed cannot be lengthened to w_scan letters;
     //        2 = only those that can, keyed by the lengthened word (mpcr_ctx_set_seed_extension)
-    if (!minus) {
-        m.len1 = (uint16_t)n1; m.len2 = (uint16_t)n2;
-        ho = first_clean_word(BlobFwd{pr1}, n1, W, &hbe);
-        ext = which != 0 && extended_seed(BlobFwd{pr1}, n1, ho, w_scan, &kext);
-        if (ho >= 0) m.tag = make_tag(BlobFwd{pr1}, n1, ho, which == 2 ? w_scan : W);
-        encode_primer(BlobFwd{pr1}, n1, plut, pwords + m.p1_word);
-        // reference (engine.py:267): primer2 literally; me-PCR-true strands: its reverse complement
-        if (true_strands) encode_primer(BlobRc{pr2, n2}, n2, plut, pwords + m.p2_word);
-        else encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p2_word);
-    } else {
-        m.len1 = (uint16_t)n2; m.len2 = (uint16_t)n1;
-        ho = first_clean_word(BlobFwd{pr2}, n2, W, &hbe);
-        ext = which != 0 && extended_seed(BlobFwd{pr2}, n2, ho, w_scan, &kext);
-        if (ho >= 0) m.tag = make_tag(BlobFwd{pr2}, n2, ho, which == 2 ? w_scan : W);
-        encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p1_word);
-        encode_primer(BlobRc{pr1, n1}, n1, plut, pwords + m.p2_word);
+    const bool ext = which != 0 && extended_seed(q1, l1, ho, w_scan, &kext);
+    m.tag = ho >= 0 ? make_tag(q1, l1, ho, which == 2 ? w_scan : W) : 0u;
+    if (lead) {
+        encode_primer(q1, l1, plut, pwords + m.p1_word);
+        if (!minus) {
+            // reference (engine.py:267): primer2 literally; me-PCR-true strands: its reverse complement
+            if (true_strands) encode_primer(BlobRc{pr2, n2}, n2, plut, pwords + m.p2_word);
+            else encode_primer(BlobFwd{pr2}, n2, plut, pwords + m.p2_word);
+        } else {
+            encode_primer(BlobRc{pr1, n1}, n1, plut, pwords + m.p2_word);
+        }
     }
-    const bool here = ho >= 0 && (which == 0 || (which == 1 ? !ext : ext)) && (parts <= 1u || line % parts == part);
+    bool here = ho >= 0 && (which == 0 || (which == 1 ? !ext : ext)) && (parts <= 1u || line % parts == part);
+    uint32_t key = which == 2 ? kext : reverse_digits(hbe, W), tag = m.tag;
+    if (samp_role != 0) {   // mpcr_ctx_set_sampling: 1 = this table holds the sampled windows, 2 = it holds the rest
+        const bool can = sampleable_seed(q1, l1, ho, samp_w, samp_s);
+        if (samp_role == 1) {
+            here = can && (parts <= 1u || line % parts == part);
+            key = 0;
+            if (can) extended_seed(q1, l1, ho + d, samp_w, &key);
+            tag = can ? make_tag(q1, l1, ho + d, samp_w) : 0u;
+        } else {
+            here = here && !can;
+        }
+    }
     m.hash_be = hbe;
     m.key = which == 2 ? kext : reverse_digits(hbe, W);
     m.hash_off = (uint16_t)(ho < 0 ? 0 : ho);
     m.flags = (ho >= 0 ? 1u : 0u) | (here ? 2u : 0u);
-    meta[r] = m;
-    pairs[r].f[0] = m.key;
-    pairs[r].f[1] = r | (here ? 0u : 0x80000000u);
+    if (lead) meta[r] = m;
+    pairs[t].f[0] = key;
+    pairs[t].f[1] = t | (here ? 0u : 0x80000000u);
+    tags[t] = tag;
     if (here) atomicAdd(&stats[2], 1u);
-    if (ho >= 0) {
+    if (ho >= 0 && lead) {
         atomicAdd(&stats[0], 1u);
         atomicMax(&stats[1], (uint32_t)ho);
     }
@@ -344,24 +362,25 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
 // After the pairs are sorted by (invalid, key, record): CSR bucket entries (with inline tags), the 16-byte slot
 // table (direct-indexed or open-addressed) and the two-bit-per-key blocked Bloom filter.
 __global__ void __launch_bounds__(256) build_buckets(const Item<2>* __restrict__ pairs, uint32_t n_valid,
-                                                     const RecMeta* __restrict__ meta, BucketEntry* __restrict__ bucket,
+                                                     const uint32_t* __restrict__ tags, BucketEntry* __restrict__ bucket,
                                                      Slot* __restrict__ slots, SlotMap sm,
                                                      uint32_t* __restrict__ filter, uint32_t filter_words, uint32_t cw,
-                                                     int W, uint32_t* __restrict__ n_keys) {
+                                                     int W, uint32_t* __restrict__ n_keys,
+                                                     uint32_t* __restrict__ bloom, uint32_t bloom_shift) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_valid) return;
     const uint32_t key = pairs[i].f[0];
     const uint32_t rec = pairs[i].f[1] & 0x7FFFFFFFu;
     const bool head = (i == 0) || (pairs[i - 1].f[0] != key);
     const bool last = (i + 1 == n_valid) || (pairs[i + 1].f[0] != key);
-    const uint32_t tag = meta[rec].tag;
+    const uint32_t tag = tags[rec];   // rec = item index: a record slot, or (record, window) of a sampled table
     bucket[i] = BucketEntry{rec | (last ? 0x80000000u : 0u), tag};
     if (head) {
         // bucket size, capped at 3, and the second record's tag
         uint32_t n = 1, tag_b = 0;
         if (!last) {
             n = 2;
-            tag_b = meta[pairs[i + 1].f[1] & 0x7FFFFFFFu].tag;
+            tag_b = tags[pairs[i + 1].f[1] & 0x7FFFFFFFu];
             if (i + 2 < n_valid && pairs[i + 2].f[0] == key) n = 3;
         }
         // one record: both tags are its tag; two: one tag each; three or more: mask 0 = never reject
@@ -380,7 +399,8 @@ __global__ void __launch_bounds__(256) build_buckets(const Item<2>* __restrict__
             reinterpret_cast<unsigned long long*>(slots + s)[0] = lo;
         }
         reinterpret_cast<unsigned long long*>(slots + s)[1] = hi;
-        atomicOr(&filter[filter_word(key, cw, filter_words)], filter_bits_of(key, W));
+        if (bloom) atomicOr(&bloom[bloom_word(key, bloom_shift)], bloom_bits(key));   // sampled table: global filter
+        else atomicOr(&filter[filter_word(key, cw, filter_words)], filter_bits_of(key, W));
         atomicAdd(n_keys, 1u);
     }
 }
@@ -429,6 +449,10 @@ struct ScanArgs {
     // Pipe balancing of stage 1: a multiplier the compiler cannot see through, so that the filter word's address stays a
     // multiply-add (IMAD, fma pipe) instead of becoming a LEA on the busier alu pipe (2.97 -> 2.89 ms).
     uint32_t k4;          // 4
+    // sampled tables (mpcr_ctx_set_sampling): every samp_s-th position is probed through a Bloom filter in global memory
+    uint32_t samp_s;      // 1 = ordinary table; else survivor codes are record * samp_s + window
+    const uint32_t* bloom;
+    uint32_t bloom_shift;
 };
 
 // shared-memory plan of the scanner CTA (dynamic shared memory): one private block per warp, then the filter
@@ -503,10 +527,12 @@ __device__ __noinline__ void verify_serial(const ScanArgs& a, uint32_t tile, uin
     const TileDesc td = a.tiles[tile];
     const int64_t gb = td.gbase + lp + a.prm.W;
     const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
-    for_each_survivor_record(a.bucket, code, gcodes, gvalid, a.prm.N, [&](uint32_t rec) {
+    for_each_survivor_record(a.bucket, code, gcodes, gvalid, a.prm.N, [&](uint32_t item) {
+        // sampled tables: item = record * samp_s + window; the window lies that many bases behind the seed
+        const uint32_t rec = a.samp_s > 1 ? item / a.samp_s : item, d = a.samp_s > 1 ? item - rec * a.samp_s : 0u;
         const RecMeta m = a.meta[rec];
-        verify_record(a.p4, td.gbase - (int64_t)td.lstart, (int64_t)td.length, (int64_t)td.lstart + lp, m, a.pwords,
-                      a.prm, HitEmitter{a.hits, a.capacity, a.count, td.contig, rec, (uint32_t)m.hash_off});
+        verify_record(a.p4, td.gbase - (int64_t)td.lstart, (int64_t)td.length, (int64_t)td.lstart + lp - (int64_t)d, m,
+                      a.pwords, a.prm, HitEmitter{a.hits, a.capacity, a.count, td.contig, rec, (uint32_t)m.hash_off});
     });
 }
 
@@ -942,6 +968,64 @@ __global__ void __launch_bounds__(256, 2) dense_scan_kernel(const ScanArgs a) {
     }
 }
 
+// Sampled tables (exact searches: mpcr_ctx_set_sampling): only every samp_s-th position of a contig is probed -- the
+// table holds, for every record, the windows of its first primer at offsets hash_off .. hash_off + samp_s - 1, so exactly
+// one probed position sees each site.  With 10^6 STS the keys (samp_s per record) outnumber anything a shared-memory
+// filter can hold, so the first level is a Bloom filter in global memory (L2-resident): one 4-byte gather per probed
+// position, no shared-memory carve-out, so plain loads run at the full L1 rate.  Neighbouring lanes take neighbouring
+// probed positions: their plane2 / valid words come from the same few cache lines.  What passes the filter (a fraction
+// of a percent) probes the open-addressed slot table and the inline tags like the other scanners; survivors carry the
+// probed position and the item (record, window).
+__global__ void __launch_bounds__(256, 4) sampled_scan_kernel(const ScanArgs a) {
+    constexpr int kChunk = 4;                      // probes in flight per lane
+    const int lane = threadIdx.x & 31;
+    const uint32_t S = a.samp_s;
+    const int W = a.prm.W, N = a.prm.N;
+    const uint32_t wmask = wmask_of(W), vmask = wmask_bits(W);
+    const uint32_t* __restrict__ p2w = reinterpret_cast<const uint32_t*>(a.p2);
+    const uint32_t* __restrict__ vw = reinterpret_cast<const uint32_t*>(a.valid);
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= a.n_tiles) return;
+        const TileDesc td = a.tiles[tile];
+        const uint32_t first = (S - td.lstart % S) % S;       // probed positions are multiples of S in contig coordinates
+        if (first >= td.nbases) continue;
+        const uint32_t count = (td.nbases - first + S - 1) / S;
+        for (uint32_t q0 = 0; q0 < count; q0 += 32 * kChunk) {
+            uint32_t lp[kChunk], key[kChunk], word[kChunk];
+            bool ok[kChunk];
+#pragma unroll
+            for (int u = 0; u < kChunk; ++u) {
+                const uint32_t q = q0 + 32 * u + lane;
+                ok[u] = q < count;
+                lp[u] = first + S * (ok[u] ? q : 0u);
+                const int64_t g = td.gbase + lp[u];
+                const uint32_t wi = (uint32_t)(g >> 4), sh = ((uint32_t)g & 15u) * 2u;
+                key[u] = __funnelshift_r(__ldg(p2w + wi), __ldg(p2w + wi + 1), sh) & wmask;
+                const uint32_t vi = (uint32_t)(g >> 5), vs = (uint32_t)g & 31u;
+                const uint32_t vv = __funnelshift_r(__ldg(vw + vi), __ldg(vw + vi + 1), vs);
+                ok[u] = ok[u] && (vv & vmask) == vmask;       // the whole window is A/C/G/T (engine.py:483, N == 0)
+                word[u] = ok[u] ? __ldg(a.bloom + bloom_word(key[u], a.bloom_shift)) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kChunk; ++u) {
+                const uint32_t bits = bloom_bits(key[u]);
+                if (!ok[u] || (word[u] & bits) != bits) continue;
+                if (a.debug & 1) { atomicAdd(a.count, 1ull); continue; }
+                Slot sl;
+                if (!find_slot(a.slots, a.smap, key[u], &sl)) continue;
+                const int64_t gb = td.gbase + lp[u] + W;
+                const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
+                if (!slot_survives(sl, gcodes, gvalid, N)) continue;
+                if (a.debug & 2) atomicAdd(a.count, 1ull);
+                else push_survivor(a, tile, lp[u], sl.code);
+            }
+        }
+    }
+}
+
 // (4)(5) verifier + hit emitter: one group of kVerifyLanes lanes per survivor (four survivors per warp: the work is
 // a chain of dependent loads, so narrow groups keep more of them in flight).  Primer 1 is compared by every lane of
 // the group (same addresses, broadcast loads); the mate search of engine.py:543-593 is spread over the lanes, one
@@ -951,11 +1035,13 @@ __global__ void __launch_bounds__(256, 2) dense_scan_kernel(const ScanArgs a) {
 #endif
 static constexpr int kVerifyLanes = MPCR_VERIFY_LANES;   // lanes per survivor (one mate-search offset each)
 
-__device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& td, uint32_t lp, uint32_t rec, int gl) {
+__device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& td, uint32_t lp, uint32_t item, int gl) {
+    // sampled tables: item = record * samp_s + window, the probed position lies `window` bases behind the seed
+    const uint32_t rec = a.samp_s > 1 ? item / a.samp_s : item, win = a.samp_s > 1 ? item - rec * a.samp_s : 0u;
     const RecMeta m = a.meta[rec];
     const int64_t gcontig = td.gbase - (int64_t)td.lstart, L = td.length;
     const int l1 = m.len1, l2 = m.len2;
-    const int64_t k = (int64_t)td.lstart + lp - (int64_t)m.hash_off;                         // engine.py:486
+    const int64_t k = (int64_t)td.lstart + lp - (int64_t)win - (int64_t)m.hash_off;          // engine.py:486
     if (k < 0 || k + l1 > L) return;                                                          // :487
     if (!compare_primer(a.p4, gcontig + k, a.pwords + m.p1_word, l1, true, a.prm)) return;    // :515
     if (L - (k + l1) < l2) return;                                                            // :521-524
@@ -1251,7 +1337,9 @@ int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
 
 static void free_table(mpcr_ctx* c) {
     cudaFree(c->d_meta); cudaFree(c->d_pwords); cudaFree(c->d_slots); cudaFree(c->d_bucket); cudaFree(c->d_filter);
+    cudaFree(c->d_bloom);
     c->d_meta = nullptr; c->d_pwords = nullptr; c->d_slots = nullptr; c->d_bucket = nullptr; c->d_filter = nullptr;
+    c->d_bloom = nullptr;
     c->table_ready = false;
 }
 
@@ -1284,6 +1372,21 @@ int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
     free_table(c);
     return MPCR_OK;
 }
+int mpcr_ctx_set_sampling(mpcr_ctx* c, int w_samp, int stride, int role) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (role < 0 || role > 2) return fail(MPCR_EINVAL, "role must be 0, 1 or 2");
+    if (role != 0) {
+        if (c->prm.mismatches != 0 || c->prm.iupac_mode != 0)
+            return fail(MPCR_EINVAL, "position sampling needs an exact search (mismatches 0, no IUPAC mode)");
+        if (w_samp <= c->prm.wordsize || w_samp > 16) return fail(MPCR_EINVAL, "sampled word must be in (wordsize, 16]");
+        if (stride < 2 || stride > 64) return fail(MPCR_EINVAL, "stride must be in [2, 64]");
+    }
+    c->samp_w = role ? w_samp : 0;
+    c->samp_s = role ? stride : 0;
+    c->samp_role = role;
+    free_table(c);
+    return MPCR_OK;
+}
 int mpcr_ctx_set_table_part(mpcr_ctx* c, uint32_t part, uint32_t parts) {
     if (!c) return fail(MPCR_EINVAL, "null argument");
     if (parts == 0) parts = 1;
@@ -1306,6 +1409,7 @@ int mpcr_ctx_set_true_strands(mpcr_ctx* c, int on) {
 }
 int mpcr_ctx_sm_count(const mpcr_ctx* c) { return c ? c->sm_count : 0; }
 uint64_t mpcr_launch_count(const mpcr_ctx* c) { return c ? c->launches : 0; }
+uint32_t mpcr_table_items(const mpcr_ctx* c) { return c && c->table_ready ? c->n_valid : 0; }
 uint64_t mpcr_fasta_workspace_bytes(uint64_t n, uint32_t max_records) {
     const uint64_t n_blk = (n + kFastaBlock - 1) / kFastaBlock, m = max_records ? max_records : 1;
     return (n_blk + 1) * 8 + ((n_blk + 1) & ~1ull) * 4 + 8 + m * (sizeof(FastaHeader) + 32) + 64;
@@ -1459,9 +1563,13 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
     GUARD(c);
     free_table(c);
     const int W = c->prm.wordsize;
-    const int WS = c->ext_which == 2 ? c->ext_w : W;   // key width of THIS table
+    const bool sampled = c->samp_role == 1;
+    const int WS = sampled ? c->samp_w : (c->ext_which == 2 ? c->ext_w : W);   // key width of THIS table
     c->scan_w = WS;
     const uint32_t n_rec = 2 * n_lines;
+    const uint32_t per_rec = sampled ? (uint32_t)c->samp_s : 1u;   // table items per record
+    if ((uint64_t)n_rec * per_rec >= (1ull << 30)) return fail(MPCR_EINVAL, "too many table items");
+    const uint32_t n_items = n_rec * per_rec;
     c->n_rec = n_rec;
     c->n_valid = 0;
     c->max_hash_off = 0;
@@ -1503,7 +1611,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
     const size_t blob_bytes = n_lines ? (size_t)h_off[2 * (size_t)n_lines] : 0;
     uint8_t *d_blob = nullptr, *d_plut = nullptr;
     uint64_t* d_off = nullptr;
-    uint32_t *d_pcr = nullptr, *d_woff = nullptr, *d_stats = nullptr;
+    uint32_t *d_pcr = nullptr, *d_woff = nullptr, *d_stats = nullptr, *d_tags = nullptr;
     Item<2>*d_pairs = nullptr, *d_pairs2 = nullptr, *d_sorted = nullptr;
     int rc = MPCR_OK;
 #define CUG(call)                                                                                        \
@@ -1531,8 +1639,9 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         CUG(cudaMalloc(&d_pcr, (size_t)n_lines * 4));
         CUG(cudaMalloc(&d_woff, word_off.size() * 4));
         CUG(cudaMalloc(&d_stats, 16));
-        CUG(cudaMalloc(&d_pairs, (size_t)n_rec * sizeof(Item<2>)));
-        CUG(cudaMalloc(&d_pairs2, (size_t)n_rec * sizeof(Item<2>)));
+        CUG(cudaMalloc(&d_pairs, (size_t)n_items * sizeof(Item<2>)));
+        CUG(cudaMalloc(&d_pairs2, (size_t)n_items * sizeof(Item<2>)));
+        CUG(cudaMalloc(&d_tags, (size_t)n_items * 4));
         CUG(cudaMalloc(&c->d_meta, (size_t)n_rec * sizeof(RecMeta)));
         CUG(cudaMalloc(&c->d_pwords, (size_t)(acc + 2) * sizeof(uint64_t)));
         CUG(cudaMemcpyAsync(d_blob, h_blob, blob_bytes, cudaMemcpyHostToDevice, st));
@@ -1541,10 +1650,10 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         CUG(cudaMemcpyAsync(d_pcr, h_pcr, (size_t)n_lines * 4, cudaMemcpyHostToDevice, st));
         CUG(cudaMemcpyAsync(d_woff, word_off.data(), word_off.size() * 4, cudaMemcpyHostToDevice, st));
         CUG(cudaMemsetAsync(d_stats, 0, 16, st));
-        encode_records<<<(n_rec + 127) / 128, 128, 0, st>>>(d_blob, d_off, d_pcr, n_lines, d_plut, d_woff, W,
-                                                             c->ext_which ? c->ext_w : W, c->ext_which, c->true_strands,
-                                                             c->part, c->parts, c->d_meta,
-                                                             c->d_pwords, d_pairs, d_stats);
+        encode_records<<<(n_items + 127) / 128, 128, 0, st>>>(d_blob, d_off, d_pcr, n_lines, d_plut, d_woff, W,
+                                                               c->ext_which ? c->ext_w : W, sampled ? 0 : c->ext_which,
+                                                               c->true_strands, c->part, c->parts, c->samp_w, c->samp_s,
+                                                               c->samp_role, c->d_meta, c->d_pwords, d_pairs, d_tags, d_stats);
         c->launches++;
         CUG(cudaGetLastError());
         uint32_t stats[4] = {0, 0, 0, 0};
@@ -1556,10 +1665,10 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         PassDesc passes[8];
         int np = add_passes(passes, 0, 0, wmask_of(WS));
         passes[np].field = 1; passes[np].shift = 31; passes[np].mask = 1; ++np;
-        const uint32_t nblk = (n_rec + kSortItemsPerBlock - 1) / kSortItemsPerBlock;
+        const uint32_t nblk = (n_items + kSortItemsPerBlock - 1) / kSortItemsPerBlock;
         rc = ensure((void**)&c->d_counts, &c->counts_cap, (size_t)256 * nblk * 4);
         if (rc) goto done;
-        c->launches += radix_sort<2>(d_pairs, d_pairs2, n_rec, nullptr, 0, nullptr, passes, np, c->d_counts, st, &d_sorted);
+        c->launches += radix_sort<2>(d_pairs, d_pairs2, n_items, nullptr, 0, nullptr, passes, np, c->d_counts, st, &d_sorted);
         CUG(cudaGetLastError());
         // slot table: direct-indexed by the key while 4^W slots stay L2-sized (W <= 11 -> 64 MiB), else open
         // addressing at load <= 1/8 (distinct seeds <= min(records, 4^W))
@@ -1578,11 +1687,19 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         CUG(cudaMemsetAsync(c->d_slots, 0xFF, (size_t)nslots * sizeof(Slot), st));
         CUG(cudaMalloc(&c->d_bucket, ((size_t)c->n_valid + 33) * sizeof(BucketEntry)));   // +32: dense walks read whole warps
         CUG(cudaMemsetAsync(c->d_bucket, 0, ((size_t)c->n_valid + 33) * sizeof(BucketEntry), st));
+        if (sampled) {   // the first-level filter of a sampled table lives in global memory: >= 32 bits per key
+            uint32_t lg = 10;
+            while (lg < 26 && (1ull << lg) < (uint64_t)c->n_valid) ++lg;
+            c->bloom_shift = 32 - lg;
+            CUG(cudaMalloc(&c->d_bloom, ((size_t)1 << lg) * 4));
+            CUG(cudaMemsetAsync(c->d_bloom, 0, ((size_t)1 << lg) * 4, st));
+        }
         if (c->n_valid) {
             CUG(cudaMemsetAsync(d_stats, 0, 16, st));
-            build_buckets<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_sorted, c->n_valid, c->d_meta, c->d_bucket,
+            build_buckets<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_sorted, c->n_valid, d_tags, c->d_bucket,
                                                                      c->d_slots, c->smap, c->d_filter,
-                                                                     c->filter_words, filter_mul(WS), WS, d_stats);
+                                                                     c->filter_words, filter_mul(WS), WS, d_stats,
+                                                                     c->d_bloom, c->bloom_shift);
             c->launches++;
             CUG(cudaGetLastError());
             if (!c->smap.direct) {
@@ -1603,7 +1720,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
     }
 done:
     cudaFree(d_blob); cudaFree(d_plut); cudaFree(d_off); cudaFree(d_pcr); cudaFree(d_woff); cudaFree(d_stats);
-    cudaFree(d_pairs); cudaFree(d_pairs2);
+    cudaFree(d_pairs); cudaFree(d_pairs2); cudaFree(d_tags);
     if (rc) free_table(c);
     return rc;
 #undef CUG
@@ -1659,7 +1776,7 @@ static void view_extent(mpcr_ctx* c) {
     const TileDesc& f = c->h_tiles[c->view_first];
     const TileDesc& l = c->h_tiles[c->view_first + c->view_count - 1];
     const int64_t f_contig = f.gbase - (int64_t)f.lstart;
-    const int64_t reach = f.gbase - (int64_t)c->max_hash_off;
+    const int64_t reach = f.gbase - (int64_t)c->max_hash_off - (c->samp_role == 1 ? (int64_t)c->samp_s : 0);
     c->tiles_min = reach > f_contig ? reach : f_contig;
     const uint64_t scan_end = (uint64_t)l.gbase + round_up(l.nbases, 2048) + 256;
     const uint64_t contig_end = (uint64_t)(l.gbase - (int64_t)l.lstart) + l.length;
@@ -1837,6 +1954,9 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
     a.debug = c->env_debug;
     a.k4 = 4u;
+    a.samp_s = c->samp_role == 1 ? (uint32_t)c->samp_s : 1u;
+    a.bloom = c->d_bloom;
+    a.bloom_shift = c->bloom_shift;
     a.hits = d_hits; a.capacity = capacity; a.count = (unsigned long long*)d_count; a.tile_counter = c->d_tile_counter;
     a.surv = c->d_surv; a.surv_cap = (uint32_t)(c->surv_bytes / sizeof(Survivor) / kSurvLists); a.surv_ctl = c->d_surv_ctl;
     if (c->env_surv_cap >= 0 && (uint32_t)c->env_surv_cap < a.surv_cap)   // test hook: force the list-full path
@@ -1845,7 +1965,9 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     uint32_t grid = (uint32_t)c->sm_count;
     if (grid > c->view_count) grid = c->view_count;
     CU(cudaEventRecord(c->ev0, st));
-    if (c->dense) {
+    if (c->samp_role == 1) {
+        sampled_scan_kernel<<<c->sm_count * 4, 256, 0, st>>>(a);
+    } else if (c->dense) {
         dense_scan_kernel<<<c->sm_count * 8, 256, 0, st>>>(a);
     } else {
         // instantiations: the open-addressed table (W >= 12), the narrow filter (W < 6), the general direct table, and

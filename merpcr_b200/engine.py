@@ -49,6 +49,8 @@ MIN_PCR_SIZE, MAX_PCR_SIZE = 1, 10000
 EXTENDED_WORDSIZE = 16        # key width of the extended tables of exact, candidate-heavy searches
 STREAM_SCAN_BASES = 1 << 26    # upload_and_scan: scan a finished contig (group) once this many bases are packed
 EXT_LINES_PER_TABLE = 125_000  # STS lines per extended table: 2.5*10^5 keys is what the scanner's filter holds at ~5 % f.p.
+SAMPLE_WORDSIZE = 16          # window width of position-sampled tables (exact, candidate-heavy searches)
+SAMPLE_STRIDE = 3             # ... and the stride: primers of >= hash_offset + 18 plain letters can be sampled
 PCR_SIZE_CLAMP = 0x7FFFFFFF   # any expected size >= a contig length behaves identically (engine.py:531-533)
 PLANE_SLACK_BASES = 1024      # read-ahead of the last strip / last primer window
 
@@ -211,6 +213,7 @@ class MerPCR:
         self._pack_rate = 50e9    # bases / s the host packer sustains (refined while it runs)
         self._h2d_rate = 50e9     # bytes / s of the host -> device link (PCIe Gen5 x16 moves ~55 GB/s)
         self._ctx_exts = []       # extended tables of exact, candidate-heavy searches (mpcr_ctx_set_seed_extension)
+        self._ctx_samp = None     # position-sampled table of the same searches (mpcr_ctx_set_sampling)
         self._create_ctx()
         # parsed STS lines kept so the table can be re-encoded if a sequence brings an unusual alphabet
         self._sts_lines = None
@@ -236,8 +239,8 @@ class MerPCR:
         self._ctx = self._new_ctx()
 
     def close(self):
-        ctxs = [getattr(self, "_ctx", None)] + list(getattr(self, "_ctx_exts", []))
-        self._ctx, self._ctx_exts = None, []
+        ctxs = [getattr(self, "_ctx", None)] + list(getattr(self, "_ctx_exts", [])) + [getattr(self, "_ctx_samp", None)]
+        self._ctx, self._ctx_exts, self._ctx_samp = None, [], None
         for ctx in ctxs:
             if ctx:
                 self._be.lib.mpcr_ctx_destroy(ctx)
@@ -262,7 +265,7 @@ class MerPCR:
         return sum(int(self._be.lib.mpcr_launch_count(c)) for c in self._all_ctxs())
 
     def _all_ctxs(self):
-        return [self._ctx] + list(self._ctx_exts)
+        return [self._ctx] + list(self._ctx_exts) + ([self._ctx_samp] if self._ctx_samp else [])
 
     # ------------------------------------------------------------------ engine.py:80-97
     def _validate_parameters(self):
@@ -418,10 +421,31 @@ class MerPCR:
         env = os.environ.get("MPCR_SEED_EXTENSION")
         if env is not None and can_extend:
             extend = env not in ("0", "")
-        parts = max(1, -(-n // EXT_LINES_PER_TABLE)) if extend else 0
+        # Position sampling on top of that: the records whose first primer offers SAMPLE_STRIDE clean 16-letter windows from
+        # its hash offset go to ONE sampled table (the scanner then probes every SAMPLE_STRIDE-th position only, through a
+        # filter in global memory); the extended / ordinary tables keep the rest.
+        stride = SAMPLE_STRIDE if extend else 0
+        env = os.environ.get("MPCR_SAMPLING")
+        if env is not None and can_extend:
+            stride = int(env) if env not in ("0", "") else 0
+        rest_lines = n
+        if stride >= 2:
+            if self._ctx_samp is None:
+                self._ctx_samp = self._new_ctx()
+            self._be.check(lib.mpcr_ctx_set_sampling(self._ctx_samp, SAMPLE_WORDSIZE, stride, 1))
+            self._be.check(lib.mpcr_table_build(self._ctx_samp, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
+                                                plut.ctypes.data, self._stream()))
+            sampled_records = int(lib.mpcr_table_items(self._ctx_samp)) // stride
+            rest_lines = max(0, n - sampled_records // 2)
+        elif self._ctx_samp is not None:
+            lib.mpcr_ctx_destroy(self._ctx_samp)
+            self._ctx_samp = None
+        role = 2 if stride >= 2 else 0
+        parts = max(1, -(-rest_lines // EXT_LINES_PER_TABLE)) if extend else 0
         if extend and os.environ.get("MPCR_SEED_PARTS"):
             parts = max(1, int(os.environ["MPCR_SEED_PARTS"]))
         self._be.check(lib.mpcr_ctx_set_seed_extension(self._ctx, w_ext if extend else 0, 1 if extend else 0))
+        self._be.check(lib.mpcr_ctx_set_sampling(self._ctx, SAMPLE_WORDSIZE if role else 0, stride if role else 0, role))
         self._be.check(lib.mpcr_table_build(self._ctx, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
                                             plut.ctypes.data, self._stream()))
         while len(self._ctx_exts) > parts:
@@ -430,6 +454,7 @@ class MerPCR:
             self._ctx_exts.append(self._new_ctx())
         for k, ctx in enumerate(self._ctx_exts):
             self._be.check(lib.mpcr_ctx_set_seed_extension(ctx, w_ext, 2))
+            self._be.check(lib.mpcr_ctx_set_sampling(ctx, SAMPLE_WORDSIZE if role else 0, stride if role else 0, role))
             self._be.check(lib.mpcr_ctx_set_table_part(ctx, k, parts))
             self._be.check(lib.mpcr_table_build(ctx, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
                                                 plut.ctypes.data, self._stream()))

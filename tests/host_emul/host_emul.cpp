@@ -44,6 +44,7 @@ struct mpcr_ctx {
     bool table_ready = false;
     uint64_t launches = 0;
     int ext_w = 0, ext_which = 0, scan_w = 0, true_strands = 0;
+    int samp_w = 0, samp_s = 0, samp_role = 0;
     uint32_t part = 0, parts = 1;
     int append = 0;
 };
@@ -82,6 +83,19 @@ int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
     c->ext_w = which ? w_ext : 0; c->ext_which = which; c->table_ready = false;
     return MPCR_OK;
 }
+int mpcr_ctx_set_sampling(mpcr_ctx* c, int w_samp, int stride, int role) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (role < 0 || role > 2) return fail(MPCR_EINVAL, "role must be 0, 1 or 2");
+    if (role != 0) {
+        if (c->prm.mismatches != 0 || c->prm.iupac_mode != 0)
+            return fail(MPCR_EINVAL, "position sampling needs an exact search (mismatches 0, no IUPAC mode)");
+        if (w_samp <= c->prm.wordsize || w_samp > 16) return fail(MPCR_EINVAL, "sampled word must be in (wordsize, 16]");
+        if (stride < 2 || stride > 64) return fail(MPCR_EINVAL, "stride must be in [2, 64]");
+    }
+    c->samp_w = role ? w_samp : 0; c->samp_s = role ? stride : 0; c->samp_role = role; c->table_ready = false;
+    return MPCR_OK;
+}
+uint32_t mpcr_table_items(const mpcr_ctx* c) { return c && c->table_ready ? c->n_valid : 0; }
 int mpcr_ctx_set_table_part(mpcr_ctx* c, uint32_t part, uint32_t parts) {
     if (!c) return fail(MPCR_EINVAL, "null argument");
     if (parts == 0) parts = 1;
@@ -213,7 +227,11 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
                      const uint8_t* plut, void*) {
     if (!c || !plut) return fail(MPCR_EINVAL, "null argument");
     const int W = c->prm.wordsize;
-    const int WS = c->ext_which == 2 ? c->ext_w : W;
+    const bool sampled = c->samp_role == 1;
+    const int which = sampled ? 0 : c->ext_which;
+    const int WS = sampled ? c->samp_w : (c->ext_which == 2 ? c->ext_w : W);
+    const uint32_t per = sampled ? (uint32_t)c->samp_s : 1u;
+    std::vector<uint32_t> tags((size_t)2 * n_lines * per, 0u);
     c->scan_w = WS;
     c->n_rec = 2 * n_lines; c->n_valid = 0; c->max_hash_off = 0; c->max_len = 0; c->max_pcr = 0;
     c->meta.assign(c->n_rec, RecMeta{});
@@ -236,25 +254,38 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
             m.p2_word = (uint32_t)c->pwords.size();
             c->pwords.resize(c->pwords.size() + 2 * ((l2 + 15) / 16));
             uint32_t hbe = 0, kext = 0; int ho; bool ext;
+            const Fwd q1{minus ? pr2 : pr1};
+            ho = first_clean_word(q1, l1, W, &hbe);
+            ext = which != 0 && extended_seed(q1, l1, ho, c->ext_w, &kext);
+            if (ho >= 0) m.tag = make_tag(q1, l1, ho, which == 2 ? c->ext_w : W);
+            encode_primer(q1, l1, plut, c->pwords.data() + m.p1_word);
             if (!minus) {
-                ho = first_clean_word(Fwd{pr1}, n1, W, &hbe);
-                ext = c->ext_which != 0 && extended_seed(Fwd{pr1}, n1, ho, c->ext_w, &kext);
-                if (ho >= 0) m.tag = make_tag(Fwd{pr1}, n1, ho, WS);
-                encode_primer(Fwd{pr1}, n1, plut, c->pwords.data() + m.p1_word);
                 if (c->true_strands) encode_primer(Rc{pr2, n2}, n2, plut, c->pwords.data() + m.p2_word);
                 else encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p2_word);
             } else {
-                ho = first_clean_word(Fwd{pr2}, n2, W, &hbe);
-                ext = c->ext_which != 0 && extended_seed(Fwd{pr2}, n2, ho, c->ext_w, &kext);
-                if (ho >= 0) m.tag = make_tag(Fwd{pr2}, n2, ho, WS);
-                encode_primer(Fwd{pr2}, n2, plut, c->pwords.data() + m.p1_word);
                 encode_primer(Rc{pr1, n1}, n1, plut, c->pwords.data() + m.p2_word);
             }
-            const bool here = ho >= 0 && (c->ext_which == 0 || (c->ext_which == 1 ? !ext : ext)) &&
-                              (c->parts <= 1u || (r >> 1) % c->parts == c->part);
-            m.hash_be = hbe; m.key = c->ext_which == 2 ? kext : reverse_digits(hbe, W);
-            m.hash_off = (uint16_t)(ho < 0 ? 0 : ho); m.flags = (ho >= 0 ? 1 : 0) | (here ? 2 : 0);
+            const bool in_part = c->parts <= 1u || (r >> 1) % c->parts == c->part;
+            bool here = ho >= 0 && (which == 0 || (which == 1 ? !ext : ext)) && in_part;
+            m.hash_be = hbe; m.key = which == 2 ? kext : reverse_digits(hbe, W);
+            m.hash_off = (uint16_t)(ho < 0 ? 0 : ho);
             if (ho >= 0) c->max_hash_off = std::max(c->max_hash_off, (uint32_t)ho);
+            if (c->samp_role != 0) {
+                const bool can = sampleable_seed(q1, l1, ho, c->samp_w, c->samp_s);
+                if (sampled) {
+                    here = false;
+                    for (int d = 0; d < c->samp_s && can && in_part; ++d) {
+                        uint32_t key = 0;
+                        extended_seed(q1, l1, ho + d, c->samp_w, &key);
+                        tags[(size_t)r * per + d] = make_tag(q1, l1, ho + d, c->samp_w);
+                        pairs.push_back({key, r * per + (uint32_t)d});
+                    }
+                } else {
+                    here = here && !can;
+                }
+            }
+            m.flags = (ho >= 0 ? 1 : 0) | (here ? 2 : 0);
+            if (!sampled) tags[r] = m.tag;
             if (here) pairs.push_back({m.key, r});
         }
     }
@@ -275,17 +306,17 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
     for (uint32_t i = 0; i < c->n_valid; ++i) {
         const uint32_t key = pairs[i].first, rec = pairs[i].second;
         const bool head = i == 0 || pairs[i - 1].first != key, last = i + 1 == c->n_valid || pairs[i + 1].first != key;
-        c->bucket[i] = BucketEntry{rec | (last ? 0x80000000u : 0u), c->meta[rec].tag};
+        c->bucket[i] = BucketEntry{rec | (last ? 0x80000000u : 0u), tags[rec]};
         if (head) {
             uint32_t n = 1, tag_b = 0;
             if (!last) {
                 n = 2;
-                tag_b = c->meta[pairs[i + 1].second].tag;
+                tag_b = tags[pairs[i + 1].second];
                 if (i + 2 < c->n_valid && pairs[i + 2].first == key) n = 3;
             }
             uint32_t s = slot_index(key, c->smap);
             if (!direct) while (c->slots[s].code != kSlotEmpty) s = (s + 1) & c->smap.mask;
-            const uint32_t tag_a = c->meta[rec].tag;
+            const uint32_t tag_a = tags[rec];
             c->slots[s] = n == 1 ? Slot{rec, tag_a, tag_a, key}
                           : n == 2 ? Slot{kWalkBucket | i, tag_a, tag_b, key} : Slot{kWalkBucket | i, 0u, 0u, key};
             c->filter[filter_word(key, cw, words)] |= filter_bits_of(key, WS);
@@ -361,6 +392,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
                 uint64_t cand = window_valid(V[gb >> 6], V[(gb >> 6) + 1], prm.W);
                 for (int j = 0; j < 64 && cand; ++j) {
                     if (!((cand >> j) & 1)) continue;
+                    if (c->samp_role == 1 && (ls + lp0 + j) % (uint64_t)c->samp_s != 0) continue;   // probed positions only
                     const uint32_t key = extract_key(P2, gb + j, wmask);
                     if (!filter_pass(c->filter[filter_word(key, cw, (uint32_t)c->filter.size())], key, prm.W)) continue;
                     const uint32_t gcodes = fetch_bits(P2, 2 * (gb + j + prm.W), 2 * kTagBases);
@@ -368,9 +400,10 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
                     Slot sl;
                     if (!find_slot(c->slots.data(), c->smap, key, &sl)) continue;
                     if (!slot_survives(sl, gcodes, gvalid, prm.N)) continue;
-                    for_each_survivor_record(c->bucket.data(), sl.code, gcodes, gvalid, prm.N, [&](uint32_t rec) {
+                    for_each_survivor_record(c->bucket.data(), sl.code, gcodes, gvalid, prm.N, [&](uint32_t item) {
+                        const uint32_t S = c->samp_role == 1 ? (uint32_t)c->samp_s : 1u, rec = item / S, win = item % S;
                         const RecMeta& m = c->meta[rec];
-                        verify_record(P4, gbase - (int64_t)ls, (int64_t)L, (int64_t)ls + lp0 + j, m, c->pwords.data(), prm,
+                        verify_record(P4, gbase - (int64_t)ls, (int64_t)L, (int64_t)ls + lp0 + j - (int64_t)win, m, c->pwords.data(), prm,
                                       [&](int64_t p1, int64_t p2, uint32_t rank) {
                                           if (n < capacity) hits[n] = mpcr_hit{ci, (uint32_t)p1, (uint32_t)p2, rec, rank, m.hash_off};
                                           ++n;

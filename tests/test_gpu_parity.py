@@ -685,3 +685,47 @@ def test_host_packed_nibble_ingest_builds_the_same_planes(tmp_path):
         for a, b in zip(*planes):
             assert torch.equal(a, b)
         assert np.array_equal(hits[0], hits[1]) and len(hits[0]) > 1000
+
+
+def test_position_sampling_equals_the_unsampled_search_on_device(tmp_path, monkeypatch):
+    """mpcr_ctx_set_sampling on the GPU (sampled_scan_kernel: every S-th position probed through the global-memory
+    filter) -- same matrix as the CPU-tier test: strides, with and without the seed extension, shards."""
+    from merpcr_b200 import MerPCR
+    from test_host_logic import _sampling_case
+    contigs, text, stsf, expected = _sampling_case(tmp_path, "samp_gpu")
+    params = dict(wordsize=8, margin=30, mismatches=0)
+    want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
+    assert len(want) >= len(expected) > 50
+    for ext, stride in (("0", "0"), ("0", "3"), ("1", "3"), ("1", "2"), ("0", "5"), ("1", "7")):
+        monkeypatch.setenv("MPCR_SEED_EXTENSION", ext)
+        monkeypatch.setenv("MPCR_SAMPLING", stride)
+        eng = MerPCR(**params)
+        assert eng.load_sts_file(stsf)
+        assert (eng._ctx_samp is not None) == (stride != "0")
+        got = parity.engine_hits(eng, _records(contigs))
+        assert np.array_equal(got, want), (ext, stride)
+        eng.close()
+    monkeypatch.setenv("MPCR_SEED_EXTENSION", "1")
+    monkeypatch.setenv("MPCR_SAMPLING", "3")
+    parts = []
+    for shard in (None, (0, 3), (1, 3), (2, 3)):
+        eng = MerPCR(**params, shard=shard)
+        assert eng.load_sts_file(stsf)
+        parts.append(eng.search_hits(_records(contigs)))
+        eng.close()
+    merged = np.concatenate(parts[1:])
+    order = np.lexsort((merged["rank"], merged["rec"], merged["hash_off"], merged["pos1"], merged["contig"]))
+    assert np.array_equal(merged[order], parts[0])
+
+
+def test_fuzz_goldens_with_position_sampling_on_device(monkeypatch):
+    from merpcr_b200 import MerPCR
+    for stride in ("2", "3"):
+        monkeypatch.setenv("MPCR_SAMPLING", stride)
+        n = 0
+        for c in goldens.fuzz_cases():
+            if c["params"].get("mismatches", 0) == 0 and not c["params"].get("iupac_mode", 0) and \
+                    c["params"].get("wordsize", 11) < 16:
+                parity.check_fuzz_case(c, MerPCR)
+                n += 1
+        assert n > 5

@@ -536,3 +536,78 @@ def test_nibble_ingest_and_ascii_ingest_agree_with_the_oracle(tmp_path, monkeypa
         want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
         assert np.array_equal(got, want) and len(want) > 50
         eng.close()
+
+
+def _sampling_case(tmp_path, tag):
+    """Primers of 18..30 letters (most can be sampled, some cannot: short ones, an ambiguity inside the windows, a late
+    hash offset), planted amplicons, a contig shorter than a window, tandem repeats that hit many probed positions."""
+    rng = synth.Rng(1411)
+    contigs = [rng.dna(n) for n in (90000, 30001, 14)]
+    unit = np.frombuffer(b"ACGGTCATTGCAGTTTGACCGGTATCAGCATGCATGAACC", dtype=np.uint8)
+    contigs[1][5000:5000 + 40 * 50] = np.tile(unit, 50)
+    sts = synth.make_sts_set(1412, 3000, 12, 30, 60, 400)
+    sts["p1"][::5, 14] = ord("N")          # an ambiguity inside the sampled windows: not sampleable
+    sts["p1"][1::9, 2] = ord("R")          # ... or in front of them: a later hash offset
+    expected = synth.plant_amplicons(1413, contigs[:2], sts, 30, plant_count=150)
+    text = synth.sts_lines(sts) + b"REP\tACGGTCATTGCAGTTTGACC\tGGTATCAGCATGCATGAACC\t80\trepeat\n"
+    stsf = tmp_path / f"{tag}.sts"
+    stsf.write_bytes(text)
+    return contigs, text, str(stsf), expected
+
+
+def test_position_sampling_equals_the_unsampled_search(tmp_path, monkeypatch):
+    """mpcr_ctx_set_sampling: the sampled table (every S-th position probed, S windows per record) + the tables of the
+    records that cannot be sampled == the plain search == the oracle, for several strides, alone and on top of the
+    seed extension, whole and cut into shards (a site belongs to the shard that holds its PROBED position)."""
+    from merpcr_b200 import FASTARecord, MerPCR
+    contigs, text, stsf, expected = _sampling_case(tmp_path, "samp")
+    params = dict(wordsize=8, margin=30, mismatches=0)
+    recs = [FASTARecord(f">c{i}", c) for i, c in enumerate(contigs)]
+    want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
+    assert len(want) >= len(expected) > 50
+    for ext, stride in (("0", "0"), ("0", "3"), ("1", "3"), ("1", "2"), ("0", "5"), ("1", "7")):
+        monkeypatch.setenv("MPCR_SEED_EXTENSION", ext)
+        monkeypatch.setenv("MPCR_SAMPLING", stride)
+        eng = MerPCR(**params)
+        assert eng.load_sts_file(stsf)
+        assert (eng._ctx_samp is not None) == (stride != "0")
+        if stride != "0":
+            items = int(eng._be.lib.mpcr_table_items(eng._ctx_samp))
+            assert items > 0 and items % int(stride) == 0
+        got = parity.engine_hits(eng, recs)
+        assert np.array_equal(got, want), (ext, stride)
+        eng.close()
+    # shards: the union of the ranks' hits, merged by the order key, is the whole
+    monkeypatch.setenv("MPCR_SEED_EXTENSION", "1")
+    monkeypatch.setenv("MPCR_SAMPLING", "3")
+    parts = []
+    for rank in range(3):
+        eng = MerPCR(**params, shard=(rank, 3))
+        assert eng.load_sts_file(stsf)
+        parts.append(eng.search_hits(recs))
+        eng.close()
+    eng = MerPCR(**params)
+    assert eng.load_sts_file(stsf)
+    whole = eng.search_hits(recs)
+    eng.close()
+    merged = np.concatenate(parts)
+    order = np.lexsort((merged["rank"], merged["rec"], merged["hash_off"], merged["pos1"], merged["contig"]))
+    assert np.array_equal(merged[order], whole) and all(len(p) for p in parts[:2])
+    # a search that allows mismatches cannot be sampled
+    eng = MerPCR(wordsize=8, mismatches=1)
+    with pytest.raises(ValueError):
+        eng._be.check(eng._be.lib.mpcr_ctx_set_sampling(eng._ctx, 16, 3, 1))
+    eng.close()
+
+
+def test_fuzz_goldens_with_position_sampling(monkeypatch):
+    from merpcr_b200 import MerPCR
+    for stride in ("2", "3"):
+        monkeypatch.setenv("MPCR_SAMPLING", stride)
+        n = 0
+        for c in goldens.fuzz_cases():
+            if c["params"].get("mismatches", 0) == 0 and not c["params"].get("iupac_mode", 0) and \
+                    c["params"].get("wordsize", 11) < 16:
+                parity.check_fuzz_case(c, MerPCR)
+                n += 1
+        assert n > 5
