@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 11
+#define MPCR_ABI_VERSION 12
 
 enum {
     MPCR_OK = 0,
@@ -176,6 +176,19 @@ int mpcr_fasta_index(mpcr_ctx *ctx, uint8_t *d_text, uint64_t n, mpcr_fasta_reco
                      uint32_t *n_records, uint32_t *flags, void *d_ws, uint64_t ws_bytes, void *stream);
 int mpcr_fasta_compact(mpcr_ctx *ctx, const uint8_t *d_text, uint64_t n, const void *d_ws, uint8_t *d_seq,
                        void *stream);
+/* The same index for a SLICE of a file (rank-local ingest of a multi-GPU run: every rank reads its own byte range plus
+ * margins; the reference has one reader, io/fasta.py:36-41).  mode bit0: the slice may start inside a line -- the bytes
+ * up to and including the first line terminator are dropped first (*flags bit1 and nothing else when there is none in
+ * the first MiB); bit1: the sequence bytes in front of the slice's first header are KEPT (they continue a record that
+ * began earlier in the file) and reported as record 0 with header_begin == header_end == the first retained byte.
+ * mode 0 == mpcr_fasta_index. */
+int mpcr_fasta_index_ex(mpcr_ctx *ctx, uint8_t *d_text, uint64_t n, uint32_t mode, mpcr_fasta_record *h_records,
+                        uint32_t max_records, uint32_t *n_records, uint32_t *flags, void *d_ws, uint64_t ws_bytes,
+                        void *stream);
+/* Kept (sequence) bytes in front of the given byte positions of an indexed text (after mpcr_fasta_index*, same d_ws):
+ * where a byte range of the file begins and ends in the compacted stream.  Synchronous. */
+int mpcr_fasta_offsets_at(mpcr_ctx *ctx, const uint8_t *d_text, uint64_t n, const void *d_ws, const uint64_t *h_pos,
+                          uint32_t n_pos, uint64_t *h_out, void *stream);
 
 /* ---- host-side text helpers (no device work) ---------------------------------------------------- */
 /* One accepted STS line: byte ranges of its fields inside the file text, its 1-based line number, and the expected

@@ -67,6 +67,23 @@ __global__ void __launch_bounds__(256) fasta_find_headers(const uint8_t* __restr
     if (high) atomicOr(flags, 1u);
 }
 
+// Slices of a file (rank-local ingest): where does the first line terminator within the first `limit` bytes end?
+// out[0] = index of the byte after it ("\r\n" counts as one terminator), 0xFFFFFFFF if there is none.
+__global__ void __launch_bounds__(256) fasta_first_line_end(const uint8_t* __restrict__ text, uint64_t n, uint32_t limit,
+                                                            uint32_t* __restrict__ out) {
+    const uint32_t m = (uint32_t)(n < limit ? n : limit);
+    uint32_t best = 0xFFFFFFFFu;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        if (fasta_is_term(text[i])) { best = i; break; }
+    }
+    atomicMin(out, best);
+    __syncthreads();
+    if (threadIdx.x == 0 && out[0] != 0xFFFFFFFFu) {
+        const uint32_t t = out[0];
+        out[0] = (text[t] == 13 && (uint64_t)t + 1 < n && text[t + 1] == 10) ? t + 2 : t + 1;
+    }
+}
+
 // Blank the header lines (sorted table) and everything before the first header, so that "kept" becomes a pure
 // per-byte property.  One thread per header; header lines are short.
 __global__ void __launch_bounds__(128) fasta_blank_headers(uint8_t* __restrict__ text, const FastaHeader* __restrict__ hdr,

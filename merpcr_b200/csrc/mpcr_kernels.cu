@@ -1475,8 +1475,9 @@ uint64_t mpcr_format_hits(const mpcr_hit* hits, uint64_t n, const uint8_t* text,
 }
 
 // ---- device-side FASTA text ingest (io/fasta.py:43-66) -------------------------------------------------------
-int mpcr_fasta_index(mpcr_ctx* c, uint8_t* d_text, uint64_t n, mpcr_fasta_record* h_records, uint32_t max_records,
-                     uint32_t* n_records, uint32_t* flags, void* d_ws, uint64_t ws_bytes, void* stream) {
+int mpcr_fasta_index_ex(mpcr_ctx* c, uint8_t* d_text, uint64_t n, uint32_t mode, mpcr_fasta_record* h_records,
+                        uint32_t max_records, uint32_t* n_records, uint32_t* flags, void* d_ws, uint64_t ws_bytes,
+                        void* stream) {
     if (!c || !n_records || !flags) return fail(MPCR_EINVAL, "null argument");
     if (n && !d_text) return fail(MPCR_EINVAL, "null text pointer");
     if (max_records && !h_records) return fail(MPCR_EINVAL, "null record buffer");
@@ -1485,6 +1486,7 @@ int mpcr_fasta_index(mpcr_ctx* c, uint8_t* d_text, uint64_t n, mpcr_fasta_record
     if (n == 0) return MPCR_OK;
     if (mpcr_fasta_workspace_bytes(n, max_records) > ws_bytes || !d_ws)
         return fail(MPCR_EINVAL, "workspace too small (need %llu bytes)", (unsigned long long)mpcr_fasta_workspace_bytes(n, max_records));
+    const bool skip_first_line = mode & 1u, keep_prologue = mode & 2u;
     cudaStream_t st = (cudaStream_t)stream;
     GUARD(c);
     // workspace: [block offsets u64 (n_blk+1)] [block counts u32 n_blk] [headers max_records] [positions/offsets 4*max] [ctr]
@@ -1496,6 +1498,20 @@ int mpcr_fasta_index(mpcr_ctx* c, uint8_t* d_text, uint64_t n, mpcr_fasta_record
     uint64_t* d_pos = (uint64_t*)w;                 w += (size_t)(max_records ? max_records : 1) * 16;
     uint64_t* d_posoff = (uint64_t*)w;              w += (size_t)(max_records ? max_records : 1) * 16;
     uint32_t* d_ctr = (uint32_t*)w;
+    // a slice that starts inside a line: that line (whatever it is a part of) is dropped first, so that header
+    // detection only ever sees whole lines
+    uint64_t text_begin = 0;
+    if (skip_first_line) {
+        CU(cudaMemsetAsync(d_ctr, 0xFF, 4, st));
+        fasta_first_line_end<<<1, 256, 0, st>>>(d_text, n, 1u << 20, d_ctr);
+        c->launches++;
+        uint32_t fe = 0;
+        CU(cudaMemcpyAsync(&fe, d_ctr, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (fe == 0xFFFFFFFFu) { *flags = 2u; return MPCR_OK; }   // no line end in the first MiB: the caller widens its slice
+        text_begin = fe;
+        CU(cudaMemsetAsync(d_text, '\n', (size_t)text_begin, st));
+    }
     CU(cudaMemsetAsync(d_ctr, 0, 8, st));
     const uint64_t n_thr = (n + 15) / 16;
     fasta_find_headers<<<(uint32_t)((n_thr + 255) / 256), 256, 0, st>>>(d_text, n, d_hdr, max_records, d_ctr, d_ctr + 1);
@@ -1504,40 +1520,76 @@ int mpcr_fasta_index(mpcr_ctx* c, uint8_t* d_text, uint64_t n, mpcr_fasta_record
     uint32_t ctr[2] = {0, 0};
     CU(cudaMemcpyAsync(ctr, d_ctr, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    *n_records = ctr[0];
+    const uint32_t lead = keep_prologue ? 1u : 0u;   // record 0 = the sequence in front of the first header
+    *n_records = ctr[0] + lead;
     *flags = ctr[1];
     if (ctr[1] & 1u) return MPCR_OK;                      // non-ASCII: the host applies the locale rules itself
-    if (ctr[0] > max_records) return MPCR_EOVERFLOW;      // *n_records holds the required capacity
+    if (ctr[0] + lead > max_records) return MPCR_EOVERFLOW;   // *n_records holds the required capacity
     const uint32_t nh = ctr[0];
-    if (nh == 0) return MPCR_OK;                          // no header: no records (everything is "before the first header")
+    if (nh == 0 && !keep_prologue) { *n_records = 0; return MPCR_OK; }   // no header: everything is "before the first header"
     std::vector<FastaHeader> hdr(nh);
-    CU(cudaMemcpy(hdr.data(), d_hdr, (size_t)nh * sizeof(FastaHeader), cudaMemcpyDeviceToHost));
-    std::sort(hdr.begin(), hdr.end(), [](const FastaHeader& a, const FastaHeader& b) { return a.begin < b.begin; });
-    CU(cudaMemcpyAsync(d_hdr, hdr.data(), (size_t)nh * sizeof(FastaHeader), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(d_text, '\n', (size_t)hdr[0].begin, st));   // data before the first header is discarded
-    fasta_blank_headers<<<(nh + 127) / 128, 128, 0, st>>>(d_text, d_hdr, nh);
+    if (nh) {
+        CU(cudaMemcpy(hdr.data(), d_hdr, (size_t)nh * sizeof(FastaHeader), cudaMemcpyDeviceToHost));
+        std::sort(hdr.begin(), hdr.end(), [](const FastaHeader& a, const FastaHeader& b) { return a.begin < b.begin; });
+        CU(cudaMemcpyAsync(d_hdr, hdr.data(), (size_t)nh * sizeof(FastaHeader), cudaMemcpyHostToDevice, st));
+        if (!keep_prologue) CU(cudaMemsetAsync(d_text, '\n', (size_t)hdr[0].begin, st));   // data before the first header is discarded
+        fasta_blank_headers<<<(nh + 127) / 128, 128, 0, st>>>(d_text, d_hdr, nh);
+        c->launches++;
+    }
     fasta_count<<<(uint32_t)n_blk, kFastaThreads, 0, st>>>(d_text, n, d_cnt);
     fasta_scan_blocks<<<1, 1024, 0, st>>>(d_cnt, n_blk, d_off);
-    c->launches += 3;
+    c->launches += 2;
     // kept-byte offsets at every record boundary: end of header r, start of header r+1 (or n)
-    std::vector<uint64_t> pos(2 * (size_t)nh);
+    const uint32_t nr = nh + lead;
+    std::vector<uint64_t> pos(2 * (size_t)nr);
+    if (lead) {
+        pos[0] = text_begin;
+        pos[1] = nh ? hdr[0].begin : n;
+    }
     for (uint32_t r = 0; r < nh; ++r) {
-        pos[2 * r] = hdr[r].end;
-        pos[2 * r + 1] = r + 1 < nh ? hdr[r + 1].begin : n;
+        pos[2 * (r + lead)] = hdr[r].end;
+        pos[2 * (r + lead) + 1] = r + 1 < nh ? hdr[r + 1].begin : n;
     }
     CU(cudaMemcpyAsync(d_pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice, st));
-    fasta_offsets_at<<<(2 * nh + 127) / 128, 128, 0, st>>>(d_text, n, d_off, d_pos, 2 * nh, d_posoff);
+    fasta_offsets_at<<<(2 * nr + 127) / 128, 128, 0, st>>>(d_text, n, d_off, d_pos, 2 * nr, d_posoff);
     c->launches++;
     CU(cudaGetLastError());
-    std::vector<uint64_t> po(2 * (size_t)nh);
+    std::vector<uint64_t> po(2 * (size_t)nr);
     CU(cudaMemcpyAsync(po.data(), d_posoff, po.size() * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    for (uint32_t r = 0; r < nh; ++r) {
-        h_records[r].header_begin = hdr[r].begin;
-        h_records[r].header_end = hdr[r].end;
+    for (uint32_t r = 0; r < nr; ++r) {
+        const bool pseudo = lead && r == 0;
+        h_records[r].header_begin = pseudo ? text_begin : hdr[r - lead].begin;
+        h_records[r].header_end = pseudo ? text_begin : hdr[r - lead].end;
         h_records[r].seq_offset = po[2 * r];
         h_records[r].seq_length = po[2 * r + 1] - po[2 * r];
     }
+    return MPCR_OK;
+}
+
+int mpcr_fasta_index(mpcr_ctx* c, uint8_t* d_text, uint64_t n, mpcr_fasta_record* h_records, uint32_t max_records,
+                     uint32_t* n_records, uint32_t* flags, void* d_ws, uint64_t ws_bytes, void* stream) {
+    return mpcr_fasta_index_ex(c, d_text, n, 0u, h_records, max_records, n_records, flags, d_ws, ws_bytes, stream);
+}
+
+int mpcr_fasta_offsets_at(mpcr_ctx* c, const uint8_t* d_text, uint64_t n, const void* d_ws, const uint64_t* h_pos,
+                          uint32_t n_pos, uint64_t* h_out, void* stream) {
+    if (!c || (n_pos && (!h_pos || !h_out))) return fail(MPCR_EINVAL, "null argument");
+    if (n_pos == 0) return MPCR_OK;
+    if (!d_text || !d_ws) return fail(MPCR_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GUARD(c);
+    uint64_t* d_io = nullptr;
+    CU(cudaMalloc(&d_io, (size_t)n_pos * 16));
+    cudaError_t e = cudaMemcpyAsync(d_io, h_pos, (size_t)n_pos * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        fasta_offsets_at<<<(n_pos + 127) / 128, 128, 0, st>>>(d_text, n, (const uint64_t*)d_ws, d_io, n_pos, d_io + n_pos);
+        c->launches++;
+        e = cudaMemcpyAsync(h_out, d_io + n_pos, (size_t)n_pos * 8, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_io);
+    if (e != cudaSuccess) return fail(MPCR_ECUDA, "mpcr_fasta_offsets_at: %s", cudaGetErrorString(e));
     return MPCR_OK;
 }
 

@@ -179,12 +179,22 @@ static bool f_keep(uint8_t c) {
     return c && strchr(K, c) != nullptr;
 }
 uint64_t mpcr_fasta_workspace_bytes(uint64_t n, uint32_t max_records) { return 64 + n / 512 + (uint64_t)max_records; }
-int mpcr_fasta_index(mpcr_ctx* c, uint8_t* text, uint64_t n, mpcr_fasta_record* recs, uint32_t max_records,
-                     uint32_t* n_records, uint32_t* flags, void* ws, uint64_t ws_bytes, void*) {
+int mpcr_fasta_index_ex(mpcr_ctx* c, uint8_t* text, uint64_t n, uint32_t mode, mpcr_fasta_record* recs, uint32_t max_records,
+                        uint32_t* n_records, uint32_t* flags, void* ws, uint64_t ws_bytes, void*) {
     if (!c || !n_records || !flags) return fail(MPCR_EINVAL, "null argument");
     *n_records = 0; *flags = 0;
     if (n == 0) return MPCR_OK;
     if (!ws || ws_bytes < mpcr_fasta_workspace_bytes(n, max_records)) return fail(MPCR_EINVAL, "workspace too small");
+    const bool skip_first_line = mode & 1u, keep_prologue = mode & 2u;
+    uint64_t text_begin = 0;
+    if (skip_first_line) {
+        uint64_t t = 0;
+        const uint64_t lim = n < (1u << 20) ? n : (1u << 20);
+        while (t < lim && !f_term(text[t])) ++t;
+        if (t >= lim) { *flags = 2u; return MPCR_OK; }
+        text_begin = (text[t] == 13 && t + 1 < n && text[t + 1] == 10) ? t + 2 : t + 1;
+        memset(text, '\n', text_begin);
+    }
     for (uint64_t i = 0; i < n; ++i) if (text[i] >= 128) { *flags = 1; return MPCR_OK; }
     std::vector<std::pair<uint64_t, uint64_t>> hdr;
     uint64_t line = 0;
@@ -197,18 +207,40 @@ int mpcr_fasta_index(mpcr_ctx* c, uint8_t* text, uint64_t n, mpcr_fasta_record* 
         line = e + 1;   // "\r\n" yields an empty line in between, which changes nothing
     }
     c->launches++;
-    *n_records = (uint32_t)hdr.size();
-    if (hdr.size() > max_records) return MPCR_EOVERFLOW;
-    if (hdr.empty()) return MPCR_OK;
-    memset(text, '\n', hdr[0].first);
+    const uint32_t lead = keep_prologue ? 1u : 0u;
+    *n_records = (uint32_t)hdr.size() + lead;
+    if (hdr.size() + lead > max_records) return MPCR_EOVERFLOW;
+    if (hdr.empty() && !keep_prologue) { *n_records = 0; return MPCR_OK; }
+    if (!hdr.empty() && !keep_prologue) memset(text, '\n', hdr[0].first);
     for (auto& h : hdr) memset(text + h.first, '\n', h.second - h.first);
     uint64_t kept = 0, pos = 0;
+    if (lead) {
+        const uint64_t stop = hdr.empty() ? n : hdr[0].first;
+        recs[0].header_begin = recs[0].header_end = text_begin; recs[0].seq_offset = 0;
+        for (; pos < stop; ++pos) kept += f_keep(text[pos]);
+        recs[0].seq_length = kept;
+    }
     for (size_t r = 0; r < hdr.size(); ++r) {
         const uint64_t stop = r + 1 < hdr.size() ? hdr[r + 1].first : n;
         for (; pos < hdr[r].second; ++pos) kept += f_keep(text[pos]);
-        recs[r].header_begin = hdr[r].first; recs[r].header_end = hdr[r].second; recs[r].seq_offset = kept;
+        recs[r + lead].header_begin = hdr[r].first; recs[r + lead].header_end = hdr[r].second; recs[r + lead].seq_offset = kept;
         for (; pos < stop; ++pos) kept += f_keep(text[pos]);
-        recs[r].seq_length = kept - recs[r].seq_offset;
+        recs[r + lead].seq_length = kept - recs[r + lead].seq_offset;
+    }
+    return MPCR_OK;
+}
+int mpcr_fasta_index(mpcr_ctx* c, uint8_t* text, uint64_t n, mpcr_fasta_record* recs, uint32_t max_records,
+                     uint32_t* n_records, uint32_t* flags, void* ws, uint64_t ws_bytes, void* st) {
+    return mpcr_fasta_index_ex(c, text, n, 0u, recs, max_records, n_records, flags, ws, ws_bytes, st);
+}
+int mpcr_fasta_offsets_at(mpcr_ctx* c, const uint8_t* text, uint64_t n, const void*, const uint64_t* pos, uint32_t n_pos,
+                          uint64_t* out, void*) {
+    if (!c || (n_pos && (!pos || !out || !text))) return fail(MPCR_EINVAL, "null argument");
+    for (uint32_t i = 0; i < n_pos; ++i) {
+        const uint64_t p = pos[i] < n ? pos[i] : n;
+        uint64_t k = 0;
+        for (uint64_t j = 0; j < p; ++j) k += f_keep(text[j]);
+        out[i] = k;
     }
     return MPCR_OK;
 }
