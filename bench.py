@@ -469,64 +469,79 @@ def run_b200(args):
 
     # ---- file -> text: the reference's whole user-visible path (io/fasta.py:19-71 + engine.py:365-451) on a FASTA file
     # in the page cache: load_fasta_file (parallel chunked read | H2D | text ingest on the device) -> search -> output
-    # file.  N = 1 only (every rank would ingest the whole file).
+    # file.  N > 1 (sharded mode): every rank ingests only its own byte range of the file (rank-local ingest), scans the
+    # positions that range starts, and rank 0 gathers the hits and writes the text.
     e2e_file = None
-    if rank == 0 and world == 1 and not args.no_e2e and not args.no_e2e_file and not args.as_shard:
+    if not args.no_e2e and not args.no_e2e_file and not args.as_shard and (strong or world == 1):
         import shutil
-        tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2.5 * sum(lengths) \
-            else tempfile.gettempdir()
-        fa_path = os.path.join(tmpdir, f"merpcr_b200_bench_{os.getpid()}.fa")
-        out_path = os.path.join(tmpdir, f"merpcr_b200_bench_{os.getpid()}.out")
+        paths = [None, None]
+        if rank == 0:
+            tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2.5 * sum(lengths) \
+                else tempfile.gettempdir()
+            paths = [os.path.join(tmpdir, f"merpcr_b200_bench_{os.getpid()}.fa"),
+                     os.path.join(tmpdir, f"merpcr_b200_bench_{os.getpid()}.out")]
+        if world > 1:
+            dist.broadcast_object_list(paths, src=0)
+        fa_path, out_path = paths
         try:
-            with open(fa_path, "wb") as f:
-                for ci, name in enumerate(synth.GRCH38_NAMES):
-                    arr = host_contigs[ci].numpy()
-                    f.write(b">%s synthetic cfg3 contig\n" % name.encode())
-                    body = arr[: len(arr) // 60 * 60].reshape(-1, 60)
-                    for s0 in range(0, body.shape[0], 1 << 18):
-                        blk = body[s0: s0 + (1 << 18)]
-                        buf = np.empty((blk.shape[0], 61), dtype=np.uint8)
-                        buf[:, :60] = blk
-                        buf[:, 60] = 10
-                        f.write(buf.tobytes())
-                    tail = arr[len(arr) // 60 * 60:]
-                    if tail.size:
-                        f.write(tail.tobytes() + b"\n")
+            if rank == 0:
+                with open(fa_path, "wb") as f:
+                    for ci, name in enumerate(synth.GRCH38_NAMES):
+                        arr = host_contigs[ci].numpy()
+                        f.write(b">%s synthetic cfg3 contig\n" % name.encode())
+                        body = arr[: len(arr) // 60 * 60].reshape(-1, 60)
+                        for s0 in range(0, body.shape[0], 1 << 18):
+                            blk = body[s0: s0 + (1 << 18)]
+                            buf = np.empty((blk.shape[0], 61), dtype=np.uint8)
+                            buf[:, :60] = blk
+                            buf[:, 60] = 10
+                            f.write(buf.tobytes())
+                        tail = arr[len(arr) // 60 * 60:]
+                        if tail.size:
+                            f.write(tail.tobytes() + b"\n")
+            barrier()
             file_bytes = os.path.getsize(fa_path)
-            reps, runs = 3, []
+            reps, runs, rank_local = 3, [], False
             for it in range(reps):
-                torch.cuda.synchronize()
+                barrier()
                 t0 = time.perf_counter()
                 recs = eng.load_fasta_file(fa_path)
                 t1 = time.perf_counter()
                 n_file = eng.search(recs, out_path)
+                torch.cuda.synchronize()
                 t2 = time.perf_counter()
+                rank_local = hasattr(recs, "owned_range")
                 if it:      # the first pass warms up (allocations, pinned staging)
-                    runs.append((t2 - t0, t1 - t0, t2 - t1))
+                    runs.append((max_over_ranks(t2 - t0), max_over_ranks(t1 - t0), max_over_ranks(t2 - t1)))
                 del recs
-            text = open(out_path, "rb").read()
-            # text-exact against the oracle for the smallest chromosome (its block of lines in the output file)
-            from oracle.oracle import Oracle
-            orc2 = Oracle(**PARAMS)
-            assert orc2.load_sts_text(sts_text)
-            small = int(np.argmin(lengths))
-            label = synth.GRCH38_NAMES[small]
-            _, want_text = orc2.search_text(label, host_contigs[small].numpy().tobytes(), threads=1)
-            got_text = b"".join(ln for ln in text.splitlines(keepends=True) if ln.startswith(label.encode() + b"\t"))
-            dt, t_load, t_search = min(runs)
-            e2e_file = dict(value=float(sum(lengths)) / dt / 1e9, unit="Gbp/s", ms=dt * 1e3, load_fasta_ms=t_load * 1e3,
-                            search_and_write_ms=t_search * 1e3, file_bytes=int(file_bytes), text_bytes=len(text),
-                            hits=int(n_file), lines=text.count(b"\n"), file_in=tmpdir,
-                            text_exact_vs_oracle=dict(contig=label, ok=got_text == want_text.encode("latin-1"),
-                                                      lines=got_text.count(b"\n")),
-                            what="FASTA file (page cache) -> load_fasta_file -> search -> output file, STS table resident")
-            assert n_file == n_hits, "file -> text and resident hit counts differ"
+            if rank == 0:
+                text = open(out_path, "rb").read()
+                # text-exact against the oracle for the smallest chromosome (its block of lines in the output file)
+                from oracle.oracle import Oracle
+                orc2 = Oracle(**PARAMS)
+                assert orc2.load_sts_text(sts_text)
+                small = int(np.argmin(lengths))
+                label = synth.GRCH38_NAMES[small]
+                _, want_text = orc2.search_text(label, host_contigs[small].numpy().tobytes(), threads=1)
+                got_text = b"".join(ln for ln in text.splitlines(keepends=True) if ln.startswith(label.encode() + b"\t"))
+                dt, t_load, t_search = min(runs)
+                e2e_file = dict(value=float(sum(lengths)) / dt / 1e9, unit="Gbp/s", ms=dt * 1e3, load_fasta_ms=t_load * 1e3,
+                                search_and_write_ms=t_search * 1e3, file_bytes=int(file_bytes), text_bytes=len(text),
+                                hits=int(n_file), lines=text.count(b"\n"), file_in=os.path.dirname(fa_path),
+                                rank_local_ingest=bool(rank_local),
+                                text_exact_vs_oracle=dict(contig=label, ok=got_text == want_text.encode("latin-1"),
+                                                          lines=got_text.count(b"\n")),
+                                what="FASTA file (page cache) -> load_fasta_file -> search -> output file, STS table "
+                                     "resident; max over ranks")
+                assert text.count(b"\n") == n_file, "file -> text: line count differs from the hit count"
+            barrier()
         finally:
-            for pth in (fa_path, out_path):
-                try:
-                    os.unlink(pth)
-                except OSError:
-                    pass
+            if rank == 0:
+                for pth in (fa_path, out_path):
+                    try:
+                        os.unlink(pth)
+                    except OSError:
+                        pass
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) + bit-exact parity against the GPU result
     cpu = None

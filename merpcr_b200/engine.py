@@ -126,6 +126,16 @@ class _STSLines:
         return self._p2s
 
 
+class _Piece:
+    """A stretch of a contig that is available on this rank (rank-local FASTA ingest): `data` holds the bases from
+    contig-local offset `start` on."""
+
+    __slots__ = ("data", "start")
+
+    def __init__(self, data, start: int):
+        self.data, self.start = data, int(start)
+
+
 class _Shard:
     """Device-resident packed genome of one shard (planes + the layout they were built for)."""
 
@@ -648,10 +658,19 @@ class MerPCR:
             self._sts_lines = _STSLines(0, [], [], ids=[], aliases=[], p1s=[], p2s=[])
             self._build_table()
         # sequences the device-side ingest left in HBM are used in place; everything else is host bytes
-        seqs = [r.sequence_device if getattr(r, "sequence_device", None) is not None and
-                r.sequence_device.device == self._tdev else r.sequence_bytes for r in fasta_records]
+        seqs = []
+        for r in fasta_records:
+            if hasattr(r, "piece"):             # rank-local ingest: only this rank's stretch of the record is here
+                seqs.append(_Piece(*r.piece) if r.piece is not None else None)
+            elif getattr(r, "sequence_device", None) is not None and r.sequence_device.device == self._tdev:
+                seqs.append(r.sequence_device)
+            else:
+                seqs.append(r.sequence_bytes)
         self._check_alphabet(fasta_records, seqs)
         layout = self.make_layout([len(r) for r in fasta_records])
+        owned = getattr(fasta_records, "owned_range", None)
+        if owned is not None:                   # ... and the rank owns the positions its file range starts
+            layout["begin"], layout["end"] = int(owned[0]), int(owned[1])
         _, hits_t, n = self.upload_and_scan(layout, seqs)
         hits = self._hits_to_host(hits_t, n, copy=copy)
         self.last_timing = dict(search_s=time.perf_counter() - t0)
@@ -735,6 +754,16 @@ class MerPCR:
             g0 = int(layout["contigs"][ci]["gstart"])
             L = int(layout["contigs"][ci]["length"])
             lo, hi = max(g0, sh.origin), min(g0 + L, sh.origin + sh.bases)
+            if isinstance(s, _Piece):           # a stretch of the contig: it must hold everything the shard touches
+                if lo >= hi:
+                    continue
+                if lo < g0 + s.start or hi > g0 + s.start + s.data.numel():
+                    raise RuntimeError(
+                        f"rank-local FASTA ingest: contig {ci} is needed on [{lo - g0}, {hi - g0}) but only "
+                        f"[{s.start}, {s.start + s.data.numel()}) was read here -- load the STS file before the FASTA "
+                        "file (the halos depend on it) or set MPCR_RANK_LOCAL_INGEST=0")
+                g0 += s.start                   # index the stretch by global coordinate
+                s = s.data
             for a in range(lo, hi, chunk):
                 b = min(hi, a + chunk)
                 if isinstance(s, torch.Tensor):
@@ -777,7 +806,8 @@ class MerPCR:
         (group of small contigs) is scanned as soon as its bases are packed -- the tables append to one hit buffer
         (mpcr_ctx_set_append), the host reads the count once at the end, the hits are sorted once.  Host -> hits time
         is then the PCIe copy plus the last contig's scan.  Returns (shard, hit tensor, n_hits)."""
-        if all(s is None or (isinstance(s, torch.Tensor) and s.device == self._tdev) for s in seqs):
+        if all(s is None or (isinstance(s, torch.Tensor) and s.device == self._tdev) or
+               (isinstance(s, _Piece) and s.data.device == self._tdev) for s in seqs):
             sh = self.upload(layout, seqs, shard)
             hits, n = self.scan_device(layout, sh, sort=sort)
             return sh, hits, n

@@ -187,3 +187,83 @@ def test_merge_hits_order_key_and_empty_ranks():
     assert key == sorted(key) and len(m) == 6
     assert np.array_equal(multi.merge_hits([r0]), r0)
     assert len(multi.merge_hits([empty, empty])) == 0 and len(multi.merge_hits([])) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# rank-local FASTA ingest: every rank reads only its own byte range of the file (+ margins), one small exchange
+# gives everybody the record table; the merged output must still be the single-process text, byte for byte
+# ---------------------------------------------------------------------------------------------------------
+def _nasty_fasta(tmp_path, seed):
+    """Records of very different sizes, CRLF / CR / LF line ends, blank lines, indented headers, an empty record, sequence
+    in front of the first header, lower case, letters that are filtered out -- so that the byte-range cuts of 2..5 ranks
+    fall into headers, line ends and tiny records."""
+    import synth
+    rng = synth.Rng(seed)
+    contigs = [rng.dna(n) for n in (70000, 17, 41000, 0, 300, 52001, 9000)]
+    sts = synth.make_sts_set(seed + 1, 150, 18, 25, 100, 600)
+    synth.plant_amplicons(seed + 2, [c for c in contigs if len(c) > 1000], sts, 50, sub_mode="cfg3")
+    sts_path, fa_path = str(tmp_path / "n.sts"), str(tmp_path / "n.fa")
+    with open(sts_path, "wb") as f:
+        f.write(synth.sts_lines(sts))
+    ends = [b"\n", b"\r\n", b"\r"]
+    with open(fa_path, "wb") as f:
+        f.write(b"ACGTACGTNNNN sequence in front of the first header is dropped\n\n")
+        for i, c in enumerate(contigs):
+            f.write(b"  " * (i % 2) + b">rec%d a header line with some text in it %s" % (i, b"x" * (40 * i)) + ends[i % 3])
+            body = c.copy()
+            if len(body) > 100:
+                body[50:60] |= 0x20                                    # lower case is kept as it is
+            width = 60 + 7 * i
+            for a in range(0, len(body), width):
+                f.write(body[a:a + width].tobytes() + (b" 12*-" if a % (width * 5) == 0 else b"") + ends[(a // width + i) % 3])
+                if a % (width * 11) == 0:
+                    f.write(ends[i % 3])                               # blank lines
+    return sts_path, fa_path
+
+
+def _rank_main_local_ingest(rank, world, port, sts_path, fa_path, out_path, info_path, margins):
+    for p in (os.path.dirname(HERE), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MPCR_DEVICE_INGEST_MIN_BYTES="1", MPCR_RANK_MARGIN_LEFT=str(margins[0]),
+                      MPCR_RANK_MARGIN_RIGHT=str(margins[1]))
+    import torch.distributed as dist
+    import emul
+    emul.inject()
+    from merpcr_b200 import MerPCR
+    from merpcr_b200.fasta import ShardedRecords
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        eng = MerPCR(**PARAMS, shard=(rank, world))
+        assert eng.load_sts_file(sts_path)
+        recs = eng.load_fasta_file(fa_path)
+        sharded = isinstance(recs, ShardedRecords)
+        held = sum(r.piece[0].numel() for r in recs if getattr(r, "piece", None) is not None) if sharded else -1
+        n = eng.search(recs, out_path)
+        with open(f"{info_path}.{rank}", "w") as f:
+            f.write(f"{int(sharded)} {n} {held} {sum(len(r) for r in recs)} {len(recs)}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,margins,expect_sharded", [(2, (4096, 60000), True), (3, (4096, 60000), True),
+                                                          (5, (4096, 60000), True), (3, (64, 60000), False),
+                                                          (2, (4096, 2000), False)])
+def test_rank_local_fasta_ingest(tmp_path, world, margins, expect_sharded):
+    """Each rank ingests its own byte range (margins hold the halos); too small a margin makes every rank fall back to
+    the whole file.  Either way rank 0 writes exactly the single-process text."""
+    import torch.multiprocessing as mp
+    sts_path, fa_path = _nasty_fasta(tmp_path, 911)
+    n1, want = _single_process_text(sts_path, fa_path, str(tmp_path / "one.txt"))
+    assert n1 > 50
+    out_path, info = str(tmp_path / "multi.txt"), str(tmp_path / "info")
+    mp.spawn(_rank_main_local_ingest, args=(world, _free_port(), sts_path, fa_path, out_path, info, margins),
+             nprocs=world, join=True)
+    assert open(out_path).read() == want
+    rows = [open(f"{info}.{r}").read().split() for r in range(world)]
+    assert [int(r[0]) for r in rows] == [int(expect_sharded)] * world
+    assert [int(r[1]) for r in rows] == [n1] * world
+    total = int(rows[0][3])
+    assert all(int(r[3]) == total and int(r[4]) == 7 for r in rows)        # every rank knows every record and its length
+    if expect_sharded:
+        assert all(int(r[2]) < (1.0 / world + 0.42) * total for r in rows)   # ... but holds only its own stretch (+ margins)
