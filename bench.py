@@ -415,6 +415,12 @@ def run_b200(args):
     launches = eng.gpu_launches - launches0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    per_rank = None
+    if world > 1:    # every rank's own numbers (the headline is the slowest rank's)
+        mine = dict(rank=rank, ms_per_step=round(t_ms / args.steps, 4), scan_kernel_ms=round(float(np.mean(scan_ms)), 4),
+                    verify_kernel_ms=round(float(np.mean(verify_ms)), 4), hits=int(n_hits))
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     t_ms = max_over_ranks(t_ms)
     ms_per_step = t_ms / args.steps
     total_bp = sum_over_ranks(float(my_bp))
@@ -611,8 +617,8 @@ def run_b200(args):
                         **({"emulated_shard": args.as_shard, "note": "tuning run: one rank's share only, not a bench line"}
                            if args.as_shard else {}),
                         l2="inputs (2.7 GB of planes per GPU) exceed the 126 MB L2; no flush needed",
-                        numa_node=numa,
-                        planted_found=planted_ok, sorted=sorted_ok),
+                        numa_node=numa, host_cpus=len(os.sched_getaffinity(0)),
+                        planted_found=planted_ok, sorted=sorted_ok, **({"per_rank": per_rank} if per_rank else {})),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,
                           traffic=traffic, traffic_source=traffic_source, kernel="scan_kernel", kernel_ms=kern_ms,
                           verify_kernel_ms=float(np.mean(verify_ms)),
