@@ -390,23 +390,39 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # samples every 20 ms from the warm-up to the end of the timed region (GPU under load)
-    for _ in range(args.warmup):
-        _, n_hits = eng.scan_device(layout, shard)
+    # Steps are queued two deep: the host reads step k's hit count (and, per slot, its kernel times) while step k+1
+    # runs, so the GPU never waits for the host round trip between steps.  Every step does all of its work -- scan,
+    # verify, ordering, count read-back -- and every count is checked; nothing is skipped or cached.
+    scan_ms, verify_ms = [], []
+
+    def run_steps(k: int, record: bool) -> int:
+        pending, n = None, 0
+        for i in range(k):
+            h = eng.scan_device_async(layout, shard, slot=i & 1)
+            if pending is not None:
+                _, n = eng.scan_finish(layout, shard, pending)
+                if record:
+                    scan_ms.append(float(lib.mpcr_slot_scan_ms(ctx, pending[0])))
+                    verify_ms.append(float(lib.mpcr_slot_verify_ms(ctx, pending[0])))
+            pending = h
+        if pending is not None:
+            _, n = eng.scan_finish(layout, shard, pending)
+            if record:
+                scan_ms.append(float(lib.mpcr_slot_scan_ms(ctx, pending[0])))
+                verify_ms.append(float(lib.mpcr_slot_verify_ms(ctx, pending[0])))
+        return n
+
+    n_hits = run_steps(args.warmup, False)
     if rank == 0:
         sampler.wait_first_sample()
-        for _ in range(2):       # keep the GPU busy while the sampler gets going (untimed)
-            eng.scan_device(layout, shard)
+        run_steps(2, False)      # keep the GPU busy while the sampler gets going (untimed)
     barrier()
     if rank == 0:
         sampler.mark()
     launches0 = eng.gpu_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scan_ms, verify_ms = [], []
     ev0.record()
-    for _ in range(args.steps):
-        _, n_hits = eng.scan_device(layout, shard)
-        scan_ms.append(float(lib.mpcr_last_scan_ms(ctx)))
-        verify_ms.append(float(lib.mpcr_last_verify_ms(ctx)))
+    n_hits = run_steps(args.steps, True)
     ev1.record()
     torch.cuda.synchronize()
     if rank == 0:
@@ -427,6 +443,16 @@ def run_b200(args):
     total_hits = sum_over_ranks(float(n_hits))
     value = total_bp / (ms_per_step * 1e-3) / 1e9
     kern_ms = float(np.mean(scan_ms))
+
+    # the same step with a host synchronisation after EVERY step (one call, one round trip): what a caller sees who
+    # needs each result before issuing the next step
+    sync_steps = max(3, min(args.steps, 10))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(sync_steps):
+        eng.scan_device(layout, shard)
+    torch.cuda.synchronize()
+    ms_synced = max_over_ranks((time.perf_counter() - t0) / sync_steps * 1e3)
 
     # planted truth + ordering sanity on the resident result (not timed)
     hits_t, n = eng.scan_device(layout, shard)
@@ -617,6 +643,7 @@ def run_b200(args):
                         **({"emulated_shard": args.as_shard, "note": "tuning run: one rank's share only, not a bench line"}
                            if args.as_shard else {}),
                         l2="inputs (2.7 GB of planes per GPU) exceed the 126 MB L2; no flush needed",
+                        steps_in_flight=2, ms_per_step_host_synced=ms_synced,
                         numa_node=numa, host_cpus=len(os.sched_getaffinity(0)),
                         planted_found=planted_ok, sorted=sorted_ok, **({"per_rank": per_rank} if per_rank else {})),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 12
+#define MPCR_ABI_VERSION 13
 
 enum {
     MPCR_OK = 0,
@@ -286,6 +286,23 @@ int mpcr_scan_sorted(mpcr_ctx *const *ctxs, uint32_t n_ctx, const mpcr_contig *h
                      const void *d_plane2, const void *d_plane4, const void *d_valid, uint64_t plane_origin,
                      uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit *d_hits, uint64_t capacity,
                      uint64_t *d_count, uint64_t *h_count, uint64_t n_hint, int sort, void *stream);
+
+/* The same step without the final synchronisation, for callers that keep two steps in flight (the host reads step k's
+ * count while step k+1 runs; consecutive steps on one stream share the context's scratch, only d_hits / d_count /
+ * h_result must differ between the two): h_result = two uint64 of PINNED host memory, [0] receives the true hit count,
+ * [1] != 0 means the short-list sort gave up and mpcr_sort_finish must run -- both valid once the caller has
+ * synchronised with `stream` (event, stream sync).  slot (0 / 1) selects the set of timing events the step records
+ * (mpcr_slot_scan_ms / mpcr_slot_verify_ms read them back without waiting for a later step). */
+int mpcr_scan_sorted_async(mpcr_ctx *const *ctxs, uint32_t n_ctx, const mpcr_contig *h_contigs, uint32_t n_contigs,
+                           const void *d_plane2, const void *d_plane4, const void *d_valid, uint64_t plane_origin,
+                           uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit *d_hits,
+                           uint64_t capacity, uint64_t *d_count, uint64_t *h_result, uint64_t n_hint, int sort, int slot,
+                           void *stream);
+/* After the caller has synchronised behind mpcr_scan_sorted_async: completes the sort when h_result[1] says so
+ * (radix passes with the count now known; synchronous), a no-op otherwise. */
+int mpcr_sort_finish(mpcr_ctx *ctx, mpcr_hit *d_hits, const uint64_t *h_result, uint64_t capacity, void *stream);
+float mpcr_slot_scan_ms(mpcr_ctx *ctx, int slot);
+float mpcr_slot_verify_ms(mpcr_ctx *ctx, int slot);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mpcr_launch_count(const mpcr_ctx *ctx);

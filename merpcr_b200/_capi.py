@@ -14,14 +14,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPCR_B200_LIB") or os.path.join(_HERE, "lib", "libmerpcr_b200.so")
 
 MPCR_OK, MPCR_EINVAL, MPCR_ECUDA, MPCR_ENOMEM, MPCR_ESTATE, MPCR_EOVERFLOW = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # every symbol include/merpcr_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_set_seed_extension", "mpcr_ctx_set_table_part", "mpcr_ctx_set_sampling", "mpcr_table_items", "mpcr_ctx_set_append", "mpcr_scan_prepare", "mpcr_ctx_set_true_strands", "mpcr_ctx_sm_count",
     "mpcr_pack_sequence", "mpcr_host_pack_nibbles", "mpcr_derive_planes", "mpcr_file_read", "mpcr_fasta_workspace_bytes", "mpcr_fasta_index", "mpcr_fasta_index_ex", "mpcr_fasta_offsets_at", "mpcr_fasta_compact",
     "mpcr_sts_parse", "mpcr_sts_blob", "mpcr_format_hits", "mpcr_table_build", "mpcr_table_records", "mpcr_table_primer_words", "mpcr_scan",
-    "mpcr_halo_left", "mpcr_halo_right", "mpcr_tile_bases", "mpcr_sort_hits", "mpcr_sort_hits_dev", "mpcr_scan_sorted", "mpcr_launch_count", "mpcr_last_scan_ms", "mpcr_last_verify_ms",
+    "mpcr_halo_left", "mpcr_halo_right", "mpcr_tile_bases", "mpcr_sort_hits", "mpcr_sort_hits_dev", "mpcr_scan_sorted", "mpcr_scan_sorted_async", "mpcr_sort_finish", "mpcr_slot_scan_ms", "mpcr_slot_verify_ms", "mpcr_launch_count", "mpcr_last_scan_ms", "mpcr_last_verify_ms",
 ]
 
 HIT_DTYPE = np.dtype([("contig", "<u4"), ("pos1", "<u4"), ("pos2", "<u4"), ("rec", "<u4"), ("rank", "<u4"),
@@ -111,6 +111,15 @@ class Backend:
         lib.mpcr_sort_hits_dev.argtypes = [vp, vp, vp, u64, u64, vp]
         lib.mpcr_scan_sorted.restype = i32
         lib.mpcr_scan_sorted.argtypes = [vp, u32, vp, u32, vp, vp, vp, u64, u64, u64, u64, vp, u64, vp, vp, u64, i32, vp]
+        lib.mpcr_scan_sorted_async.restype = i32
+        lib.mpcr_scan_sorted_async.argtypes = [vp, u32, vp, u32, vp, vp, vp, u64, u64, u64, u64, vp, u64, vp, vp, u64, i32, i32,
+                                               vp]
+        lib.mpcr_sort_finish.restype = i32
+        lib.mpcr_sort_finish.argtypes = [vp, vp, vp, u64, vp]
+        lib.mpcr_slot_scan_ms.restype = C.c_float
+        lib.mpcr_slot_scan_ms.argtypes = [vp, i32]
+        lib.mpcr_slot_verify_ms.restype = C.c_float
+        lib.mpcr_slot_verify_ms.argtypes = [vp, i32]
         lib.mpcr_launch_count.restype = u64
         lib.mpcr_launch_count.argtypes = [vp]
         lib.mpcr_last_scan_ms.restype = C.c_float

@@ -115,8 +115,11 @@ struct mpcr_ctx {
     size_t counts_cap = 0;
     uint8_t* d_lut = nullptr;  // 256 B genome LUT for pack
     uint64_t launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-    bool scan_timed = false;
+    // scan / verify timing events, one set per pipeline slot (a caller that keeps two steps in flight reads step k's
+    // times while step k+1 records its own, see mpcr_scan_sorted_async)
+    cudaEvent_t evs[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    int ev_slot = 0;
+    bool scan_timed[2] = {false, false};
     int env_debug = 0;          // $MPCR_DEBUG, read once at context creation
     long env_surv_cap = -1;     // $MPCR_SURVIVOR_CAP (test hook), ditto
     bool ctl_dirty = false;     // the scanner's control words were left non-zero (debug runs skip the verifier)
@@ -1324,9 +1327,8 @@ int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
     step(cudaMalloc(&c->d_lut, 256));
     if (err == cudaSuccess) step(cudaMemset(c->d_tile_counter, 0, 256));
     if (err == cudaSuccess) step(cudaMemset(c->d_surv_ctl, 0, (size_t)kSurvLists * kSurvCtlStride * 4));
-    step(cudaEventCreate(&c->ev0));
-    step(cudaEventCreate(&c->ev1));
-    step(cudaEventCreate(&c->ev2));
+    for (int sl = 0; sl < 2; ++sl)
+        for (int k = 0; k < 3; ++k) step(cudaEventCreate(&c->evs[sl][k]));
     if (err != cudaSuccess) {
         mpcr_ctx_destroy(c);   // frees whatever was allocated
         return fail(MPCR_ECUDA, "context setup failed: %s", cudaGetErrorString(err));
@@ -1348,9 +1350,9 @@ void mpcr_ctx_destroy(mpcr_ctx* c) {
     DeviceGuard guard_(c->device);
     free_table(c);
     cudaFree(c->d_tiles); cudaFree(c->d_tile_counter); cudaFree(c->d_sort_tmp); cudaFree(c->d_long_runs); cudaFree(c->d_counts); cudaFree(c->d_lut);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->ev2) cudaEventDestroy(c->ev2);
+    for (int sl = 0; sl < 2; ++sl)
+        for (int k = 0; k < 3; ++k)
+            if (c->evs[sl][k]) cudaEventDestroy(c->evs[sl][k]);
     cudaFree(c->d_surv);
     cudaFree(c->d_surv_ctl);
     cudaFree(c->d_contig_g);
@@ -1968,7 +1970,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     int rc = build_tiles(c, h_contigs, n_contigs, plane_origin, shard_begin, shard_end, st);
     if (rc) return rc;
     if (!c->append) CU(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
-    c->scan_timed = false;
+    c->scan_timed[c->ev_slot] = false;
     if (c->view_count == 0 || c->n_valid == 0) return MPCR_OK;
     // The planes must hold every base the kernels touch: units are staged whole (2048 positions + 128 bases of
     // read-ahead), the verifier reads up to the mate window's end (+ 64 bases of word over-read), and nothing lies in
@@ -2016,7 +2018,8 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     const size_t smem = (size_t)ScanSmem::kFilterOff + (size_t)c->filter_words * 4;
     uint32_t grid = (uint32_t)c->sm_count;
     if (grid > c->view_count) grid = c->view_count;
-    CU(cudaEventRecord(c->ev0, st));
+    cudaEvent_t* ev = c->evs[c->ev_slot];
+    CU(cudaEventRecord(ev[0], st));
     if (c->samp_role == 1) {
         sampled_scan_kernel<<<c->sm_count * 4, 256, 0, st>>>(a);
     } else if (c->dense) {
@@ -2037,7 +2040,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
         }
         kern<<<grid, kScanThreads, smem, st>>>(a);
     }
-    CU(cudaEventRecord(c->ev1, st));
+    CU(cudaEventRecord(ev[1], st));
     c->launches++;
     CU(cudaGetLastError());
     if (!a.debug) {
@@ -2047,18 +2050,20 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     } else {
         c->ctl_dirty = true;
     }
-    CU(cudaEventRecord(c->ev2, st));
-    c->scan_timed = true;
+    CU(cudaEventRecord(ev[2], st));
+    c->scan_timed[c->ev_slot] = true;
     return MPCR_OK;
 }
 
 static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const unsigned long long* d_n,
                           uint64_t n_hint, cudaStream_t st, bool optimistic, bool* only_bucket);
-int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* h_contigs, uint32_t n_contigs,
-                     const void* d_plane2, const void* d_plane4, const void* d_valid, uint64_t plane_origin,
-                     uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit* d_hits, uint64_t capacity,
-                     uint64_t* d_count, uint64_t* h_count, uint64_t n_hint, int sort, void* stream) {
+int mpcr_scan_sorted_async(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* h_contigs, uint32_t n_contigs,
+                           const void* d_plane2, const void* d_plane4, const void* d_valid, uint64_t plane_origin,
+                           uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit* d_hits,
+                           uint64_t capacity, uint64_t* d_count, uint64_t* h_result, uint64_t n_hint, int sort, int slot,
+                           void* stream) {
     if (!ctxs || n_ctx == 0 || !d_count) return fail(MPCR_EINVAL, "null argument");
+    if (slot < 0 || slot > 1) return fail(MPCR_EINVAL, "slot must be 0 or 1");
     for (uint32_t i = 0; i < n_ctx; ++i)
         if (!ctxs[i]) return fail(MPCR_EINVAL, "null context");
     int rc = MPCR_OK;
@@ -2066,6 +2071,7 @@ int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* h
     for (uint32_t i = 0; i < n_ctx; ++i) saved[i] = ctxs[i]->append;
     for (uint32_t i = 0; i < n_ctx && rc == MPCR_OK; ++i) {
         ctxs[i]->append = i == 0 ? 0 : 1;    // the first table zeroes the count, the others append behind it
+        ctxs[i]->ev_slot = slot;
         rc = mpcr_scan(ctxs[i], h_contigs, n_contigs, d_plane2, d_plane4, d_valid, plane_origin, plane_bases, shard_begin,
                        shard_end, d_hits, capacity, d_count, stream);
     }
@@ -2076,50 +2082,75 @@ int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* h
     if (sort && capacity >= 2) {
         if (!d_hits) return fail(MPCR_EINVAL, "null hit buffer");
         GUARD(c0);
+        // with a result buffer the caller looks at the bucket sort's fall-back flag itself (mpcr_sort_finish): a list
+        // hinted short then gets the four bucket-sort launches and nothing else
         rc = sort_hits_impl(c0, d_hits, capacity, (const unsigned long long*)d_count, n_hint, (cudaStream_t)stream,
-                            h_count != nullptr, &only_bucket);
+                            h_result != nullptr, &only_bucket);
         if (rc) return rc;
     }
-    if (h_count) {
+    if (h_result) {
         GUARD(c0);
         cudaStream_t st = (cudaStream_t)stream;
-        CU(cudaMemcpyAsync(h_count, d_count, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        uint32_t* h_flag = nullptr;
-        if (only_bucket) {   // the bucket sort's fall-back flag comes back with the count
-            if (!c0->h_flag) CU(cudaMallocHost(&c0->h_flag, 16));
-            h_flag = c0->h_flag;
-            CU(cudaMemcpyAsync(h_flag, c0->d_bsort + (size_t)kSortBuckets * 2 + 4 + kBucketSortMax, 4, cudaMemcpyDeviceToHost, st));
-        }
-        CU(cudaStreamSynchronize(st));
-        if (h_flag && *h_flag) {   // the list piled up in one slice (or outgrew the hint): radix passes, count known now
-            const uint64_t n = *h_count < capacity ? *h_count : capacity;
-            if (n >= 2) {
-                rc = sort_hits_impl(c0, d_hits, n, nullptr, 0, st, false, nullptr);
-                if (rc) return rc;
-                CU(cudaStreamSynchronize(st));
-            }
-        }
+        h_result[1] = 0;
+        CU(cudaMemcpyAsync(h_result, d_count, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (only_bucket)   // the fall-back flag comes back with the count (4 bytes into the low half of h_result[1])
+            CU(cudaMemcpyAsync(h_result + 1, c0->d_bsort + (size_t)kSortBuckets * 2 + 4 + kBucketSortMax, 4, cudaMemcpyDeviceToHost, st));
     }
     return MPCR_OK;
 }
 
-float mpcr_last_scan_ms(mpcr_ctx* c) {
-    if (!c || !c->scan_timed) return 0.f;
-    float ms = 0.f;
-    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return 0.f;
-    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return 0.f;
-    return ms;
-}
-float mpcr_last_verify_ms(mpcr_ctx* c) {
-    if (!c || !c->scan_timed) return 0.f;
-    float ms = 0.f;
-    if (cudaEventSynchronize(c->ev2) != cudaSuccess) return 0.f;
-    if (cudaEventElapsedTime(&ms, c->ev1, c->ev2) != cudaSuccess) return 0.f;
-    return ms;
+int mpcr_sort_finish(mpcr_ctx* c, mpcr_hit* d_hits, const uint64_t* h_result, uint64_t capacity, void* stream) {
+    if (!c || !h_result) return fail(MPCR_EINVAL, "null argument");
+    if (!h_result[1]) return MPCR_OK;
+    // the list piled up in one slice (or outgrew the hint): radix passes, with the count known now
+    const uint64_t n = h_result[0] < capacity ? h_result[0] : capacity;
+    if (n < 2) return MPCR_OK;
+    if (!d_hits) return fail(MPCR_EINVAL, "null hit buffer");
+    GUARD(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = sort_hits_impl(c, d_hits, n, nullptr, 0, st, false, nullptr);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
+    return MPCR_OK;
 }
 
-// Shared by both sort entry points: n_host records, or -- with d_n -- as many as *d_n says (at most n_host, the
-// buffer's capacity), read on the device so that the sort queues up behind the scan without a host round trip.
+int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* h_contigs, uint32_t n_contigs,
+                     const void* d_plane2, const void* d_plane4, const void* d_valid, uint64_t plane_origin,
+                     uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit* d_hits, uint64_t capacity,
+                     uint64_t* d_count, uint64_t* h_count, uint64_t n_hint, int sort, void* stream) {
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return fail(MPCR_EINVAL, "null argument");
+    mpcr_ctx* c0 = ctxs[0];
+    uint64_t* h_result = nullptr;
+    if (h_count) {
+        if (!c0->h_flag) {
+            GUARD(c0);
+            CU(cudaMallocHost(&c0->h_flag, 32));
+        }
+        h_result = reinterpret_cast<uint64_t*>(c0->h_flag);
+    }
+    int rc = mpcr_scan_sorted_async(ctxs, n_ctx, h_contigs, n_contigs, d_plane2, d_plane4, d_valid, plane_origin, plane_bases,
+                                    shard_begin, shard_end, d_hits, capacity, d_count, h_result, n_hint, sort, 0, stream);
+    if (rc || !h_count) return rc;
+    {
+        GUARD(c0);
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    *h_count = h_result[0];
+    return mpcr_sort_finish(c0, d_hits, h_result, capacity, stream);
+}
+
+static float event_ms(mpcr_ctx* c, int slot, int from, int to) {
+    if (!c || slot < 0 || slot > 1 || !c->scan_timed[slot]) return 0.f;
+    float ms = 0.f;
+    if (cudaEventSynchronize(c->evs[slot][to]) != cudaSuccess) return 0.f;
+    if (cudaEventElapsedTime(&ms, c->evs[slot][from], c->evs[slot][to]) != cudaSuccess) return 0.f;
+    return ms;
+}
+float mpcr_last_scan_ms(mpcr_ctx* c) { return c ? event_ms(c, c->ev_slot, 0, 1) : 0.f; }
+float mpcr_last_verify_ms(mpcr_ctx* c) { return c ? event_ms(c, c->ev_slot, 1, 2) : 0.f; }
+float mpcr_slot_scan_ms(mpcr_ctx* c, int slot) { return event_ms(c, slot, 0, 1); }
+float mpcr_slot_verify_ms(mpcr_ctx* c, int slot) { return event_ms(c, slot, 1, 2); }
+
 // optimistic: the caller synchronises right behind the sort and looks at the bucket sort's fall-back flag itself
 // (mpcr_scan_sorted) -- then a list hinted short gets the four bucket-sort launches and nothing else.
 static int sort_hits_impl(mpcr_ctx* c, mpcr_hit* d_hits, uint64_t n_host, const unsigned long long* d_n,

@@ -212,6 +212,7 @@ class MerPCR:
         self._copy_stream = None  # upload_and_scan: the H2D copies run beside pack + scan
         self._host_stage = None   # pinned staging buffers of the host-side nibble packer
         self._count_host = None   # pinned landing place of a step's hit count
+        self._slots = None        # scan_device_async: two pipeline slots (hit buffer, count, pinned result, event)
         # host-resident sequence goes over PCIe as packed nibbles (0.5 byte/base) unless switched off
         self.host_pack = os.environ.get("MPCR_HOST_PACK", "1") not in ("0", "")
         try:
@@ -988,6 +989,58 @@ class MerPCR:
         self._sync()
         out = stage.numpy().view(_capi.HIT_DTYPE)
         return out.copy() if copy else out
+
+    def scan_device_async(self, layout: dict, sh: _Shard, slot: int = 0, sort: bool = True):
+        """One step (scan + verify + ordering) queued WITHOUT waiting for it: for callers that keep two steps in flight
+        -- the host reads step k's result (`scan_finish`) while step k+1 runs.  Consecutive steps share the stream and
+        the contexts' scratch; each slot (0 / 1) has its own hit buffer, count and pinned result words.  Returns a
+        handle for `scan_finish`."""
+        import ctypes as C
+        lib = self._be.lib
+        contigs = layout["contigs"]
+        isz = _capi.HIT_DTYPE.itemsize
+        if self._slots is None:
+            self._slots = [dict(hits=None, count=None, result=None, event=None, last_n=0) for _ in range(2)]
+        st = self._slots[slot]
+        gpu = self._tdev.type == "cuda"
+        if st["count"] is None:
+            st["count"] = torch.zeros(1, dtype=torch.int64, device=self._tdev)
+            st["result"] = torch.zeros(2, dtype=torch.int64)
+            if gpu:
+                st["result"] = st["result"].pin_memory()
+                st["event"] = torch.cuda.Event()
+        if st["hits"] is None:
+            cap0 = 1 << 16 if sh.hits is None else sh.hits.numel() // isz
+            st["hits"] = torch.empty(cap0 * isz, dtype=torch.uint8, device=self._tdev)
+        cap = st["hits"].numel() // isz
+        ctxs = self._all_ctxs()
+        arr = (C.c_void_p * len(ctxs))(*[c.value if hasattr(c, "value") else c for c in ctxs])
+        stream = self._stream()
+        self._be.check(lib.mpcr_scan_sorted_async(arr, len(ctxs), contigs.ctypes.data, len(contigs), sh.plane2.data_ptr(),
+                                                  sh.plane4.data_ptr(), sh.valid.data_ptr(), sh.origin, sh.alloc, sh.begin,
+                                                  sh.end, st["hits"].data_ptr(), cap, st["count"].data_ptr(),
+                                                  st["result"].data_ptr(), st["last_n"], 1 if sort else 0, slot, stream))
+        if gpu:
+            st["event"].record(torch.cuda.current_stream(self._tdev))
+        return (slot, cap, sort)
+
+    def scan_finish(self, layout: dict, sh: _Shard, handle):
+        """Wait for the step `scan_device_async` queued and return (hit tensor, n_hits) like `scan_device`.  A hit list
+        that outgrew the slot's buffer is scanned again with room (synchronously; nothing is ever truncated)."""
+        slot, cap, sort = handle
+        lib = self._be.lib
+        st = self._slots[slot]
+        if st["event"] is not None:
+            st["event"].synchronize()
+        need = int(st["result"][0])
+        if need > cap:
+            isz = _capi.HIT_DTYPE.itemsize
+            st["hits"] = torch.empty(max(need, 2 * cap) * isz, dtype=torch.uint8, device=self._tdev)
+            return self.scan_finish(layout, sh, self.scan_device_async(layout, sh, slot, sort))
+        if sort and int(st["result"][1]):
+            self._be.check(lib.mpcr_sort_finish(self._ctx, st["hits"].data_ptr(), st["result"].data_ptr(), cap, self._stream()))
+        st["last_n"] = need
+        return st["hits"], need
 
     def scan_device(self, layout: dict, sh: _Shard, sort: bool = True):
         """Device-resident scan: returns (uint8 tensor holding mpcr_hit records, n_hits).  Re-runs with a larger

@@ -479,4 +479,22 @@ int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* c
     return MPCR_OK;
 }
 
+int mpcr_scan_sorted_async(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* contigs, uint32_t n_contigs, const void* p2,
+                           const void* p4, const void* valid, uint64_t origin, uint64_t plane_bases, uint64_t sb, uint64_t se,
+                           mpcr_hit* hits, uint64_t capacity, uint64_t* count, uint64_t* h_result, uint64_t hint, int sort,
+                           int slot, void* st) {
+    if (slot < 0 || slot > 1) return fail(MPCR_EINVAL, "slot must be 0 or 1");
+    uint64_t n = 0;
+    const int rc = mpcr_scan_sorted(ctxs, n_ctx, contigs, n_contigs, p2, p4, valid, origin, plane_bases, sb, se, hits, capacity,
+                                    count, &n, hint, sort, st);
+    if (h_result) { h_result[0] = n; h_result[1] = 0; }
+    return rc;
+}
+int mpcr_sort_finish(mpcr_ctx* c, mpcr_hit*, const uint64_t* h_result, uint64_t, void*) {
+    if (!c || !h_result) return fail(MPCR_EINVAL, "null argument");
+    return MPCR_OK;
+}
+float mpcr_slot_scan_ms(mpcr_ctx*, int) { return 0.f; }
+float mpcr_slot_verify_ms(mpcr_ctx*, int) { return 0.f; }
+
 }  // extern "C"

@@ -729,3 +729,9 @@ def test_fuzz_goldens_with_position_sampling_on_device(monkeypatch):
                 parity.check_fuzz_case(c, MerPCR)
                 n += 1
         assert n > 5
+
+
+def test_two_steps_in_flight_on_device(tmp_path):
+    from merpcr_b200 import MerPCR
+    from test_host_logic import _two_in_flight_check
+    _two_in_flight_check(MerPCR, _records, tmp_path)

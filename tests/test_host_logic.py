@@ -611,3 +611,39 @@ def test_fuzz_goldens_with_position_sampling(monkeypatch):
                 parity.check_fuzz_case(c, MerPCR)
                 n += 1
         assert n > 5
+
+
+def _two_in_flight_check(MerPCR, make_records, tmp_path):
+    """scan_device_async / scan_finish (two steps in flight, one hit buffer and count per slot) == scan_device, including a
+    hit list that outgrows the slot's first buffer and a list that piles up in one place (the short-list sort gives up
+    and scan_finish completes it)."""
+    unit = "ACGGTCATTGCAGT" + "TTGACCGGTATCAG" + "CATGCATGAACC"
+    seq = np.frombuffer(("G" * 300 + unit * 5000 + "C" * 300).encode(), dtype=np.uint8).copy()
+    sts_text = "".join(f"R{i}\tACGGTCATTGCAGT\tTTGACCGGTATCAG\t{68 + (i % 3)}\trep\n" for i in range(4)).encode()
+    p = tmp_path / "two.sts"
+    p.write_bytes(sts_text)
+    eng = MerPCR(wordsize=8, margin=45, mismatches=0)
+    assert eng.load_sts_file(str(p))
+    recs = make_records([seq, seq[:50_000].copy()])
+    layout = eng.make_layout([len(r) for r in recs])
+    sh = eng.upload(layout, [r.sequence_bytes for r in recs])
+    first = eng.scan_device_async(layout, sh, slot=0)          # the slots start with room for 65 536 hits ...
+    h0, n0 = eng.scan_finish(layout, sh, first)                  # ... so this one is scanned again with more
+    got0 = eng._hits_to_host(h0, n0)
+    hits, n = eng.scan_device(layout, sh)
+    want = eng._hits_to_host(hits, n)
+    assert n == n0 > 65536 and np.array_equal(got0, want)
+    handles = [eng.scan_device_async(layout, sh, slot=0), eng.scan_device_async(layout, sh, slot=1)]
+    for k in range(4):
+        h, m = eng.scan_finish(layout, sh, handles[k & 1])
+        assert m == n and np.array_equal(eng._hits_to_host(h, m), want), k
+        handles[k & 1] = eng.scan_device_async(layout, sh, slot=k & 1)
+    for hd in handles:
+        h, m = eng.scan_finish(layout, sh, hd)
+        assert m == n and np.array_equal(eng._hits_to_host(h, m), want)
+    eng.close()
+
+
+def test_two_steps_in_flight(tmp_path):
+    from merpcr_b200 import FASTARecord, MerPCR
+    _two_in_flight_check(MerPCR, lambda seqs: [FASTARecord(f">c{i}", s) for i, s in enumerate(seqs)], tmp_path)
