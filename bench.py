@@ -5,9 +5,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]           # our arm (CUDA, one process per GPU)
     python bench.py --impl reference [...]                         # the reference's CPU algorithm (C port of it)
 
-One "step" = one pass of the hot path (scan + verify + emit + sort) over the rank's resident genome shard.
-`value` is whole-job throughput with the packed genome and the table resident in HBM; `e2e` repeats the step
-from pinned HOST bytes (H2D + pack + scan + sort + D2H of the hits inside the timed region).
+One "step" = one pass of the hot path (scan + verify + emit + sort + read-back of the hit count) over the rank's
+resident genome shard.  `value` is whole-job throughput with the packed genome and the table resident in HBM, steps
+queued two deep (the host reads step k's count while step k+1 runs; `config.ms_per_step_host_synced` is the same
+step with a host synchronisation after every one); `e2e` repeats the step from pinned HOST bytes (host-side nibble
+packing / H2D + plane building + scan + sort + D2H of the hits inside the timed region); `e2e_file` starts from a
+FASTA file in the page cache and ends with the output text on disk.
 N > 1: strong scaling by default -- ONE 3.1 Gbp genome cut into bp-balanced ranges (+ halos), one per rank, through
 the engine's (rank, world) sharding (BASELINE.json config 3); there is no collective on the scan path, NCCL only
 carries the timing barrier / max-over-ranks.  `--scaling weak` gives every rank its own genome copy instead.
@@ -447,6 +450,7 @@ def run_b200(args):
     # the same step with a host synchronisation after EVERY step (one call, one round trip): what a caller sees who
     # needs each result before issuing the next step
     sync_steps = max(3, min(args.steps, 10))
+    eng.scan_device(layout, shard)      # untimed: this path's own hit buffer grows to size here
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(sync_steps):
