@@ -31,40 +31,86 @@ struct FastaHeader {
     uint64_t end;    // byte offset of the line terminator (or n)
 };
 
-// One thread per 16 bytes: report every header '>' and whether any byte is >= 128.
-__global__ void __launch_bounds__(256) fasta_find_headers(const uint8_t* __restrict__ text, uint64_t n,
-                                                          FastaHeader* __restrict__ out, uint32_t cap,
-                                                          uint32_t* __restrict__ count, uint32_t* __restrict__ flags) {
-    const uint64_t b0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (b0 >= n) return;
-    uint8_t c[16];
-    if (b0 + 16 <= n && ((reinterpret_cast<uintptr_t>(text) & 15u) == 0)) {
-        *reinterpret_cast<uint4*>(c) = *reinterpret_cast<const uint4*>(text + b0);
-    } else {
-        for (int k = 0; k < 16; ++k) c[k] = b0 + k < n ? text[b0 + k] : (uint8_t)'\n';
-    }
-    bool high = false;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        high |= c[k] >= 128;
-        if (c[k] != '>') continue;
-        const uint64_t i = b0 + k;
-        // first non-blank character of its line?
-        uint64_t j = i;
-        bool first = true;
-        while (j > 0) {
-            const uint8_t p = text[j - 1];
-            if (fasta_is_term(p)) break;
-            if (!fasta_is_blank(p)) { first = false; break; }
-            --j;
+// Per-byte classes for the fused pass: bit0 = kept sequence letter, bit1 = '>', bit2 = byte >= 128.
+__device__ __forceinline__ uint8_t fasta_class_of(uint32_t c) {
+    return (uint8_t)((fasta_keep((uint8_t)c) ? 1u : 0u) | (c == '>' ? 2u : 0u) | (c >= 128u ? 4u : 0u));
+}
+
+// ONE pass over the text instead of two (fasta_find_headers + fasta_count): every thread classifies 16 bytes through a
+// 256-entry table in shared memory, the block's kept letters are counted, '>' bytes take the (rare) header test, bytes
+// >= 128 raise the flag.  The counts still include the letters of header lines and of the text in front of the first
+// header -- fasta_blank_headers / fasta_blank_range take those out again when they blank them.
+__global__ void __launch_bounds__(kFastaThreads) fasta_classify(const uint8_t* __restrict__ text, uint64_t n,
+                                                                FastaHeader* __restrict__ out, uint32_t cap,
+                                                                uint32_t* __restrict__ count, uint32_t* __restrict__ flags,
+                                                                uint32_t* __restrict__ block_count) {
+    __shared__ uint8_t lut[256];
+    __shared__ uint32_t warp_sum[kFastaThreads / 32];
+    lut[threadIdx.x] = fasta_class_of(threadIdx.x);
+    __syncthreads();
+    const uint64_t b0 = (uint64_t)blockIdx.x * kFastaBlock + (uint64_t)threadIdx.x * 16;
+    uint32_t kept = 0, any = 0;
+    if (b0 < n) {
+        uint32_t w[4];
+        if (b0 + 16 <= n && ((reinterpret_cast<uintptr_t>(text) & 15u) == 0)) {
+            const uint4 t = *reinterpret_cast<const uint4*>(text + b0);
+            w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+        } else {
+            for (int k = 0; k < 4; ++k) {
+                uint32_t x = 0;
+                for (int b = 0; b < 4; ++b) x |= (uint32_t)(b0 + 4 * k + b < n ? text[b0 + 4 * k + b] : (uint8_t)'\n') << (8 * b);
+                w[k] = x;
+            }
         }
-        if (!first) continue;
-        uint64_t e = i + 1;
-        while (e < n && !fasta_is_term(text[e])) ++e;
-        const uint32_t slot = atomicAdd(count, 1u);
-        if (slot < cap) out[slot] = FastaHeader{i, e};
+        uint32_t gt = 0;   // bit j: byte j is '>'
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t e = lut[(w[k] >> (8 * b)) & 0xFFu];
+                kept += e & 1u;
+                gt |= ((e >> 1) & 1u) << (4 * k + b);
+                any |= e;
+            }
+        }
+        while (gt) {   // rare: is this '>' the first non-blank character of its line?
+            const int j = __ffs(gt) - 1;
+            gt &= gt - 1;
+            const uint64_t i = b0 + j;
+            uint64_t q = i;
+            bool first = true;
+            while (q > 0) {
+                const uint8_t p = text[q - 1];
+                if (fasta_is_term(p)) break;
+                if (!fasta_is_blank(p)) { first = false; break; }
+                --q;
+            }
+            if (!first) continue;
+            uint64_t e = i + 1;
+            while (e < n && !fasta_is_term(text[e])) ++e;
+            const uint32_t slot = atomicAdd(count, 1u);
+            if (slot < cap) out[slot] = FastaHeader{i, e};
+        }
     }
-    if (high) atomicOr(flags, 1u);
+    if (any & 4u) atomicOr(flags, 1u);
+    for (int d = 16; d; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = kept;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w2 = 0; w2 < kFastaThreads / 32; ++w2) t += warp_sum[w2];
+        block_count[blockIdx.x] = t;
+    }
+}
+
+// Blank the bytes [a, b) (the text in front of the first header) and take their kept letters out of the block counts.
+__global__ void __launch_bounds__(256) fasta_blank_range(uint8_t* __restrict__ text, uint64_t a, uint64_t b,
+                                                         uint32_t* __restrict__ block_count) {
+    const uint64_t i0 = a + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    for (uint64_t i = i0; i < i0 + 16 && i < b; ++i) {
+        if (fasta_keep(text[i])) atomicSub(&block_count[i / kFastaBlock], 1u);
+        text[i] = '\n';
+    }
 }
 
 // Slices of a file (rank-local ingest): where does the first line terminator within the first `limit` bytes end?
@@ -87,59 +133,95 @@ __global__ void __launch_bounds__(256) fasta_first_line_end(const uint8_t* __res
 // Blank the header lines (sorted table) and everything before the first header, so that "kept" becomes a pure
 // per-byte property.  One thread per header; header lines are short.
 __global__ void __launch_bounds__(128) fasta_blank_headers(uint8_t* __restrict__ text, const FastaHeader* __restrict__ hdr,
-                                                           uint32_t n_hdr) {
+                                                           uint32_t n_hdr, uint32_t* __restrict__ block_count) {
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= n_hdr) return;
-    for (uint64_t i = hdr[h].begin; i < hdr[h].end; ++i) text[i] = '\n';
-}
-
-__device__ __forceinline__ uint32_t fasta_keep_mask16(const uint8_t* __restrict__ text, uint64_t b0, uint64_t n, uint8_t* c) {
-    if (b0 + 16 <= n && ((reinterpret_cast<uintptr_t>(text) & 15u) == 0)) {
-        *reinterpret_cast<uint4*>(c) = *reinterpret_cast<const uint4*>(text + b0);
-    } else {
-        for (int k = 0; k < 16; ++k) c[k] = b0 + k < n ? text[b0 + k] : (uint8_t)'\n';
-    }
-    uint32_t m = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m |= (fasta_keep(c[k]) ? 1u : 0u) << k;
-    return m;
-}
-
-// kept bytes per 4096-byte block
-__global__ void __launch_bounds__(kFastaThreads) fasta_count(const uint8_t* __restrict__ text, uint64_t n,
-                                                             uint32_t* __restrict__ block_count) {
-    __shared__ uint32_t warp_sum[kFastaThreads / 32];
-    const uint64_t b0 = (uint64_t)blockIdx.x * kFastaBlock + (uint64_t)threadIdx.x * 16;
-    uint8_t c[16];
-    uint32_t k = b0 < n ? __popc(fasta_keep_mask16(text, b0, n, c)) : 0u;
-    for (int d = 16; d; d >>= 1) k += __shfl_xor_sync(0xffffffffu, k, d);
-    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = k;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kFastaThreads / 32; ++w) t += warp_sum[w];
-        block_count[blockIdx.x] = t;
+    for (uint64_t i = hdr[h].begin; i < hdr[h].end; ++i) {
+        // block_count (fasta_classify) still counts the letters of this line: take them out
+        if (block_count && fasta_keep(text[i])) atomicSub(&block_count[i / kFastaBlock], 1u);
+        text[i] = '\n';
     }
 }
 
-// exclusive prefix of n_blk uint32 counts into uint64 offsets (one CTA; n_blk is ~1e6 for a human genome)
-__global__ void __launch_bounds__(1024) fasta_scan_blocks(const uint32_t* __restrict__ cnt, uint64_t n_blk,
-                                                          uint64_t* __restrict__ off /* n_blk + 1 */) {
-    __shared__ uint64_t part[1024];
-    const uint64_t per = (n_blk + 1023) / 1024;
-    const uint64_t lo = min(n_blk, (uint64_t)threadIdx.x * per), hi = min(n_blk, lo + per);
+// exclusive prefix of n_blk uint32 counts into uint64 offsets, in three small launches (n_blk is ~10^6 for a human
+// genome: one CTA walking it serially took 0.12 ms): per chunk of 16 384 counts a sum, one CTA scans the chunk sums (up
+// to 1024 chunks = 64 GiB of text), then every chunk scans itself from its base.
+static constexpr int kScanChunk = 16384;
+__global__ void __launch_bounds__(1024) fasta_scan_reduce(const uint32_t* __restrict__ cnt, uint64_t n_blk,
+                                                          uint64_t* __restrict__ chunk_sum) {
+    __shared__ uint64_t ws[32];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanChunk;
     uint64_t s = 0;
-    for (uint64_t i = lo; i < hi; ++i) s += cnt[i];
-    part[threadIdx.x] = s;
+    for (int k = 0; k < kScanChunk / 1024; ++k) {
+        const uint64_t i = base + (uint64_t)k * 1024 + threadIdx.x;
+        if (i < n_blk) s += cnt[i];
+    }
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint64_t run = 0;
-        for (int t = 0; t < 1024; ++t) { const uint64_t v = part[t]; part[t] = run; run += v; }
-        off[n_blk] = run;
+        uint64_t t = 0;
+        for (int w = 0; w < 32; ++w) t += ws[w];
+        chunk_sum[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) fasta_scan_top(uint64_t* __restrict__ chunk_sum, uint32_t n_chunks,
+                                                       uint64_t* __restrict__ total) {
+    __shared__ uint64_t ws[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t v = threadIdx.x < n_chunks ? chunk_sum[threadIdx.x] : 0ull;
+    uint64_t incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) ws[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint64_t w = ws[lane];
+        uint64_t wi = w;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        ws[lane] = wi - w;
     }
     __syncthreads();
-    uint64_t run = part[threadIdx.x];
-    for (uint64_t i = lo; i < hi; ++i) { off[i] = run; run += cnt[i]; }
+    if (threadIdx.x < n_chunks) chunk_sum[threadIdx.x] = ws[wid] + incl - v;   // exclusive
+    if (threadIdx.x == 1023) *total = ws[wid] + incl;
+}
+__global__ void __launch_bounds__(1024) fasta_scan_down(const uint32_t* __restrict__ cnt, uint64_t n_blk,
+                                                        const uint64_t* __restrict__ chunk_base, uint64_t* __restrict__ off) {
+    __shared__ uint32_t ws[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int kPer = kScanChunk / 1024;   // 16 consecutive counts per thread
+    const uint64_t i0 = (uint64_t)blockIdx.x * kScanChunk + (uint64_t)threadIdx.x * kPer;
+    uint32_t v[kPer], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { v[k] = i0 + k < n_blk ? cnt[i0 + k] : 0u; sum += v[k]; }
+    uint32_t incl = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) ws[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t w = ws[lane];
+        uint32_t wi = w;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        ws[lane] = wi - w;
+    }
+    __syncthreads();
+    uint64_t run = chunk_base[blockIdx.x] + ws[wid] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        if (i0 + k < n_blk) off[i0 + k] = run;
+        run += v[k];
+    }
 }
 
 // compaction: block b writes its kept bytes at out[off[b] ...] in order
@@ -147,10 +229,22 @@ __global__ void __launch_bounds__(kFastaThreads) fasta_compact(const uint8_t* __
                                                                const uint64_t* __restrict__ off, uint8_t* __restrict__ out) {
     __shared__ uint32_t warp_sum[kFastaThreads / 32];
     __shared__ uint8_t stage[kFastaBlock];
+    __shared__ uint8_t lut[256];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    lut[tid] = fasta_keep((uint8_t)tid) ? 1 : 0;      // per-byte classification through a table: one LDS instead of ~6 ALU ops
+    __syncthreads();
     const uint64_t b0 = (uint64_t)blockIdx.x * kFastaBlock + (uint64_t)tid * 16;
     uint8_t c[16];
-    const uint32_t m = b0 < n ? fasta_keep_mask16(text, b0, n, c) : 0u;
+    uint32_t m = 0;
+    if (b0 < n) {
+        if (b0 + 16 <= n && ((reinterpret_cast<uintptr_t>(text) & 15u) == 0)) {
+            *reinterpret_cast<uint4*>(c) = *reinterpret_cast<const uint4*>(text + b0);
+        } else {
+            for (int k = 0; k < 16; ++k) c[k] = b0 + k < n ? text[b0 + k] : (uint8_t)'\n';
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) m |= (uint32_t)lut[c[k]] << k;
+    }
     const uint32_t k = __popc(m);
     uint32_t incl = k;
     for (int d = 1; d < 32; d <<= 1) {
@@ -173,17 +267,21 @@ __global__ void __launch_bounds__(kFastaThreads) fasta_compact(const uint8_t* __
     for (uint32_t i = tid; i < total; i += kFastaThreads) dst[i] = stage[i];
 }
 
-// kept bytes before text position pos[i] (positions inside blanked/ordinary text; one thread each)
+// kept bytes before text position pos[i] (positions inside blanked / ordinary text): one warp per position, every lane
+// counts 128 bytes of the position's block
 __global__ void __launch_bounds__(128) fasta_offsets_at(const uint8_t* __restrict__ text, uint64_t n,
                                                         const uint64_t* __restrict__ off, const uint64_t* __restrict__ pos,
                                                         uint32_t n_pos, uint64_t* __restrict__ out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= n_pos) return;
     const uint64_t p = pos[i] < n ? pos[i] : n;
     const uint64_t blk = p / kFastaBlock;
-    uint64_t r = off[blk];
-    for (uint64_t j = blk * kFastaBlock; j < p; ++j) r += fasta_keep(text[j]) ? 1u : 0u;
-    out[i] = r;
+    uint32_t k = 0;
+    const uint64_t j0 = blk * kFastaBlock + (uint64_t)lane * (kFastaBlock / 32);
+    for (uint64_t j = j0; j < j0 + kFastaBlock / 32 && j < p; ++j) k += fasta_keep(text[j]) ? 1u : 0u;
+    for (int d = 16; d; d >>= 1) k += __shfl_xor_sync(0xffffffffu, k, d);
+    if (lane == 0) out[i] = off[blk] + k;
 }
 
 }  // namespace mpcr

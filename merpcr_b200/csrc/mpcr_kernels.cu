@@ -1515,8 +1515,9 @@ int mpcr_fasta_index_ex(mpcr_ctx* c, uint8_t* d_text, uint64_t n, uint32_t mode,
         CU(cudaMemsetAsync(d_text, '\n', (size_t)text_begin, st));
     }
     CU(cudaMemsetAsync(d_ctr, 0, 8, st));
-    const uint64_t n_thr = (n + 15) / 16;
-    fasta_find_headers<<<(uint32_t)((n_thr + 255) / 256), 256, 0, st>>>(d_text, n, d_hdr, max_records, d_ctr, d_ctr + 1);
+    // one pass: headers, non-ASCII flag and the kept letters per 4096-byte block (header lines and the text in front
+    // of the first header are still counted; blanking them below takes them out again)
+    fasta_classify<<<(uint32_t)n_blk, kFastaThreads, 0, st>>>(d_text, n, d_hdr, max_records, d_ctr, d_ctr + 1, d_cnt);
     c->launches++;
     CU(cudaGetLastError());
     uint32_t ctr[2] = {0, 0};
@@ -1534,13 +1535,31 @@ int mpcr_fasta_index_ex(mpcr_ctx* c, uint8_t* d_text, uint64_t n, uint32_t mode,
         CU(cudaMemcpy(hdr.data(), d_hdr, (size_t)nh * sizeof(FastaHeader), cudaMemcpyDeviceToHost));
         std::sort(hdr.begin(), hdr.end(), [](const FastaHeader& a, const FastaHeader& b) { return a.begin < b.begin; });
         CU(cudaMemcpyAsync(d_hdr, hdr.data(), (size_t)nh * sizeof(FastaHeader), cudaMemcpyHostToDevice, st));
-        if (!keep_prologue) CU(cudaMemsetAsync(d_text, '\n', (size_t)hdr[0].begin, st));   // data before the first header is discarded
-        fasta_blank_headers<<<(nh + 127) / 128, 128, 0, st>>>(d_text, d_hdr, nh);
+        if (!keep_prologue && hdr[0].begin > text_begin) {   // data before the first header is discarded
+            const uint64_t len = hdr[0].begin - text_begin;
+            fasta_blank_range<<<(uint32_t)((len + 4095) / 4096), 256, 0, st>>>(d_text, text_begin, hdr[0].begin, d_cnt);
+            c->launches++;
+        }
+        fasta_blank_headers<<<(nh + 127) / 128, 128, 0, st>>>(d_text, d_hdr, nh, d_cnt);
         c->launches++;
     }
-    fasta_count<<<(uint32_t)n_blk, kFastaThreads, 0, st>>>(d_text, n, d_cnt);
-    fasta_scan_blocks<<<1, 1024, 0, st>>>(d_cnt, n_blk, d_off);
-    c->launches += 2;
+    {
+        const uint32_t n_chunks = (uint32_t)((n_blk + kScanChunk - 1) / kScanChunk);
+        if (n_chunks > 1024) return fail(MPCR_EINVAL, "FASTA text of more than 64 GiB per call is not supported");
+        uint64_t* d_chunk = d_posoff;   // scratch: the record-offset area is not in use yet (>= 1024 u64 checked below)
+        if ((size_t)(max_records ? max_records : 1) * 16 < 1024 * 8 + 8) {
+            // tiny record capacity: fall back to a private scratch
+            CU(cudaMalloc(&d_chunk, 1025 * 8));
+        }
+        fasta_scan_reduce<<<n_chunks, 1024, 0, st>>>(d_cnt, n_blk, d_chunk);
+        fasta_scan_top<<<1, 1024, 0, st>>>(d_chunk, n_chunks, d_off + n_blk);
+        fasta_scan_down<<<n_chunks, 1024, 0, st>>>(d_cnt, n_blk, d_chunk, d_off);
+        c->launches += 3;
+        if (d_chunk != d_posoff) {
+            CU(cudaStreamSynchronize(st));
+            cudaFree(d_chunk);
+        }
+    }
     // kept-byte offsets at every record boundary: end of header r, start of header r+1 (or n)
     const uint32_t nr = nh + lead;
     std::vector<uint64_t> pos(2 * (size_t)nr);
@@ -1553,7 +1572,7 @@ int mpcr_fasta_index_ex(mpcr_ctx* c, uint8_t* d_text, uint64_t n, uint32_t mode,
         pos[2 * (r + lead) + 1] = r + 1 < nh ? hdr[r + 1].begin : n;
     }
     CU(cudaMemcpyAsync(d_pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice, st));
-    fasta_offsets_at<<<(2 * nr + 127) / 128, 128, 0, st>>>(d_text, n, d_off, d_pos, 2 * nr, d_posoff);
+    fasta_offsets_at<<<(2 * nr + 3) / 4, 128, 0, st>>>(d_text, n, d_off, d_pos, 2 * nr, d_posoff);
     c->launches++;
     CU(cudaGetLastError());
     std::vector<uint64_t> po(2 * (size_t)nr);
@@ -1585,7 +1604,7 @@ int mpcr_fasta_offsets_at(mpcr_ctx* c, const uint8_t* d_text, uint64_t n, const 
     CU(cudaMalloc(&d_io, (size_t)n_pos * 16));
     cudaError_t e = cudaMemcpyAsync(d_io, h_pos, (size_t)n_pos * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        fasta_offsets_at<<<(n_pos + 127) / 128, 128, 0, st>>>(d_text, n, (const uint64_t*)d_ws, d_io, n_pos, d_io + n_pos);
+        fasta_offsets_at<<<(n_pos + 3) / 4, 128, 0, st>>>(d_text, n, (const uint64_t*)d_ws, d_io, n_pos, d_io + n_pos);
         c->launches++;
         e = cudaMemcpyAsync(h_out, d_io + n_pos, (size_t)n_pos * 8, cudaMemcpyDeviceToHost, st);
     }
