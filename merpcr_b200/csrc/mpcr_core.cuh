@@ -59,6 +59,9 @@ static_assert(sizeof(TileDesc) == 24, "TileDesc layout");
 
 struct SearchParams {
     int W, M, N, X, iupac;
+    // Block tables (mpcr_ctx_set_seed_blocks): the key is the reference's seed (the first W - block letters) plus ONE block
+    // of `block` letters that starts `gap` letters behind the seed.  gap = block = 0: an ordinary (contiguous) key.
+    int gap = 0, block = 0;
 };
 
 MPCR_HD uint32_t wmask_of(int W) { return W >= 16 ? 0xFFFFFFFFu : ((1u << (2 * W)) - 1u); }
@@ -134,6 +137,30 @@ MPCR_HD bool extended_seed(CharAt at, int len, int ho, int w_ext, uint32_t* key_
     *key_le = k;
     return true;
 }
+
+// Block tables (searches that allow N >= 1 mismatches, see mpcr_ctx_set_seed_blocks).  The reference finds a site only
+// where the seed word matches exactly and at most N of the primer's OTHER letters differ, so of N + 1 disjoint blocks of
+// letters behind the seed at least one matches exactly: table i is keyed on seed + block i, and every site is found by
+// the table of its first exact block.  A record takes part iff all `span` = W + n_blocks * block letters from its hash
+// offset exist and are plain A/C/G/T.  Returns the key of the block that starts `gap` letters behind the seed
+// (little-endian digits: seed in the low 2W bits, the block above it).
+template <class CharAt>
+MPCR_HD bool blocked_seed(CharAt at, int len, int ho, int W, int block, int gap, int span, uint32_t* key_le) {
+    if (ho < 0 || ho + span > len) return false;
+    uint32_t all = 0;   // codes of all span (<= 16) letters
+    for (int i = 0; i < span; ++i) {
+        const uint8_t c = at(ho + i);
+        uint32_t code;
+        if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3;
+        else return false;
+        all |= code << (2 * i);
+    }
+    *key_le = (all & wmask_of(W)) | (((all >> (2 * (W + gap))) & wmask_of(block)) << (2 * W));
+    return true;
+}
+// The same key out of a register that holds the 16 bases from a hash position on (2 bits each, little-endian); wk = key
+// width W + block.  Bits above 2 * wk are garbage.
+MPCR_HD uint32_t gap_key_raw(uint32_t x, uint32_t seed_mask, int gap) { return (x & seed_mask) | ((x >> (2 * gap)) & ~seed_mask); }
 
 // Position sampling (exact searches only, see mpcr_ctx_set_sampling): with no mismatch allowed EVERY window of the
 // primer matches where the primer does, so a table may hold the w-letter windows at offsets ho .. ho+S-1 and the
@@ -316,6 +343,26 @@ MPCR_HD bool compare_view(const uint64_t* p4, int64_t gb, const PrimerView& v, c
     return n0 + popc64(m1) <= prm.N;
 }
 
+// Block tables: is one of the blocks IN FRONT of this table's block (letters [ws, ws + gap) behind the hash offset, in
+// pieces of `block`) identical to the genome?  Then an earlier table finds this site and this one must not report it again.
+// The blocks hold plain A/C/G/T primer letters, and the nibble code is a bijection on the sequence alphabet, so "identical
+// letters" is nibble equality -- exactly the condition under which the earlier table's key matches.
+// gb = plane-relative base of the primer's first letter, pw = its nibble words, ws = the reference's word size.
+MPCR_HD bool earlier_block_exact(const uint64_t* p4, int64_t gb, const uint64_t* pw, int hash_off, int ws, int block, int gap) {
+    for (int o = 0; o + block <= gap; o += block) {
+        bool same = true;
+        for (int i = 0; i < block; ++i) {
+            const int pi = hash_off + ws + o + i;
+            const int64_t gi = gb + pi;
+            const uint32_t pn = (uint32_t)(pw[pi >> 4] >> (4 * (pi & 15))) & 15u;
+            const uint32_t gn = (uint32_t)(p4[(uint64_t)gi >> 4] >> (4 * ((unsigned)gi & 15u))) & 15u;
+            same = same && pn == gn;
+        }
+        if (same) return true;
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // engine.py:486-489 + 507-597: one bucket entry met at hash position p of a contig of true length L.
 // gcontig = plane-relative base index of the contig's first base (may be negative for a shard that starts
@@ -329,6 +376,8 @@ MPCR_HD void verify_record(const uint64_t* p4, int64_t gcontig, int64_t L, int64
     const int64_t k = p - (int64_t)m.hash_off;                                   // :486
     if (k < 0 || k + l1 > L) return;                                              // :487
     if (!compare_primer(p4, gcontig + k, pwords + m.p1_word, l1, true, prm)) return;   // :515
+    if (prm.gap > 0 && earlier_block_exact(p4, gcontig + k, pwords + m.p1_word, m.hash_off, prm.W - prm.block, prm.block, prm.gap))
+        return;                                                                   // an earlier block table reports this site
     const int64_t avail = L - (k + l1);                                           // :521
     if (avail < l2) return;                                                       // :524
     int64_t E = (int64_t)m.pcr_size, hi, lo;
@@ -533,6 +582,13 @@ MPCR_HD uint64_t window_valid(uint64_t v0, uint64_t v1, int W) {
         }
     }
     return r;
+}
+
+// The same for a block-table key: the seed's ws letters from j on and the block's letters from j + ws + gap on.
+MPCR_HD uint64_t window_valid_gapped(uint64_t v0, uint64_t v1, int ws, int block, int gap) {
+    const int off = ws + gap;   // 1 .. 15
+    const uint64_t s0 = (v0 >> off) | (v1 << (64 - off)), s1 = v1 >> off;
+    return window_valid(v0, v1, ws) & window_valid(s0, s1, block);
 }
 
 }  // namespace mpcr

@@ -82,7 +82,8 @@ struct mpcr_ctx {
     uint32_t filter_words = 0;
     uint32_t n_keys = 0;
     bool dense = false;
-    int ext_w = 0, ext_which = 0;   // seed extension (mpcr_ctx_set_seed_extension)
+    int ext_w = 0, ext_which = 0;   // seed extension (mpcr_ctx_set_seed_extension / mpcr_ctx_set_seed_blocks)
+    int ext_block = 0, ext_gap = 0, ext_span = 0;   // block tables: letters per block, letters between seed and block, letters needed
     int samp_w = 0, samp_s = 0, samp_role = 0;   // position sampling (mpcr_ctx_set_sampling)
     uint32_t* d_bloom = nullptr;    // sampled tables: the first-level filter in global memory
     uint32_t bloom_shift = 0;
@@ -293,7 +294,8 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
                                                       const uint32_t* __restrict__ pcr, uint32_t n_lines,
                                                       const uint8_t* __restrict__ plut,
                                                       const uint32_t* __restrict__ word_off,  // 2*n_rec+1 prefix
-                                                      int W, int w_scan, int which, int true_strands,
+                                                      int W, int w_scan, int which, int ext_block, int ext_gap, int ext_span,
+                                                      int true_strands,
                                                       uint32_t part, uint32_t parts, int samp_w, int samp_s, int samp_role,
                                                       RecMeta* __restrict__ meta,
                                                       uint64_t* __restrict__ pwords, Item<2>* __restrict__ pairs,
@@ -322,8 +324,11 @@ __global__ void __launch_bounds__(128) encode_records(const uint8_t* __restrict_
     const int ho = first_clean_word(q1, l1, W, &hbe);
     // which: 0 = every record keyed by its W-mer; 1 = only records whose seed cannot be lengthened to w_scan letters;
     //        2 = only those that can, keyed by the lengthened word (mpcr_ctx_set_seed_extension)
-    const bool ext = which != 0 && extended_seed(q1, l1, ho, w_scan, &kext);
-    m.tag = ho >= 0 ? make_tag(q1, l1, ho, which == 2 ? w_scan : W) : 0u;
+    // block tables (mpcr_ctx_set_seed_blocks): "can be lengthened" = all ext_span letters are plain, and the key is the seed
+    // plus the block ext_gap letters behind it; the tag starts behind that block
+    const bool ext = which != 0 && (ext_block ? blocked_seed(q1, l1, ho, W, ext_block, ext_gap, ext_span, &kext)
+                                              : extended_seed(q1, l1, ho, w_scan, &kext));
+    m.tag = ho >= 0 ? make_tag(q1, l1, ho, which == 2 ? w_scan + ext_gap : W) : 0u;
     if (lead) {
         encode_primer(q1, l1, plut, pwords + m.p1_word);
         if (!minus) {
@@ -474,7 +479,9 @@ struct ScanSmem {
         uint16_t queue[kQCap];
         unsigned long long mbar[2];
     };
-    static constexpr int kFilterOff = (int)((sizeof(Warp) * kWarps + 127) / 128 * 128);
+    static constexpr int kCtaBarOff = (int)(sizeof(Warp) * kWarps);                 // one mbarrier for the filter's arrival
+    static constexpr int kFilterOff = (kCtaBarOff + 8 + 127) / 128 * 128;
+    static_assert(sizeof(Warp) % 8 == 0, "mbarrier alignment");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -528,7 +535,7 @@ struct HitEmitter {
 // engine.py:483-489 + 507-597 for one survivor, serially in one thread (overflow path of the survivor list).
 __device__ __noinline__ void verify_serial(const ScanArgs& a, uint32_t tile, uint32_t lp, uint32_t code) {
     const TileDesc td = a.tiles[tile];
-    const int64_t gb = td.gbase + lp + a.prm.W;
+    const int64_t gb = td.gbase + lp + a.prm.W + a.prm.gap;
     const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
     for_each_survivor_record(a.bucket, code, gcodes, gvalid, a.prm.N, [&](uint32_t item) {
         // sampled tables: item = record * samp_s + window; the window lies that many bases behind the seed
@@ -581,7 +588,7 @@ __device__ __forceinline__ uint32_t filter_probe(const FilterView& f, const Scan
 // gathers in flight, then the tag check on what came back).  Straight-line code: lanes past the end of the queue
 // re-probe entry 0 and are masked out, so the R rounds interleave freely.  CLEAN: every base of the unit (and its
 // read-ahead) is A/C/G/T, so the tag verdict can be used without looking at the valid bits.
-template <bool CLEAN, bool HASHED, int R, int WC, int NC>
+template <bool CLEAN, bool HASHED, int R, int WC, int NC, bool GAPPED>
 __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
                                              const uint32_t* __restrict__ s_p2, const uint32_t* __restrict__ s_v,
                                              uint32_t base, uint32_t cnt, int lane, uint32_t tile, uint32_t ubase,
@@ -590,6 +597,9 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
     // = read them from the arguments
     const int W = WC ? WC : a.prm.W, N = NC >= 0 ? NC : a.prm.N;
     const uint32_t wmask = wmask_of(W);
+    // block tables: the key's second part and the tag window lie `gap` letters further on (W + gap <= 16)
+    const int gap = GAPPED ? a.prm.gap : 0;
+    const uint32_t seed_mask = GAPPED ? wmask_of(W - a.prm.block) : 0u;
     uint32_t lpv[R], key[R], gcodes[R];
     bool ok[R], dirty[R];
 #pragma unroll
@@ -601,12 +611,12 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
         const uint32_t wi = lp >> 4, sh = (lp & 15u) * 2u;
         const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1], w2 = s_p2[wi + 2];
         const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
-        key[u] = x0 & wmask;
-        gcodes[u] = __funnelshift_rc(x0, x1, 2 * W);  // clamped: 2W == 32 -> x1; only the low 16 bits are used
+        key[u] = (GAPPED ? gap_key_raw(x0, seed_mask, gap) : x0) & wmask;
+        gcodes[u] = __funnelshift_rc(x0, x1, 2 * (W + gap));  // clamped: 32 -> x1; only the low 16 bits are used
         lpv[u] = lp;
         dirty[u] = false;
         if (!CLEAN) {
-            const uint32_t vb = lp + (uint32_t)W, vi = vb >> 5, vs = vb & 31u;
+            const uint32_t vb = lp + (uint32_t)(W + gap), vi = vb >> 5, vs = vb & 31u;
             dirty[u] = !tag_window_clean(__funnelshift_r(s_v[vi], s_v[vi + 1], vs));
         }
         gather16_async(&landing[u][lane], a.slots + (HASHED ? (slot_hash(key[u]) & a.smap.mask) : key[u]));
@@ -642,7 +652,7 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
 #else
 #define MPCR_PROBE_INLINE __forceinline__
 #endif
-template <bool CLEAN, bool HASHED, int WC, int NC>
+template <bool CLEAN, bool HASHED, int WC, int NC, bool GAPPED>
 __device__ MPCR_PROBE_INLINE void probe_queue(const ScanArgs& a, const uint16_t* __restrict__ queue, uint4 (*landing)[32],
                                             const uint32_t* __restrict__ s_p2, const uint32_t* __restrict__ s_v,
                                             uint32_t cnt, int lane, uint32_t tile, uint32_t ubase,
@@ -651,17 +661,17 @@ __device__ MPCR_PROBE_INLINE void probe_queue(const ScanArgs& a, const uint16_t*
     static_assert(kIlp >= 1 && kIlp <= 4, "kIlp");
     uint32_t base = 0;
     for (; base + 32 * kIlp <= cnt; base += 32 * kIlp)
-        probe_rounds<CLEAN, HASHED, kIlp, WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+        probe_rounds<CLEAN, HASHED, kIlp, WC, NC, GAPPED>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
     const uint32_t rounds = (cnt - base + 31) >> 5;  // tail: only the rounds that hold something
-    if (rounds == 1) probe_rounds<CLEAN, HASHED, 1, WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 2) probe_rounds<CLEAN, HASHED, (kIlp >= 2 ? 2 : 1), WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 3) probe_rounds<CLEAN, HASHED, (kIlp >= 3 ? 3 : 1), WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
-    else if (rounds == 4) probe_rounds<CLEAN, HASHED, (kIlp >= 4 ? 4 : 1), WC, NC>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    if (rounds == 1) probe_rounds<CLEAN, HASHED, 1, WC, NC, GAPPED>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 2) probe_rounds<CLEAN, HASHED, (kIlp >= 2 ? 2 : 1), WC, NC, GAPPED>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 3) probe_rounds<CLEAN, HASHED, (kIlp >= 3 ? 3 : 1), WC, NC, GAPPED>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
+    else if (rounds == 4) probe_rounds<CLEAN, HASHED, (kIlp >= 4 ? 4 : 1), WC, NC, GAPPED>(a, queue, landing, s_p2, s_v, base, cnt, lane, tile, ubase, n_dbg);
 }
 
 // Stage 1 for one unit of 2048 positions: lane l owns positions [64l, 64l+64) -- rolling keys by funnel shift out of
 // five registers, one shared-memory Bloom probe (two bits of one word) per position.  c_lo / c_hi: pass masks.
-template <bool WIDE>
+template <bool WIDE, bool GAPPED>
 __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs& a, const uint32_t* __restrict__ s_p2,
                                             const uint32_t* __restrict__ s_v, int lane, uint32_t unit_nbases, int W,
                                             uint32_t& c_lo, uint32_t& c_hi, bool& my_clean) {
@@ -672,7 +682,10 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
         my_clean = (v0.x & v0.y & v1.x) == 0xFFFFFFFFu;  // own 64 bases + the 32 behind them (W + tag <= 24)
         // W-mer validity of the 64 positions: all ones on clean sequence, else log-doubling over the valid bits
         uint64_t wv = ~0ull;
-        if (!my_clean) wv = window_valid(((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v1.y << 32) | v1.x, W);
+        if (!my_clean)
+            wv = GAPPED ? window_valid_gapped(((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v1.y << 32) | v1.x, W - a.prm.block,
+                                              a.prm.block, a.prm.gap)
+                        : window_valid(((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v1.y << 32) | v1.x, W);
         const uint32_t left = unit_nbases - lp0;
         if (left < 64u) wv &= (1ull << left) - 1ull;
         if (wv) {
@@ -682,13 +695,19 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
             auto raw = [&](int j) -> uint32_t {
                 return (j & 15) ? __funnelshift_r(r[j >> 4], r[(j >> 4) + 1], 2 * (j & 15)) : r[j >> 4];
             };
+            // block tables: seed letters + the block `gap` letters behind them (garbage above the key cancels in the probe)
+            const uint32_t seed_mask = GAPPED ? wmask_of(W - a.prm.block) : 0u;
+            const int gap = GAPPED ? a.prm.gap : 0;
+            auto probe = [&](int j) -> uint32_t {
+                if (!GAPPED) return filter_probe<WIDE>(f, a, raw(j), raw(j + 3));
+                const uint32_t k = gap_key_raw(raw(j), seed_mask, gap);
+                return filter_probe<WIDE>(f, a, k, k >> 6);
+            };
             // collect the MSB of each probe result as bit j of the pass mask (descending j: one funnel shift each)
 #pragma unroll
-            for (int j = 31; j >= 0; --j)
-                c_lo = __funnelshift_l(filter_probe<WIDE>(f, a, raw(j), raw(j + 3)), c_lo, 1);
+            for (int j = 31; j >= 0; --j) c_lo = __funnelshift_l(probe(j), c_lo, 1);
 #pragma unroll
-            for (int j = 63; j >= 32; --j)
-                c_hi = __funnelshift_l(filter_probe<WIDE>(f, a, raw(j), raw(j + 3)), c_hi, 1);
+            for (int j = 63; j >= 32; --j) c_hi = __funnelshift_l(probe(j), c_hi, 1);
             c_lo &= (uint32_t)wv;
             c_hi &= (uint32_t)(wv >> 32);
         }
@@ -706,7 +725,7 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
 //             16-byte L1-bypassing async gathers of the slot table in flight per lane; key + tag window come
 //             from the staged unit; inline tag check.
 //   What is left (about one position in 10^4) goes to the survivor list for verify_kernel.
-template <bool WIDE, bool HASHED, int WC, int NC>
+template <bool WIDE, bool HASHED, int WC, int NC, bool GAPPED = false>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -748,14 +767,22 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         mbar_init(&ws.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // The filter (~160 KB) arrives by TMA bulk copies that one thread starts: a few large transfers per SM instead of
+    // 10^4 16-byte loads through the LSU, and the warps' first units are already on their way behind it.
+    unsigned long long* fbar = reinterpret_cast<unsigned long long*>(smem + ScanSmem::kCtaBarOff);
+    if (tid == 0) {
+        mbar_init(fbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = a.filter_words * 4u;
+        mbar_expect_tx(fbar, bytes);
+        for (uint32_t o = 0; o < bytes; o += 32768u)
+            tma_load_1d(reinterpret_cast<uint8_t*>(s_filter) + o, reinterpret_cast<const uint8_t*>(a.filter) + o,
+                        min(32768u, bytes - o), fbar);
+    }
     __syncwarp();
     if (l_tile < a.n_tiles) issue_next(0);
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(a.filter);
-        uint4* dst = reinterpret_cast<uint4*>(s_filter);
-        for (uint32_t i = tid; i < a.filter_words / 4; i += kScanThreads) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
+    __syncthreads();            // fbar is initialised
+    while (!mbar_try_wait(fbar, 0u)) {}
 
     const int W = WC ? WC : a.prm.W;
     const FilterView fv{s_filter, smem_u32(s_filter), a.cw, a.filter_words};
@@ -782,7 +809,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         const uint32_t lp0 = (uint32_t)lane * kPosPerThread;  // unit-local
         uint32_t c_lo = 0, c_hi = 0;
         bool my_clean = false;
-        stage1_unit<WIDE>(fv, a, s_p2, s_v, lane, unit_nbases, W, c_lo, c_hi, my_clean);
+        stage1_unit<WIDE, GAPPED>(fv, a, s_p2, s_v, lane, unit_nbases, W, c_lo, c_hi, my_clean);
 #ifdef MPCR_STAGE1_ONLY   // tuning builds: the kernel without its stage 2 (what the register allocator does to stage 1 alone)
         n_dbg += __popc(c_lo) + __popc(c_hi);
         __syncwarp();
@@ -824,8 +851,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
                                      ? total
                                      : __shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));  // lane 0 always fits
             __syncwarp();
-            if (all_clean) probe_queue<true, HASHED, WC, NC>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
-            else probe_queue<false, HASHED, WC, NC>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
+            if (all_clean) probe_queue<true, HASHED, WC, NC, GAPPED>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
+            else probe_queue<false, HASHED, WC, NC, GAPPED>(a, ws.queue, ws.landing, s_p2, s_v, cnt, lane, tile, ubase, n_dbg);
             __syncwarp();
             if (fit_mask == 0xffffffffu) break;
         }
@@ -1047,6 +1074,9 @@ __device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& 
     const int64_t k = (int64_t)td.lstart + lp - (int64_t)win - (int64_t)m.hash_off;          // engine.py:486
     if (k < 0 || k + l1 > L) return;                                                          // :487
     if (!compare_primer(a.p4, gcontig + k, a.pwords + m.p1_word, l1, true, a.prm)) return;    // :515
+    if (a.prm.gap > 0 && earlier_block_exact(a.p4, gcontig + k, a.pwords + m.p1_word, m.hash_off, a.prm.W - a.prm.block,
+                                             a.prm.block, a.prm.gap))
+        return;   // block tables: the table of an earlier block reports this site
     if (L - (k + l1) < l2) return;                                                            // :521-524
     int64_t E = (int64_t)m.pcr_size, hi, lo;
     if (E > L - k) { E = L - k; hi = 0; }                                                     // :531-533
@@ -1119,7 +1149,7 @@ __device__ __forceinline__ void verify_body(const ScanArgs& a) {
             if (!(sv.code & kWalkBucket)) {
                 verify_group(a, td, sv.lp, sv.code, gl);
             } else {  // a seed shared by several records: bucket order, each entry behind its own tag
-                const int64_t gb = td.gbase + sv.lp + a.prm.W;
+                const int64_t gb = td.gbase + sv.lp + a.prm.W + a.prm.gap;
                 const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
                 const bool clean = tag_window_clean(gvalid);
                 for (uint32_t e = sv.code & ~kWalkBucket;; ++e) {
@@ -1134,8 +1164,77 @@ __device__ __forceinline__ void verify_body(const ScanArgs& a) {
     }
 }
 
-__global__ void __launch_bounds__(256) verify_kernel(const ScanArgs a) {
-    verify_body(a);
+// One survivor for the lane group `gl` belongs to (shared by the dynamic and the static schedule).
+__device__ __forceinline__ void verify_survivor(const ScanArgs& a, const Survivor& sv, int gl) {
+    const TileDesc td = a.tiles[sv.tile];
+    if (!(sv.code & kWalkBucket)) {
+        verify_group(a, td, sv.lp, sv.code, gl);
+    } else {  // a seed shared by several records: bucket order, each entry behind its own tag
+        const int64_t gb = td.gbase + sv.lp + a.prm.W + a.prm.gap;
+        const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
+        const bool clean = tag_window_clean(gvalid);
+        for (uint32_t e = sv.code & ~kWalkBucket;; ++e) {
+            const BucketEntry b = a.bucket[e];
+            if (!clean || !tag_rejects(b.tag, gcodes, a.prm.N)) verify_group(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, gl);
+            if (b.rec_last >> 31) break;
+        }
+    }
+}
+
+#ifndef MPCR_VERIFY_CTAS_PER_SM
+#define MPCR_VERIFY_CTAS_PER_SM 3
+#endif
+#ifndef MPCR_VERIFY_STATIC_DEPTH
+#define MPCR_VERIFY_STATIC_DEPTH 64
+#endif
+static constexpr int kVerifyCtasPerSm = MPCR_VERIFY_CTAS_PER_SM;            // 80 registers x 256 threads: three CTAs per SM
+static constexpr uint32_t kStaticVerifyDepth = MPCR_VERIFY_STATIC_DEPTH;  // survivors per lane group dealt out statically
+__global__ void __launch_bounds__(256, kVerifyCtasPerSm) verify_kernel(const ScanArgs a) {
+    // Survivor lists of up to kStaticVerifyDepth entries per lane group are dealt out STATICALLY: every CTA sums the 256
+    // sub-list counts itself (one load per thread, a block scan) and its lane groups stride over the concatenated lists
+    // -- no cursor atomics, no polling of control lines that other warps are draining.  The grid is what fits the GPU at
+    // once (kVerifyCtasPerSm per SM), so no CTA starts behind another.  Longer lists keep the dynamic schedule of
+    // verify_body, which balances survivors of very different cost (mate windows, bucket walks).
+    static_assert(kSurvLists == 256, "one sub-list per thread of the CTA");
+    __shared__ uint32_t pre[kSurvLists + 1];
+    __shared__ uint32_t wsum[8];
+    {
+        const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+        const uint32_t cnt = min(__ldcg(a.surv_ctl + tid * kSurvCtlStride), a.surv_cap);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < wid; ++w) base += wsum[w];
+        pre[tid] = base + incl - cnt;
+        if (tid == 255) pre[256] = base + incl;
+        __syncthreads();
+    }
+    const uint32_t total = pre[kSurvLists];
+    constexpr uint32_t kGroupsPerWarp = 32 / kVerifyLanes;
+    const uint32_t n_groups = gridDim.x * (blockDim.x >> 5) * kGroupsPerWarp;
+    if (total <= n_groups * kStaticVerifyDepth) {
+        // lane group G takes the survivors G, G + n_groups, ... of the concatenated sub-lists: neighbouring groups of a
+        // warp look at neighbouring survivors (same producer warp, nearby bases), and a costly stretch of the genome
+        // (an N-run in IUPAC mode, a repeat) is spread over all groups
+        const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
+        const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        for (uint32_t g = warp_id * kGroupsPerWarp + group; g < total; g += n_groups) {
+            uint32_t lo = 0, hi = kSurvLists;           // the sub-list that holds global index g
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (pre[mid] <= g) lo = mid; else hi = mid;
+            }
+            verify_survivor(a, a.surv[(size_t)lo * a.surv_cap + (g - pre[lo])], gl);
+        }
+    } else {
+        verify_body(a);
+    }
     // The last CTA to finish zeroes the scanner's control words (survivor counters and cursors, tile counter), so the
     // next scan needs no memset launches in front of it.  tile_counter[4] counts finished CTAs.
     __shared__ bool s_last;
@@ -1371,9 +1470,30 @@ int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
     }
     c->ext_w = which ? w_ext : 0;
     c->ext_which = which;
+    c->ext_block = c->ext_gap = c->ext_span = 0;
     free_table(c);
     return MPCR_OK;
 }
+int mpcr_ctx_set_seed_blocks(mpcr_ctx* c, int block, int n_blocks, int which) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (which < 0 || (which >= 2 && which - 2 >= n_blocks)) return fail(MPCR_EINVAL, "which must be 0, 1 or 2 + block index");
+    if (which != 0) {
+        if (c->prm.iupac_mode != 0) return fail(MPCR_EINVAL, "block tables need letter-identity compares (no IUPAC mode)");
+        if (block < 1 || n_blocks < 1) return fail(MPCR_EINVAL, "block and n_blocks must be positive");
+        if (n_blocks <= c->prm.mismatches)
+            return fail(MPCR_EINVAL, "block tables need more blocks than mismatches (%d blocks, -N %d)", n_blocks, c->prm.mismatches);
+        if (c->prm.wordsize + n_blocks * block > 16)
+            return fail(MPCR_EINVAL, "wordsize + n_blocks * block must not exceed 16 letters");
+    }
+    c->ext_w = which ? c->prm.wordsize + block : 0;
+    c->ext_which = which >= 2 ? 2 : which;
+    c->ext_block = which ? block : 0;
+    c->ext_gap = which >= 2 ? (which - 2) * block : 0;
+    c->ext_span = which ? c->prm.wordsize + n_blocks * block : 0;
+    free_table(c);
+    return MPCR_OK;
+}
+
 int mpcr_ctx_set_sampling(mpcr_ctx* c, int w_samp, int stride, int role) {
     if (!c) return fail(MPCR_EINVAL, "null argument");
     if (role < 0 || role > 2) return fail(MPCR_EINVAL, "role must be 0, 1 or 2");
@@ -1725,7 +1845,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         CUG(cudaMemsetAsync(d_stats, 0, 16, st));
         encode_records<<<(n_items + 127) / 128, 128, 0, st>>>(d_blob, d_off, d_pcr, n_lines, d_plut, d_woff, W,
                                                                c->ext_which ? c->ext_w : W, sampled ? 0 : c->ext_which,
-                                                               c->true_strands, c->part, c->parts, c->samp_w, c->samp_s,
+                                                               c->ext_block, c->ext_gap, c->ext_span, c->true_strands, c->part, c->parts, c->samp_w, c->samp_s,
                                                                c->samp_role, c->d_meta, c->d_pwords, d_pairs, d_tags, d_stats);
         c->launches++;
         CUG(cudaGetLastError());
@@ -1789,6 +1909,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         c->dense = c->n_keys && (c->n_valid >= 3ull * c->n_keys ||
                                  (2 * WS < 32 && 4ull * c->n_keys >= (1ull << (2 * WS))));
         if (const char* env = getenv("MPCR_DENSE")) c->dense = atoi(env) != 0;
+        if (c->ext_which == 2 && c->ext_gap > 0) c->dense = false;   // only the sparse scanner assembles split keys
         c->table_ready = true;
     }
 done:
@@ -2025,6 +2146,9 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.filter = c->d_filter; a.filter_words = c->filter_words; a.cw = filter_mul(c->scan_w);
     a.prm.W = c->scan_w; a.prm.M = c->prm.margin; a.prm.N = c->prm.mismatches; a.prm.X = c->prm.three_prime_match;
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
+    const bool gapped = c->ext_which == 2 && c->ext_block > 0 && c->samp_role != 1;   // a block table (gap 0: the first block)
+    a.prm.gap = gapped ? c->ext_gap : 0;
+    a.prm.block = gapped ? c->ext_block : 0;
     a.debug = c->env_debug;
     a.k4 = 4u;
     a.samp_s = c->samp_role == 1 ? (uint32_t)c->samp_s : 1u;
@@ -2047,7 +2171,8 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
         // instantiations: the open-addressed table (W >= 12), the narrow filter (W < 6), the general direct table, and
         // the reference's default word size with the usual mismatch budgets fixed at compile time
         void (*kern)(const ScanArgs) = scan_kernel<true, false, 0, -1>;
-        if (!c->smap.direct) kern = scan_kernel<true, true, 0, -1>;
+        if (a.prm.gap > 0) kern = c->smap.direct ? scan_kernel<true, false, 0, -1, true> : scan_kernel<true, true, 0, -1, true>;
+        else if (!c->smap.direct) kern = scan_kernel<true, true, 0, -1>;
         else if (a.prm.W < 6) kern = scan_kernel<false, false, 0, -1>;
         else if (a.prm.W == 11 && a.prm.N == 0) kern = scan_kernel<true, false, 11, 0>;
         else if (a.prm.W == 11 && a.prm.N == 1) kern = scan_kernel<true, false, 11, 1>;
@@ -2063,7 +2188,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     c->launches++;
     CU(cudaGetLastError());
     if (!a.debug) {
-        verify_kernel<<<c->sm_count * 8, 256, 0, st>>>(a);
+        verify_kernel<<<c->sm_count * kVerifyCtasPerSm, 256, 0, st>>>(a);
         c->launches++;
         CU(cudaGetLastError());
     } else {
