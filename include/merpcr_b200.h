@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 13
+#define MPCR_ABI_VERSION 14
 
 enum {
     MPCR_OK = 0,
@@ -93,6 +93,23 @@ void mpcr_ctx_destroy(mpcr_ctx *ctx);
  * Scanning both tables over the same planes and sorting the concatenated hits gives exactly the one-table result.
  * Call before mpcr_table_build; drops the current table. */
 int mpcr_ctx_set_seed_extension(mpcr_ctx *ctx, int w_ext, int which);
+/* Block tables for searches that ALLOW mismatches (mismatches = N >= 0, no IUPAC mode; MPCR_EINVAL otherwise; no
+ * reference counterpart -- the reference walks its whole bucket at every position, core/engine.py:483-489).  The
+ * reference reports a site only where the seed word matches exactly and at most N of the first primer's other letters
+ * differ (core/engine.py:467-489, 515, 599-642), so of n_blocks > N disjoint blocks of `block` letters right behind the
+ * seed at least one is identical to the genome.  A record whose wordsize + n_blocks * block (<= 16) letters from its
+ * hash offset exist and are plain A/C/G/T goes to n_blocks tables, table i keyed on seed + block i (a split key of
+ * wordsize + block letters); a site is reported by the table of its FIRST identical block only (the verifier of table i
+ * drops a site whose block j < i is identical), so the concatenated hits hold every site once.  The other records stay
+ * in an ordinary table.
+ *   which = 1     : this context's next table holds only the records that can NOT be keyed this way, keyed by wordsize;
+ *   which = 2 + i : only those that can, keyed on seed + block i (0 <= i < n_blocks);
+ *   which = 0     : back to one table with every record (default).
+ * Scanning all n_blocks + 1 tables over the same planes and sorting the concatenated hits gives exactly the one-table
+ * result; candidate-heavy searches (small -W, 10^5..10^6 STS, -N >= 1) then run on sparse keys instead of bucket walks.
+ * Combines with mpcr_ctx_set_table_part.  Call before mpcr_table_build; drops the current table and replaces any
+ * mpcr_ctx_set_seed_extension setting (and vice versa). */
+int mpcr_ctx_set_seed_blocks(mpcr_ctx *ctx, int block, int n_blocks, int which);
 /* Position sampling for EXACT searches (mismatches 0, no IUPAC mode; MPCR_EINVAL otherwise; no reference counterpart --
  * the reference probes its dict at every base, core/engine.py:467-489).  With no mismatch allowed every window of a
  * record's first primer matches wherever the primer does, so a table may hold, per record, the w_samp-letter windows at

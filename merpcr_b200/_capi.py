@@ -14,11 +14,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPCR_B200_LIB") or os.path.join(_HERE, "lib", "libmerpcr_b200.so")
 
 MPCR_OK, MPCR_EINVAL, MPCR_ECUDA, MPCR_ENOMEM, MPCR_ESTATE, MPCR_EOVERFLOW = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # every symbol include/merpcr_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_set_seed_extension", "mpcr_ctx_set_table_part", "mpcr_ctx_set_sampling", "mpcr_table_items", "mpcr_ctx_set_append", "mpcr_scan_prepare", "mpcr_ctx_set_true_strands", "mpcr_ctx_sm_count",
+    "mpcr_abi_version", "mpcr_last_error", "mpcr_ctx_create", "mpcr_ctx_destroy", "mpcr_ctx_set_seed_extension", "mpcr_ctx_set_seed_blocks", "mpcr_ctx_set_table_part", "mpcr_ctx_set_sampling", "mpcr_table_items", "mpcr_ctx_set_append", "mpcr_scan_prepare", "mpcr_ctx_set_true_strands", "mpcr_ctx_sm_count",
     "mpcr_pack_sequence", "mpcr_host_pack_nibbles", "mpcr_derive_planes", "mpcr_file_read", "mpcr_fasta_workspace_bytes", "mpcr_fasta_index", "mpcr_fasta_index_ex", "mpcr_fasta_offsets_at", "mpcr_fasta_compact",
     "mpcr_sts_parse", "mpcr_sts_blob", "mpcr_format_hits", "mpcr_table_build", "mpcr_table_records", "mpcr_table_primer_words", "mpcr_scan",
     "mpcr_halo_left", "mpcr_halo_right", "mpcr_tile_bases", "mpcr_sort_hits", "mpcr_sort_hits_dev", "mpcr_scan_sorted", "mpcr_scan_sorted_async", "mpcr_sort_finish", "mpcr_slot_scan_ms", "mpcr_slot_verify_ms", "mpcr_launch_count", "mpcr_last_scan_ms", "mpcr_last_verify_ms",
@@ -52,6 +52,8 @@ class Backend:
         lib.mpcr_ctx_destroy.argtypes = [vp]
         lib.mpcr_ctx_set_seed_extension.restype = i32
         lib.mpcr_ctx_set_seed_extension.argtypes = [vp, i32, i32]
+        lib.mpcr_ctx_set_seed_blocks.restype = i32
+        lib.mpcr_ctx_set_seed_blocks.argtypes = [vp, i32, i32, i32]
         lib.mpcr_ctx_set_sampling.restype = i32
         lib.mpcr_ctx_set_sampling.argtypes = [vp, i32, i32, i32]
         lib.mpcr_table_items.restype = u32

@@ -49,6 +49,7 @@ MIN_PCR_SIZE, MAX_PCR_SIZE = 1, 10000
 EXTENDED_WORDSIZE = 16        # key width of the extended tables of exact, candidate-heavy searches
 STREAM_SCAN_BASES = 1 << 26    # upload_and_scan: scan a finished contig (group) once this many bases are packed
 EXT_LINES_PER_TABLE = 125_000  # STS lines per extended table: 2.5*10^5 keys is what the scanner's filter holds at ~5 % f.p.
+BLOCK_MIN_KEY = 12            # block tables (searches with mismatches): used when seed + block make at least this many letters
 SAMPLE_WORDSIZE = 16          # window width of position-sampled tables (exact, candidate-heavy searches)
 SAMPLE_STRIDE = 3             # ... and the stride: primers of >= hash_offset + 18 plain letters can be sampled
 PCR_SIZE_CLAMP = 0x7FFFFFFF   # any expected size >= a contig length behaves identically (engine.py:531-533)
@@ -453,20 +454,42 @@ class MerPCR:
             self._ctx_samp = None
         role = 2 if stride >= 2 else 0
         parts = max(1, -(-rest_lines // EXT_LINES_PER_TABLE)) if extend else 0
-        if extend and os.environ.get("MPCR_SEED_PARTS"):
+        # Candidate-heavy searches that ALLOW mismatches (-N >= 1, no IUPAC mode): block tables.  At most N of the first
+        # primer's letters behind the seed differ, so of N + 1 disjoint blocks right behind the seed one is identical:
+        # every record whose W + (N + 1) * block letters are plain goes to N + 1 tables keyed on seed + one block each
+        # (a site is reported by the table of its first identical block), the rest stay in the ordinary table.
+        n_blocks = self.mismatches + 1
+        block = (16 - self.wordsize) // n_blocks
+        can_block = self.mismatches >= 1 and not self.iupac_mode and block >= 1
+        blocks = can_block and self.wordsize + block >= BLOCK_MIN_KEY and 8 * n >= 4 ** self.wordsize
+        env = os.environ.get("MPCR_SEED_BLOCKS")
+        if env is not None and can_block:
+            blocks = env not in ("0", "")
+            if blocks and env != "1":      # tests: letters per block
+                block = max(1, min(block, int(env)))
+        if blocks:
+            parts = max(1, -(-n // EXT_LINES_PER_TABLE))
+        if (extend or blocks) and os.environ.get("MPCR_SEED_PARTS"):
             parts = max(1, int(os.environ["MPCR_SEED_PARTS"]))
-        self._be.check(lib.mpcr_ctx_set_seed_extension(self._ctx, w_ext if extend else 0, 1 if extend else 0))
+        if blocks:
+            self._be.check(lib.mpcr_ctx_set_seed_blocks(self._ctx, block, n_blocks, 1))
+        else:
+            self._be.check(lib.mpcr_ctx_set_seed_extension(self._ctx, w_ext if extend else 0, 1 if extend else 0))
         self._be.check(lib.mpcr_ctx_set_sampling(self._ctx, SAMPLE_WORDSIZE if role else 0, stride if role else 0, role))
         self._be.check(lib.mpcr_table_build(self._ctx, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
                                             plut.ctypes.data, self._stream()))
-        while len(self._ctx_exts) > parts:
+        n_ext = parts * (n_blocks if blocks else 1)
+        while len(self._ctx_exts) > n_ext:
             lib.mpcr_ctx_destroy(self._ctx_exts.pop())
-        while len(self._ctx_exts) < parts:
+        while len(self._ctx_exts) < n_ext:
             self._ctx_exts.append(self._new_ctx())
         for k, ctx in enumerate(self._ctx_exts):
-            self._be.check(lib.mpcr_ctx_set_seed_extension(ctx, w_ext, 2))
+            if blocks:
+                self._be.check(lib.mpcr_ctx_set_seed_blocks(ctx, block, n_blocks, 2 + k // parts))
+            else:
+                self._be.check(lib.mpcr_ctx_set_seed_extension(ctx, w_ext, 2))
             self._be.check(lib.mpcr_ctx_set_sampling(ctx, SAMPLE_WORDSIZE if role else 0, stride if role else 0, role))
-            self._be.check(lib.mpcr_ctx_set_table_part(ctx, k, parts))
+            self._be.check(lib.mpcr_ctx_set_table_part(ctx, k % parts, parts))
             self._be.check(lib.mpcr_table_build(ctx, blob.ctypes.data, off.ctypes.data, pcr.ctypes.data, n,
                                                 plut.ctypes.data, self._stream()))
         ho = np.full(2 * n, -1, dtype=np.int32)

@@ -44,6 +44,7 @@ struct mpcr_ctx {
     bool table_ready = false;
     uint64_t launches = 0;
     int ext_w = 0, ext_which = 0, scan_w = 0, true_strands = 0;
+    int ext_block = 0, ext_gap = 0, ext_span = 0;
     int samp_w = 0, samp_s = 0, samp_role = 0;
     uint32_t part = 0, parts = 1;
     int append = 0;
@@ -81,6 +82,24 @@ int mpcr_ctx_set_seed_extension(mpcr_ctx* c, int w_ext, int which) {
         if (w_ext <= c->prm.wordsize || w_ext > 16) return fail(MPCR_EINVAL, "extended word must be in (wordsize, 16]");
     }
     c->ext_w = which ? w_ext : 0; c->ext_which = which; c->table_ready = false;
+    c->ext_block = c->ext_gap = c->ext_span = 0;
+    return MPCR_OK;
+}
+int mpcr_ctx_set_seed_blocks(mpcr_ctx* c, int block, int n_blocks, int which) {
+    if (!c) return fail(MPCR_EINVAL, "null argument");
+    if (which < 0 || (which >= 2 && which - 2 >= n_blocks)) return fail(MPCR_EINVAL, "which must be 0, 1 or 2 + block index");
+    if (which != 0) {
+        if (c->prm.iupac_mode != 0) return fail(MPCR_EINVAL, "block tables need letter-identity compares (no IUPAC mode)");
+        if (block < 1 || n_blocks < 1) return fail(MPCR_EINVAL, "block and n_blocks must be positive");
+        if (n_blocks <= c->prm.mismatches) return fail(MPCR_EINVAL, "block tables need more blocks than mismatches");
+        if (c->prm.wordsize + n_blocks * block > 16) return fail(MPCR_EINVAL, "wordsize + n_blocks * block must not exceed 16 letters");
+    }
+    c->ext_w = which ? c->prm.wordsize + block : 0;
+    c->ext_which = which >= 2 ? 2 : which;
+    c->ext_block = which ? block : 0;
+    c->ext_gap = which >= 2 ? (which - 2) * block : 0;
+    c->ext_span = which ? c->prm.wordsize + n_blocks * block : 0;
+    c->table_ready = false;
     return MPCR_OK;
 }
 int mpcr_ctx_set_sampling(mpcr_ctx* c, int w_samp, int stride, int role) {
@@ -288,8 +307,9 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
             uint32_t hbe = 0, kext = 0; int ho; bool ext;
             const Fwd q1{minus ? pr2 : pr1};
             ho = first_clean_word(q1, l1, W, &hbe);
-            ext = which != 0 && extended_seed(q1, l1, ho, c->ext_w, &kext);
-            if (ho >= 0) m.tag = make_tag(q1, l1, ho, which == 2 ? c->ext_w : W);
+            ext = which != 0 && (c->ext_block ? blocked_seed(q1, l1, ho, W, c->ext_block, c->ext_gap, c->ext_span, &kext)
+                                              : extended_seed(q1, l1, ho, c->ext_w, &kext));
+            if (ho >= 0) m.tag = make_tag(q1, l1, ho, which == 2 ? c->ext_w + c->ext_gap : W);
             encode_primer(q1, l1, plut, c->pwords.data() + m.p1_word);
             if (!minus) {
                 if (c->true_strands) encode_primer(Rc{pr2, n2}, n2, plut, c->pwords.data() + m.p2_word);
@@ -401,6 +421,10 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
     if ((origin & 127u) || (sb & 127u)) return fail(MPCR_EINVAL, "origin / shard_begin must be multiples of 128");
     const uint64_t *P2 = (const uint64_t*)plane2, *P4 = (const uint64_t*)plane4, *V = (const uint64_t*)valid;
     SearchParams prm{c->scan_w, c->prm.margin, c->prm.mismatches, c->prm.three_prime_match, c->prm.iupac_mode ? 1 : 0};
+    const bool gapped = c->ext_which == 2 && c->ext_block > 0 && c->samp_role != 1;
+    prm.gap = gapped ? c->ext_gap : 0;
+    prm.block = gapped ? c->ext_block : 0;
+    const uint32_t seed_mask = wmask_of(prm.W - prm.block);
     const int W_ref = c->prm.wordsize;   // the contig-length rule of engine.py:458 uses the reference's word size
     const uint32_t wmask = wmask_of(prm.W), cw = filter_mul(prm.W);
     uint64_t n = c->append ? *count : 0;   // append mode: keep counting behind the previous calls' hits
@@ -421,14 +445,16 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
             for (uint32_t lp0 = 0; lp0 < nb; lp0 += 64) {
                 const int64_t gb = gbase + lp0;
                 if ((uint64_t)gb + 128 > plane_bases + 128) return fail(MPCR_EINVAL, "planes too small for the shard");
-                uint64_t cand = window_valid(V[gb >> 6], V[(gb >> 6) + 1], prm.W);
+                uint64_t cand = prm.gap > 0 ? window_valid_gapped(V[gb >> 6], V[(gb >> 6) + 1], prm.W - prm.block, prm.block, prm.gap)
+                                            : window_valid(V[gb >> 6], V[(gb >> 6) + 1], prm.W);
                 for (int j = 0; j < 64 && cand; ++j) {
                     if (!((cand >> j) & 1)) continue;
                     if (c->samp_role == 1 && (ls + lp0 + j) % (uint64_t)c->samp_s != 0) continue;   // probed positions only
-                    const uint32_t key = extract_key(P2, gb + j, wmask);
+                    const uint32_t key = prm.gap > 0 ? (gap_key_raw(extract_key(P2, gb + j, 0xFFFFFFFFu), seed_mask, prm.gap) & wmask)
+                                                     : extract_key(P2, gb + j, wmask);
                     if (!filter_pass(c->filter[filter_word(key, cw, (uint32_t)c->filter.size())], key, prm.W)) continue;
-                    const uint32_t gcodes = fetch_bits(P2, 2 * (gb + j + prm.W), 2 * kTagBases);
-                    const uint32_t gvalid = fetch_bits(V, gb + j + prm.W, kTagBases);
+                    const uint32_t gcodes = fetch_bits(P2, 2 * (gb + j + prm.W + prm.gap), 2 * kTagBases);
+                    const uint32_t gvalid = fetch_bits(V, gb + j + prm.W + prm.gap, kTagBases);
                     Slot sl;
                     if (!find_slot(c->slots.data(), c->smap, key, &sl)) continue;
                     if (!slot_survives(sl, gcodes, gvalid, prm.N)) continue;

@@ -242,3 +242,37 @@ def dna_torch(seed: int, start: int, n: int, device, chunk: int = 1 << 26):
         codes = ((z[:, None] >> shifts) & 3).reshape(-1)
         out[s - start: e - start] = lut[codes[s - w0 * 32: e - w0 * 32]]
     return out
+
+
+def block_table_case(seed: int, wordsize: int, mismatches: int, n_sts: int = 3000, contig_lens=(70000, 30000, 11),
+                     margin: int = 30, plant_count: int = 90):
+    """A workload for the block tables of searches that allow mismatches (mpcr_ctx_set_seed_blocks): exact plants whose
+    LEFT primer site is then damaged at chosen offsets behind the seed -- one substitution walking through the first
+    block, the second block and the letters behind them (two for -N 2), a genome N inside a block, plus STS lines that
+    cannot be keyed by blocks (short primers, an ambiguity code in a block) and a duplicated line.
+    Returns (contigs, sts_text, expected_planted_hits)."""
+    rng = Rng(seed)
+    contigs = [rng.dna(n) for n in contig_lens]
+    sts = make_sts_set(seed + 1, n_sts, wordsize + 1, 26, 80, 400)
+    sts["p1"][::11, wordsize + 2] = ord("N")          # ambiguity code right behind the seed: not blockable
+    sts["p2"][5::13, wordsize + 1] = ord("R")
+    expected = plant_amplicons(seed + 2, contigs[:2], sts, margin, plant_count=plant_count)
+    for n, (ci, pos1, _pos2, i, strand) in enumerate(expected):
+        seq = contigs[ci]
+        ln = int(sts["l1"][i] if strand == "+" else sts["l2"][i])
+        kind = n % 4
+        offs = [wordsize + (n // 4) % 10]
+        if mismatches >= 2 and kind == 1:
+            offs.append(wordsize + (n // 4 + 3) % 10)
+        if kind == 3:
+            continue                                   # left exact
+        for o in offs:
+            if o < ln:
+                if kind == 2:
+                    seq[pos1 + o] = ord("N")           # a genome base that equals nothing
+                else:
+                    seq[pos1 + o] = ACGT[(int(np.searchsorted(ACGT, seq[pos1 + o])) + 1 + n % 3) % 4]
+    text = sts_lines(sts)
+    lines = text.split(b"\n")
+    text = b"\n".join(lines[:-1] + [lines[3].replace(b"STS000003", b"DUP000003"), b""])   # same primers, another id
+    return contigs, text, expected

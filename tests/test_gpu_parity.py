@@ -513,6 +513,41 @@ def test_fuzz_goldens_with_seed_extension_on_device(monkeypatch):
     assert n > 5
 
 
+@pytest.mark.parametrize("wordsize,mismatches,block_env,n_sts", [(8, 1, "1", 30000), (8, 1, "2", 3000), (10, 2, "1", 30000),
+                                                                 (6, 1, "3", 3000), (11, 1, "1", 30000)])
+def test_block_tables_equal_one_table_on_device(tmp_path, monkeypatch, wordsize, mismatches, block_env, n_sts):
+    """mpcr_ctx_set_seed_blocks on the GPU: a search that allows mismatches keyed on seed + one of N + 1 blocks (split
+    keys through the sparse scanner, direct and open-addressed slot tables) + the table of the records that cannot be
+    keyed that way == the plain one-table search == the oracle, every site once."""
+    from merpcr_b200 import MerPCR
+    contigs, text, expected = synth.block_table_case(900 + wordsize, wordsize, mismatches, n_sts=n_sts,
+                                                     contig_lens=(400_000, 150_000, 11), plant_count=400)
+    stsf = _write(tmp_path, "s.sts", text)
+    params = dict(wordsize=wordsize, margin=30, mismatches=mismatches)
+    want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
+    assert len(want) > 150
+    for flag, parts in (("0", "1"), (block_env, "1"), (block_env, "3")):
+        monkeypatch.setenv("MPCR_SEED_BLOCKS", flag)
+        monkeypatch.setenv("MPCR_SEED_PARTS", parts)
+        eng = MerPCR(**params)
+        assert eng.load_sts_file(stsf)
+        assert len(eng._ctx_exts) == (int(parts) * (mismatches + 1) if flag != "0" else 0)
+        got = parity.engine_hits(eng, _records(contigs))
+        assert np.array_equal(got, want), (flag, parts)
+        eng.close()
+
+
+def test_fuzz_goldens_with_block_tables_on_device(monkeypatch):
+    from merpcr_b200 import MerPCR
+    monkeypatch.setenv("MPCR_SEED_BLOCKS", "1")
+    n = 0
+    for c in goldens.fuzz_cases():
+        if c["params"].get("mismatches", 0) >= 1 and not c["params"].get("iupac_mode", 0):
+            parity.check_fuzz_case(c, MerPCR)
+            n += 1
+    assert n > 20
+
+
 def test_cli_subprocess_on_the_fixture(tmp_path):
     """`python -m merpcr_b200 <sts> <fasta>` -- the reference's CLI surface end to end on the GPU (cli.py:217-266)."""
     import subprocess

@@ -360,6 +360,70 @@ def test_seed_extension_two_tables_equal_one(tmp_path, monkeypatch):
     assert len(want) >= len(expected) > 20
 
 
+@pytest.mark.parametrize("wordsize,mismatches,block_env", [(8, 1, "1"), (8, 1, "2"), (10, 2, "1"), (6, 1, "3"), (11, 1, "1")])
+def test_block_tables_equal_one_table(tmp_path, monkeypatch, wordsize, mismatches, block_env):
+    """Searches that allow mismatches may be keyed on seed + one of N + 1 blocks behind it (mpcr_ctx_set_seed_blocks):
+    the block tables and the table of the records that cannot be keyed that way, scanned separately and merged, must
+    give the one-table result (== the oracle) -- every site once, whichever blocks its mismatches fall into."""
+    from merpcr_b200 import FASTARecord, MerPCR
+    contigs, text, expected = synth.block_table_case(700 + wordsize, wordsize, mismatches)
+    stsf = tmp_path / "s.sts"
+    stsf.write_bytes(text)
+    params = dict(wordsize=wordsize, margin=30, mismatches=mismatches)
+    recs = [FASTARecord(f">c{i}", c) for i, c in enumerate(contigs)]
+    want = parity.oracle_hits(params, text.decode(), [c.tobytes() for c in contigs])
+    assert len(want) > 40
+    for flag, parts in (("0", "1"), (block_env, "1"), (block_env, "2")):
+        monkeypatch.setenv("MPCR_SEED_BLOCKS", flag)
+        monkeypatch.setenv("MPCR_SEED_PARTS", parts)
+        eng = MerPCR(**params)
+        assert eng.load_sts_file(str(stsf))
+        assert len(eng._ctx_exts) == (int(parts) * (mismatches + 1) if flag != "0" else 0)
+        if flag != "0":    # blockable records went to the block tables, the others stayed
+            items = [int(eng._be.lib.mpcr_table_items(c)) for c in eng._all_ctxs()]
+            assert items[0] > 0 and all(x > 0 for x in items[1:]) and len(set(items[1::int(parts)])) == 1
+        got = parity.engine_hits(eng, recs)
+        assert np.array_equal(got, want), (flag, parts)
+        eng.close()
+    # two shards of the blocked search merge to the whole
+    monkeypatch.setenv("MPCR_SEED_BLOCKS", block_env)
+    monkeypatch.setenv("MPCR_SEED_PARTS", "1")
+    pieces = []
+    for rank in range(2):
+        eng = MerPCR(**params, shard=(rank, 2))
+        assert eng.load_sts_file(str(stsf))
+        pieces.append(eng.search_hits(recs))
+        eng.close()
+    eng = MerPCR(**params)
+    assert eng.load_sts_file(str(stsf))
+    whole = eng.search_hits(recs)
+    # the C ABI refuses settings that would lose sites
+    lib, chk = eng._be.lib, eng._be.check
+    with pytest.raises(ValueError):
+        chk(lib.mpcr_ctx_set_seed_blocks(eng._ctx, 2, mismatches, 1))          # needs more blocks than mismatches
+    with pytest.raises(ValueError):
+        chk(lib.mpcr_ctx_set_seed_blocks(eng._ctx, 9, mismatches + 1, 1))      # seed + blocks beyond 16 letters
+    eng.close()
+    merged = np.concatenate(pieces)
+    order = np.lexsort((merged["rank"], merged["rec"], merged["hash_off"], merged["pos1"], merged["contig"]))
+    assert np.array_equal(merged[order], whole)
+    eng = MerPCR(wordsize=8, mismatches=1, iupac_mode=1)
+    with pytest.raises(ValueError):
+        eng._be.check(eng._be.lib.mpcr_ctx_set_seed_blocks(eng._ctx, 4, 2, 1))   # IUPAC compares are not letter identity
+    eng.close()
+
+
+def test_fuzz_goldens_with_block_tables(monkeypatch):
+    monkeypatch.setenv("MPCR_SEED_BLOCKS", "1")
+    from merpcr_b200 import MerPCR
+    n = 0
+    for c in goldens.fuzz_cases():
+        if c["params"].get("mismatches", 0) >= 1 and not c["params"].get("iupac_mode", 0):
+            parity.check_fuzz_case(c, MerPCR)
+            n += 1
+    assert n > 20
+
+
 def test_fuzz_goldens_with_seed_extension(monkeypatch):
     monkeypatch.setenv("MPCR_SEED_EXTENSION", "1")
     from merpcr_b200 import MerPCR
