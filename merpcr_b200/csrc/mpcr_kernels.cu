@@ -1182,12 +1182,14 @@ __device__ __forceinline__ void verify_survivor(const ScanArgs& a, const Survivo
 }
 
 #ifndef MPCR_VERIFY_CTAS_PER_SM
-#define MPCR_VERIFY_CTAS_PER_SM 3
+#define MPCR_VERIFY_CTAS_PER_SM 4
 #endif
 #ifndef MPCR_VERIFY_STATIC_DEPTH
 #define MPCR_VERIFY_STATIC_DEPTH 64
 #endif
-static constexpr int kVerifyCtasPerSm = MPCR_VERIFY_CTAS_PER_SM;            // 80 registers x 256 threads: three CTAs per SM
+// 64 registers x 256 threads: the verifier is a chain of dependent loads per survivor, so a fourth resident CTA per SM
+// is worth the handful of spilled registers (whole genome 0.215 -> 0.202 ms, 1/8 shard 49 -> 45.5 us against three CTAs)
+static constexpr int kVerifyCtasPerSm = MPCR_VERIFY_CTAS_PER_SM;
 static constexpr uint32_t kStaticVerifyDepth = MPCR_VERIFY_STATIC_DEPTH;  // survivors per lane group dealt out statically
 __global__ void __launch_bounds__(256, kVerifyCtasPerSm) verify_kernel(const ScanArgs a) {
     // Survivor lists of up to kStaticVerifyDepth entries per lane group are dealt out STATICALLY: every CTA sums the 256
@@ -1218,7 +1220,7 @@ __global__ void __launch_bounds__(256, kVerifyCtasPerSm) verify_kernel(const Sca
     const uint32_t total = pre[kSurvLists];
     constexpr uint32_t kGroupsPerWarp = 32 / kVerifyLanes;
     const uint32_t n_groups = gridDim.x * (blockDim.x >> 5) * kGroupsPerWarp;
-    if (total <= n_groups * kStaticVerifyDepth) {
+    if (total / n_groups < kStaticVerifyDepth) {
         // lane group G takes the survivors G, G + n_groups, ... of the concatenated sub-lists: neighbouring groups of a
         // warp look at neighbouring survivors (same producer warp, nearby bases), and a costly stretch of the genome
         // (an N-run in IUPAC mode, a repeat) is spread over all groups

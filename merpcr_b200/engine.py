@@ -222,6 +222,10 @@ class MerPCR:
             cpus = os.cpu_count() or 1
         self._pack_threads = max(1, cpus // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
         self.hybrid_wire = os.environ.get("MPCR_HYBRID_WIRE", "1") not in ("0", "")
+        # a piece is packed on the host while the copy engine has at least this share of a pack's duration queued
+        self.hybrid_backlog = float(os.environ.get("MPCR_HYBRID_BACKLOG", "0.7"))
+        if os.environ.get("MPCR_PACK_THREADS"):
+            self._pack_threads = max(1, int(os.environ["MPCR_PACK_THREADS"]))
         self._pack_rate = 50e9    # bases / s the host packer sustains (refined while it runs)
         self._h2d_rate = 50e9     # bytes / s of the host -> device link (PCIe Gen5 x16 moves ~55 GB/s)
         self._ctx_exts = []       # extended tables of exact, candidate-heavy searches (mpcr_ctx_set_seed_extension)
@@ -907,7 +911,7 @@ class MerPCR:
                 pack_it = on_host and use_nibbles
                 if pack_it and gpu and self.hybrid_wire and src.is_pinned():
                     backlog = busy_until - time.perf_counter()
-                    pack_it = backlog >= 0.7 * (b - a) / self._pack_rate
+                    pack_it = backlog >= self.hybrid_backlog * (b - a) / self._pack_rate
                 if pack_it:
                     slot = kn % n_stage
                     if gpu and kn >= n_stage:

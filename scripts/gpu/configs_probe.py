@@ -22,7 +22,7 @@ def main():
     dev = torch.device("cuda", 0)
     cfgs = fullsize.configs(scale)
     for k in which:
-        fullsize.run(*cfgs[k], dev, oracle=("slices", 16, 2_000_000) if k == "cfg5" else "whole")
+        fullsize.run(*cfgs[k], dev, oracle=("slices", 16, 2_000_000) if k.startswith("cfg5") else "whole")
 
 
 if __name__ == "__main__":

@@ -232,6 +232,10 @@ def configs(scale: float = 1.0):
                  dict(wordsize=11, margin=50, mismatches=2, three_prime_match=1, iupac_mode=1), "cfg3", False, 1004, True),
         "cfg5": ("cfg5: 3.1 Gbp x 1M STS, ranged sizes, -W 8 -M 500 -N 0", g38, max(1000, int(1000000 * scale)),
                  dict(wordsize=8, margin=500, mismatches=0), "none", True, 1005, False),
+        # not a BASELINE config: config 5 with one mismatch allowed -- the candidate-heavy search that can use neither the
+        # seed extension nor position sampling and runs on block tables (mpcr_ctx_set_seed_blocks)
+        "cfg5n1": ("cfg5n1: 3.1 Gbp x 1M STS, ranged sizes, -W 8 -M 500 -N 1", g38, max(1000, int(1000000 * scale)),
+                   dict(wordsize=8, margin=500, mismatches=1), "cfg3", True, 1006, False),
     }
 
 
