@@ -1099,71 +1099,6 @@ __device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& 
     }
 }
 
-__device__ __forceinline__ void verify_body(const ScanArgs& a) {
-    constexpr int kGroups = 32 / kVerifyLanes;
-    constexpr uint32_t kGrab = kGroups;       // survivors a warp takes per cursor atomic (one per lane group)
-    const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
-    const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    // Every warp looks at 32 sub-lists at a time (one per lane: count and cursor, two loads per lane, all in flight
-    // together), takes the first one that still has work -- starting from a lane that differs between the warps that share
-    // the window -- drains it, and looks again.  A fresh look per list costs one round trip; walking a stale mask cost
-    // one round trip per ALREADY DRAINED list, 32 in a row, which was most of this kernel's time on short survivor lists.
-    // A warp drains its own window of 32 sub-lists (every sub-list lies in the window of 1/8 of the warps) and helps with
-    // the other windows only when its own turned out to be heavy: on light runs every window is equally light, and
-    // 9472 warps polling all 256 control lines cost more L2 round trips on those few hot lines than the work itself.
-    const uint32_t rot = (warp_id / kSurvLists) & 31u;
-    uint32_t grabs = 0;
-    for (uint32_t round = 0; round < kSurvLists / 32; ++round) {
-      if (round > 0 && grabs < 2) break;
-      const uint32_t my_list = (warp_id + 32 * round + lane) & (kSurvLists - 1u);
-      const uint32_t* my_ctl = a.surv_ctl + my_list * kSurvCtlStride;
-      const uint32_t my_n = min(__ldcg(my_ctl), a.surv_cap);      // final: the scanner has finished
-      // walk the sub-lists that had work when the window was polled; two visits in a row that find a list already
-      // drained by other warps mean the picture is stale (short lists empty at once): poll again instead of paying one
-      // round trip per drained list
-      uint32_t open = __ballot_sync(0xffffffffu, __ldcg(my_ctl + 1) < my_n);
-      int stale = 0;
-      while (open) {
-        const int l = (int)((__ffs(__funnelshift_r(open, open, rot)) - 1 + rot) & 31u);
-        open &= ~(1u << l);
-        const uint32_t list = (warp_id + 32 * round + l) & (kSurvLists - 1u);
-        uint32_t* ctl = a.surv_ctl + list * kSurvCtlStride;
-        const uint32_t n = __shfl_sync(0xffffffffu, my_n, l);
-        const Survivor* surv = a.surv + (size_t)list * a.surv_cap;
-        for (bool first_try = true;; first_try = false) {
-            uint32_t first = 0;
-            if (lane == 0) first = __ldcg(ctl + 1) < n ? atomicAdd(ctl + 1, kGrab) : n;   // look before touching the line
-            first = __shfl_sync(0xffffffffu, first, 0);
-            if (first >= n) {
-                if (first_try && ++stale >= 2) {
-                    open = __ballot_sync(0xffffffffu, __ldcg(my_ctl + 1) < my_n);
-                    stale = 0;
-                }
-                break;
-            }
-            stale = 0;
-            ++grabs;
-          for (uint32_t idx = first + group; idx < min(first + kGrab, n); idx += kGroups) {
-            const Survivor sv = surv[idx];
-            const TileDesc td = a.tiles[sv.tile];
-            if (!(sv.code & kWalkBucket)) {
-                verify_group(a, td, sv.lp, sv.code, gl);
-            } else {  // a seed shared by several records: bucket order, each entry behind its own tag
-                const int64_t gb = td.gbase + sv.lp + a.prm.W + a.prm.gap;
-                const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
-                const bool clean = tag_window_clean(gvalid);
-                for (uint32_t e = sv.code & ~kWalkBucket;; ++e) {
-                    const BucketEntry b = a.bucket[e];
-                    if (!clean || !tag_rejects(b.tag, gcodes, a.prm.N)) verify_group(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, gl);
-                    if (b.rec_last >> 31) break;
-                }
-            }
-          }
-        }
-      }
-    }
-}
-
 // One survivor for the lane group `gl` belongs to (shared by the dynamic and the static schedule).
 __device__ __forceinline__ void verify_survivor(const ScanArgs& a, const Survivor& sv, int gl) {
     const TileDesc td = a.tiles[sv.tile];
@@ -1178,6 +1113,35 @@ __device__ __forceinline__ void verify_survivor(const ScanArgs& a, const Survivo
             if (!clean || !tag_rejects(b.tag, gcodes, a.prm.N)) verify_group(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, gl);
             if (b.rec_last >> 31) break;
         }
+    }
+}
+
+__device__ __forceinline__ void verify_body(const ScanArgs& a) {
+    constexpr int kGroups = 32 / kVerifyLanes;
+    constexpr uint32_t kGrab = kGroups;       // survivors a warp takes per cursor atomic (one per lane group)
+    const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
+    const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // every warp starts at its own sub-list and moves on when that one is drained, until it has seen them all;
+    // 32 sub-lists are looked at per round (one per lane) so that drained ones cost nothing
+    for (uint32_t round = 0; round < kSurvLists / 32; ++round) {
+      const uint32_t my_list = (warp_id + 32 * round + lane) & (kSurvLists - 1u);
+      const uint32_t* my_ctl = a.surv_ctl + my_list * kSurvCtlStride;
+      uint32_t open = __ballot_sync(0xffffffffu, __ldcg(my_ctl + 1) < min(__ldcg(my_ctl), a.surv_cap));
+      while (open) {
+        const int l = __ffs(open) - 1;
+        open &= open - 1;
+        const uint32_t list = (warp_id + 32 * round + l) & (kSurvLists - 1u);
+        uint32_t* ctl = a.surv_ctl + list * kSurvCtlStride;
+        const uint32_t n = min(__ldcg(ctl), a.surv_cap);
+        const Survivor* surv = a.surv + (size_t)list * a.surv_cap;
+        for (;;) {
+            uint32_t first = 0;
+            if (lane == 0) first = __ldcg(ctl + 1) < n ? atomicAdd(ctl + 1, kGrab) : n;   // look before touching the line
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (first >= n) break;
+            for (uint32_t idx = first + group; idx < min(first + kGrab, n); idx += kGroups) verify_survivor(a, surv[idx], gl);
+        }
+      }
     }
 }
 
@@ -2173,8 +2137,11 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
         // instantiations: the open-addressed table (W >= 12), the narrow filter (W < 6), the general direct table, and
         // the reference's default word size with the usual mismatch budgets fixed at compile time
         void (*kern)(const ScanArgs) = scan_kernel<true, false, 0, -1>;
-        if (a.prm.gap > 0) kern = c->smap.direct ? scan_kernel<true, false, 0, -1, true> : scan_kernel<true, true, 0, -1, true>;
-        else if (!c->smap.direct) kern = scan_kernel<true, true, 0, -1>;
+        const bool w12n1 = a.prm.W == 12 && a.prm.N == 1;   // block tables of -W 8 / -W 9 searches with one mismatch
+        if (a.prm.gap > 0)
+            kern = c->smap.direct ? scan_kernel<true, false, 0, -1, true>
+                                  : (w12n1 ? scan_kernel<true, true, 12, 1, true> : scan_kernel<true, true, 0, -1, true>);
+        else if (!c->smap.direct) kern = w12n1 ? scan_kernel<true, true, 12, 1> : scan_kernel<true, true, 0, -1>;
         else if (a.prm.W < 6) kern = scan_kernel<false, false, 0, -1>;
         else if (a.prm.W == 11 && a.prm.N == 0) kern = scan_kernel<true, false, 11, 0>;
         else if (a.prm.W == 11 && a.prm.N == 1) kern = scan_kernel<true, false, 11, 1>;

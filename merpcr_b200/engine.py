@@ -221,9 +221,12 @@ class MerPCR:
         except AttributeError:  # pragma: no cover
             cpus = os.cpu_count() or 1
         self._pack_threads = max(1, cpus // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+        if self._pack_threads >= 8:     # the packer shares the host's memory system with the DMA engine: 3/4 of the cores
+            self._pack_threads = self._pack_threads * 3 // 4    # pack as fast as all of them (scripts/gpu/hybrid_probe.py)
         self.hybrid_wire = os.environ.get("MPCR_HYBRID_WIRE", "1") not in ("0", "")
         # a piece is packed on the host while the copy engine has at least this share of a pack's duration queued
-        self.hybrid_backlog = float(os.environ.get("MPCR_HYBRID_BACKLOG", "0.7"))
+        # (0.7 packed 70 % of a human genome: 42.9 ms; 1.4 - 2.0 pack ~60 %, which is where link and host memory balance: 40 ms)
+        self.hybrid_backlog = float(os.environ.get("MPCR_HYBRID_BACKLOG", "1.7"))
         if os.environ.get("MPCR_PACK_THREADS"):
             self._pack_threads = max(1, int(os.environ["MPCR_PACK_THREADS"]))
         self._pack_rate = 50e9    # bases / s the host packer sustains (refined while it runs)
