@@ -259,7 +259,9 @@ inline int radix_sort(Item<NF>* d_a, Item<NF>* d_b, uint64_t n_host, const unsig
 // that range hold a handful of records each: count per slice (one atomic per record), one-CTA scan of the counts,
 // scatter, and one thread per slice puts its few records into the complete order (contig, pos1, hash_off, rec, rank)
 // -- no tie pass needed afterwards.  Four small launches, ~15 us, against ~110 us for five cooperative radix passes
-// (a rank sort and a one-CTA shared-memory radix were measured first: 88 us and 161 us for 10^4 hits).  A list that
+// (a rank sort and a one-CTA shared-memory radix were measured first: 88 us and 161 us for 10^4 hits; the same bucket
+// sort by ONE CTA in one launch, counters and offsets in shared memory: ~100 us -- a lone CTA pays every L2 round trip
+// of its ten records per thread in sequence).  A list that
 // piles up in one slice (> kBucketMaxFill records: repeats, an N-run in IUPAC mode) raises *fallback and is left to
 // the radix passes, which check the flag on the device.
 static constexpr uint32_t kBucketSortMax = 1u << 17;

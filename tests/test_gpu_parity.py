@@ -592,8 +592,9 @@ def test_true_strands_option_on_device():
     _true_strands_check(MerPCR, _records)
 
 
-@pytest.mark.parametrize("n,long_run", [(2, False), (37, False), (1000, True), (9000, False), (70000, False), (70000, True),
-                                        (131072, False), (131073, False), (300000, True)])
+@pytest.mark.parametrize("n,long_run", [(2, False), (37, False), (1000, True), (9000, False), (9000, True), (16384, False),
+                                        (16385, False), (70000, False), (70000, True), (131072, False), (131073, False),
+                                        (300000, True)])
 def test_sort_with_the_count_on_the_device(n, long_run):
     """mpcr_sort_hits_dev (count read on the device; bucket sort on the global coordinate for lists of up to 2^17 hits,
     radix passes + tie kernels for longer ones and for lists that pile up in one place; any hint) and mpcr_sort_hits
