@@ -7,7 +7,7 @@
 
 One "step" = one pass of the hot path (scan + verify + emit + sort + read-back of the hit count) over the rank's
 resident genome shard.  `value` is whole-job throughput with the packed genome and the table resident in HBM, steps
-queued two deep (the host reads step k's count while step k+1 runs; `config.ms_per_step_host_synced` is the same
+queued four deep (the host reads step k's count while the next ones run; `config.ms_per_step_host_synced` is the same
 step with a host synchronisation after every one); `e2e` repeats the step from pinned HOST bytes (host-side nibble
 packing / H2D + plane building + scan + sort + D2H of the hits inside the timed region); `e2e_file` starts from a
 FASTA file in the page cache and ends with the output text on disk.
@@ -43,6 +43,7 @@ PARAMS = dict(wordsize=11, margin=50, mismatches=1, three_prime_match=1, iupac_m
 METRIC = "Gbp/s scanned (3.1 Gbp genome, 100k STS, N=1)"
 ALGO_BYTES_PER_BP = 0.75   # plane2 0.25 + plane4 0.5, each read once
 ALGO_BYTES_PER_HIT = 16.0
+IN_FLIGHT = 4              # steps queued ahead of the host's read-back of their hit counts
 
 
 def parse_args():
@@ -393,26 +394,30 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # samples every 20 ms from the warm-up to the end of the timed region (GPU under load)
-    # Steps are queued two deep: the host reads step k's hit count (and, per slot, its kernel times) while step k+1
-    # runs, so the GPU never waits for the host round trip between steps.  Every step does all of its work -- scan,
-    # verify, ordering, count read-back -- and every count is checked; nothing is skipped or cached.
+    # Steps are queued IN_FLIGHT deep: the host reads step k's hit count (and, per slot, its kernel times) while the next
+    # ones run, so the GPU never waits for the host round trip between steps (a sharded step takes 0.45 ms on eight GPUs;
+    # one scheduling hiccup of a host thread is several steps long).  Every step does all of its work -- scan, verify,
+    # ordering, count read-back -- and every count is checked; nothing is skipped or cached.
     scan_ms, verify_ms = [], []
 
     def run_steps(k: int, record: bool) -> int:
-        pending, n = None, 0
-        for i in range(k):
-            h = eng.scan_device_async(layout, shard, slot=i & 1)
-            if pending is not None:
-                _, n = eng.scan_finish(layout, shard, pending)
-                if record:
-                    scan_ms.append(float(lib.mpcr_slot_scan_ms(ctx, pending[0])))
-                    verify_ms.append(float(lib.mpcr_slot_verify_ms(ctx, pending[0])))
-            pending = h
-        if pending is not None:
-            _, n = eng.scan_finish(layout, shard, pending)
+        from collections import deque
+        pending, n = deque(), 0
+
+        def finish_oldest():
+            h = pending.popleft()
+            _, n_ = eng.scan_finish(layout, shard, h)
             if record:
-                scan_ms.append(float(lib.mpcr_slot_scan_ms(ctx, pending[0])))
-                verify_ms.append(float(lib.mpcr_slot_verify_ms(ctx, pending[0])))
+                scan_ms.append(float(lib.mpcr_slot_scan_ms(ctx, h[0])))
+                verify_ms.append(float(lib.mpcr_slot_verify_ms(ctx, h[0])))
+            return n_
+
+        for i in range(k):
+            if len(pending) == IN_FLIGHT:
+                n = finish_oldest()
+            pending.append(eng.scan_device_async(layout, shard, slot=i % IN_FLIGHT))
+        while pending:
+            n = finish_oldest()
         return n
 
     n_hits = run_steps(args.warmup, False)
@@ -424,10 +429,14 @@ def run_b200(args):
         sampler.mark()
     launches0 = eng.gpu_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()            # a collector pause on the host is longer than a sharded step
     ev0.record()
     n_hits = run_steps(args.steps, True)
     ev1.record()
     torch.cuda.synchronize()
+    gc.enable()
     if rank == 0:
         sampler.mark_end()
     t_ms = ev0.elapsed_time(ev1)
@@ -647,7 +656,7 @@ def run_b200(args):
                         **({"emulated_shard": args.as_shard, "note": "tuning run: one rank's share only, not a bench line"}
                            if args.as_shard else {}),
                         l2="inputs (2.7 GB of planes per GPU) exceed the 126 MB L2; no flush needed",
-                        steps_in_flight=2, ms_per_step_host_synced=ms_synced,
+                        steps_in_flight=IN_FLIGHT, ms_per_step_host_synced=ms_synced,
                         numa_node=numa, host_cpus=len(os.sched_getaffinity(0)),
                         planted_found=planted_ok, sorted=sorted_ok, **({"per_rank": per_rank} if per_rank else {})),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,

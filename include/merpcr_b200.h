@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MPCR_ABI_VERSION 14
+#define MPCR_ABI_VERSION 15
 
 enum {
     MPCR_OK = 0,
@@ -304,12 +304,13 @@ int mpcr_scan_sorted(mpcr_ctx *const *ctxs, uint32_t n_ctx, const mpcr_contig *h
                      uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit *d_hits, uint64_t capacity,
                      uint64_t *d_count, uint64_t *h_count, uint64_t n_hint, int sort, void *stream);
 
-/* The same step without the final synchronisation, for callers that keep two steps in flight (the host reads step k's
- * count while step k+1 runs; consecutive steps on one stream share the context's scratch, only d_hits / d_count /
- * h_result must differ between the two): h_result = two uint64 of PINNED host memory, [0] receives the true hit count,
- * [1] != 0 means the short-list sort gave up and mpcr_sort_finish must run -- both valid once the caller has
- * synchronised with `stream` (event, stream sync).  slot (0 / 1) selects the set of timing events the step records
- * (mpcr_slot_scan_ms / mpcr_slot_verify_ms read them back without waiting for a later step). */
+/* The same step without the final synchronisation, for callers that keep several steps in flight (the host reads step
+ * k's count while steps k+1 .. run; consecutive steps on one stream share the context's scratch, only d_hits / d_count /
+ * h_result must differ between the steps in flight): h_result = two uint64 of PINNED host memory, [0] receives the true
+ * hit count, [1] != 0 means the short-list sort gave up and mpcr_sort_finish must run -- both valid once the caller has
+ * synchronised with `stream` (event, stream sync).  slot (0 .. MPCR_MAX_SLOTS - 1) selects the set of timing events
+ * the step records (mpcr_slot_scan_ms / mpcr_slot_verify_ms read them back without waiting for a later step). */
+#define MPCR_MAX_SLOTS 8
 int mpcr_scan_sorted_async(mpcr_ctx *const *ctxs, uint32_t n_ctx, const mpcr_contig *h_contigs, uint32_t n_contigs,
                            const void *d_plane2, const void *d_plane4, const void *d_valid, uint64_t plane_origin,
                            uint64_t plane_bases, uint64_t shard_begin, uint64_t shard_end, mpcr_hit *d_hits,

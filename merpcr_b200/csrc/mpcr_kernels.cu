@@ -118,9 +118,9 @@ struct mpcr_ctx {
     uint64_t launches = 0;
     // scan / verify timing events, one set per pipeline slot (a caller that keeps two steps in flight reads step k's
     // times while step k+1 records its own, see mpcr_scan_sorted_async)
-    cudaEvent_t evs[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    cudaEvent_t evs[MPCR_MAX_SLOTS][3] = {};
     int ev_slot = 0;
-    bool scan_timed[2] = {false, false};
+    bool scan_timed[MPCR_MAX_SLOTS] = {};
     int env_debug = 0;          // $MPCR_DEBUG, read once at context creation
     long env_surv_cap = -1;     // $MPCR_SURVIVOR_CAP (test hook), ditto
     bool ctl_dirty = false;     // the scanner's control words were left non-zero (debug runs skip the verifier)
@@ -1392,7 +1392,7 @@ int mpcr_ctx_create(int device, const mpcr_params* p, mpcr_ctx** out) {
     step(cudaMalloc(&c->d_lut, 256));
     if (err == cudaSuccess) step(cudaMemset(c->d_tile_counter, 0, 256));
     if (err == cudaSuccess) step(cudaMemset(c->d_surv_ctl, 0, (size_t)kSurvLists * kSurvCtlStride * 4));
-    for (int sl = 0; sl < 2; ++sl)
+    for (int sl = 0; sl < MPCR_MAX_SLOTS; ++sl)
         for (int k = 0; k < 3; ++k) step(cudaEventCreate(&c->evs[sl][k]));
     if (err != cudaSuccess) {
         mpcr_ctx_destroy(c);   // frees whatever was allocated
@@ -1415,7 +1415,7 @@ void mpcr_ctx_destroy(mpcr_ctx* c) {
     DeviceGuard guard_(c->device);
     free_table(c);
     cudaFree(c->d_tiles); cudaFree(c->d_tile_counter); cudaFree(c->d_sort_tmp); cudaFree(c->d_long_runs); cudaFree(c->d_counts); cudaFree(c->d_lut);
-    for (int sl = 0; sl < 2; ++sl)
+    for (int sl = 0; sl < MPCR_MAX_SLOTS; ++sl)
         for (int k = 0; k < 3; ++k)
             if (c->evs[sl][k]) cudaEventDestroy(c->evs[sl][k]);
     cudaFree(c->d_surv);
@@ -2176,7 +2176,7 @@ int mpcr_scan_sorted_async(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_con
                            uint64_t capacity, uint64_t* d_count, uint64_t* h_result, uint64_t n_hint, int sort, int slot,
                            void* stream) {
     if (!ctxs || n_ctx == 0 || !d_count) return fail(MPCR_EINVAL, "null argument");
-    if (slot < 0 || slot > 1) return fail(MPCR_EINVAL, "slot must be 0 or 1");
+    if (slot < 0 || slot >= MPCR_MAX_SLOTS) return fail(MPCR_EINVAL, "slot must be in [0, %d)", MPCR_MAX_SLOTS);
     for (uint32_t i = 0; i < n_ctx; ++i)
         if (!ctxs[i]) return fail(MPCR_EINVAL, "null context");
     int rc = MPCR_OK;
@@ -2253,7 +2253,7 @@ int mpcr_scan_sorted(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_contig* h
 }
 
 static float event_ms(mpcr_ctx* c, int slot, int from, int to) {
-    if (!c || slot < 0 || slot > 1 || !c->scan_timed[slot]) return 0.f;
+    if (!c || slot < 0 || slot >= MPCR_MAX_SLOTS || !c->scan_timed[slot]) return 0.f;
     float ms = 0.f;
     if (cudaEventSynchronize(c->evs[slot][to]) != cudaSuccess) return 0.f;
     if (cudaEventElapsedTime(&ms, c->evs[slot][from], c->evs[slot][to]) != cudaSuccess) return 0.f;

@@ -1021,16 +1021,16 @@ class MerPCR:
         return out.copy() if copy else out
 
     def scan_device_async(self, layout: dict, sh: _Shard, slot: int = 0, sort: bool = True):
-        """One step (scan + verify + ordering) queued WITHOUT waiting for it: for callers that keep two steps in flight
-        -- the host reads step k's result (`scan_finish`) while step k+1 runs.  Consecutive steps share the stream and
-        the contexts' scratch; each slot (0 / 1) has its own hit buffer, count and pinned result words.  Returns a
-        handle for `scan_finish`."""
+        """One step (scan + verify + ordering) queued WITHOUT waiting for it: for callers that keep several steps in
+        flight -- the host reads step k's result (`scan_finish`) while the next ones run.  Consecutive steps share the
+        stream and the contexts' scratch; each slot (0 .. _capi.MAX_SLOTS - 1) has its own hit buffer, count and pinned
+        result words.  Returns a handle for `scan_finish`."""
         import ctypes as C
         lib = self._be.lib
         contigs = layout["contigs"]
         isz = _capi.HIT_DTYPE.itemsize
         if self._slots is None:
-            self._slots = [dict(hits=None, count=None, result=None, event=None, last_n=0) for _ in range(2)]
+            self._slots = [dict(hits=None, count=None, result=None, event=None, last_n=0) for _ in range(_capi.MAX_SLOTS)]
         st = self._slots[slot]
         gpu = self._tdev.type == "cuda"
         if st["count"] is None:

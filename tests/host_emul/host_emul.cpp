@@ -509,7 +509,7 @@ int mpcr_scan_sorted_async(mpcr_ctx* const* ctxs, uint32_t n_ctx, const mpcr_con
                            const void* p4, const void* valid, uint64_t origin, uint64_t plane_bases, uint64_t sb, uint64_t se,
                            mpcr_hit* hits, uint64_t capacity, uint64_t* count, uint64_t* h_result, uint64_t hint, int sort,
                            int slot, void* st) {
-    if (slot < 0 || slot > 1) return fail(MPCR_EINVAL, "slot must be 0 or 1");
+    if (slot < 0 || slot >= MPCR_MAX_SLOTS) return fail(MPCR_EINVAL, "slot must be in [0, %d)", MPCR_MAX_SLOTS);
     uint64_t n = 0;
     const int rc = mpcr_scan_sorted(ctxs, n_ctx, contigs, n_contigs, p2, p4, valid, origin, plane_bases, sb, se, hits, capacity,
                                     count, &n, hint, sort, st);
