@@ -577,7 +577,13 @@ struct FilterView {
 template <bool WIDE>
 __device__ __forceinline__ uint32_t filter_probe(const FilterView& f, const ScanArgs& a, uint32_t x, uint32_t x3) {
     uint32_t word;
+#ifdef MPCR_STAGE1_NOCONFLICT   // tuning build, WRONG results: every lane reads its own bank -- what stage 1 would cost without bank conflicts
+    uint32_t lane_id;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane_id));
+    const uint32_t addr = ((__umulhi(x * f.cw, f.n_words - 32u) & ~31u) | lane_id) * a.k4 + f.base32;
+#else
     const uint32_t addr = __umulhi(x * f.cw, f.n_words) * a.k4 + f.base32;
+#endif
     asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
     const uint32_t t1 = __funnelshift_l(0u, word, x);  // word << (x & 31)
     if (!WIDE) return t1;
