@@ -420,6 +420,7 @@ def run_b200(args):
             n = finish_oldest()
         return n
 
+    run_steps(IN_FLIGHT, False)   # untimed: every pipeline slot allocates its hit buffer and pinned result words here
     n_hits = run_steps(args.warmup, False)
     if rank == 0:
         sampler.wait_first_sample()
