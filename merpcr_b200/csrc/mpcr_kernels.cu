@@ -80,6 +80,8 @@ struct mpcr_ctx {
     BucketEntry* d_bucket = nullptr;
     uint32_t* d_filter = nullptr;
     uint32_t filter_words = 0;
+    bool filter_linear = false;     // the filter of THIS table uses the linear map (mpcr_core.cuh: 11-letter keys)
+    float filter_scale = 0.f, filter_bias = 0.f;
     uint32_t n_keys = 0;
     bool dense = false;
     int ext_w = 0, ext_which = 0;   // seed extension (mpcr_ctx_set_seed_extension / mpcr_ctx_set_seed_blocks)
@@ -374,7 +376,8 @@ __global__ void __launch_bounds__(256) build_buckets(const Item<2>* __restrict__
                                                      Slot* __restrict__ slots, SlotMap sm,
                                                      uint32_t* __restrict__ filter, uint32_t filter_words, uint32_t cw,
                                                      int W, uint32_t* __restrict__ n_keys,
-                                                     uint32_t* __restrict__ bloom, uint32_t bloom_shift) {
+                                                     uint32_t* __restrict__ bloom, uint32_t bloom_shift, bool linear,
+                                                     float lin_scale, float lin_bias) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_valid) return;
     const uint32_t key = pairs[i].f[0];
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(256) build_buckets(const Item<2>* __restrict__
         }
         reinterpret_cast<unsigned long long*>(slots + s)[1] = hi;
         if (bloom) atomicOr(&bloom[bloom_word(key, bloom_shift)], bloom_bits(key));   // sampled table: global filter
+        else if (linear) atomicOr(&filter[filter_word_linear(key, lin_scale, lin_bias)], filter_bits_linear(key));
         else atomicOr(&filter[filter_word(key, cw, filter_words)], filter_bits_of(key, W));
         atomicAdd(n_keys, 1u);
     }
@@ -445,6 +449,8 @@ struct ScanArgs {
     const uint32_t* filter;
     uint32_t filter_words;
     uint32_t cw;  // filter_mul(W)
+    float lin_scale, lin_bias;   // linear filter map (11-letter keys): word index = mantissa of fma(2^23 + key, scale, bias)
+    uint32_t lin_exp;            // kLinearExp, as an argument: a register operand keeps (x & mask) | exp ONE LOP3
     SearchParams prm;
     mpcr_hit* hits;
     unsigned long long capacity;
@@ -614,7 +620,7 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
         ok[u] = qi < cnt;
         const uint32_t lp = queue[ok[u] ? qi : 0u];
         // key (2W bits) and the 8-base tag window (16 bits) out of three staged words
-        const uint32_t wi = lp >> 4, sh = (lp & 15u) * 2u;
+        const uint32_t wi = lp >> 4, sh = lp * 2u;   // the funnel shifts below wrap: only (2 * lp) & 31 counts
         const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1], w2 = s_p2[wi + 2];
         const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
         key[u] = (GAPPED ? gap_key_raw(x0, seed_mask, gap) : x0) & wmask;
@@ -625,7 +631,12 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
             const uint32_t vb = lp + (uint32_t)(W + gap), vi = vb >> 5, vs = vb & 31u;
             dirty[u] = !tag_window_clean(__funnelshift_r(s_v[vi], s_v[vi + 1], vs));
         }
-        gather16_async(&landing[u][lane], a.slots + (HASHED ? (slot_hash(key[u]) & a.smap.mask) : key[u]));
+        {   // slot address as a wide multiply-add: mask + LEA + LEA.HI.X (the compiler's shift + mask + 64-bit add takes four)
+            const uint32_t si = HASHED ? (slot_hash(key[u]) & a.smap.mask) : key[u];
+            unsigned long long sa;
+            asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(sa) : "r"(si), "l"(a.slots));   // becomes LEA + LEA.HI.X
+            gather16_async(&landing[u][lane], reinterpret_cast<const void*>(sa));
+        }
         gather_commit();
     }
 #pragma unroll
@@ -677,7 +688,7 @@ __device__ MPCR_PROBE_INLINE void probe_queue(const ScanArgs& a, const uint16_t*
 
 // Stage 1 for one unit of 2048 positions: lane l owns positions [64l, 64l+64) -- rolling keys by funnel shift out of
 // five registers, one shared-memory Bloom probe (two bits of one word) per position.  c_lo / c_hi: pass masks.
-template <bool WIDE, bool GAPPED>
+template <bool WIDE, bool GAPPED, bool LINEAR>
 __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs& a, const uint32_t* __restrict__ s_p2,
                                             const uint32_t* __restrict__ s_v, int lane, uint32_t unit_nbases, int W,
                                             uint32_t& c_lo, uint32_t& c_hi, bool& my_clean) {
@@ -709,11 +720,59 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
                 const uint32_t k = gap_key_raw(raw(j), seed_mask, gap);
                 return filter_probe<WIDE>(f, a, k, k >> 6);
             };
-            // collect the MSB of each probe result as bit j of the pass mask (descending j: one funnel shift each)
+            if (LINEAR) {
+                // Linear map (mpcr_core.cuh).  Every warp instruction of this loop costs an issue slot of ~1.6 clocks whatever
+                // pipe it runs on (scripts/ubench/pipes.cu), so the work is packed two positions per FP32 instruction
+                // (FFMA2, sm_100): positions (j, j + 22) share the index fma, the address fma and the accumulate.  Per
+                // position: SHF (key), LOP3 (key -> float 2^23 + key), 1/2 FFMA2 (word index in the mantissa), 1/2 FFMA2
+                // (index -> byte address: (2^23 + i) * 2^-147 + (base - 2^25) * 2^-149 is the DENORMAL whose bit pattern is
+                // 4 i + base), LDS, two rotates that bring the tested bits to bit 23 -- the float 2^-126 --, LOP3 (and),
+                // 1/2 FFMA2 (Horner step acc = 2 acc + t, exact for 22 steps): 7.5 instructions against 10.
+                const uint32_t lin_exp = a.lin_exp;
+                const float addr_c = -(float)(33554432u - f.base32) * __uint_as_float(1u);   // (base - 2^25) * 2^-149, exact
+                auto pair_step = [&](int ja, int jb, uint32_t& acc_a, uint32_t& acc_b) {
+                    const uint32_t xa = raw(ja), xa1 = raw(ja + 1), xb = raw(jb), xb1 = raw(jb + 1);
+                    uint32_t fa, fb, ga, gb;
+                    asm("lop3.b32 %0, %1, 0x3FFFFF, %2, 0xEA;" : "=r"(fa) : "r"(xa), "r"(lin_exp));
+                    asm("lop3.b32 %0, %1, 0x3FFFFF, %2, 0xEA;" : "=r"(fb) : "r"(xb), "r"(lin_exp));
+                    asm("{\n .reg .b64 v, s, b;\n mov.b64 v, {%2, %3};\n mov.b64 s, {%4, %4};\n mov.b64 b, {%5, %5};\n"
+                        " fma.rn.f32x2 v, v, s, b;\n mov.b64 {%0, %1}, v;\n}\n"
+                        : "=r"(ga), "=r"(gb)
+                        : "r"(fa), "r"(fb), "f"(a.lin_scale), "f"(a.lin_bias));
+                    uint32_t addr_a, addr_b;
+                    asm("{\n .reg .b64 v, s, b;\n mov.b64 v, {%2, %3};\n mov.b64 s, {%4, %4};\n mov.b64 b, {%5, %5};\n"
+                        " fma.rn.f32x2 v, v, s, b;\n mov.b64 {%0, %1}, v;\n}\n"
+                        : "=r"(addr_a), "=r"(addr_b)
+                        : "r"(ga), "r"(gb), "f"(__uint_as_float(4u)), "f"(addr_c));
+                    uint32_t wa, wb;
+                    asm("ld.shared.u32 %0, [%1];" : "=r"(wa) : "r"(addr_a));
+                    asm("ld.shared.u32 %0, [%1];" : "=r"(wb) : "r"(addr_b));
+                    const uint32_t ta = __funnelshift_l(wa, wa, xa) & __funnelshift_l(wa, wa, xa1) & 0x00800000u;
+                    const uint32_t tb = __funnelshift_l(wb, wb, xb) & __funnelshift_l(wb, wb, xb1) & 0x00800000u;
+                    asm("{\n .reg .b64 v, s, t;\n mov.b64 v, {%0, %1};\n mov.b64 s, {%4, %4};\n mov.b64 t, {%2, %3};\n"
+                        " fma.rn.f32x2 v, v, s, t;\n mov.b64 {%0, %1}, v;\n}\n"
+                        : "+r"(acc_a), "+r"(acc_b)
+                        : "r"(ta), "r"(tb), "f"(2.0f));
+                };
+                uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;   // positions 0..21, 22..43, 44..53, 54..63 (float bits)
 #pragma unroll
-            for (int j = 31; j >= 0; --j) c_lo = __funnelshift_l(probe(j), c_lo, 1);
+                for (int i = 21; i >= 0; --i) pair_step(i, i + 22, acc0, acc1);
 #pragma unroll
-            for (int j = 63; j >= 32; --j) c_hi = __funnelshift_l(probe(j), c_hi, 1);
+                for (int i = 9; i >= 0; --i) pair_step(44 + i, 54 + i, acc2, acc3);
+                // acc = sum of pass bits * 2^(k - 126): times 2^126, plus 2^23, and the mantissa is the bit mask
+                auto mask_of = [](uint32_t acc) -> uint32_t {
+                    return __float_as_uint(__fmaf_rn(__uint_as_float(acc), __uint_as_float(0x7E800000u), 8388608.0f)) & 0x3FFFFFu;
+                };
+                const uint32_t m0 = mask_of(acc0), m1 = mask_of(acc1), m2 = mask_of(acc2), m3 = mask_of(acc3);
+                c_lo = m0 | (m1 << 22);
+                c_hi = (m1 >> 10) | (m2 << 12) | (m3 << 22);
+            } else {
+                // collect the MSB of each probe result as bit j of the pass mask (descending j: one funnel shift each)
+#pragma unroll
+                for (int j = 31; j >= 0; --j) c_lo = __funnelshift_l(probe(j), c_lo, 1);
+#pragma unroll
+                for (int j = 63; j >= 32; --j) c_hi = __funnelshift_l(probe(j), c_hi, 1);
+            }
             c_lo &= (uint32_t)wv;
             c_hi &= (uint32_t)(wv >> 32);
         }
@@ -733,6 +792,8 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
 //   What is left (about one position in 10^4) goes to the survivor list for verify_kernel.
 template <bool WIDE, bool HASHED, int WC, int NC, bool GAPPED = false>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a) {
+    // the instantiations for contiguous 11-letter keys in a direct table read the filter through the linear map
+    constexpr bool LINEAR = MPCR_LINEAR_FILTER && WC == kLinearW && !HASHED && !GAPPED;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     ScanSmem::Warp& ws = reinterpret_cast<ScanSmem::Warp*>(smem)[warp];
@@ -815,7 +876,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         const uint32_t lp0 = (uint32_t)lane * kPosPerThread;  // unit-local
         uint32_t c_lo = 0, c_hi = 0;
         bool my_clean = false;
-        stage1_unit<WIDE, GAPPED>(fv, a, s_p2, s_v, lane, unit_nbases, W, c_lo, c_hi, my_clean);
+        stage1_unit<WIDE, GAPPED, LINEAR>(fv, a, s_p2, s_v, lane, unit_nbases, W, c_lo, c_hi, my_clean);
 #ifdef MPCR_STAGE1_ONLY   // tuning builds: the kernel without its stage 2 (what the register allocator does to stage 1 alone)
         n_dbg += __popc(c_lo) + __popc(c_hi);
         __syncwarp();
@@ -843,13 +904,16 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
             const bool fits = incl <= (uint32_t)ScanSmem::kQCap;
             if (fits && n) {
                 uint16_t* q = ws.queue + (incl - n);
+                // highest bit first (FLO alone; the lowest bit needs BREV + FLO): the order inside the queue is free
                 while (c_lo) {
-                    *q++ = (uint16_t)(lp0 + __ffs(c_lo) - 1);
-                    c_lo &= c_lo - 1;
+                    const uint32_t b = 31u - (uint32_t)__clz(c_lo);
+                    *q++ = (uint16_t)(lp0 + b);
+                    c_lo ^= 1u << b;
                 }
                 while (c_hi) {
-                    *q++ = (uint16_t)(lp0 + 31 + __ffs(c_hi));
-                    c_hi &= c_hi - 1;
+                    const uint32_t b = 31u - (uint32_t)__clz(c_hi);
+                    *q++ = (uint16_t)(lp0 + 32u + b);
+                    c_hi ^= 1u << b;
                 }
             }
             const uint32_t fit_mask = __ballot_sync(0xffffffffu, fits);
@@ -1771,6 +1835,10 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
         }
         if (words < 64) return fail(MPCR_ECUDA, "device shared memory too small for the scanner (%d bytes opt-in)", c->max_smem_optin);
         c->filter_words = (uint32_t)words & ~3u;
+        // contiguous 11-letter keys in a direct table are scanned by the instantiations that read the filter through the
+        // linear map (scan_kernel: LINEAR); split keys (a block table behind a gap) and sampled tables are not
+        c->filter_linear = MPCR_LINEAR_FILTER && WS == kLinearW && !sampled && !(c->ext_which == 2 && c->ext_gap > 0) &&
+                           filter_linear_setup(c->filter_words, &c->filter_scale, &c->filter_bias);
     }
     c->n_keys = 0;
     const size_t blob_bytes = n_lines ? (size_t)h_off[2 * (size_t)n_lines] : 0;
@@ -1864,7 +1932,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* h_blob, const uint64_t* h_off, 
             build_buckets<<<(c->n_valid + 255) / 256, 256, 0, st>>>(d_sorted, c->n_valid, d_tags, c->d_bucket,
                                                                      c->d_slots, c->smap, c->d_filter,
                                                                      c->filter_words, filter_mul(WS), WS, d_stats,
-                                                                     c->d_bloom, c->bloom_shift);
+                                                                     c->d_bloom, c->bloom_shift, c->filter_linear,
+                                                                     c->filter_scale, c->filter_bias);
             c->launches++;
             CUG(cudaGetLastError());
             if (!c->smap.direct) {
@@ -2116,6 +2185,7 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
     a.tiles = c->d_tiles + c->view_first; a.n_tiles = c->view_count;
     a.slots = c->d_slots; a.smap = c->smap; a.bucket = c->d_bucket; a.meta = c->d_meta; a.pwords = c->d_pwords;
     a.filter = c->d_filter; a.filter_words = c->filter_words; a.cw = filter_mul(c->scan_w);
+    a.lin_scale = c->filter_scale; a.lin_bias = c->filter_bias; a.lin_exp = kLinearExp;
     a.prm.W = c->scan_w; a.prm.M = c->prm.margin; a.prm.N = c->prm.mismatches; a.prm.X = c->prm.three_prime_match;
     a.prm.iupac = c->prm.iupac_mode ? 1 : 0;
     const bool gapped = c->ext_which == 2 && c->ext_block > 0 && c->samp_role != 1;   // a block table (gap 0: the first block)
@@ -2152,6 +2222,10 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* h_contigs, uint32_t n_contigs, con
         else if (a.prm.W == 11 && a.prm.N == 0) kern = scan_kernel<true, false, 11, 0>;
         else if (a.prm.W == 11 && a.prm.N == 1) kern = scan_kernel<true, false, 11, 1>;
         else if (a.prm.W == 11 && a.prm.N == 2) kern = scan_kernel<true, false, 11, 2>;
+        else if (a.prm.W == 11) kern = scan_kernel<true, false, 11, -1>;
+        // the filter was built for the map the chosen instantiation reads it through
+        const bool kern_linear = MPCR_LINEAR_FILTER && a.prm.W == kLinearW && c->smap.direct && a.prm.gap == 0;
+        if (kern_linear != c->filter_linear) return fail(MPCR_ESTATE, "filter map / scanner instantiation mismatch");
         if (c->attr_kern != (const void*)kern || c->attr_smem != smem) {   // once per (kernel, size), not per launch
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             c->attr_kern = (const void*)kern;

@@ -39,6 +39,8 @@ struct mpcr_ctx {
     SlotMap smap{1023u, 0u};
     std::vector<BucketEntry> bucket;
     std::vector<uint32_t> filter;
+    bool filter_linear = false;   // same rule as the CUDA library: contiguous 11-letter keys in a direct table
+    float filter_scale = 0.f, filter_bias = 0.f;
     uint32_t max_hash_off = 0, max_len = 0;
     uint64_t max_pcr = 0;
     bool table_ready = false;
@@ -353,6 +355,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
     if (direct) nslots = 1u << (2 * WS);
     else while (nslots < 2u * c->n_valid + 2u) nslots <<= 1;
     c->smap = SlotMap{nslots - 1, direct ? 1u : 0u};
+    c->filter_linear = MPCR_LINEAR_FILTER && WS == kLinearW && direct && !sampled && !(c->ext_which == 2 && c->ext_gap > 0) &&
+                       filter_linear_setup(words, &c->filter_scale, &c->filter_bias);
     c->slots.assign(nslots, Slot{~0u, ~0u, ~0u, ~0u});
     c->bucket.assign(c->n_valid + 1, BucketEntry{0, 0});
     for (uint32_t i = 0; i < c->n_valid; ++i) {
@@ -371,7 +375,8 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
             const uint32_t tag_a = tags[rec];
             c->slots[s] = n == 1 ? Slot{rec, tag_a, tag_a, key}
                           : n == 2 ? Slot{kWalkBucket | i, tag_a, tag_b, key} : Slot{kWalkBucket | i, 0u, 0u, key};
-            c->filter[filter_word(key, cw, words)] |= filter_bits_of(key, WS);
+            if (c->filter_linear) c->filter[filter_word_linear(key, c->filter_scale, c->filter_bias)] |= filter_bits_linear(key);
+            else c->filter[filter_word(key, cw, words)] |= filter_bits_of(key, WS);
         }
     }
     c->table_ready = true;
@@ -452,7 +457,10 @@ int mpcr_scan(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_contigs, const
                     if (c->samp_role == 1 && (ls + lp0 + j) % (uint64_t)c->samp_s != 0) continue;   // probed positions only
                     const uint32_t key = prm.gap > 0 ? (gap_key_raw(extract_key(P2, gb + j, 0xFFFFFFFFu), seed_mask, prm.gap) & wmask)
                                                      : extract_key(P2, gb + j, wmask);
-                    if (!filter_pass(c->filter[filter_word(key, cw, (uint32_t)c->filter.size())], key, prm.W)) continue;
+                    if (c->filter_linear) {
+                        const uint32_t fw = c->filter[filter_word_linear(key, c->filter_scale, c->filter_bias)], fm = filter_bits_linear(key);
+                        if ((fw & fm) != fm) continue;
+                    } else if (!filter_pass(c->filter[filter_word(key, cw, (uint32_t)c->filter.size())], key, prm.W)) continue;
                     const uint32_t gcodes = fetch_bits(P2, 2 * (gb + j + prm.W + prm.gap), 2 * kTagBases);
                     const uint32_t gvalid = fetch_bits(V, gb + j + prm.W + prm.gap, kTagBases);
                     Slot sl;
@@ -522,5 +530,14 @@ int mpcr_sort_finish(mpcr_ctx* c, mpcr_hit*, const uint64_t* h_result, uint64_t,
 }
 float mpcr_slot_scan_ms(mpcr_ctx*, int) { return 0.f; }
 float mpcr_slot_verify_ms(mpcr_ctx*, int) { return 0.f; }
+
+// Test-only probes of the linear filter map (mpcr_core.cuh): word index and bit mask of a key for n_words filter words.
+int emul_filter_linear(uint32_t n_words, uint32_t key, uint32_t* word, uint32_t* mask) {
+    float scale = 0.f, bias = 0.f;
+    if (!filter_linear_setup(n_words, &scale, &bias)) return 0;
+    *word = filter_word_linear(key, scale, bias);
+    *mask = filter_bits_linear(key);
+    return 1;
+}
 
 }  // extern "C"

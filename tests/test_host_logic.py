@@ -711,3 +711,38 @@ def _two_in_flight_check(MerPCR, make_records, tmp_path):
 def test_two_steps_in_flight(tmp_path):
     from merpcr_b200 import FASTARecord, MerPCR
     _two_in_flight_check(MerPCR, lambda seqs: [FASTARecord(f">c{i}", s) for i, s in enumerate(seqs)], tmp_path)
+
+
+def test_linear_filter_map_properties():
+    """mpcr_core.cuh's linear filter map (11-letter keys): the float fma must give an in-range, monotone word index
+    for every key, and the keys of one word must get (all but a few) distinct bit pairs -- what keeps its false-positive
+    rate low: of 128 consecutive keys six pairs share a mask (bits [0,5) and [2,7) swapped)."""
+    import ctypes
+    lib = ctypes.CDLL(emul.build())
+    lib.emul_filter_linear.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32),
+                                       ctypes.POINTER(ctypes.c_uint32)]
+    w, m = ctypes.c_uint32(), ctypes.c_uint32()
+
+    def probe(n_words, key):
+        assert lib.emul_filter_linear(n_words, key, ctypes.byref(w), ctypes.byref(m)) == 1
+        return w.value, m.value
+
+    rng = np.random.default_rng(5)
+    for n_words in (64, 1000, 39616, 40128, 57000):
+        assert probe(n_words, 0)[0] == 0 and probe(n_words, (1 << 22) - 1)[0] == n_words - 1
+        keys = np.unique(np.concatenate([rng.integers(0, 1 << 22, 4000), np.arange(0, 3000), np.arange((1 << 22) - 3000, 1 << 22)]))
+        res = [probe(n_words, int(k)) for k in keys]
+        words = np.array([r[0] for r in res])
+        assert words.min() >= 0 and words.max() < n_words
+        assert np.all(np.diff(words) >= 0)                       # monotone in the key
+        assert all(bin(r[1]).count("1") in (1, 2) for r in res)
+        # consecutive keys that share a word: pairwise distinct masks (here on the dense runs at both ends)
+        dense = np.arange(0, 3000)
+        by_word = {}
+        for k in dense:
+            wd, mk = probe(n_words, int(k))
+            by_word.setdefault(wd, []).append(mk)
+        if n_words >= 1 << 15:                                   # <= 128 keys per word: bits [0,5) + [2,7) separate them
+            assert all(len(v) - len(set(v)) <= 6 for v in by_word.values())
+            assert sum(len(v) - len(set(v)) for v in by_word.values()) <= 0.06 * len(dense)
+    assert lib.emul_filter_linear(1, 0, ctypes.byref(w), ctypes.byref(m)) == 0      # refused: the caller keeps the other map
