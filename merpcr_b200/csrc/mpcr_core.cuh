@@ -69,6 +69,41 @@ struct SearchParams {
 MPCR_HD uint32_t wmask_of(int W) { return W >= 16 ? 0xFFFFFFFFu : ((1u << (2 * W)) - 1u); }
 MPCR_HD uint32_t wmask_bits(int W) { return (1u << W) - 1u; }  // W one-bits (W <= 16)
 
+// Three-input bitwise function by truth table (index = a << 2 | b << 1 | c), the GPU's LOP3.
+template <uint32_t LUT>
+MPCR_HD uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+#else
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < 8; ++i)
+        if ((LUT >> i) & 1u) r |= ((i & 4u) ? a : ~a) & ((i & 2u) ? b : ~b) & ((i & 1u) ? c : ~c);
+    return r;
+#endif
+}
+
+// FASTA keep set (io/fasta.py:60: ACGTBDHKMNRSVWXY in either case), FOUR bytes at a time: bit 0 of every byte of the
+// result says "kept".  A byte is kept iff b7 = 0, b6 = 1 and T[b4..b0] with T = the letter set as a 32-entry table (b5 is
+// the case bit); the table is evaluated bit-sliced -- four 3-input sub-tables over (b2, b1, b0), muxed by b3 and b4 --
+// on shifted copies of the word, 16 instructions for 4 bytes where a per-byte table look-up takes ~32.
+MPCR_HD uint32_t fasta_keep_flags4(uint32_t w) {
+    constexpr uint32_t T = 0x03DC699Eu;   // bit v: letter '@' + v is in the set (A=1 B=2 C=3 D=4 G=7 H=8 K=11 M=13 N=14 R=18 S=19 T=20 V=22 W=23 X=24 Y=25)
+    const uint32_t x1 = w >> 1, x2 = w >> 2, x3 = w >> 3, x4 = w >> 4, x6 = w >> 6, x7 = w >> 7;
+    const uint32_t h0 = lop3<(T >> 0) & 0xFFu>(x2, x1, w), h1 = lop3<(T >> 8) & 0xFFu>(x2, x1, w);
+    const uint32_t h2 = lop3<(T >> 16) & 0xFFu>(x2, x1, w), h3 = lop3<(T >> 24) & 0xFFu>(x2, x1, w);
+    const uint32_t m0 = lop3<0xCAu>(x3, h1, h0), m1 = lop3<0xCAu>(x3, h3, h2);   // 0xCA: a ? b : c
+    const uint32_t f = lop3<0xCAu>(x4, m1, m0);
+    return lop3<0x40u>(f, x6, x7) & 0x01010101u;                               // 0x40: a & b & ~c
+}
+// bytes equal to `c` (c replicated into every byte of c4): bit 7 of the byte is set for the LOWEST such byte and possibly
+// for bytes above it (borrow) -- a trigger for a per-byte look, exact as "any?"
+MPCR_HD uint32_t bytes_equal_trigger4(uint32_t w, uint32_t c4) {
+    const uint32_t t = w ^ c4;
+    return (t - 0x01010101u) & ~t & 0x80808080u;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Alphabet (engine.py:99-172).  The genome-side LUT is built by the host (merpcr_b200/alphabet.py) because it
 // depends on the mode; the primer-side tables below are fixed.

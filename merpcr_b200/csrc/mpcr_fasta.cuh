@@ -31,23 +31,16 @@ struct FastaHeader {
     uint64_t end;    // byte offset of the line terminator (or n)
 };
 
-// Per-byte classes for the fused pass: bit0 = kept sequence letter, bit1 = '>', bit2 = byte >= 128.
-__device__ __forceinline__ uint8_t fasta_class_of(uint32_t c) {
-    return (uint8_t)((fasta_keep((uint8_t)c) ? 1u : 0u) | (c == '>' ? 2u : 0u) | (c >= 128u ? 4u : 0u));
-}
-
-// ONE pass over the text instead of two (fasta_find_headers + fasta_count): every thread classifies 16 bytes through a
-// 256-entry table in shared memory, the block's kept letters are counted, '>' bytes take the (rare) header test, bytes
+// ONE pass over the text instead of two (fasta_find_headers + fasta_count): every thread classifies 16 bytes, four at a
+// time in registers (mpcr_core.cuh: fasta_keep_flags4 -- the per-byte table in shared memory this replaces cost one LDS
+// and ~8 ALU instructions per byte), the block's kept letters are counted, '>' bytes take the (rare) header test, bytes
 // >= 128 raise the flag.  The counts still include the letters of header lines and of the text in front of the first
 // header -- fasta_blank_headers / fasta_blank_range take those out again when they blank them.
 __global__ void __launch_bounds__(kFastaThreads) fasta_classify(const uint8_t* __restrict__ text, uint64_t n,
                                                                 FastaHeader* __restrict__ out, uint32_t cap,
                                                                 uint32_t* __restrict__ count, uint32_t* __restrict__ flags,
                                                                 uint32_t* __restrict__ block_count) {
-    __shared__ uint8_t lut[256];
     __shared__ uint32_t warp_sum[kFastaThreads / 32];
-    lut[threadIdx.x] = fasta_class_of(threadIdx.x);
-    __syncthreads();
     const uint64_t b0 = (uint64_t)blockIdx.x * kFastaBlock + (uint64_t)threadIdx.x * 16;
     uint32_t kept = 0, any = 0;
     if (b0 < n) {
@@ -65,12 +58,11 @@ __global__ void __launch_bounds__(kFastaThreads) fasta_classify(const uint8_t* _
         uint32_t gt = 0;   // bit j: byte j is '>'
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t e = lut[(w[k] >> (8 * b)) & 0xFFu];
-                kept += e & 1u;
-                gt |= ((e >> 1) & 1u) << (4 * k + b);
-                any |= e;
+            kept += __popc(fasta_keep_flags4(w[k]));
+            any |= w[k];
+            if (bytes_equal_trigger4(w[k], 0x3E3E3E3Eu)) {   // rare: which bytes exactly
+                for (int b = 0; b < 4; ++b)
+                    if (((w[k] >> (8 * b)) & 0xFFu) == (uint32_t)'>') gt |= 1u << (4 * k + b);
             }
         }
         while (gt) {   // rare: is this '>' the first non-blank character of its line?
@@ -92,7 +84,7 @@ __global__ void __launch_bounds__(kFastaThreads) fasta_classify(const uint8_t* _
             if (slot < cap) out[slot] = FastaHeader{i, e};
         }
     }
-    if (any & 4u) atomicOr(flags, 1u);
+    if (any & 0x80808080u) atomicOr(flags, 1u);
     for (int d = 16; d; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
     if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = kept;
     __syncthreads();
@@ -229,10 +221,7 @@ __global__ void __launch_bounds__(kFastaThreads) fasta_compact(const uint8_t* __
                                                                const uint64_t* __restrict__ off, uint8_t* __restrict__ out) {
     __shared__ uint32_t warp_sum[kFastaThreads / 32];
     __shared__ uint8_t stage[kFastaBlock];
-    __shared__ uint8_t lut[256];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    lut[tid] = fasta_keep((uint8_t)tid) ? 1 : 0;      // per-byte classification through a table: one LDS instead of ~6 ALU ops
-    __syncthreads();
     const uint64_t b0 = (uint64_t)blockIdx.x * kFastaBlock + (uint64_t)tid * 16;
     uint8_t c[16];
     uint32_t m = 0;
@@ -242,8 +231,13 @@ __global__ void __launch_bounds__(kFastaThreads) fasta_compact(const uint8_t* __
         } else {
             for (int k = 0; k < 16; ++k) c[k] = b0 + k < n ? text[b0 + k] : (uint8_t)'\n';
         }
+        // keep flags four bytes at a time (mpcr_core.cuh); the multiply gathers the four flag bits of a word into a nibble
 #pragma unroll
-        for (int k = 0; k < 16; ++k) m |= (uint32_t)lut[c[k]] << k;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t wk = (uint32_t)c[4 * k] | ((uint32_t)c[4 * k + 1] << 8) | ((uint32_t)c[4 * k + 2] << 16) |
+                                ((uint32_t)c[4 * k + 3] << 24);
+            m |= (((fasta_keep_flags4(wk) * 0x01020408u) >> 24) & 0xFu) << (4 * k);
+        }
     }
     const uint32_t k = __popc(m);
     uint32_t incl = k;

@@ -531,6 +531,9 @@ int mpcr_sort_finish(mpcr_ctx* c, mpcr_hit*, const uint64_t* h_result, uint64_t,
 float mpcr_slot_scan_ms(mpcr_ctx*, int) { return 0.f; }
 float mpcr_slot_verify_ms(mpcr_ctx*, int) { return 0.f; }
 
+// Test-only probe of the four-bytes-at-a-time FASTA keep test (mpcr_core.cuh)
+uint32_t emul_fasta_keep_flags4(uint32_t w) { return fasta_keep_flags4(w); }
+uint32_t emul_bytes_equal_trigger4(uint32_t w, uint32_t c4) { return bytes_equal_trigger4(w, c4); }
 // Test-only probes of the linear filter map (mpcr_core.cuh): word index and bit mask of a key for n_words filter words.
 int emul_filter_linear(uint32_t n_words, uint32_t key, uint32_t* word, uint32_t* mask) {
     float scale = 0.f, bias = 0.f;

@@ -22,7 +22,9 @@ def _real_backend():
     from merpcr_b200 import _capi
     _capi._inject_backend_for_tests("", "cpu")          # drop any emulation a CPU-tier module left behind
     be = _capi.backend()
-    assert be.device_kind == "cuda" and os.path.basename(_capi.LIB_PATH) == "libmerpcr_b200.so"
+    # (MPCR_TEST_ALLOW_VARIANT: development runs of a tuning build through this tier; the driver never sets it)
+    assert be.device_kind == "cuda" and (os.path.basename(_capi.LIB_PATH) == "libmerpcr_b200.so" or
+                                         os.environ.get("MPCR_TEST_ALLOW_VARIANT") == "1")
     assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
     yield
 
@@ -191,6 +193,10 @@ CASES = [
      dict(wordsize=11, margin=50, mismatches=2, three_prime_match=1, iupac_mode=1), "cfg3", True, False),
     ("cfg5-like", [400_000, 150_000], 20000, dict(wordsize=8, margin=500, mismatches=0), "none", False, True),
     ("w16", [600_000], 800, dict(wordsize=16, margin=20, mismatches=3, three_prime_match=0), "cfg3", False, False),
+    # -W 11 with a mismatch budget that has no compile-time instantiation (scan_kernel<.., 11, -1>: linear filter map, N at
+    # run time), and the neighbouring word size (general direct table, multiplicative filter map)
+    ("w11-n3", [900_000, 300_000], 1500, dict(wordsize=11, margin=40, mismatches=3, three_prime_match=2), "cfg3", False, False),
+    ("w10-n1", [700_000, 200_000], 1200, dict(wordsize=10, margin=50, mismatches=1, three_prime_match=1), "cfg3", False, False),
     # several records per seed on average -> the bucket-parallel dense scanner
     ("dense-w8", [300_000, 120_000], 150000, dict(wordsize=8, margin=100, mismatches=0), "none", False, True),
     ("dense-w6-iupac", [250_000, 101_000], 20000,

@@ -746,3 +746,33 @@ def test_linear_filter_map_properties():
             assert all(len(v) - len(set(v)) <= 6 for v in by_word.values())
             assert sum(len(v) - len(set(v)) for v in by_word.values()) <= 0.06 * len(dense)
     assert lib.emul_filter_linear(1, 0, ctypes.byref(w), ctypes.byref(m)) == 0      # refused: the caller keeps the other map
+
+
+def test_fasta_keep_flags_four_bytes_at_a_time():
+    """mpcr_core.cuh: the bit-sliced keep test of the device-side FASTA ingest against io/fasta.py:60's letter set, for
+    every byte value in every byte position next to arbitrary neighbours; and the byte-equality trigger."""
+    import ctypes
+    lib = ctypes.CDLL(emul.build())
+    lib.emul_fasta_keep_flags4.argtypes = [ctypes.c_uint32]
+    lib.emul_fasta_keep_flags4.restype = ctypes.c_uint32
+    lib.emul_bytes_equal_trigger4.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
+    lib.emul_bytes_equal_trigger4.restype = ctypes.c_uint32
+    keep = set(b"ACGTBDHKMNRSVWXYacgtbdhkmnrsvwxy")
+    rng = np.random.default_rng(11)
+    for v in range(256):
+        for pos in range(4):
+            for other in (0x00000000, 0xFFFFFFFF, 0x41414141, int(rng.integers(0, 1 << 32))):
+                w = (other & ~(0xFF << (8 * pos)) | (v << (8 * pos))) & 0xFFFFFFFF
+                flags = lib.emul_fasta_keep_flags4(w)
+                assert flags & ~0x01010101 == 0
+                assert ((flags >> (8 * pos)) & 1) == (1 if v in keep else 0), (v, pos, hex(w), hex(flags))
+    for _ in range(20000):
+        w = int(rng.integers(0, 1 << 32))
+        if rng.random() < 0.5:
+            w = (w & ~(0xFF << (8 * int(rng.integers(0, 4)))) | (0x3E << (8 * int(rng.integers(0, 4))))) & 0xFFFFFFFF
+        has = any(((w >> (8 * k)) & 0xFF) == 0x3E for k in range(4))
+        trig = lib.emul_bytes_equal_trigger4(w, 0x3E3E3E3E)
+        assert (trig != 0) == has
+        if has:   # the lowest flagged byte is a true match
+            low = min(k for k in range(4) if (trig >> (8 * k + 7)) & 1)
+            assert ((w >> (8 * low)) & 0xFF) == 0x3E
