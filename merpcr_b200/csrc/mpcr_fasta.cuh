@@ -31,30 +31,42 @@ struct FastaHeader {
     uint64_t end;    // byte offset of the line terminator (or n)
 };
 
-// ONE pass over the text instead of two (fasta_find_headers + fasta_count): every thread classifies 16 bytes, four at a
-// time in registers (mpcr_core.cuh: fasta_keep_flags4 -- the per-byte table in shared memory this replaces cost one LDS
-// and ~8 ALU instructions per byte), the block's kept letters are counted, '>' bytes take the (rare) header test, bytes
-// >= 128 raise the flag.  The counts still include the letters of header lines and of the text in front of the first
-// header -- fasta_blank_headers / fasta_blank_range take those out again when they blank them.
+// ONE pass over the text instead of two (fasta_find_headers + fasta_count).  One WARP per 4096-byte counting block, eight
+// blocks per CTA and no CTA-wide barrier (one CTA per block with a __syncthreads reduction spent its time on CTA launches:
+// 1.3 * 10^5 CTAs of 4 KB each for a 512 Mbp file): the warp walks its block in eight steps of 512 bytes, every lane
+// classifies 16 bytes, four at a time in registers (mpcr_core.cuh: fasta_keep_flags4), kept letters are counted, '>' bytes
+// take the (rare) header test, bytes >= 128 raise the flag.  The counts still include the letters of header lines and of
+// the text in front of the first header -- fasta_blank_headers / fasta_blank_range take those out again when they blank
+// them.
+static constexpr int kFastaWarps = kFastaThreads / 32;   // counting blocks per CTA
+__device__ __forceinline__ void fasta_load16(const uint8_t* __restrict__ text, uint64_t n, uint64_t b0, bool aligned, uint32_t w[4]) {
+    if (aligned && b0 + 16 <= n) {
+        const uint4 t = *reinterpret_cast<const uint4*>(text + b0);
+        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+    } else {
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = 0;
+            for (int b = 0; b < 4; ++b) x |= (uint32_t)(b0 + 4 * k + b < n ? text[b0 + 4 * k + b] : (uint8_t)'\n') << (8 * b);
+            w[k] = x;
+        }
+    }
+}
 __global__ void __launch_bounds__(kFastaThreads) fasta_classify(const uint8_t* __restrict__ text, uint64_t n,
                                                                 FastaHeader* __restrict__ out, uint32_t cap,
                                                                 uint32_t* __restrict__ count, uint32_t* __restrict__ flags,
                                                                 uint32_t* __restrict__ block_count) {
-    __shared__ uint32_t warp_sum[kFastaThreads / 32];
-    const uint64_t b0 = (uint64_t)blockIdx.x * kFastaBlock + (uint64_t)threadIdx.x * 16;
+    const int lane = threadIdx.x & 31;
+    const uint64_t blk = (uint64_t)blockIdx.x * kFastaWarps + (threadIdx.x >> 5);
+    const uint64_t base = blk * kFastaBlock;
+    if (base >= n) return;   // the whole warp
+    const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15u) == 0;
     uint32_t kept = 0, any = 0;
-    if (b0 < n) {
+#pragma unroll
+    for (int it = 0; it < kFastaBlock / 512; ++it) {
+        const uint64_t b0 = base + (uint64_t)it * 512 + (uint64_t)lane * 16;
+        if (b0 >= n) continue;
         uint32_t w[4];
-        if (b0 + 16 <= n && ((reinterpret_cast<uintptr_t>(text) & 15u) == 0)) {
-            const uint4 t = *reinterpret_cast<const uint4*>(text + b0);
-            w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
-        } else {
-            for (int k = 0; k < 4; ++k) {
-                uint32_t x = 0;
-                for (int b = 0; b < 4; ++b) x |= (uint32_t)(b0 + 4 * k + b < n ? text[b0 + 4 * k + b] : (uint8_t)'\n') << (8 * b);
-                w[k] = x;
-            }
-        }
+        fasta_load16(text, n, b0, aligned, w);
         uint32_t gt = 0;   // bit j: byte j is '>'
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -84,14 +96,12 @@ __global__ void __launch_bounds__(kFastaThreads) fasta_classify(const uint8_t* _
             if (slot < cap) out[slot] = FastaHeader{i, e};
         }
     }
-    if (any & 0x80808080u) atomicOr(flags, 1u);
+    __syncwarp();
+    const bool high = __any_sync(0xffffffffu, (any & 0x80808080u) != 0);
     for (int d = 16; d; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
-    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = kept;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w2 = 0; w2 < kFastaThreads / 32; ++w2) t += warp_sum[w2];
-        block_count[blockIdx.x] = t;
+    if (lane == 0) {
+        if (high) atomicOr(flags, 1u);
+        block_count[blk] = kept;
     }
 }
 
@@ -216,49 +226,58 @@ __global__ void __launch_bounds__(1024) fasta_scan_down(const uint32_t* __restri
     }
 }
 
-// compaction: block b writes its kept bytes at out[off[b] ...] in order
+// compaction: block b writes its kept bytes at out[off[b] ...] in order.  One warp per 4096-byte block (eight per CTA, no
+// CTA-wide barrier): eight steps of 512 bytes -- keep flags four bytes at a time, a warp scan of the lanes' counts, the kept
+// bytes into the warp's staging row -- and the row goes out in 16-byte vectors: it is filled from index (address of
+// out[off[b]]) mod 16, so staging row and destination are aligned with each other and only the first and last few bytes
+// are single-byte stores.
 __global__ void __launch_bounds__(kFastaThreads) fasta_compact(const uint8_t* __restrict__ text, uint64_t n,
                                                                const uint64_t* __restrict__ off, uint8_t* __restrict__ out) {
-    __shared__ uint32_t warp_sum[kFastaThreads / 32];
-    __shared__ uint8_t stage[kFastaBlock];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t b0 = (uint64_t)blockIdx.x * kFastaBlock + (uint64_t)tid * 16;
-    uint8_t c[16];
-    uint32_t m = 0;
-    if (b0 < n) {
-        if (b0 + 16 <= n && ((reinterpret_cast<uintptr_t>(text) & 15u) == 0)) {
-            *reinterpret_cast<uint4*>(c) = *reinterpret_cast<const uint4*>(text + b0);
-        } else {
-            for (int k = 0; k < 16; ++k) c[k] = b0 + k < n ? text[b0 + k] : (uint8_t)'\n';
-        }
-        // keep flags four bytes at a time (mpcr_core.cuh); the multiply gathers the four flag bits of a word into a nibble
+    __shared__ __align__(16) uint8_t stage_all[kFastaWarps][kFastaBlock + 16];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t blk = (uint64_t)blockIdx.x * kFastaWarps + wid;
+    const uint64_t base = blk * kFastaBlock;
+    if (base >= n) return;   // the whole warp
+    uint8_t* stage = stage_all[wid];
+    const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15u) == 0;
+    uint8_t* const dst0 = out + off[blk];
+    const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(dst0) & 15u);
+    uint32_t run = skew;
+#pragma unroll 2
+    for (int it = 0; it < kFastaBlock / 512; ++it) {
+        const uint64_t b0 = base + (uint64_t)it * 512 + (uint64_t)lane * 16;
+        uint32_t w[4] = {0u, 0u, 0u, 0u}, m = 0;
+        if (b0 < n) {
+            fasta_load16(text, n, b0, aligned, w);
+            // the multiply gathers the four flag bits of a word (bit 0 of every byte) into a nibble
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t wk = (uint32_t)c[4 * k] | ((uint32_t)c[4 * k + 1] << 8) | ((uint32_t)c[4 * k + 2] << 16) |
-                                ((uint32_t)c[4 * k + 3] << 24);
-            m |= (((fasta_keep_flags4(wk) * 0x01020408u) >> 24) & 0xFu) << (4 * k);
+            for (int k = 0; k < 4; ++k) m |= (((fasta_keep_flags4(w[k]) * 0x01020408u) >> 24) & 0xFu) << (4 * k);
         }
-    }
-    const uint32_t k = __popc(m);
-    uint32_t incl = k;
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += up;
-    }
-    if (lane == 31) warp_sum[wid] = incl;
-    __syncthreads();
-    uint32_t base = 0, total = 0;
-    for (int w = 0; w < kFastaThreads / 32; ++w) {
-        if (w < wid) base += warp_sum[w];
-        total += warp_sum[w];
-    }
-    uint32_t p = base + incl - k;
+        const uint32_t k = __popc(m);
+        uint32_t incl = k;
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-        if ((m >> j) & 1u) stage[p++] = c[j];
-    __syncthreads();
-    uint8_t* dst = out + off[blockIdx.x];
-    for (uint32_t i = tid; i < total; i += kFastaThreads) dst[i] = stage[i];
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        uint32_t p = run + incl - k;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if ((m >> j) & 1u) stage[p++] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    // stage[skew, run) -> dst0[0, run - skew): index i of the row goes to address (dst0 - skew) + i, 16-byte aligned at i % 16 == 0
+    uint8_t* const dst = dst0 - skew;
+    const uint32_t lo = skew, hi = run, va = (lo + 15u) & ~15u, vb = hi & ~15u;
+    if (va >= vb) {
+        for (uint32_t i = lo + lane; i < hi; i += 32) dst[i] = stage[i];
+    } else {
+        if (lo + lane < va) dst[lo + lane] = stage[lo + lane];                      // at most 15 bytes
+        for (uint32_t v = va + 16u * lane; v < vb; v += 512u)
+            *reinterpret_cast<uint4*>(dst + v) = *reinterpret_cast<const uint4*>(stage + v);
+        if (vb + lane < hi) dst[vb + lane] = stage[vb + lane];                      // at most 15 bytes
+    }
 }
 
 // kept bytes before text position pos[i] (positions inside blanked / ordinary text): one warp per position, every lane

@@ -1673,7 +1673,7 @@ int mpcr_fasta_index_ex(mpcr_ctx* c, uint8_t* d_text, uint64_t n, uint32_t mode,
     CU(cudaMemsetAsync(d_ctr, 0, 8, st));
     // one pass: headers, non-ASCII flag and the kept letters per 4096-byte block (header lines and the text in front
     // of the first header are still counted; blanking them below takes them out again)
-    fasta_classify<<<(uint32_t)n_blk, kFastaThreads, 0, st>>>(d_text, n, d_hdr, max_records, d_ctr, d_ctr + 1, d_cnt);
+    fasta_classify<<<(uint32_t)((n_blk + kFastaWarps - 1) / kFastaWarps), kFastaThreads, 0, st>>>(d_text, n, d_hdr, max_records, d_ctr, d_ctr + 1, d_cnt);
     c->launches++;
     CU(cudaGetLastError());
     uint32_t ctr[2] = {0, 0};
@@ -1777,7 +1777,7 @@ int mpcr_fasta_compact(mpcr_ctx* c, const uint8_t* d_text, uint64_t n, const voi
     cudaStream_t st = (cudaStream_t)stream;
     GUARD(c);
     const uint64_t n_blk = (n + kFastaBlock - 1) / kFastaBlock;
-    fasta_compact<<<(uint32_t)n_blk, kFastaThreads, 0, st>>>(d_text, n, (const uint64_t*)d_ws, d_seq);
+    fasta_compact<<<(uint32_t)((n_blk + kFastaWarps - 1) / kFastaWarps), kFastaThreads, 0, st>>>(d_text, n, (const uint64_t*)d_ws, d_seq);
     c->launches++;
     CU(cudaGetLastError());
     return MPCR_OK;

@@ -195,7 +195,7 @@ CASES = [
     ("w16", [600_000], 800, dict(wordsize=16, margin=20, mismatches=3, three_prime_match=0), "cfg3", False, False),
     # -W 11 with a mismatch budget that has no compile-time instantiation (scan_kernel<.., 11, -1>: linear filter map, N at
     # run time), and the neighbouring word size (general direct table, multiplicative filter map)
-    ("w11-n3", [900_000, 300_000], 1500, dict(wordsize=11, margin=40, mismatches=3, three_prime_match=2), "cfg3", False, False),
+    ("w11-n3", [900_000, 300_000], 1500, dict(wordsize=11, margin=40, mismatches=3, three_prime_match=1), "cfg3", False, False),
     ("w10-n1", [700_000, 200_000], 1200, dict(wordsize=10, margin=50, mismatches=1, three_prime_match=1), "cfg3", False, False),
     # several records per seed on average -> the bucket-parallel dense scanner
     ("dense-w8", [300_000, 120_000], 150000, dict(wordsize=8, margin=100, mismatches=0), "none", False, True),
