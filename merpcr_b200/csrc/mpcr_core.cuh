@@ -33,9 +33,7 @@ static constexpr uint64_t kLane1 = 0x1111111111111111ull;  // LSB of every nibbl
 static constexpr int kScanThreads = MPCR_SCAN_THREADS;     // threads of one scanner CTA (one CTA per SM)
 static constexpr int kPosPerThread = 64;                   // hash positions per lane and unit
 static constexpr int kTileBases = 32768;                   // hash positions per tile descriptor (multiple of 2048)
-static constexpr int kTagBases = 10;                       // bases after the seed carried inline in the table
-static constexpr int kTagShift = 5;                        // tag layout: bits [0,5) = 2 * (kTagBases - letters), codes above
-static constexpr uint32_t kTagOpen = 2 * kTagBases;        // a tag without letters: never rejects
+static constexpr int kTagBases = 8;                        // bases after the seed carried inline in the table
 
 // One record = one strand of one STS line (core/models.py:17-29 + engine.py:253-281).
 struct RecMeta {
@@ -47,7 +45,7 @@ struct RecMeta {
     uint16_t len1, len2;
     uint16_t hash_off;  // engine.py:339-353
     uint16_t flags;     // bit0: the reference inserts the record (it has a clean W-mer); bit1: it is in THIS table
-    uint32_t tag;       // primer1 letters right after the seed (make_tag: codes above bit 5, lane-mask shift below)
+    uint32_t tag;       // primer1 bases right after the seed: 2-bit codes in bits [0,16), compare mask in [16,32)
 };
 static_assert(sizeof(RecMeta) == 32, "RecMeta layout");
 
@@ -531,7 +529,7 @@ inline bool filter_linear_setup(uint32_t n_words, float* scale, float* bias) {
 
 struct Slot {          // 16 bytes, one 128-bit gather; the scanner usually needs only the first 8 of them
     uint32_t code;     // survivor code: record index (one record) or kWalkBucket | first bucket entry; kSlotEmpty = free
-    uint32_t tag_a;    // tag of the first record  (one record: tag_b == tag_a; three or more: both tags are kTagOpen,
+    uint32_t tag_a;    // tag of the first record  (one record: tag_b == tag_a; three or more: both tags have mask 0,
     uint32_t tag_b;    // tag of the second record  i.e. they never reject)
     uint32_t key;      // exact seed key (little-endian digits); checked only in hashed mode
 };
@@ -572,50 +570,37 @@ MPCR_HD uint32_t bloom_bits(uint32_t key) {
 
 
 // engine.py:614-640 restricted to the tag: true iff the full primer-1 compare is CERTAIN to fail because the
-// bases right after the seed already carry more than N mismatches.  A tag holds the 2-bit codes of the first t <=
-// kTagBases primer letters behind the seed -- as long as they are plain A/C/G/T -- in bits [5, 5 + 2t) and the shift
-// amount 2 * (kTagBases - t) in bits [0,5): ONE funnel shift of a constant by the tag itself yields the lane mask (its
-// wrap looks at the low five bits only), so ten letters cost what eight did with a 16-bit mask next to 16 bits of
-// codes -- and ten letters let through 1 random position in 3.4 * 10^4 with one mismatch allowed where eight let
-// through 1 in 2.6 * 10^3.  g5 = the 2-bit codes of the genome bases following the seed, shifted left by kTagShift
-// (the scanner extracts them that way for free; whatever lies below and above is masked here).  A clean genome base
-// whose code differs from an A/C/G/T primer letter mismatches in both compare modes; the caller must not use the
-// verdict when one of the kTagBases genome bases is not clean (tag_window_clean) -- those positions go to the full
-// compare.
-MPCR_HD bool tag_rejects_g5(uint32_t tag, uint32_t g5, int N) {
-    constexpr uint32_t kLanes = ((1u << (2 * kTagBases)) - 1u) << kTagShift;   // all lanes
-    constexpr uint32_t kEven = (0x55555555u & ((1u << (2 * kTagBases)) - 1u)) << kTagShift;
-#ifdef __CUDA_ARCH__
-    const uint32_t m = __funnelshift_r(kLanes, 0u, tag);   // kLanes >> (tag & 31): the first t lanes (+ bits below kTagShift)
-#else
-    const uint32_t m = kLanes >> (tag & 31u);
-#endif
-    uint32_t d = (tag ^ g5) & m;
-    d = (d | (d >> 1)) & kEven;
+// bases right after the seed already carry more than N mismatches.  tag = 2-bit codes of up to kTagBases
+// A/C/G/T primer letters (bits [0,16)) and the mask of the 2-bit lanes that hold one (bits [16,32)); gcodes are
+// the 2-bit codes of the genome bases following the seed.  A clean genome base whose code differs from an
+// A/C/G/T primer letter mismatches in both compare modes; the caller must not use the verdict when one of the
+// kTagBases genome bases is not clean (tag_window_clean) -- those positions go to the full compare.
+MPCR_HD bool tag_rejects(uint32_t tag, uint32_t gcodes, int N) {
+    uint32_t d = (tag ^ gcodes) & (tag >> 16);
+    d = (d | (d >> 1)) & 0x5555u;
 #ifdef __CUDA_ARCH__
     return __popc(d) > N;
 #else
     return __builtin_popcount(d) > N;
 #endif
 }
-MPCR_HD bool tag_rejects(uint32_t tag, uint32_t gcodes, int N) { return tag_rejects_g5(tag, gcodes << kTagShift, N); }
-MPCR_HD bool tag_is_open(uint32_t tag) { return (tag & 31u) == kTagOpen; }
-MPCR_HD bool tag_window_clean(uint32_t gvalid) { return (gvalid & ((1u << kTagBases) - 1u)) == ((1u << kTagBases) - 1u); }
+MPCR_HD bool tag_window_clean(uint32_t gvalid) { return (gvalid & 0xFFu) == 0xFFu; }
 
-// the tag of a primer: the letters following the seed, [ho+W, ho+W+kTagBases), up to the first one that is not a plain
-// A/C/G/T (a degenerate or foreign letter could match or not, so it and everything behind it stay out) or the primer's end
+// the tag of a primer: the kTagBases letters following the seed [ho+W, ho+W+kTagBases), lane i = letter i; lanes that
+// hold a plain A/C/G/T letter are masked in, every other lane (degenerate or foreign letter, past the primer's end) is
+// left out -- it could match or not, so it must not count as a mismatch
 template <class CharAt>
 MPCR_HD uint32_t make_tag(CharAt at, int len, int ho, int W) {
-    uint32_t codes = 0;
-    int t = 0;
-    for (int i = ho + W; i < len && t < kTagBases; ++i, ++t) {
+    uint32_t codes = 0, mask = 0;
+    for (int i = ho + W, n = 0; i < len && n < kTagBases; ++i, ++n) {
         const uint8_t c = at(i);
         uint32_t code;
         if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3;
-        else break;
-        codes |= code << (2 * t);
+        else continue;
+        codes |= code << (2 * n);
+        mask |= 3u << (2 * n);
     }
-    return (codes << kTagShift) | (uint32_t)(2 * (kTagBases - t));
+    return codes | (mask << 16);
 }
 
 // n bits of a little-endian bit plane starting at bit index b (n <= 32)

@@ -394,9 +394,9 @@ __global__ void __launch_bounds__(256) build_buckets(const Item<2>* __restrict__
             tag_b = tags[pairs[i + 1].f[1] & 0x7FFFFFFFu];
             if (i + 2 < n_valid && pairs[i + 2].f[0] == key) n = 3;
         }
-        // one record: both tags are its tag; two: one tag each; three or more: open tags = never reject
+        // one record: both tags are its tag; two: one tag each; three or more: mask 0 = never reject
         const uint32_t code = n == 1 ? rec : (kWalkBucket | i);
-        const uint32_t ta = n >= 3 ? kTagOpen : tag, tb = n == 1 ? tag : (n == 2 ? tag_b : kTagOpen);
+        const uint32_t ta = n >= 3 ? 0u : tag, tb = n == 1 ? tag : (n == 2 ? tag_b : 0u);
         const unsigned long long lo = (unsigned long long)code | ((unsigned long long)ta << 32);
         const unsigned long long hi = (unsigned long long)tb | ((unsigned long long)key << 32);
         uint32_t s = slot_index(key, sm);
@@ -619,13 +619,12 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
         const uint32_t qi = base + 32 * u + lane;
         ok[u] = qi < cnt;
         const uint32_t lp = queue[ok[u] ? qi : 0u];
-        // key (2W bits) and the tag window (kTagBases bases) out of three staged words
+        // key (2W bits) and the 8-base tag window (16 bits) out of three staged words
         const uint32_t wi = lp >> 4, sh = lp * 2u;   // the funnel shifts below wrap: only (2 * lp) & 31 counts
         const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1], w2 = s_p2[wi + 2];
         const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
         key[u] = (GAPPED ? gap_key_raw(x0, seed_mask, gap) : x0) & wmask;
-        // the tag window's codes, already at bit kTagShift (W + gap <= 16: the shift stays below 32); the rest is masked in the check
-        gcodes[u] = __funnelshift_r(x0, x1, 2 * (W + gap) - kTagShift);
+        gcodes[u] = __funnelshift_rc(x0, x1, 2 * (W + gap));  // clamped: 32 -> x1; only the low 16 bits are used
         lpv[u] = lp;
         dirty[u] = false;
         if (!CLEAN) {
@@ -655,13 +654,11 @@ __device__ __forceinline__ void probe_rounds(const ScanArgs& a, const uint16_t* 
         // sequence runs through it (kSlotChain); direct tables never collide
         const bool other = HASHED && skey != key[u];
         const bool collide = other && (v.x & kSlotChain);
-        const bool pass = !other && (dirty[u] || !(tag_rejects_g5(v.y, gcodes[u], N) && tag_rejects_g5(tag_b, gcodes[u], N)));
+        const bool pass = !other && (dirty[u] || !(tag_rejects(v.y, gcodes[u], N) && tag_rejects(tag_b, gcodes[u], N)));
         if (ok[u] && v.x != kSlotEmpty && (collide || pass)) {  // about one queued position in a thousand
             const uint32_t lp = ubase + lpv[u];
             if (a.debug & 2) ++n_dbg;
-            else if (collide)
-                probe_collision(a, key[u], (gcodes[u] >> kTagShift) & ((1u << (2 * kTagBases)) - 1u),
-                                dirty[u] ? 0u : (1u << kTagBases) - 1u, tile, lp);
+            else if (collide) probe_collision(a, key[u], gcodes[u] & 0xFFFFu, dirty[u] ? 0u : 0xFFu, tile, lp);
             else push_survivor(a, tile, lp, HASHED ? (v.x & ~kSlotChain) : v.x);
         }
     }
@@ -699,7 +696,7 @@ __device__ __forceinline__ void stage1_unit(const FilterView& f, const ScanArgs&
     if (lp0 < unit_nbases) {
         const uint2 v0 = *reinterpret_cast<const uint2*>(s_v + 2 * lane);
         const uint2 v1 = *reinterpret_cast<const uint2*>(s_v + 2 * lane + 2);
-        my_clean = (v0.x & v0.y & v1.x) == 0xFFFFFFFFu;  // own 64 bases + the 32 behind them (W + tag <= 26)
+        my_clean = (v0.x & v0.y & v1.x) == 0xFFFFFFFFu;  // own 64 bases + the 32 behind them (W + tag <= 24)
         // W-mer validity of the 64 positions: all ones on clean sequence, else log-doubling over the valid bits
         uint64_t wv = ~0ull;
         if (!my_clean)
@@ -1004,10 +1001,10 @@ __global__ void __launch_bounds__(256, 2) dense_scan_kernel(const ScanArgs a) {
                             for (int u = 0; u < kChunk; ++u) {
                                 const int j = c0 + u;
                                 if (sl[u].code == kSlotEmpty) continue;
-                                // the tag window: the kTagBases bases behind the seed (W == 16: the next register)
+                                // the tag window: the 8 bases behind the seed (W == 16: the next register)
                                 const uint32_t gc = __funnelshift_rc(raw(j), raw(j + 16), 2 * W);
                                 const bool clean = (wt16 >> j) & 1u;
-                                if (!(sl[u].code & kWalkBucket) || !(tag_is_open(sl[u].tag_a) && tag_is_open(sl[u].tag_b))) {
+                                if (!(sl[u].code & kWalkBucket) || ((sl[u].tag_a | sl[u].tag_b) >> 16)) {
                                     if (!clean || !(tag_rejects(sl[u].tag_a, gc, N) && tag_rejects(sl[u].tag_b, gc, N)))
                                         push_survivor(a, tile, lp0 + 16 * g + j, sl[u].code);
                                 } else {

@@ -374,7 +374,7 @@ int mpcr_table_build(mpcr_ctx* c, const uint8_t* blob, const uint64_t* off, cons
             if (!direct) while (c->slots[s].code != kSlotEmpty) s = (s + 1) & c->smap.mask;
             const uint32_t tag_a = tags[rec];
             c->slots[s] = n == 1 ? Slot{rec, tag_a, tag_a, key}
-                          : n == 2 ? Slot{kWalkBucket | i, tag_a, tag_b, key} : Slot{kWalkBucket | i, kTagOpen, kTagOpen, key};
+                          : n == 2 ? Slot{kWalkBucket | i, tag_a, tag_b, key} : Slot{kWalkBucket | i, 0u, 0u, key};
             if (c->filter_linear) c->filter[filter_word_linear(key, c->filter_scale, c->filter_bias)] |= filter_bits_linear(key);
             else c->filter[filter_word(key, cw, words)] |= filter_bits_of(key, WS);
         }
