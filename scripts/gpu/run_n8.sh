@@ -1,14 +1,14 @@
+# 8-GPU call: the sharded bench at N = 8 and N = 4 on the final kernels
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l; nproc
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 30 --warmup 5 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err; echo "bench n8 rc=$?"; grep -v "OMP_NUM\|^\*\*\*\|unbatched P2P" gpurun_out/r2_bench_n8.err | tail -5
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 30 --warmup 5 --no-e2e > gpurun_out/r2_bench_n4.json 2> gpurun_out/r2_bench_n4.err; echo "bench n4 rc=$?"
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; echo "bench n2 rc=$?"
-timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 500 > gpurun_out/r2_gpu_multi_pytest.log 2>&1; echo "multi pytest rc=$?"; tail -3 gpurun_out/r2_gpu_multi_pytest.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err; echo "bench n8 rc=$?"; grep -v "OMP_NUM\|^\*\*\*\|unbatched P2P" gpurun_out/r2_bench_n8.err | tail -5
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2_bench_n4.json 2> gpurun_out/r2_bench_n4.err; echo "bench n4 rc=$?"
 python - <<'PY'
 import json
-for n in (8,4,2):
+for n in (8,4):
     try:
         j=json.loads([l for l in open(f'gpurun_out/r2_bench_n{n}.json') if l.startswith('{')][-1])
         print(n, 'step', round(j['ms_per_step'],4), 'synced', round(j['config']['ms_per_step_host_synced'],4), 'scan', round(j['roofline']['kernel_ms'],4), 'verify', round(j['roofline']['verify_kernel_ms'],4), 'e2e', (j.get('e2e') or {}).get('ms_per_step'), 'file', (j.get('e2e_file') or {}).get('ms'))
+        print('  per rank', [r['ms_per_step'] for r in j['config']['per_rank']])
     except Exception as e: print(n, 'failed', e)
 PY
