@@ -287,7 +287,7 @@ def bind_to_gpu_numa_node(torch, local: int):
         bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
         if node < 0:
-            return None
+            return "none exposed (sysfs numa_node = -1: a single-node VM)"
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
