@@ -1126,62 +1126,133 @@ __global__ void __launch_bounds__(256, 4) sampled_scan_kernel(const ScanArgs a) 
     }
 }
 
-// (4)(5) verifier + hit emitter: one group of kVerifyLanes lanes per survivor (four survivors per warp: the work is
-// a chain of dependent loads, so narrow groups keep more of them in flight).  Primer 1 is compared by every lane of
-// the group (same addresses, broadcast loads); the mate search of engine.py:543-593 is spread over the lanes, one
-// delta per lane and round (rank 0: delta 0, 2i-1: -i, 2i: +i), neighbouring lanes touching neighbouring plane4 words.
+// (4)(5) verifier + hit emitter: kVerifyLanes lanes (one) per survivor for the primer-1 half -- the work is a chain of
+// dependent loads, so the narrower the groups the more chains a warp keeps in flight --, the whole warp for the mate
+// search of whatever passes (verify_quad).
 #ifndef MPCR_VERIFY_LANES
-#define MPCR_VERIFY_LANES 8
+#define MPCR_VERIFY_LANES 1
 #endif
-static constexpr int kVerifyLanes = MPCR_VERIFY_LANES;   // lanes per survivor (one mate-search offset each)
+// lanes per survivor in the primer-1 half; cfg3 verifier with 8 / 4 / 2 / 1: 0.183 / 0.156 / 0.139 / 0.133 ms, cfg4 0.57 /
+// 0.45 / 0.39 / 0.36 ms, one eighth of cfg3 0.037 / 0.032 / 0.033 / 0.033 ms
+static constexpr int kVerifyLanes = MPCR_VERIFY_LANES;
 
-__device__ __forceinline__ void verify_group(const ScanArgs& a, const TileDesc& td, uint32_t lp, uint32_t item, int gl) {
+// What the primer-1 half of engine.py:507-597 leaves for the mate search of one (survivor, record) pair.
+struct MateJob {
+    int64_t k, p2, gcontig;
+    int32_t lo, hi, l2;
+    uint32_t rec, p2_word, hash_off, contig, n_rank;
+    bool pass;
+};
+
+// engine.py:486-543 for one record at one seed position: primer 1, the end-of-sequence clamp, the mate window.
+__device__ __forceinline__ MateJob primer1_phase(const ScanArgs& a, const TileDesc& td, uint32_t lp, uint32_t item) {
+    MateJob j;
+    j.pass = false;
     // sampled tables: item = record * samp_s + window, the probed position lies `window` bases behind the seed
     const uint32_t rec = a.samp_s > 1 ? item / a.samp_s : item, win = a.samp_s > 1 ? item - rec * a.samp_s : 0u;
     const RecMeta m = a.meta[rec];
     const int64_t gcontig = td.gbase - (int64_t)td.lstart, L = td.length;
     const int l1 = m.len1, l2 = m.len2;
     const int64_t k = (int64_t)td.lstart + lp - (int64_t)win - (int64_t)m.hash_off;          // engine.py:486
-    if (k < 0 || k + l1 > L) return;                                                          // :487
-    if (!compare_primer(a.p4, gcontig + k, a.pwords + m.p1_word, l1, true, a.prm)) return;    // :515
+    if (k < 0 || k + l1 > L) return j;                                                        // :487
+    if (!compare_primer(a.p4, gcontig + k, a.pwords + m.p1_word, l1, true, a.prm)) return j;  // :515
     if (a.prm.gap > 0 && earlier_block_exact(a.p4, gcontig + k, a.pwords + m.p1_word, m.hash_off, a.prm.W - a.prm.block,
                                              a.prm.block, a.prm.gap))
-        return;   // block tables: the table of an earlier block reports this site
-    if (L - (k + l1) < l2) return;                                                            // :521-524
+        return j;   // block tables: the table of an earlier block reports this site
+    if (L - (k + l1) < l2) return j;                                                          // :521-524
     int64_t E = (int64_t)m.pcr_size, hi, lo;
     if (E > L - k) { E = L - k; hi = 0; }                                                     // :531-533
     else { hi = L - k - E; if (hi > a.prm.M) hi = a.prm.M; }                                  // :535
     lo = E - l1 - l2; if (lo > a.prm.M) lo = a.prm.M; if (lo < 0) lo = 0;                     // :538-540
-    const int64_t p2 = k + E - l2;                                                            // :543
-    const uint32_t n_rank = 2u * (uint32_t)(lo > hi ? lo : hi) + 1u;
-    const uint64_t* q2 = a.pwords + m.p2_word;
-    const PrimerView v2 = make_primer_view(q2, l2, false, a.prm);   // hoisted out of the delta loop
-    const HitEmitter emit{a.hits, a.capacity, a.count, td.contig, rec, (uint32_t)m.hash_off};
-    for (uint32_t rank = (uint32_t)gl; rank < n_rank; rank += kVerifyLanes) {                 // :545-593
+    j.k = k; j.p2 = k + E - l2; j.gcontig = gcontig;                                          // :543
+    j.lo = (int32_t)lo; j.hi = (int32_t)hi; j.l2 = l2;
+    j.rec = rec; j.p2_word = m.p2_word; j.hash_off = (uint32_t)m.hash_off; j.contig = td.contig;
+    j.n_rank = 2u * (uint32_t)(lo > hi ? lo : hi) + 1u;
+    j.pass = true;
+    return j;
+}
+
+// engine.py:545-593: the mate search of one job, one delta per lane of the team and round (rank 0: delta 0, 2i-1: -i,
+// 2i: +i), neighbouring lanes touching neighbouring plane4 words.
+__device__ __forceinline__ void mate_phase(const ScanArgs& a, const MateJob& j, uint32_t lane_in_team, uint32_t team) {
+    const uint64_t* q2 = a.pwords + j.p2_word;
+    const PrimerView v2 = make_primer_view(q2, j.l2, false, a.prm);   // hoisted out of the delta loop
+    const HitEmitter emit{a.hits, a.capacity, a.count, j.contig, j.rec, j.hash_off};
+    for (uint32_t rank = lane_in_team; rank < j.n_rank; rank += team) {
         const int64_t i = (rank + 1) >> 1;
         const bool neg = rank & 1u;
-        if (rank == 0 || (neg ? i <= lo : i <= hi)) {
-            const int64_t q = p2 + (neg ? -i : i);
-            const bool ok = v2.nw ? compare_view(a.p4, gcontig + q, v2, a.prm)
-                                  : compare_primer(a.p4, gcontig + q, q2, l2, false, a.prm);
-            if (ok) emit(k, q + l2 - 1, rank);
+        if (rank == 0 || (neg ? i <= j.lo : i <= j.hi)) {
+            const int64_t q = j.p2 + (neg ? -i : i);
+            const bool ok = v2.nw ? compare_view(a.p4, j.gcontig + q, v2, a.prm)
+                                  : compare_primer(a.p4, j.gcontig + q, q2, j.l2, false, a.prm);
+            if (ok) emit(j.k, q + j.l2 - 1, rank);
         }
     }
 }
 
-// One survivor for the lane group `gl` belongs to (shared by the dynamic and the static schedule).
-__device__ __forceinline__ void verify_survivor(const ScanArgs& a, const Survivor& sv, int gl) {
-    const TileDesc td = a.tiles[sv.tile];
-    if (!(sv.code & kWalkBucket)) {
-        verify_group(a, td, sv.lp, sv.code, gl);
-    } else {  // a seed shared by several records: bucket order, each entry behind its own tag
-        const int64_t gb = td.gbase + sv.lp + a.prm.W + a.prm.gap;
-        const uint32_t gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases), gvalid = fetch_bits(a.valid, gb, kTagBases);
-        const bool clean = tag_window_clean(gvalid);
-        for (uint32_t e = sv.code & ~kWalkBucket;; ++e) {
-            const BucketEntry b = a.bucket[e];
-            if (!clean || !tag_rejects(b.tag, gcodes, a.prm.N)) verify_group(a, td, sv.lp, b.rec_last & 0x7FFFFFFFu, gl);
-            if (b.rec_last >> 31) break;
+// One survivor per lane group of the warp (`have`: this group has one).  The groups walk their survivors' records side
+// by side -- one record for an ordinary survivor, the bucket entries their tags do not rule out for a seed shared by
+// several records -- and compare primer 1 on their own (the lanes of a group read the same addresses: broadcast loads;
+// one chain of dependent loads per group).  The mate searches of the records
+// that pass are then done by the WHOLE warp, one job after the other: a +-50 window is 13 rounds for a group of 8 lanes
+// but 4 for the warp, and of the survivors a warp looks at side by side most do not get this far -- their groups used
+// to sit through the others' rounds idle.  (cfg3 verifier 0.204 -> 0.133 ms, cfg4 0.76 -> 0.36, cfg5 5.2 -> 4.1.)
+__device__ __forceinline__ void verify_quad(const ScanArgs& a, const Survivor* __restrict__ mine, bool have) {
+    const uint32_t lane = threadIdx.x & 31;
+    TileDesc td = {};
+    uint32_t lp = 0, cur = 0, gcodes = 0;
+    bool walk = false, clean = false, more = have;
+    if (have) {
+        const Survivor sv = *mine;
+        td = a.tiles[sv.tile];
+        lp = sv.lp;
+        walk = (sv.code & kWalkBucket) != 0;
+        cur = sv.code & ~kWalkBucket;          // the record, or the first bucket entry
+        if (walk) {   // a seed shared by several records: bucket order, each entry behind its own tag
+            const int64_t gb = td.gbase + sv.lp + a.prm.W + a.prm.gap;
+            gcodes = fetch_bits(a.p2, 2 * gb, 2 * kTagBases);
+            clean = tag_window_clean(fetch_bits(a.valid, gb, kTagBases));
+        }
+    }
+    while (__any_sync(0xffffffffu, more)) {
+        MateJob job;
+        job.pass = false;
+        if (more) {
+            uint32_t item = cur;
+            bool has = true;
+            if (!walk) {
+                more = false;
+            } else {
+                for (;;) {   // the next entry its tag does not rule out
+                    const BucketEntry b = a.bucket[cur++];
+                    const bool last = (b.rec_last >> 31) != 0;
+                    has = !clean || !tag_rejects(b.tag, gcodes, a.prm.N);
+                    item = b.rec_last & 0x7FFFFFFFu;
+                    if (last) more = false;
+                    if (has || last) break;
+                }
+            }
+            if (has) job = primer1_phase(a, td, lp, item);
+        }
+        // the first lane of every group that has a job
+        uint32_t todo = __ballot_sync(0xffffffffu, job.pass && (lane % kVerifyLanes) == 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            MateJob t;
+            t.k = __shfl_sync(0xffffffffu, job.k, src);
+            t.p2 = __shfl_sync(0xffffffffu, job.p2, src);
+            t.gcontig = __shfl_sync(0xffffffffu, job.gcontig, src);
+            t.lo = __shfl_sync(0xffffffffu, job.lo, src);
+            t.hi = __shfl_sync(0xffffffffu, job.hi, src);
+            t.l2 = __shfl_sync(0xffffffffu, job.l2, src);
+            t.rec = __shfl_sync(0xffffffffu, job.rec, src);
+            t.p2_word = __shfl_sync(0xffffffffu, job.p2_word, src);
+            t.hash_off = __shfl_sync(0xffffffffu, job.hash_off, src);
+            t.contig = __shfl_sync(0xffffffffu, job.contig, src);
+            t.n_rank = __shfl_sync(0xffffffffu, job.n_rank, src);
+            t.pass = true;
+            mate_phase(a, t, lane, 32u);
         }
     }
 }
@@ -1189,7 +1260,7 @@ __device__ __forceinline__ void verify_survivor(const ScanArgs& a, const Survivo
 __device__ __forceinline__ void verify_body(const ScanArgs& a) {
     constexpr int kGroups = 32 / kVerifyLanes;
     constexpr uint32_t kGrab = kGroups;       // survivors a warp takes per cursor atomic (one per lane group)
-    const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
+    const int lane = threadIdx.x & 31, group = lane / kVerifyLanes;
     const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     // every warp starts at its own sub-list and moves on when that one is drained, until it has seen them all;
     // 32 sub-lists are looked at per round (one per lane) so that drained ones cost nothing
@@ -1209,7 +1280,8 @@ __device__ __forceinline__ void verify_body(const ScanArgs& a) {
             if (lane == 0) first = __ldcg(ctl + 1) < n ? atomicAdd(ctl + 1, kGrab) : n;   // look before touching the line
             first = __shfl_sync(0xffffffffu, first, 0);
             if (first >= n) break;
-            for (uint32_t idx = first + group; idx < min(first + kGrab, n); idx += kGroups) verify_survivor(a, surv[idx], gl);
+            const uint32_t idx = first + group;
+            verify_quad(a, surv + idx, idx < n);
         }
       }
     }
@@ -1253,20 +1325,24 @@ __global__ void __launch_bounds__(256, kVerifyCtasPerSm) verify_kernel(const Sca
     }
     const uint32_t total = pre[kSurvLists];
     constexpr uint32_t kGroupsPerWarp = 32 / kVerifyLanes;
-    const uint32_t n_groups = gridDim.x * (blockDim.x >> 5) * kGroupsPerWarp;
-    if (total / n_groups < kStaticVerifyDepth) {
-        // lane group G takes the survivors G, G + n_groups, ... of the concatenated sub-lists: neighbouring groups of a
-        // warp look at neighbouring survivors (same producer warp, nearby bases), and a costly stretch of the genome
-        // (an N-run in IUPAC mode, a repeat) is spread over all groups
-        const int lane = threadIdx.x & 31, group = lane / kVerifyLanes, gl = lane % kVerifyLanes;
+    // (the switch-over point is counted in survivors per warp, four to the unit, whatever the group width)
+    if (total / (gridDim.x * (blockDim.x >> 5) * 4u) < kStaticVerifyDepth) {
+        // survivor g of the concatenated sub-lists goes to warp g % n_warps; a warp takes its survivors as many at a time
+        // as it has lane groups.  (Dealing consecutive survivors to the groups of ONE warp left most warps of a short list
+        // -- a rank of an 8-GPU run -- without work once the groups became narrow.)
+        const int lane = threadIdx.x & 31, group = lane / kVerifyLanes;
+        const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
         const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        for (uint32_t g = warp_id * kGroupsPerWarp + group; g < total; g += n_groups) {
+        for (uint32_t slot0 = 0; (uint64_t)slot0 * n_warps + warp_id < total; slot0 += kGroupsPerWarp) {   // warp-uniform
+            const uint64_t g64 = (uint64_t)(slot0 + group) * n_warps + warp_id;
+            const bool have = g64 < total;
+            const uint32_t g = have ? (uint32_t)g64 : 0u;
             uint32_t lo = 0, hi = kSurvLists;           // the sub-list that holds global index g
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
                 if (pre[mid] <= g) lo = mid; else hi = mid;
             }
-            verify_survivor(a, a.surv[(size_t)lo * a.surv_cap + (g - pre[lo])], gl);
+            verify_quad(a, a.surv + ((size_t)lo * a.surv_cap + (g - pre[lo])), have);
         }
     } else {
         verify_body(a);
