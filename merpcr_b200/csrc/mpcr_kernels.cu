@@ -2145,7 +2145,12 @@ static int build_tiles_impl(mpcr_ctx* c, const mpcr_contig* contigs, uint32_t n_
     uint64_t tb = kTileBases;
     // (32 tiles per warp: the warps walk their tiles in lock step, so the launch ends with up to one tile-time of
     // partly idle SMs -- 3 % of the launch at 32 tiles per warp, 10 % at 10)
-    const uint64_t want_tiles = 32ull * (uint64_t)c->sm_count * (kScanThreads / 32);
+    // (tuning builds, scan kernel for one eighth of cfg3 / all of it: 16 tiles per warp 0.350 / 2.620 ms, 32: 0.353 / 2.620,
+    // 64: 0.363 / 2.626, 128: 0.363 / 2.644 -- finer tiles cost more in descriptor fetches than they balance)
+#ifndef MPCR_WANT_TILES
+#define MPCR_WANT_TILES 32
+#endif
+    const uint64_t want_tiles = (uint64_t)MPCR_WANT_TILES * (uint64_t)c->sm_count * (kScanThreads / 32);
     while (tb > 2048 && span / tb < want_tiles) tb >>= 1;
     std::vector<TileDesc> tiles;
     for (uint32_t i = 0; i < n_contigs; ++i) {
