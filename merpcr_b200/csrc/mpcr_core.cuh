@@ -380,6 +380,38 @@ MPCR_HD bool compare_view(const uint64_t* p4, int64_t gb, const PrimerView& v, c
     return n0 + popc64(m1) <= prm.N;
 }
 
+// compare_view's first check (the 8-base word that decides almost every position of a mate window) for m <= 32
+// CONSECUTIVE positions starting at plane-relative base gb, in rolling form: six 32-bit words of plane4 are loaded once,
+// aligned to gb, and every position's 8 nibbles are one funnel shift away -- where the per-position form pays address
+// arithmetic and two loads each time.  Bit t of the result: position gb + t passes the check (exactly the same test, so
+// a position that fails it fails compare_view).  Reads 48 bases from gb on.
+MPCR_HD uint32_t mate_precheck32(const uint64_t* p4, int64_t gb, uint32_t m, const PrimerView& v, const SearchParams& prm) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p4);
+    const uint64_t i0 = (uint64_t)gb >> 3;
+    const unsigned a = ((unsigned)gb & 7u) * 4u;
+    uint32_t r[6], al[5];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r[k] = w[i0 + k];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) al[k] = a ? ((r[k] >> a) | (r[k + 1] << (32u - a))) : r[k];
+    const uint32_t q8 = (uint32_t)v.q[0], aux8 = (uint32_t)v.aux[0], lanes8 = (uint32_t)v.lanes[0], prot8 = (uint32_t)v.prot[0];
+    uint32_t out = 0;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        if ((uint32_t)t >= m) break;
+        const int k = t >> 3, sft = 4 * (t & 7);
+        const uint32_t x = sft ? ((al[k] >> sft) | (al[k + 1] << (32 - sft))) : al[k];
+        const uint32_t m8 = mismatch_lanes32(x, q8, aux8, lanes8, prm.iupac);
+#ifdef __CUDA_ARCH__
+        const int n8 = __popc(m8);
+#else
+        const int n8 = __builtin_popcount(m8);
+#endif
+        if (!((m8 & prot8) || n8 > prm.N)) out |= 1u << t;
+    }
+    return out;
+}
+
 // Block tables: is one of the blocks IN FRONT of this table's block (letters [ws, ws + gap) behind the hash offset, in
 // pieces of `block`) identical to the genome?  Then an earlier table finds this site and this one must not report it again.
 // The blocks hold plain A/C/G/T primer letters, and the nibble code is a bijection on the sequence alphabet, so "identical

@@ -1172,20 +1172,46 @@ __device__ __forceinline__ MateJob primer1_phase(const ScanArgs& a, const TileDe
     return j;
 }
 
-// engine.py:545-593: the mate search of one job, one delta per lane of the team and round (rank 0: delta 0, 2i-1: -i,
-// 2i: +i), neighbouring lanes touching neighbouring plane4 words.
+// The 8-base pre-check of up to 32 consecutive mate positions (mpcr_core.cuh: mate_precheck32), out of line: the
+// unrolled block is large and the verifier lives on 64 registers.
+__device__ __noinline__ uint32_t mate_block(const uint64_t* __restrict__ p4, int64_t gb, uint32_t m, const PrimerView& v,
+                                            const SearchParams& prm) {
+    return mate_precheck32(p4, gb, m, v, prm);
+}
+
+// engine.py:545-593: the mate search of one job by a team of lanes.  The window's positions p2 - lo .. p2 + hi are dealt
+// out in CONSECUTIVE stretches, one per lane, so that a lane can check its stretch in rolling form (blocks of 32
+// positions: six words of plane4 loaded once, one funnel shift per position) and runs the full compare only where the
+// first eight bases pass; a hit's rank is the reference's order of deltas (0, -1, +1, -2, ...), which the sort restores.
+// Primers longer than 32 bases keep the position-by-position compare.
 __device__ __forceinline__ void mate_phase(const ScanArgs& a, const MateJob& j, uint32_t lane_in_team, uint32_t team) {
     const uint64_t* q2 = a.pwords + j.p2_word;
     const PrimerView v2 = make_primer_view(q2, j.l2, false, a.prm);   // hoisted out of the delta loop
     const HitEmitter emit{a.hits, a.capacity, a.count, j.contig, j.rec, j.hash_off};
-    for (uint32_t rank = lane_in_team; rank < j.n_rank; rank += team) {
-        const int64_t i = (rank + 1) >> 1;
-        const bool neg = rank & 1u;
-        if (rank == 0 || (neg ? i <= j.lo : i <= j.hi)) {
-            const int64_t q = j.p2 + (neg ? -i : i);
-            const bool ok = v2.nw ? compare_view(a.p4, j.gcontig + q, v2, a.prm)
-                                  : compare_primer(a.p4, j.gcontig + q, q2, j.l2, false, a.prm);
-            if (ok) emit(j.k, q + j.l2 - 1, rank);
+    const uint32_t n_off = (uint32_t)(j.lo + j.hi) + 1u;               // positions of the window
+    const int64_t q_first = j.p2 - j.lo;
+    const uint32_t per = (n_off + team - 1u) / team;
+    const uint32_t t0 = lane_in_team * per;
+    if (t0 >= n_off) return;
+    const uint32_t cnt = min(per, n_off - t0);
+    auto rank_of = [&](int64_t q) -> uint32_t {
+        const int64_t d = q - j.p2;
+        return d == 0 ? 0u : (d < 0 ? (uint32_t)(-2 * d - 1) : (uint32_t)(2 * d));
+    };
+    if (v2.nw) {
+        for (uint32_t c0 = 0; c0 < cnt; c0 += 32u) {
+            const int64_t qb = q_first + t0 + c0;
+            uint32_t cand = mate_block(a.p4, j.gcontig + qb, min(32u, cnt - c0), v2, a.prm);
+            while (cand) {
+                const int64_t q = qb + (__ffs(cand) - 1);
+                cand &= cand - 1;
+                if (compare_view(a.p4, j.gcontig + q, v2, a.prm)) emit(j.k, q + j.l2 - 1, rank_of(q));
+            }
+        }
+    } else {
+        for (uint32_t t = 0; t < cnt; ++t) {
+            const int64_t q = q_first + t0 + t;
+            if (compare_primer(a.p4, j.gcontig + q, q2, j.l2, false, a.prm)) emit(j.k, q + j.l2 - 1, rank_of(q));
         }
     }
 }

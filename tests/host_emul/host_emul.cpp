@@ -531,6 +531,23 @@ int mpcr_sort_finish(mpcr_ctx* c, mpcr_hit*, const uint64_t* h_result, uint64_t,
 float mpcr_slot_scan_ms(mpcr_ctx*, int) { return 0.f; }
 float mpcr_slot_verify_ms(mpcr_ctx*, int) { return 0.f; }
 
+// Test-only probe of the rolling mate pre-check (mpcr_core.cuh): the block form against compare_view's own first check,
+// position by position.  Returns the number of positions where they differ.
+uint32_t emul_mate_precheck_diff(const uint64_t* p4, int64_t gb, uint32_t m, const uint64_t* pw, int len, int N, int X, int iupac) {
+    SearchParams prm{11, 50, N, X, iupac};
+    const PrimerView v = make_primer_view(pw, len, false, prm);
+    if (!v.nw) return 0;
+    const uint32_t block = mate_precheck32(p4, gb, m, v, prm);
+    uint32_t diff = 0;
+    for (uint32_t t = 0; t < m; ++t) {
+        const uint32_t m8 = mismatch_lanes32(fetch8(p4, gb + t), (uint32_t)v.q[0], (uint32_t)v.aux[0], (uint32_t)v.lanes[0], prm.iupac);
+        const bool pass = !((m8 & (uint32_t)v.prot[0]) || __builtin_popcount(m8) > prm.N);
+        if (pass != (((block >> t) & 1u) != 0)) ++diff;
+        if (!pass && compare_view(p4, gb + t, v, prm)) ++diff;   // the pre-check is a necessary condition
+    }
+    if (m < 32 && (block >> m)) ++diff;
+    return diff;
+}
 // Test-only probe of the four-bytes-at-a-time FASTA keep test (mpcr_core.cuh)
 uint32_t emul_fasta_keep_flags4(uint32_t w) { return fasta_keep_flags4(w); }
 uint32_t emul_bytes_equal_trigger4(uint32_t w, uint32_t c4) { return bytes_equal_trigger4(w, c4); }

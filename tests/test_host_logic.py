@@ -776,3 +776,41 @@ def test_fasta_keep_flags_four_bytes_at_a_time():
         if has:   # the lowest flagged byte is a true match
             low = min(k for k in range(4) if (trig >> (8 * k + 7)) & 1)
             assert ((w >> (8 * low)) & 0xFF) == 0x3E
+
+
+def test_rolling_mate_precheck_equals_the_per_position_check():
+    """mpcr_core.cuh: mate_precheck32 (the verifier's rolling 8-base check over up to 32 consecutive mate positions) must
+    be exactly compare_view's own first check at every position, for every alignment of the block, both compare modes."""
+    import ctypes
+    lib = ctypes.CDLL(emul.build())
+    lib.emul_mate_precheck_diff.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.emul_mate_precheck_diff.restype = ctypes.c_uint32
+    rng = np.random.default_rng(21)
+    n_bases = 4096
+    # plane4: mostly A/C/G/T nibbles (1, 2, 4, 8), some N (15), some IUPAC masks, some zero (X / foreign)
+    nib = rng.choice(np.array([1, 2, 4, 8, 15, 3, 5, 0], dtype=np.uint8), size=n_bases + 128, p=[.23, .23, .23, .23, .03, .02, .02, .01])
+    plane = np.zeros((n_bases + 128) // 16, dtype=np.uint64)
+    for i, v in enumerate(nib):
+        plane[i // 16] |= np.uint64(int(v)) << np.uint64(4 * (i % 16))
+    checked = 0
+    for trial in range(300):
+        length = int(rng.integers(8, 33))
+        pos = int(rng.integers(0, n_bases - 200))
+        # primer = a genome stretch with a few substitutions / a degenerate letter, so that some positions pass
+        pn = nib[pos: pos + length].copy()
+        pn[pn == 0] = 1
+        for _ in range(int(rng.integers(0, 3))):
+            pn[int(rng.integers(0, length))] = int(rng.choice([1, 2, 4, 8, 15, 5]))
+        nw = (length + 15) // 16
+        words = np.zeros(2 * nw, dtype=np.uint64)       # nibble words, then aux words (no flags)
+        for i, v in enumerate(pn):
+            words[i // 16] |= np.uint64(int(v)) << np.uint64(4 * (i % 16))
+        for gb in (pos - int(rng.integers(0, 31)), pos - 17, pos):
+            gb = max(gb, 0)
+            for m in (32, int(rng.integers(1, 32))):
+                for N, X, iupac in ((0, 0, 0), (1, 1, 0), (2, 2, 1), (0, 1, 1)):
+                    d = lib.emul_mate_precheck_diff(plane.ctypes.data, gb, m, words.ctypes.data, length, N, X, iupac)
+                    assert d == 0, (trial, gb, m, N, X, iupac)
+                    checked += 1
+    assert checked > 5000
